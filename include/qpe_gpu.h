@@ -1,0 +1,141 @@
+/*
+ * qpe_gpu.h -- low-level C-ABI of libqpegpu.so (new; nothing like it exists in the reference).
+ *
+ * executeEngine-gpu.h is the drop-in surface (resultSetS of strings, as the reference's bridge
+ * expects).  This header exposes the same hot path WITHOUT string materialisation, for
+ * benchmarks, parity tests and host languages that want row ids: the match phase of
+ * executeQuerySelectSerial (engine/serial/executeEngine-serial.c:355-476), the DELETE match
+ * mask (:646-677), and batched findRange / find_rows lookups (engine/bplus.c:282-314, :361-411).
+ *
+ * Conventions: every function returns 0 on success and a negative value on failure, with a
+ * message retrievable through qpe_gpu_last_error().  Buffers returned through an out-pointer
+ * are malloc-owned by the caller and released with qpe_gpu_free().  Row ids are positions in
+ * table order (index into the reference's all_records[]), local to the engine's shard.
+ */
+#ifndef QPE_GPU_H
+#define QPE_GPU_H
+
+#include "qpe_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qpe_scan_stats {
+    double kernel_ms;       /* device time of the match phase (CUDA events on the engine's stream) */
+    double total_ms;        /* host wall time of the call */
+    long long rows_scanned; /* rows the match phase evaluated (N on the scan path, candidates on the index path) */
+    long long candidates;   /* index path: sum of segment lengths; 0 on the scan path */
+    long long matches;
+    long long algo_bytes;   /* N * sum(width of distinct WHERE columns) + 4 * matches   */
+    int path;               /* 0 = full scan (K1), 1 = index (K3 + K1g) */
+    int launches;           /* kernels launched by this call */
+    int tile_rows;
+    int stages;
+    int grid;
+    int reserved;
+} qpe_scan_stats;
+
+/* 1 when a CUDA device is usable by this process, else 0 (then every engine call fails loudly). */
+int qpe_gpu_available(void);
+const char *qpe_gpu_last_error(void);
+void qpe_gpu_free(void *p);
+
+/* Engine over rows already in host memory (array-of-structs), instead of a CSV file.
+ * datafile may be NULL (then INSERT/DELETE have no file side effect). */
+struct engineS *qpe_gpu_engine_from_records(const record *rows, long long n_rows, int num_indexes,
+                                            const char *indexed_attributes[], const int attribute_types[],
+                                            const char *datafile, const char *tableName);
+
+/* Engine over a synthetic table generated ON THE DEVICE (distributions of the reference's
+ * data-generation/generate_commands.py, restated for a counter-based generator; see
+ * csrc/synth.cuh).  Rows [row_base, row_base + n_rows) of the virtual table of `total_rows`
+ * rows; column_mask selects which columns are materialised (bit c = schema column c). */
+struct engineS *qpe_gpu_engine_synth(unsigned long long total_rows, unsigned long long row_base,
+                                     unsigned long long n_rows, unsigned long long seed,
+                                     unsigned int column_mask, int num_indexes,
+                                     const char *indexed_attributes[], const int attribute_types[]);
+
+long long qpe_gpu_num_rows(const struct engineS *engine);
+
+/* Match phase of SELECT with the reference's path rule (index path iff a top-level condition
+ * names a u64/int index; else full scan).  *ids_out receives the matching row ids in the
+ * reference's result order. */
+int qpe_gpu_select_ids(struct engineS *engine, struct whereClauseS *whereClause, unsigned int **ids_out,
+                       size_t *n_out, qpe_scan_stats *stats);
+
+/* Same match phase, result left in HBM (device pointer valid until the next call on this
+ * engine).  flags: bit0 = force the full-scan path even if an index applies;
+ * bit1 = count only (no ids written). */
+#define QPE_SCAN_FORCE 1
+#define QPE_SCAN_COUNT_ONLY 2
+int qpe_gpu_select_ids_device(struct engineS *engine, struct whereClauseS *whereClause, int flags,
+                              unsigned long long *count_out, const unsigned int **d_ids_out,
+                              qpe_scan_stats *stats);
+
+/* Same as qpe_gpu_select_ids, into a caller-provided (ideally pinned) host buffer of `cap` ids.
+ * *n_out always receives the match count; returns -5 when it exceeds cap. flags: QPE_SCAN_FORCE. */
+int qpe_gpu_select_ids_into(struct engineS *engine, struct whereClauseS *whereClause, int flags, unsigned int *ids,
+                            size_t cap, size_t *n_out, qpe_scan_stats *stats);
+
+/* cudaMemcpy device -> host for pointers handed out by the *_device calls. 0 on success. */
+int qpe_gpu_copy_from_device(void *dst_host, const void *src_device, size_t bytes);
+
+/* Statistics of the engine's most recent match phase. */
+int qpe_gpu_last_stats(struct engineS *engine, qpe_scan_stats *stats);
+
+/* Write the whole table as a CSV in the data generator's format (header line, QUOTE_MINIMAL
+ * quoting, \r\n line ends, sudo_used as true/false: data-generation/generate_commands.py:812-816)
+ * so that the reference's loader and ours can both ingest it.  Every column must be resident. */
+int qpe_gpu_write_csv(struct engineS *engine, const char *path);
+
+/* DELETE's match mask without deleting: bit r of the bitmap = row r matches.  bitmap must hold
+ * (num_rows + 31) / 32 words. */
+int qpe_gpu_match_mask(struct engineS *engine, struct whereClauseS *whereClause, unsigned int *bitmap,
+                       size_t n_words, unsigned long long *count_out, qpe_scan_stats *stats);
+
+/* Batched inclusive-range probes [lo[q], hi[q]] on the index of `attribute` (point lookup:
+ * lo == hi).  first[q] / count[q] delimit the answer inside the index order
+ * (key ascending, table position descending == the reference's leaf chain). */
+int qpe_gpu_probe_batch(struct engineS *engine, const char *attribute, const KEY_T *lo, const KEY_T *hi,
+                        size_t n_queries, unsigned int *first, unsigned int *count, qpe_scan_stats *stats);
+/* Row ids of index entries [first, first + count) of `attribute`'s index. */
+int qpe_gpu_index_slice(struct engineS *engine, const char *attribute, unsigned int first, unsigned int count,
+                        unsigned int *row_ids_out);
+
+/* Copy n_rows values of a column to the host in device layout (u64 / int32 / u8 / fixed-width
+ * NUL-padded text); *width_out = bytes per row.  out must hold n_rows * width bytes; pass
+ * out == NULL to query the width only. */
+int qpe_gpu_fetch_column(struct engineS *engine, const char *attribute, long long first_row, long long n_rows,
+                         void *out, unsigned int *width_out);
+
+/* Tuning override for the scan kernel (0 = automatic). */
+int qpe_gpu_set_tile(struct engineS *engine, int tile_rows, int stages);
+
+/* SQL front end (same grammar and quirks as the reference's tokenizer/src/tokenizer.c +
+ * connectEngine.c bridge).  qpe_sql_run executes one statement and writes what the
+ * reference's run_test_query prints (connectEngine.c:125-245) to `out` (stdout if NULL). */
+void qpe_sql_run(struct engineS *engine, const char *statement, int max_rows, void *out_FILE);
+/* Same, into a malloc'ed NUL-terminated buffer. */
+char *qpe_sql_run_to_text(struct engineS *engine, const char *statement, int max_rows);
+/* Parse `statement`, run only the match phase of its WHERE (SELECT or DELETE text). */
+int qpe_sql_select_ids(struct engineS *engine, const char *statement, int flags, unsigned int **ids_out,
+                       size_t *n_out, qpe_scan_stats *stats);
+int qpe_sql_select_ids_device(struct engineS *engine, const char *statement, int flags,
+                              unsigned long long *count_out, const unsigned int **d_ids_out,
+                              qpe_scan_stats *stats);
+int qpe_sql_select_ids_into(struct engineS *engine, const char *statement, int flags, unsigned int *ids, size_t cap,
+                            size_t *n_out, qpe_scan_stats *stats);
+int qpe_sql_match_mask(struct engineS *engine, const char *statement, unsigned int *bitmap, size_t n_words,
+                       unsigned long long *count_out, qpe_scan_stats *stats);
+/* Full SELECT through executeQuerySelectGPU; NULL if `statement` is not a SELECT.  Release with
+ * freeResultSet (executeEngine-gpu.h). */
+struct resultSetS *qpe_sql_select(struct engineS *engine, const char *statement);
+/* The whereClauseS list the front end builds for `statement`, rendered as text (malloc'ed). */
+char *qpe_sql_where_to_text(const char *statement);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* QPE_GPU_H */

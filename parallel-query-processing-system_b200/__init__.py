@@ -1,0 +1,339 @@
+"""Host-side mirror of the B200 SELECT/WHERE engine (libqpegpu.so) for Python callers.
+
+The product is the C-ABI shared library next to this file (``libqpegpu.so``: sm_100a CUDA
+kernels behind the reference's ``executeEngine-*.h`` entry-point shape, see ``include/``).  This
+module is a thin ``ctypes`` binding used by the tests, ``bench.py`` and ``__graft_entry__.py``;
+it adds no compute of its own and has NO fallback: if the library is missing, or no CUDA device
+is usable, it raises.
+
+Names follow the reference (engine, SELECT/DELETE/INSERT, indexes, row ids):
+  reference entry point (include/executeEngine-serial.h:69-151)   here
+  initializeEngineSerial                                          Engine.from_csv
+  executeQuerySelectSerial                                        Engine.select / Engine.select_ids
+  executeQueryDeleteSerial / executeQueryInsertSerial             Engine.run("DELETE ..." / "INSERT ...")
+  run_test_query (connectEngine.c:125)                            Engine.run
+  findRange / find_rows (engine/bplus.c:282,361)                  Engine.probe_batch / Engine.index_slice
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqpegpu.so")
+
+COLUMNS = ("command_id", "raw_command", "base_command", "shell_type", "exit_code", "timestamp", "sudo_used",
+           "working_directory", "user_id", "user_name", "host_name", "risk_level")
+# the reference's default index set (connectEngine.c:48-62): attribute -> type code 0=u64 1=int 2=string 3=bool
+DEFAULT_INDEXES = (("command_id", 0), ("user_id", 1), ("risk_level", 1), ("exit_code", 1), ("sudo_used", 3))
+NUMERIC_DTYPES = {"command_id": np.uint64, "exit_code": np.int32, "user_id": np.int32, "risk_level": np.int32,
+                  "sudo_used": np.uint8}
+
+SCAN_FORCE = 1
+SCAN_COUNT_ONLY = 2
+
+
+class QpeError(RuntimeError):
+    pass
+
+
+class ScanStats(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("total_ms", C.c_double), ("rows_scanned", C.c_longlong),
+                ("candidates", C.c_longlong), ("matches", C.c_longlong), ("algo_bytes", C.c_longlong),
+                ("path", C.c_int), ("launches", C.c_int), ("tile_rows", C.c_int), ("stages", C.c_int),
+                ("grid", C.c_int), ("reserved", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class KeyT(C.Structure):
+    """KEY_T of include/bplus.h:22-30 (16-byte tagged union)."""
+
+    class _V(C.Union):
+        _fields_ = [("u64", C.c_uint64), ("i32", C.c_int), ("b", C.c_bool), ("str", C.c_char_p)]
+
+    _fields_ = [("type", C.c_int), ("v", _V)]
+
+
+class ResultSet(C.Structure):
+    """struct resultSetS (include/executeEngine-serial.h:30-38)."""
+    _fields_ = [("numRecords", C.c_int), ("numColumns", C.c_int), ("columnNames", C.POINTER(C.c_char_p)),
+                ("columnTypes", C.POINTER(C.c_int)), ("data", C.POINTER(C.POINTER(C.c_char_p))),
+                ("queryTime", C.c_double), ("success", C.c_bool)]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libqpegpu.so (built in-tree by ``__graft_entry__.build()`` / ``make``). No fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QpeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, cp, i, ll, ull, sz = C.c_void_p, C.c_char_p, C.c_int, C.c_longlong, C.c_ulonglong, C.c_size_t
+    pstats = C.POINTER(ScanStats)
+    sig = {
+        "qpe_gpu_available": (i, []),
+        "qpe_gpu_last_error": (cp, []),
+        "qpe_gpu_free": (None, [vp]),
+        "initializeEngineGPU": (vp, [i, C.POINTER(cp), C.POINTER(i), cp, cp]),
+        "destroyEngineGPU": (None, [vp]),
+        "freeResultSet": (None, [vp]),
+        "qpe_gpu_engine_synth": (vp, [ull, ull, ull, ull, C.c_uint, i, C.POINTER(cp), C.POINTER(i)]),
+        "qpe_gpu_engine_from_records": (vp, [vp, ll, i, C.POINTER(cp), C.POINTER(i), cp, cp]),
+        "qpe_gpu_num_rows": (ll, [vp]),
+        "qpe_gpu_probe_batch": (i, [vp, cp, C.POINTER(KeyT), C.POINTER(KeyT), sz, vp, vp, pstats]),
+        "qpe_gpu_index_slice": (i, [vp, cp, C.c_uint, C.c_uint, vp]),
+        "qpe_gpu_fetch_column": (i, [vp, cp, ll, ll, vp, C.POINTER(C.c_uint)]),
+        "qpe_gpu_set_tile": (i, [vp, i, i]),
+        "qpe_gpu_copy_from_device": (i, [vp, vp, sz]),
+        "qpe_gpu_last_stats": (i, [vp, pstats]),
+        "qpe_gpu_write_csv": (i, [vp, cp]),
+        "qpe_sql_run": (None, [vp, cp, i, vp]),
+        "qpe_sql_run_to_text": (vp, [vp, cp, i]),
+        "qpe_sql_select_ids": (i, [vp, cp, i, C.POINTER(vp), C.POINTER(sz), pstats]),
+        "qpe_sql_select_ids_device": (i, [vp, cp, i, C.POINTER(ull), C.POINTER(vp), pstats]),
+        "qpe_sql_select_ids_into": (i, [vp, cp, i, vp, sz, C.POINTER(sz), pstats]),
+        "qpe_sql_match_mask": (i, [vp, cp, vp, sz, C.POINTER(ull), pstats]),
+        "qpe_sql_select": (C.POINTER(ResultSet), [vp, cp]),
+        "qpe_sql_where_to_text": (vp, [cp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def gpu_available() -> bool:
+    return bool(load_library().qpe_gpu_available())
+
+
+def _index_args(indexes):
+    n = len(indexes)
+    names = (C.c_char_p * max(n, 1))(*[a.encode() for a, _ in indexes])
+    types = (C.c_int * max(n, 1))(*[t for _, t in indexes])
+    return n, names, types
+
+
+def column_mask(columns: Sequence[str]) -> int:
+    m = 0
+    for c in columns:
+        m |= 1 << COLUMNS.index(c)
+    return m
+
+
+def where_text(statement: str) -> str:
+    """The WHERE list our front end builds for `statement` (parity aid for the tokenizer restatement)."""
+    lib = load_library()
+    p = lib.qpe_sql_where_to_text(statement.encode())
+    try:
+        return C.string_at(p).decode()
+    finally:
+        lib.qpe_gpu_free(p)
+
+
+class Engine:
+    """One table resident in HBM as columns, plus its flattened indexes (struct engineS* underneath)."""
+
+    def __init__(self, handle, lib):
+        if not handle:
+            raise QpeError("engine creation failed: " + (lib.qpe_gpu_last_error() or b"").decode())
+        self._h = handle
+        self._lib = lib
+
+    # ---- construction ---------------------------------------------------------------------
+    @classmethod
+    def from_csv(cls, path: str, indexes=DEFAULT_INDEXES, table: str = "commands") -> "Engine":
+        lib = load_library()
+        n, names, types = _index_args(indexes)
+        return cls(lib.initializeEngineGPU(n, names, types, path.encode(), table.encode()), lib)
+
+    @classmethod
+    def from_synth(cls, total_rows: int, n_rows: Optional[int] = None, row_base: int = 0, seed: int = 12345,
+                   columns: Sequence[str] = COLUMNS, indexes=()) -> "Engine":
+        lib = load_library()
+        n, names, types = _index_args(indexes)
+        if n_rows is None:
+            n_rows = total_rows
+        return cls(lib.qpe_gpu_engine_synth(total_rows, row_base, n_rows, seed, column_mask(columns), n, names, types),
+                   lib)
+
+    def close(self):
+        if self._h:
+            self._lib.destroyEngineGPU(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers --------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise QpeError(f"{what} failed (rc={rc}): " + (self._lib.qpe_gpu_last_error() or b"").decode())
+
+    @property
+    def num_rows(self) -> int:
+        return int(self._lib.qpe_gpu_num_rows(self._h))
+
+    def set_tile(self, tile_rows: int = 0, stages: int = 0):
+        self._check(self._lib.qpe_gpu_set_tile(self._h, tile_rows, stages), "set_tile")
+
+    def last_stats(self) -> dict:
+        st = ScanStats()
+        self._check(self._lib.qpe_gpu_last_stats(self._h, C.byref(st)), "last_stats")
+        return st.as_dict()
+
+    # ---- SQL surface ----------------------------------------------------------------------
+    def run(self, statement: str, max_rows: int = 20) -> str:
+        """run_test_query: execute one statement, return exactly what the reference would print."""
+        p = self._lib.qpe_sql_run_to_text(self._h, statement.encode(), max_rows)
+        if not p:
+            raise QpeError("qpe_sql_run_to_text failed")
+        try:
+            return C.string_at(p).decode(errors="replace")
+        finally:
+            self._lib.qpe_gpu_free(p)
+
+    def select(self, statement: str) -> Tuple[List[str], List[List[str]], float]:
+        """executeQuerySelectGPU: (column names, rows of cell text, match-phase seconds)."""
+        res = self._lib.qpe_sql_select(self._h, statement.encode())
+        if not res:
+            raise QpeError("not a SELECT statement: " + statement)
+        try:
+            r = res.contents
+            if not r.success:
+                raise QpeError("SELECT failed: " + (self._lib.qpe_gpu_last_error() or b"").decode())
+            names = [r.columnNames[j].decode() for j in range(r.numColumns)]
+            rows = [[r.data[i][j].decode(errors="replace") for j in range(r.numColumns)] for i in range(r.numRecords)]
+            return names, rows, r.queryTime
+        finally:
+            self._lib.freeResultSet(res)
+
+    def select_ids(self, statement: str, force_scan: bool = False) -> Tuple[np.ndarray, dict]:
+        """Match phase only: row ids (table positions) in the reference's result order."""
+        ids = C.c_void_p()
+        n = C.c_size_t()
+        st = ScanStats()
+        rc = self._lib.qpe_sql_select_ids(self._h, statement.encode(), SCAN_FORCE if force_scan else 0, C.byref(ids),
+                                          C.byref(n), C.byref(st))
+        self._check(rc, "select_ids")
+        try:
+            out = np.ctypeslib.as_array(C.cast(ids, C.POINTER(C.c_uint32)), shape=(max(n.value, 1),))[:n.value].copy()
+        finally:
+            self._lib.qpe_gpu_free(ids)
+        return out, st.as_dict()
+
+    def select_ids_into(self, statement: str, out: np.ndarray, force_scan: bool = False) -> Tuple[int, dict]:
+        """Match phase with the ids copied into a caller-owned (ideally pinned) uint32 buffer."""
+        n = C.c_size_t()
+        st = ScanStats()
+        rc = self._lib.qpe_sql_select_ids_into(self._h, statement.encode(), SCAN_FORCE if force_scan else 0,
+                                               out.ctypes.data, out.size, C.byref(n), C.byref(st))
+        self._check(rc, "select_ids_into")
+        return int(n.value), st.as_dict()
+
+    def select_ids_device(self, statement: str, force_scan: bool = False, count_only: bool = False):
+        """Match phase, result left in HBM: (count, device pointer, stats)."""
+        cnt = C.c_ulonglong()
+        dptr = C.c_void_p()
+        st = ScanStats()
+        flags = (SCAN_FORCE if force_scan else 0) | (SCAN_COUNT_ONLY if count_only else 0)
+        rc = self._lib.qpe_sql_select_ids_device(self._h, statement.encode(), flags, C.byref(cnt), C.byref(dptr),
+                                                 C.byref(st))
+        self._check(rc, "select_ids_device")
+        return int(cnt.value), dptr.value, st.as_dict()
+
+    def copy_from_device(self, dptr: int, n_items: int, dtype=np.uint32) -> np.ndarray:
+        out = np.empty(n_items, dtype=dtype)
+        if n_items:
+            self._check(self._lib.qpe_gpu_copy_from_device(out.ctypes.data, dptr, out.nbytes), "copy_from_device")
+        return out
+
+    def match_mask(self, statement: str) -> Tuple[np.ndarray, int]:
+        """DELETE's match mask (bit r = row r matches) without deleting."""
+        n = self.num_rows
+        words = np.zeros((n + 31) // 32 + 1, dtype=np.uint32)
+        cnt = C.c_ulonglong()
+        st = ScanStats()
+        rc = self._lib.qpe_sql_match_mask(self._h, statement.encode(), words.ctypes.data, words.size, C.byref(cnt),
+                                          C.byref(st))
+        self._check(rc, "match_mask")
+        bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:n].astype(bool)
+        return bits, int(cnt.value)
+
+    # ---- index surface --------------------------------------------------------------------
+    def probe_batch(self, attribute: str, lo: np.ndarray, hi: np.ndarray) -> Tuple[np.ndarray, np.ndarray, dict]:
+        """Batched findRange: inclusive [lo[q], hi[q]] -> (first, count) into the index order."""
+        q = len(lo)
+        is_u64 = attribute == "command_id"
+        keys_lo = (KeyT * max(q, 1))()
+        keys_hi = (KeyT * max(q, 1))()
+        # bulk-fill through numpy views of the 16-byte structs
+        dt = np.dtype([("type", np.int32), ("pad", np.int32), ("v", np.uint64)])
+        vlo = np.frombuffer(keys_lo, dtype=dt, count=q)
+        vhi = np.frombuffer(keys_hi, dtype=dt, count=q)
+        if is_u64:
+            vlo["type"] = 1
+            vhi["type"] = 1
+            vlo["v"] = np.asarray(lo, dtype=np.uint64)
+            vhi["v"] = np.asarray(hi, dtype=np.uint64)
+        else:
+            vlo["type"] = 0
+            vhi["type"] = 0
+            vlo["v"] = np.asarray(lo, dtype=np.int32).astype(np.int64).astype(np.uint64) & np.uint64(0xffffffff)
+            vhi["v"] = np.asarray(hi, dtype=np.int32).astype(np.int64).astype(np.uint64) & np.uint64(0xffffffff)
+        first = np.zeros(max(q, 1), dtype=np.uint32)
+        count = np.zeros(max(q, 1), dtype=np.uint32)
+        st = ScanStats()
+        rc = self._lib.qpe_gpu_probe_batch(self._h, attribute.encode(), keys_lo, keys_hi, q, first.ctypes.data,
+                                           count.ctypes.data, C.byref(st))
+        self._check(rc, "probe_batch")
+        return first[:q], count[:q], st.as_dict()
+
+    def index_slice(self, attribute: str, first: int, count: int) -> np.ndarray:
+        out = np.zeros(max(count, 1), dtype=np.uint32)
+        self._check(self._lib.qpe_gpu_index_slice(self._h, attribute.encode(), first, count, out.ctypes.data),
+                    "index_slice")
+        return out[:count]
+
+    # ---- column access --------------------------------------------------------------------
+    def column_width(self, attribute: str) -> int:
+        w = C.c_uint()
+        self._check(self._lib.qpe_gpu_fetch_column(self._h, attribute.encode(), 0, 0, None, C.byref(w)), "fetch_column")
+        return int(w.value)
+
+    def fetch_column(self, attribute: str, first_row: int = 0, n_rows: Optional[int] = None) -> np.ndarray:
+        """Device column -> numpy: numeric columns as their dtype, text columns as (n, width) uint8."""
+        if n_rows is None:
+            n_rows = self.num_rows - first_row
+        w = self.column_width(attribute)
+        raw = np.zeros(max(n_rows * w, 1), dtype=np.uint8)
+        self._check(self._lib.qpe_gpu_fetch_column(self._h, attribute.encode(), first_row, n_rows, raw.ctypes.data,
+                                                   None), "fetch_column")
+        raw = raw[:n_rows * w]
+        if attribute in NUMERIC_DTYPES:
+            return raw.view(NUMERIC_DTYPES[attribute])
+        return raw.reshape(n_rows, w)
+
+    def write_csv(self, path: str):
+        self._check(self._lib.qpe_gpu_write_csv(self._h, path.encode()), "write_csv")

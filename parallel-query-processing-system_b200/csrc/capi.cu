@@ -1,0 +1,730 @@
+// capi.cu -- the C-ABI of libqpegpu.so: include/executeEngine-gpu.h (drop-in surface, mirrors
+// include/executeEngine-serial.h:69-151 of the reference), include/buildEngine-gpu.h and the
+// low-level row-id interface of include/qpe_gpu.h.
+
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+#include <chrono>
+#include <mutex>
+#include <unordered_map>
+
+#include "engine.cuh"
+#include "executeEngine-gpu.h"
+#include "buildEngine-gpu.h"
+#include "qpe_gpu.h"
+
+using namespace qpe;
+
+namespace {
+
+std::mutex g_api_mutex;  // the engine is not re-entrant (one stream, one scratch set)
+
+// results produced by this library keep their cells in one arena; freeResultSet recognises them
+struct ResultArena {
+    char *text = nullptr;
+    char **rows = nullptr;
+};
+std::mutex g_result_mutex;
+std::unordered_map<const struct resultSetS *, ResultArena> g_results;
+
+const char *const kAllColumns[NUM_COLS] = {"command_id", "raw_command", "base_command", "shell_type",
+                                           "exit_code",  "timestamp",   "sudo_used",    "working_directory",
+                                           "user_id",    "user_name",   "host_name",    "risk_level"};
+
+struct resultSetS *new_result() {
+    struct resultSetS *r = static_cast<struct resultSetS *>(std::malloc(sizeof(struct resultSetS)));
+    if (!r) {
+        std::perror("Failed to allocate memory for result set");
+        std::exit(EXIT_FAILURE);
+    }
+    r->numRecords = 0;
+    r->numColumns = 0;
+    r->columnNames = nullptr;
+    r->columnTypes = nullptr;
+    r->data = nullptr;
+    r->queryTime = 0.0;
+    r->success = false;
+    return r;
+}
+
+inline size_t fmt_u64(unsigned long long v, char *out) {  // "%llu"
+    char tmp[24];
+    size_t n = 0;
+    do {
+        tmp[n++] = static_cast<char>('0' + v % 10);
+        v /= 10;
+    } while (v);
+    for (size_t i = 0; i < n; ++i) out[i] = tmp[n - 1 - i];
+    out[n] = '\0';
+    return n;
+}
+inline size_t fmt_i32(int v, char *out) {  // "%d"
+    if (v < 0) {
+        out[0] = '-';
+        return 1 + fmt_u64(static_cast<unsigned long long>(-(static_cast<long long>(v))), out + 1);
+    }
+    return fmt_u64(static_cast<unsigned long long>(v), out);
+}
+
+void fill_stats(const GpuEngine *g, qpe_scan_stats *s) {
+    if (!s) return;
+    const ScanStats &a = g->last;
+    s->kernel_ms = a.kernel_ms;
+    s->total_ms = a.total_ms;
+    s->rows_scanned = a.rows_scanned;
+    s->candidates = a.candidates;
+    s->matches = a.matches;
+    s->algo_bytes = a.algo_bytes;
+    s->path = a.path;
+    s->launches = a.launches;
+    s->tile_rows = a.tile_rows;
+    s->stages = a.stages;
+    s->grid = a.grid;
+    s->reserved = 0;
+}
+
+// SELECT projection: get_attribute_string_value (executeEngine-serial.c:216-248) for every
+// (match, selected column), from gathered device columns.
+bool materialise(GpuEngine *g, const char **selectItems, int numItems, int64_t m, struct resultSetS *res) {
+    if (selectItems == nullptr || numItems == 0) {  // SELECT * (:490-493)
+        selectItems = const_cast<const char **>(kAllColumns);
+        numItems = NUM_COLS;
+    }
+    res->numRecords = static_cast<int>(m);
+    res->numColumns = numItems;
+    res->columnNames = static_cast<char **>(std::malloc(sizeof(char *) * (numItems > 0 ? numItems : 1)));
+    for (int j = 0; j < numItems; ++j) res->columnNames[j] = strdup(selectItems[j]);
+
+    // fetch each distinct known column once
+    std::vector<uint8_t> colbuf[NUM_COLS];
+    bool have[NUM_COLS] = {false};
+    std::vector<int> colid(numItems);
+    for (int j = 0; j < numItems; ++j) {
+        const int c = col_by_name(selectItems[j]);
+        colid[j] = c;
+        if (c >= 0 && !have[c]) {
+            if (!engine_fetch_rows(g, c, g->d_ids, m, &colbuf[c])) return false;
+            have[c] = true;
+        }
+    }
+    // size the text arena
+    size_t text_bytes = 16;
+    for (int j = 0; j < numItems; ++j) {
+        const int c = colid[j];
+        if (c < 0)
+            text_bytes += static_cast<size_t>(m) * 5;  // "NULL"
+        else if (kCols[c].type == T_U64)
+            text_bytes += static_cast<size_t>(m) * 21;
+        else if (kCols[c].type == T_I32)
+            text_bytes += static_cast<size_t>(m) * 12;
+        else if (kCols[c].type == T_BOOL)
+            text_bytes += static_cast<size_t>(m) * 6;
+        else
+            text_bytes += static_cast<size_t>(m) * (g->table.col[c].width + 1);
+    }
+    ResultArena arena;
+    arena.text = static_cast<char *>(std::malloc(text_bytes));
+    arena.rows = static_cast<char **>(std::malloc(sizeof(char *) * (static_cast<size_t>(m) * numItems + 1)));
+    res->data = static_cast<char ***>(std::malloc(sizeof(char **) * static_cast<size_t>(m)));  // malloc(0) != NULL on glibc
+    if (!arena.text || !arena.rows || (m > 0 && !res->data)) {
+        std::fprintf(stderr, "Memory allocation failed\n");
+        std::exit(EXIT_FAILURE);
+    }
+    if (!res->data) res->data = static_cast<char ***>(std::malloc(1));
+    char *tp = arena.text;
+    for (int64_t i = 0; i < m; ++i) {
+        char **row = arena.rows + static_cast<size_t>(i) * numItems;
+        res->data[i] = row;
+        for (int j = 0; j < numItems; ++j) {
+            const int c = colid[j];
+            row[j] = tp;
+            if (c < 0) {
+                std::memcpy(tp, "NULL", 5);
+                tp += 5;
+                continue;
+            }
+            const uint32_t w = g->table.col[c].width;
+            const uint8_t *cell = colbuf[c].data() + static_cast<size_t>(i) * w;
+            switch (kCols[c].type) {
+                case T_U64: {
+                    unsigned long long v;
+                    std::memcpy(&v, cell, 8);
+                    tp += fmt_u64(v, tp) + 1;
+                    break;
+                }
+                case T_I32: {
+                    int v;
+                    std::memcpy(&v, cell, 4);
+                    tp += fmt_i32(v, tp) + 1;
+                    break;
+                }
+                case T_BOOL:
+                    if (cell[0]) {
+                        std::memcpy(tp, "true", 5);
+                        tp += 5;
+                    } else {
+                        std::memcpy(tp, "false", 6);
+                        tp += 6;
+                    }
+                    break;
+                default: {
+                    const size_t len = strnlen(reinterpret_cast<const char *>(cell), w);
+                    std::memcpy(tp, cell, len);
+                    tp[len] = '\0';
+                    tp += len + 1;
+                    break;
+                }
+            }
+        }
+    }
+    res->columnTypes = static_cast<FieldType *>(std::calloc(numItems > 0 ? numItems : 1, sizeof(FieldType)));  // :524-525
+    {
+        std::lock_guard<std::mutex> lk(g_result_mutex);
+        g_results[res] = arena;
+    }
+    return true;
+}
+
+bool engine_load_indexes(GpuEngine *g, int num_indexes, const char *indexed_attributes[], const int attribute_types[]) {
+    for (int i = 0; i < num_indexes; ++i) {
+        if (!engine_add_index(g, indexed_attributes[i], attribute_types ? attribute_types[i] : -1))
+            std::fprintf(stderr, "Failed to create index for attribute: %s\n",
+                         indexed_attributes[i] ? indexed_attributes[i] : "(null)");
+    }
+    return true;
+}
+
+// CSV line format shared by INSERT's append and DELETE's rewrite (:562-575, :687-700)
+void write_csv_row(FILE *f, const HostColumns &hc, int64_t i) {
+    auto cell = [&](int c) { return hc.data[c].data() + static_cast<size_t>(i) * hc.width[c]; };
+    auto str = [&](int c, char *buf) {
+        const size_t len = strnlen(reinterpret_cast<const char *>(cell(c)), hc.width[c]);
+        std::memcpy(buf, cell(c), len);
+        buf[len] = '\0';
+        return buf;
+    };
+    unsigned long long id;
+    int exit_code, user_id, risk;
+    std::memcpy(&id, cell(C_COMMAND_ID), 8);
+    std::memcpy(&exit_code, cell(C_EXIT_CODE), 4);
+    std::memcpy(&user_id, cell(C_USER_ID), 4);
+    std::memcpy(&risk, cell(C_RISK_LEVEL), 4);
+    char b1[528], b2[128], b3[48], b4[48], b5[224], b6[80], b7[128];
+    std::fprintf(f, "%llu,%s,%s,%s,%d,%s,%d,%s,%d,%s,%s,%d\n", id, str(C_RAW_COMMAND, b1), str(C_BASE_COMMAND, b2),
+                 str(C_SHELL_TYPE, b3), exit_code, str(C_TIMESTAMP, b4), cell(C_SUDO_USED)[0] ? 1 : 0,
+                 str(C_WORKING_DIRECTORY, b5), user_id, str(C_USER_NAME, b6), str(C_HOST_NAME, b7), risk);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------
+// include/qpe_gpu.h : utilities
+// ------------------------------------------------------------------------------------------
+int qpe_gpu_available(void) { return device_count() > 0 ? 1 : 0; }
+const char *qpe_gpu_last_error(void) { return last_error_cstr(); }
+void qpe_gpu_free(void *p) { std::free(p); }
+
+// ------------------------------------------------------------------------------------------
+// include/executeEngine-gpu.h
+// ------------------------------------------------------------------------------------------
+struct engineS *initializeEngineGPU(int num_indexes, const char *indexed_attributes[], const int attribute_types[],
+                                    const char *datafile, const char *tableName) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!datafile) datafile = "../data/commands_50k.csv";  // the reference's default (executeEngine-serial.c:757)
+    GpuEngine *g = engine_create(tableName ? tableName : "", datafile, num_indexes);
+    if (!g) return nullptr;
+    HostColumns hc;
+    if (load_csv_columns(datafile, &hc) < 0) hc.init_widths_minimal();  // unreadable file: empty table
+    if (!engine_upload(g, hc)) {
+        engine_destroy(g);
+        return nullptr;
+    }
+    engine_load_indexes(g, num_indexes, indexed_attributes, attribute_types);
+    return &g->head;
+}
+
+struct engineS *qpe_gpu_engine_from_records(const record *rows, long long n_rows, int num_indexes,
+                                            const char *indexed_attributes[], const int attribute_types[],
+                                            const char *datafile, const char *tableName) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = engine_create(tableName ? tableName : "", datafile, num_indexes);
+    if (!g) return nullptr;
+    HostColumns hc;
+    hc.init_widths_minimal();
+    hc.reserve_rows(n_rows);
+    for (long long i = 0; i < n_rows; ++i) hc.append_record(rows[i]);
+    if (!engine_upload(g, hc)) {
+        engine_destroy(g);
+        return nullptr;
+    }
+    engine_load_indexes(g, num_indexes, indexed_attributes, attribute_types);
+    return &g->head;
+}
+
+void destroyEngineGPU(struct engineS *engine) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (engine == nullptr) {
+        std::fprintf(stderr, "Attempted to destroy a NULL engine pointer\n");  // executeEngine-serial.c:811
+        return;
+    }
+    GpuEngine *g = as_engine(engine);
+    if (!g) {
+        std::fprintf(stderr, "libqpegpu: %s\n", qpe_gpu_last_error());
+        return;
+    }
+    engine_destroy(g);
+}
+
+struct resultSetS *executeQuerySelectGPU(struct engineS *engine, const char **selectItems, int numSelectItems,
+                                         const char *tableName, struct whereClauseS *whereClause) {
+    (void)tableName;  // ignored by every reference engine
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    struct resultSetS *res = new_result();
+    GpuEngine *g = as_engine(engine);
+    if (!g) {
+        std::fprintf(stderr, "libqpegpu: executeQuerySelectGPU: %s\n", qpe_gpu_last_error());
+        return res;  // success == false, data == NULL -> printTable prints "No data found."
+    }
+    uint64_t m = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!engine_match(g, whereClause, false, false, false, false, &m)) {
+        std::fprintf(stderr, "libqpegpu: executeQuerySelectGPU: %s\n", qpe_gpu_last_error());
+        return res;
+    }
+    const double match_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (m > static_cast<uint64_t>(INT_MAX)) {
+        set_error("result has more than INT_MAX rows");
+        return res;
+    }
+    if (!materialise(g, selectItems, numSelectItems, static_cast<int64_t>(m), res)) {
+        std::fprintf(stderr, "libqpegpu: executeQuerySelectGPU: %s\n", qpe_gpu_last_error());
+        return res;
+    }
+    res->queryTime = match_s;  // the reference reports the match phase only (:355,:475-476)
+    res->success = true;
+    return res;
+}
+
+struct resultSetS *executeQueryDeleteGPU(struct engineS *engine, const char *tableName,
+                                         struct whereClauseS *whereClause) {
+    (void)tableName;
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    struct resultSetS *res = new_result();
+    GpuEngine *g = as_engine(engine);
+    if (!g) {
+        std::fprintf(stderr, "libqpegpu: executeQueryDeleteGPU: %s\n", qpe_gpu_last_error());
+        return res;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    int64_t deleted = 0;
+    if (!engine_delete(g, whereClause, &deleted)) {
+        std::fprintf(stderr, "libqpegpu: executeQueryDeleteGPU: %s\n", qpe_gpu_last_error());
+        return res;
+    }
+    // the reference rewrites the whole CSV after every DELETE, matched rows or not (:683-706)
+    if (g->head.datafile) {
+        HostColumns hc;
+        if (engine_download_all(g, &hc)) {
+            FILE *f = std::fopen(g->head.datafile, "w");
+            if (f) {
+                static thread_local std::vector<char> iobuf(1 << 20);
+                std::setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
+                for (int64_t i = 0; i < hc.n; ++i) write_csv_row(f, hc, i);
+                std::fclose(f);
+            }
+        }
+    }
+    res->numRecords = static_cast<int>(deleted);
+    res->queryTime = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    res->success = true;
+    return res;
+}
+
+bool executeQueryInsertGPU(struct engineS *engine, const char *tableName, const record *r) {
+    (void)tableName;
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g || !r) return false;
+    // validation of executeEngine-serial.c:544-551
+    if (r->command_id == 0 || r->raw_command[0] == '\0' || r->base_command[0] == '\0' || r->shell_type[0] == '\0' ||
+        r->timestamp[0] == '\0' || r->working_directory[0] == '\0' || r->user_name[0] == '\0' ||
+        r->host_name[0] == '\0')
+        return false;
+    if (g->head.datafile) {
+        FILE *f = std::fopen(g->head.datafile, "a");
+        if (!f) return false;
+        std::fprintf(f, "%llu,%s,%s,%s,%d,%s,%d,%s,%d,%s,%s,%d\n", r->command_id, r->raw_command, r->base_command,
+                     r->shell_type, r->exit_code, r->timestamp, r->sudo_used, r->working_directory, r->user_id,
+                     r->user_name, r->host_name, r->risk_level);
+        std::fclose(f);
+    }
+    if (!engine_append(g, *r)) {
+        std::fprintf(stderr, "libqpegpu: executeQueryInsertGPU: %s\n", qpe_gpu_last_error());
+        return false;
+    }
+    return true;
+}
+
+bool addAttributeIndexGPU(struct engineS *engine, const char *tableName, const char *attributeName,
+                          int attributeType) {
+    (void)tableName;
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return true;
+    // the reference returns FALSE when the index was created (inverted test, :833-840)
+    return !engine_add_index(g, attributeName, attributeType);
+}
+
+bool makeIndexGPU(struct engineS *engine, const char *indexName, int attributeType) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return false;
+    return engine_add_index(g, indexName, attributeType);
+}
+
+FieldType mapAttributeTypeGPU(int attributeType) {
+    switch (attributeType) {
+        case 0: return FIELD_UINT64;
+        case 1: return FIELD_INT;
+        case 2: return FIELD_STRING;
+        case 3: return FIELD_BOOL;
+        default: return static_cast<FieldType>(-1);
+    }
+}
+
+int isAttributeIndexed(struct engineS *engine, const char *attributeName) {
+    if (!engine || !attributeName) return -1;
+    for (int i = 0; i < engine->num_indexes; ++i)
+        if (std::strcmp(engine->indexed_attributes[i], attributeName) == 0) return i;
+    return -1;
+}
+
+void freeResultSet(struct resultSetS *result) {
+    if (!result) return;
+    ResultArena arena;
+    bool ours = false;
+    {
+        std::lock_guard<std::mutex> lk(g_result_mutex);
+        auto it = g_results.find(result);
+        if (it != g_results.end()) {
+            arena = it->second;
+            g_results.erase(it);
+            ours = true;
+        }
+    }
+    if (result->columnNames) {
+        for (int i = 0; i < result->numColumns; ++i) std::free(result->columnNames[i]);
+        std::free(result->columnNames);
+    }
+    std::free(result->columnTypes);
+    if (ours) {
+        std::free(arena.text);
+        std::free(arena.rows);
+        std::free(result->data);
+    } else if (result->data) {
+        // a result built by someone else, cell by cell: the reference's destructor (:881-908)
+        for (int i = 0; i < result->numRecords; ++i) {
+            if (result->data[i]) {
+                for (int j = 0; j < result->numColumns; ++j) std::free(result->data[i][j]);
+                std::free(result->data[i]);
+            }
+        }
+        std::free(result->data);
+    }
+    std::free(result);
+}
+
+// ------------------------------------------------------------------------------------------
+// include/qpe_gpu.h : row-id interface
+// ------------------------------------------------------------------------------------------
+long long qpe_gpu_num_rows(const struct engineS *engine) {
+    GpuEngine *g = as_engine(const_cast<struct engineS *>(engine));
+    return g ? g->table.n : -1;
+}
+
+int qpe_gpu_select_ids_device(struct engineS *engine, struct whereClauseS *whereClause, int flags,
+                              unsigned long long *count_out, const unsigned int **d_ids_out, qpe_scan_stats *stats) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    uint64_t m = 0;
+    const bool count_only = (flags & QPE_SCAN_COUNT_ONLY) != 0;
+    if (!engine_match(g, whereClause, (flags & QPE_SCAN_FORCE) != 0, false, count_only, false, &m)) return -2;
+    if (count_out) *count_out = m;
+    if (d_ids_out) *d_ids_out = count_only ? nullptr : g->d_ids;
+    fill_stats(g, stats);
+    return 0;
+}
+
+int qpe_gpu_select_ids(struct engineS *engine, struct whereClauseS *whereClause, unsigned int **ids_out, size_t *n_out,
+                       qpe_scan_stats *stats) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    const double t0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    uint64_t m = 0;
+    if (!engine_match(g, whereClause, false, false, false, false, &m)) return -2;
+    unsigned int *ids = static_cast<unsigned int *>(std::malloc(sizeof(unsigned int) * (m ? m : 1)));
+    if (!ids) {
+        set_error("out of host memory");
+        return -3;
+    }
+    if (m && !cuda_ok(cudaMemcpy(ids, g->d_ids, sizeof(unsigned int) * m, cudaMemcpyDeviceToHost), "download ids")) {
+        std::free(ids);
+        return -4;
+    }
+    if (ids_out)
+        *ids_out = ids;
+    else
+        std::free(ids);
+    if (n_out) *n_out = static_cast<size_t>(m);
+    fill_stats(g, stats);
+    if (stats)
+        stats->total_ms =
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0;
+    return 0;
+}
+
+// same as qpe_gpu_select_ids but into a caller-provided (ideally pinned) host buffer of `cap` ids
+int qpe_gpu_select_ids_into(struct engineS *engine, struct whereClauseS *whereClause, int flags, unsigned int *ids,
+                            size_t cap, size_t *n_out, qpe_scan_stats *stats) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    const double t0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    uint64_t m = 0;
+    if (!engine_match(g, whereClause, (flags & QPE_SCAN_FORCE) != 0, false, false, false, &m)) return -2;
+    if (n_out) *n_out = static_cast<size_t>(m);
+    if (m > cap) {
+        set_error("id buffer too small");
+        return -5;
+    }
+    if (m && !cuda_ok(cudaMemcpyAsync(ids, g->d_ids, sizeof(unsigned int) * m, cudaMemcpyDeviceToHost, g->stream),
+                      "download ids"))
+        return -4;
+    if (!cuda_ok(cudaStreamSynchronize(g->stream), "download ids")) return -4;
+    fill_stats(g, stats);
+    if (stats)
+        stats->total_ms =
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0;
+    return 0;
+}
+
+int qpe_gpu_match_mask(struct engineS *engine, struct whereClauseS *whereClause, unsigned int *bitmap, size_t n_words,
+                       unsigned long long *count_out, qpe_scan_stats *stats) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    const size_t need = static_cast<size_t>((g->table.n + 31) / 32);
+    if (n_words < need) {
+        set_error("bitmap too small");
+        return -5;
+    }
+    uint64_t m = 0;
+    if (!engine_match(g, whereClause, true, false, true, true, &m)) return -2;
+    if (need && !cuda_ok(cudaMemcpy(bitmap, g->d_bitmap, need * 4, cudaMemcpyDeviceToHost), "download bitmap")) return -4;
+    if (count_out) *count_out = m;
+    fill_stats(g, stats);
+    return 0;
+}
+
+int qpe_gpu_probe_batch(struct engineS *engine, const char *attribute, const KEY_T *lo, const KEY_T *hi,
+                        size_t n_queries, unsigned int *first, unsigned int *count, qpe_scan_stats *stats) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    cudaSetDevice(g->device);
+    const int slot = isAttributeIndexed(engine, attribute);
+    if (slot < 0 || !g->idx[slot].usable) {
+        set_error("attribute has no probe-able (u64 / int) index");
+        return -6;
+    }
+    DevIndex &ix = g->idx[slot];
+    int launches = 0;
+    if (ix.dirty && !cuda_ok(index_build(&ix, g->table, g->stream, &launches), "index rebuild")) return -2;
+    const size_t ksz = ix.type == T_U64 ? 8 : 4;
+    std::vector<uint8_t> hlo(n_queries * ksz), hhi(n_queries * ksz);
+    for (size_t q = 0; q < n_queries; ++q) {
+        if (ix.type == T_U64) {
+            const unsigned long long a = lo[q].v.u64, b = hi[q].v.u64;
+            std::memcpy(&hlo[q * 8], &a, 8);
+            std::memcpy(&hhi[q * 8], &b, 8);
+        } else {
+            const int a = lo[q].v.i32, b = hi[q].v.i32;
+            std::memcpy(&hlo[q * 4], &a, 4);
+            std::memcpy(&hhi[q * 4], &b, 4);
+        }
+    }
+    void *dlo = nullptr, *dhi = nullptr;
+    uint32_t *dfirst = nullptr, *dcount = nullptr;
+    bool ok = cuda_ok(cudaMalloc(&dlo, n_queries * ksz + 16), "cudaMalloc probe") &&
+              cuda_ok(cudaMalloc(&dhi, n_queries * ksz + 16), "cudaMalloc probe") &&
+              cuda_ok(cudaMalloc(&dfirst, n_queries * 4 + 16), "cudaMalloc probe") &&
+              cuda_ok(cudaMalloc(&dcount, n_queries * 4 + 16), "cudaMalloc probe");
+    const auto t0 = std::chrono::steady_clock::now();
+    ok = ok && cuda_ok(cudaMemcpyAsync(dlo, hlo.data(), n_queries * ksz, cudaMemcpyHostToDevice, g->stream), "probe h2d");
+    ok = ok && cuda_ok(cudaMemcpyAsync(dhi, hhi.data(), n_queries * ksz, cudaMemcpyHostToDevice, g->stream), "probe h2d");
+    if (ok) cudaEventRecord(g->ev0, g->stream);
+    ok = ok && cuda_ok(index_probe(ix, dlo, dhi, static_cast<long long>(n_queries), dfirst, dcount, g->stream),
+                       "probe kernel launch");
+    if (ok) cudaEventRecord(g->ev1, g->stream);
+    ok = ok && cuda_ok(cudaMemcpyAsync(first, dfirst, n_queries * 4, cudaMemcpyDeviceToHost, g->stream), "probe d2h");
+    ok = ok && cuda_ok(cudaMemcpyAsync(count, dcount, n_queries * 4, cudaMemcpyDeviceToHost, g->stream), "probe d2h");
+    ok = cuda_ok(cudaStreamSynchronize(g->stream), "probe sync") && ok;
+    if (ok && stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g->ev0, g->ev1);
+        stats->kernel_ms = ms;
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        stats->rows_scanned = static_cast<long long>(n_queries);
+        stats->path = 1;
+        stats->launches = 1 + launches;
+        // per probe: two descents, each reading one node (fanout keys) per level incl. the leaf array
+        stats->algo_bytes = static_cast<long long>(n_queries) * 2 * (ix.n_levels + 1) * ix.fanout * static_cast<long long>(ksz) +
+                            static_cast<long long>(n_queries) * (2 * ksz + 8);
+    }
+    cudaFree(dlo);
+    cudaFree(dhi);
+    cudaFree(dfirst);
+    cudaFree(dcount);
+    return ok ? 0 : -4;
+}
+
+int qpe_gpu_index_slice(struct engineS *engine, const char *attribute, unsigned int first, unsigned int count,
+                        unsigned int *row_ids_out) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    cudaSetDevice(g->device);
+    const int slot = isAttributeIndexed(engine, attribute);
+    if (slot < 0 || !g->idx[slot].usable) {
+        set_error("attribute has no probe-able (u64 / int) index");
+        return -6;
+    }
+    DevIndex &ix = g->idx[slot];
+    int launches = 0;
+    if (ix.dirty && !cuda_ok(index_build(&ix, g->table, g->stream, &launches), "index rebuild")) return -2;
+    if (static_cast<long long>(first) + count > ix.n) {
+        set_error("index slice out of range");
+        return -5;
+    }
+    if (count && !cuda_ok(cudaMemcpy(row_ids_out, ix.perm + first, static_cast<size_t>(count) * 4, cudaMemcpyDeviceToHost),
+                          "download slice"))
+        return -4;
+    return 0;
+}
+
+int qpe_gpu_fetch_column(struct engineS *engine, const char *attribute, long long first_row, long long n_rows, void *out,
+                         unsigned int *width_out) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    cudaSetDevice(g->device);
+    const int c = col_by_name(attribute);
+    if (c < 0) {
+        set_error("unknown column");
+        return -6;
+    }
+    const DevColumn &dc = g->table.col[c];
+    if (width_out) *width_out = dc.width;
+    if (!out) return 0;
+    if (!dc.d) {
+        set_error("column is not resident on the device");
+        return -6;
+    }
+    if (first_row < 0 || n_rows < 0 || first_row + n_rows > g->table.n) {
+        set_error("row range out of bounds");
+        return -5;
+    }
+    if (n_rows && !cuda_ok(cudaMemcpy(out, dc.d + static_cast<size_t>(first_row) * dc.width,
+                                      static_cast<size_t>(n_rows) * dc.width, cudaMemcpyDeviceToHost),
+                           "download column"))
+        return -4;
+    return 0;
+}
+
+int qpe_gpu_copy_from_device(void *dst_host, const void *src_device, size_t bytes) {
+    if (bytes == 0) return 0;
+    return cuda_ok(cudaMemcpy(dst_host, src_device, bytes, cudaMemcpyDeviceToHost), "copy from device") ? 0 : -4;
+}
+
+int qpe_gpu_last_stats(struct engineS *engine, qpe_scan_stats *stats) {
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    fill_stats(g, stats);
+    return 0;
+}
+
+int qpe_gpu_write_csv(struct engineS *engine, const char *path) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    HostColumns hc;
+    if (!engine_download_all(g, &hc)) return -4;
+    FILE *f = std::fopen(path, "w");
+    if (!f) {
+        set_error(std::string("cannot open ") + path);
+        return -8;
+    }
+    std::vector<char> iobuf(1 << 20);
+    std::setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
+    std::fputs("command_id,raw_command,base_command,shell_type,exit_code,timestamp,sudo_used,working_directory,"
+               "user_id,user_name,host_name,risk_level\r\n", f);
+    auto put_text = [&](int c, int64_t i) {
+        const uint8_t *cell = hc.data[c].data() + static_cast<size_t>(i) * hc.width[c];
+        const size_t len = strnlen(reinterpret_cast<const char *>(cell), hc.width[c]);
+        bool quote = false;
+        for (size_t k = 0; k < len; ++k)
+            if (cell[k] == ',' || cell[k] == '"' || cell[k] == '\n' || cell[k] == '\r') quote = true;
+        if (!quote) {
+            std::fwrite(cell, 1, len, f);
+            return;
+        }
+        std::fputc('"', f);
+        for (size_t k = 0; k < len; ++k) {
+            if (cell[k] == '"') std::fputc('"', f);
+            std::fputc(cell[k], f);
+        }
+        std::fputc('"', f);
+    };
+    for (int64_t i = 0; i < hc.n; ++i) {
+        for (int c = 0; c < NUM_COLS; ++c) {
+            if (c) std::fputc(',', f);
+            const uint8_t *cell = hc.data[c].data() + static_cast<size_t>(i) * hc.width[c];
+            switch (kCols[c].type) {
+                case T_U64: {
+                    unsigned long long v;
+                    std::memcpy(&v, cell, 8);
+                    std::fprintf(f, "%llu", v);
+                    break;
+                }
+                case T_I32: {
+                    int v;
+                    std::memcpy(&v, cell, 4);
+                    std::fprintf(f, "%d", v);
+                    break;
+                }
+                case T_BOOL: std::fputs(cell[0] ? "true" : "false", f); break;
+                default: put_text(c, i); break;
+            }
+        }
+        std::fputs("\r\n", f);
+    }
+    std::fclose(f);
+    return 0;
+}
+
+int qpe_gpu_set_tile(struct engineS *engine, int tile_rows, int stages) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    g->force_tile_rows = tile_rows;
+    g->force_stages = stages;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,672 @@
+// engine.cu -- the engine object behind `struct engineS *`: device table management, the match
+// phase (scan path / index path), projection download, DELETE / INSERT maintenance.
+//
+// Mirrors the control flow of the reference's serial engine, with the per-row loops replaced by
+// kernel launches:
+//   executeQuerySelectSerial  engine/serial/executeEngine-serial.c:328-528
+//       :358-459 candidate generation per (top-level condition x index)  -> plan_segments + K3 probe
+//       :464-474 linearSearchRecords on the table / on the candidates    -> K1 scan / K1g filter
+//       :504-515 projection                                              -> K2 gather + host format
+//   executeQueryDeleteSerial  :627-715   mask + stable compaction + CSV rewrite
+//   executeQueryInsertSerial  :538-617   validation, CSV append, row append, index update
+//
+// There is NO CPU fallback anywhere in this file: without a usable CUDA device engine_create fails.
+
+#include "engine.cuh"
+
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+#include <chrono>
+#include <mutex>
+
+namespace qpe {
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+const char *last_error_cstr() { return g_last_error.c_str(); }
+
+bool cuda_ok(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    std::fprintf(stderr, "libqpegpu: %s: %s\n", what, cudaGetErrorString(e));
+    return false;
+}
+
+static double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+GpuEngine *as_engine(struct engineS *e) {
+    if (!e) {
+        set_error("NULL engine");
+        return nullptr;
+    }
+    GpuEngine *g = reinterpret_cast<GpuEngine *>(e);
+    if (g->magic != kEngineMagic) {
+        set_error("engine handle was not created by initializeEngineGPU");
+        return nullptr;
+    }
+    return g;
+}
+
+int device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// creation / destruction
+// ------------------------------------------------------------------------------------------
+static int pick_device() {
+    // one process per GPU: honour LOCAL_RANK (torchrun) unless QPE_GPU_DEVICE overrides it
+    const char *s = std::getenv("QPE_GPU_DEVICE");
+    if (!s) s = std::getenv("LOCAL_RANK");
+    int d = s ? std::atoi(s) : 0;
+    const int n = device_count();
+    if (n > 0) d %= n;
+    return d;
+}
+
+GpuEngine *engine_create(const char *tableName, const char *datafile, int index_slots) {
+    if (device_count() <= 0) {
+        set_error("no CUDA device is usable by this process (the B200 engine has no CPU fallback)");
+        std::fprintf(stderr, "libqpegpu: %s\n", g_last_error.c_str());
+        return nullptr;
+    }
+    GpuEngine *g = new GpuEngine();
+    g->device = pick_device();
+    if (!cuda_ok(cudaSetDevice(g->device), "cudaSetDevice")) {
+        delete g;
+        return nullptr;
+    }
+    std::memset(&g->head, 0, sizeof(g->head));
+    g->head.tableName = strdup(tableName ? tableName : "");
+    g->head.datafile = datafile ? strdup(datafile) : nullptr;
+    if (index_slots < 8) index_slots = 8;
+    g->idx_slots = index_slots;
+    g->head.bplus_tree_roots = static_cast<node **>(std::calloc(index_slots, sizeof(node *)));
+    g->head.indexed_attributes = static_cast<char **>(std::calloc(index_slots, sizeof(char *)));
+    g->head.attribute_types = static_cast<FieldType *>(std::calloc(index_slots, sizeof(FieldType)));
+    g->head.num_indexes = 0;
+    g->head.all_records = nullptr;
+    g->head.record_block = nullptr;
+    g->head.num_records = 0;
+
+    bool ok = cuda_ok(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    ok = ok && cuda_ok(cudaEventCreate(&g->ev0), "cudaEventCreate");
+    ok = ok && cuda_ok(cudaEventCreate(&g->ev1), "cudaEventCreate");
+    ok = ok && cuda_ok(cudaMalloc(&g->d_ctl, sizeof(QueryCtl)), "cudaMalloc ctl");
+    ok = ok && cuda_ok(cudaMallocHost(&g->h_ctl, sizeof(QueryCtl)), "cudaMallocHost ctl");
+    ok = ok && cuda_ok(cudaMalloc(&g->d_probe_lo, sizeof(unsigned long long) * kMaxSegments), "cudaMalloc probe");
+    ok = ok && cuda_ok(cudaMalloc(&g->d_probe_hi, sizeof(unsigned long long) * kMaxSegments), "cudaMalloc probe");
+    ok = ok && cuda_ok(cudaMalloc(&g->d_probe_first, sizeof(uint32_t) * kMaxSegments), "cudaMalloc probe");
+    ok = ok && cuda_ok(cudaMalloc(&g->d_probe_count, sizeof(uint32_t) * kMaxSegments), "cudaMalloc probe");
+    ok = ok && cuda_ok(cudaMallocHost(&g->h_probe_keys, sizeof(unsigned long long) * 2 * kMaxSegments),
+                       "cudaMallocHost probe");
+    ok = ok && cuda_ok(cudaMallocHost(&g->h_probe_out, sizeof(uint32_t) * 2 * kMaxSegments), "cudaMallocHost probe");
+    if (!ok) {
+        engine_destroy(g);
+        return nullptr;
+    }
+    return g;
+}
+
+static void free_table(DevTable *t) {
+    for (int c = 0; c < NUM_COLS; ++c) {
+        if (t->col[c].d) cudaFree(t->col[c].d);
+        t->col[c] = DevColumn();
+    }
+    t->n = 0;
+}
+
+void engine_destroy(GpuEngine *g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    free_table(&g->table);
+    for (auto &ix : g->idx) index_free(&ix);
+    if (g->d_ctl) cudaFree(g->d_ctl);
+    if (g->h_ctl) cudaFreeHost(g->h_ctl);
+    if (g->d_tile_desc) cudaFree(g->d_tile_desc);
+    if (g->d_ids) cudaFree(g->d_ids);
+    if (g->d_bitmap) cudaFree(g->d_bitmap);
+    if (g->d_probe_lo) cudaFree(g->d_probe_lo);
+    if (g->d_probe_hi) cudaFree(g->d_probe_hi);
+    if (g->d_probe_first) cudaFree(g->d_probe_first);
+    if (g->d_probe_count) cudaFree(g->d_probe_count);
+    if (g->h_probe_keys) cudaFreeHost(g->h_probe_keys);
+    if (g->h_probe_out) cudaFreeHost(g->h_probe_out);
+    if (g->ev0) cudaEventDestroy(g->ev0);
+    if (g->ev1) cudaEventDestroy(g->ev1);
+    if (g->stream) cudaStreamDestroy(g->stream);
+    for (int i = 0; i < g->head.num_indexes; ++i) std::free(g->head.indexed_attributes[i]);
+    std::free(g->head.indexed_attributes);
+    std::free(g->head.attribute_types);
+    std::free(g->head.bplus_tree_roots);
+    std::free(g->head.tableName);
+    std::free(g->head.datafile);
+    g->magic = 0;
+    delete g;
+}
+
+// rows to allocate for a table of n rows: head-room for INSERTs plus one full tile of slack so
+// a bulk copy of the last (partial) tile never leaves the allocation
+static int64_t cap_for(int64_t n) {
+    int64_t want = n + n / 16 + 1;
+    want = (want + kRowPad - 1) / kRowPad * kRowPad;
+    return want + kRowPad;
+}
+
+bool column_alloc(DevColumn *col, uint32_t width, int64_t cap_rows, cudaStream_t stream) {
+    col->d = nullptr;
+    col->width = width;
+    col->cap = cap_rows;
+    const size_t bytes = static_cast<size_t>(cap_rows) * width;
+    if (!cuda_ok(cudaMalloc(&col->d, bytes), "cudaMalloc column")) return false;
+    return cuda_ok(cudaMemsetAsync(col->d, 0, bytes, stream), "cudaMemset column");
+}
+
+bool engine_upload(GpuEngine *g, const HostColumns &hc) {
+    cudaSetDevice(g->device);
+    free_table(&g->table);
+    const int64_t cap = cap_for(hc.n);
+    for (int c = 0; c < NUM_COLS; ++c) {
+        if (!column_alloc(&g->table.col[c], hc.width[c], cap, g->stream)) return false;
+        if (hc.n > 0 &&
+            !cuda_ok(cudaMemcpyAsync(g->table.col[c].d, hc.data[c].data(), static_cast<size_t>(hc.n) * hc.width[c],
+                                     cudaMemcpyHostToDevice, g->stream),
+                     "upload column"))
+            return false;
+    }
+    if (!cuda_ok(cudaStreamSynchronize(g->stream), "upload sync")) return false;
+    g->table.n = hc.n;
+    g->table.row_base = 0;
+    g->head.num_records = static_cast<int>(hc.n);
+    for (auto &ix : g->idx) ix.dirty = true;
+    return true;
+}
+
+// makeIndexSerial (buildEngine-serial.c:13-31): the attribute is appended to the engine's index
+// arrays whatever its type; only u64 / int indexes are ever probed (executeEngine-serial.c:425-429).
+bool engine_add_index(GpuEngine *g, const char *name, int attributeType) {
+    if (!name) return false;
+    if (g->head.num_indexes >= g->idx_slots) {
+        const int ns = g->idx_slots * 2;
+        g->head.bplus_tree_roots = static_cast<node **>(std::realloc(g->head.bplus_tree_roots, ns * sizeof(node *)));
+        g->head.indexed_attributes =
+            static_cast<char **>(std::realloc(g->head.indexed_attributes, ns * sizeof(char *)));
+        g->head.attribute_types =
+            static_cast<FieldType *>(std::realloc(g->head.attribute_types, ns * sizeof(FieldType)));
+        for (int i = g->idx_slots; i < ns; ++i) {
+            g->head.bplus_tree_roots[i] = nullptr;
+            g->head.indexed_attributes[i] = nullptr;
+        }
+        g->idx_slots = ns;
+    }
+    const int slot = g->head.num_indexes;
+    g->head.bplus_tree_roots[slot] = nullptr;
+    g->head.indexed_attributes[slot] = strdup(name);
+    g->head.attribute_types[slot] =
+        (attributeType >= 0 && attributeType <= 3) ? static_cast<FieldType>(attributeType) : static_cast<FieldType>(-1);
+    g->head.num_indexes = slot + 1;
+
+    DevIndex ix;
+    ix.col = col_by_name(name);
+    ix.type = (attributeType == 0) ? T_U64 : T_I32;
+    // probed only when the declared type is u64/int AND it is the column's real type
+    ix.usable = ix.col >= 0 && (attributeType == 0 || attributeType == 1) &&
+                static_cast<int>(kCols[ix.col].type) == attributeType && g->table.resident(ix.col);
+    ix.dirty = true;
+    g->idx.push_back(ix);
+    DevIndex &ref = g->idx.back();
+    if (ref.usable) {
+        int launches = 0;
+        cudaSetDevice(g->device);
+        if (!cuda_ok(index_build(&ref, g->table, g->stream, &launches), "index build")) return false;
+    }
+    return true;
+}
+
+static bool ensure_index(GpuEngine *g, DevIndex *ix, int *launches) {
+    if (!ix->usable || !ix->dirty) return true;
+    return cuda_ok(index_build(ix, g->table, g->stream, launches), "index rebuild");
+}
+
+bool engine_ensure_ids(GpuEngine *g, int64_t n) {
+    if (n <= g->ids_cap && g->d_ids) return true;
+    if (g->d_ids) cudaFree(g->d_ids);
+    g->d_ids = nullptr;
+    g->ids_cap = 0;
+    const int64_t cap = n + n / 8 + 1024;
+    if (!cuda_ok(cudaMalloc(&g->d_ids, static_cast<size_t>(cap) * sizeof(uint32_t)), "cudaMalloc ids")) return false;
+    g->ids_cap = cap;
+    return true;
+}
+
+static bool ensure_desc(GpuEngine *g, int64_t n_tiles) {
+    if (n_tiles <= g->desc_cap && g->d_tile_desc) return true;
+    if (g->d_tile_desc) cudaFree(g->d_tile_desc);
+    g->d_tile_desc = nullptr;
+    const int64_t cap = n_tiles + n_tiles / 4 + 1024;
+    if (!cuda_ok(cudaMalloc(&g->d_tile_desc, static_cast<size_t>(cap) * 8), "cudaMalloc descriptors")) return false;
+    if (!cuda_ok(cudaMemsetAsync(g->d_tile_desc, 0, static_cast<size_t>(cap) * 8, g->stream), "memset descriptors"))
+        return false;
+    g->desc_cap = cap;
+    return true;
+}
+
+static bool ensure_bitmap(GpuEngine *g, int64_t words) {
+    if (words <= g->bitmap_cap_words && g->d_bitmap) return true;
+    if (g->d_bitmap) cudaFree(g->d_bitmap);
+    g->d_bitmap = nullptr;
+    const int64_t cap = words + 1024;
+    if (!cuda_ok(cudaMalloc(&g->d_bitmap, static_cast<size_t>(cap) * 4), "cudaMalloc bitmap")) return false;
+    g->bitmap_cap_words = cap;
+    return true;
+}
+
+static uint32_t next_epoch(GpuEngine *g) {
+    // descriptors carry (epoch << 2 | state) in their upper word: 30 usable bits, 0 = never written
+    if (g->epoch >= 0x3ffffff0u) {
+        if (g->d_tile_desc) cudaMemsetAsync(g->d_tile_desc, 0, static_cast<size_t>(g->desc_cap) * 8, g->stream);
+        g->epoch = 0;
+    }
+    return ++g->epoch;
+}
+
+// ------------------------------------------------------------------------------------------
+// index-path planning: executeEngine-serial.c:358-459
+// ------------------------------------------------------------------------------------------
+static int plan_segments(const GpuEngine *g, const struct whereClauseS *wc, SegmentPlan *out, int max_out,
+                         bool *too_many) {
+    int n = 0;
+    *too_many = false;
+    for (const struct whereClauseS *w = wc; w; w = w->next) {
+        if (w->attribute == nullptr) continue;  // parenthesised groups are skipped (:361-364)
+        for (int i = 0; i < g->head.num_indexes; ++i) {
+            if (std::strcmp(w->attribute, g->head.indexed_attributes[i]) != 0) continue;
+            const FieldType type = g->head.attribute_types[i];
+            if (type != FIELD_UINT64 && type != FIELD_INT) continue;  // bool / string: unsupported (:425-429)
+            const DevIndex &ix = g->idx[i];
+            if (!ix.usable) continue;
+            const char *op = w->op_ ? w->op_ : "";
+            const char *val = w->value ? w->value : "";
+            SegmentPlan s{};
+            s.index_slot = i;
+            if (type == FIELD_UINT64) {
+                const unsigned long long v = std::strtoull(val, nullptr, 10);
+                s.is_u64 = true;
+                if (!std::strcmp(op, "=")) {
+                    s.lo_u64 = v; s.hi_u64 = v;
+                } else if (!std::strcmp(op, ">")) {
+                    s.lo_u64 = v + 1; s.hi_u64 = UINT64_MAX;  // wraps at v == MAX exactly like the reference
+                } else if (!std::strcmp(op, ">=")) {
+                    s.lo_u64 = v; s.hi_u64 = UINT64_MAX;
+                } else if (!std::strcmp(op, "<")) {
+                    s.lo_u64 = 0; s.hi_u64 = v - 1;           // wraps at v == 0 exactly like the reference
+                } else if (!std::strcmp(op, "<=")) {
+                    s.lo_u64 = 0; s.hi_u64 = v;
+                } else {
+                    s.lo_u64 = 0; s.hi_u64 = UINT64_MAX;
+                }
+            } else {
+                const int v = std::atoi(val);
+                s.is_u64 = false;
+                // v + 1 / v - 1 overflow is UB in the reference; wrap-around is what gcc -O2 emits
+                const int vp = static_cast<int>(static_cast<unsigned>(v) + 1u);
+                const int vm = static_cast<int>(static_cast<unsigned>(v) - 1u);
+                if (!std::strcmp(op, "=")) {
+                    s.lo_i32 = v; s.hi_i32 = v;
+                } else if (!std::strcmp(op, ">")) {
+                    s.lo_i32 = vp; s.hi_i32 = INT_MAX;
+                } else if (!std::strcmp(op, ">=")) {
+                    s.lo_i32 = v; s.hi_i32 = INT_MAX;
+                } else if (!std::strcmp(op, "<")) {
+                    s.lo_i32 = INT_MIN; s.hi_i32 = vm;
+                } else if (!std::strcmp(op, "<=")) {
+                    s.lo_i32 = INT_MIN; s.hi_i32 = v;
+                } else {
+                    s.lo_i32 = INT_MIN; s.hi_i32 = INT_MAX;
+                }
+            }
+            if (n >= max_out) {
+                *too_many = true;
+                return n;
+            }
+            out[n++] = s;
+        }
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// match phase
+// ------------------------------------------------------------------------------------------
+bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, bool invert, bool count_only,
+                  bool want_bitmap, uint64_t *count) {
+    cudaSetDevice(g->device);
+    const double t_begin = now_ms();
+    ScanStats st;
+    const DevTable &t = g->table;
+
+    uint32_t widths[NUM_COLS];
+    for (int c = 0; c < NUM_COLS; ++c) widths[c] = t.col[c].width;
+    QueryCtl *hc = g->h_ctl;
+    const std::string err = compile_where(wc, widths, &hc->prog, invert);
+    if (!err.empty()) {
+        set_error(err);
+        return false;
+    }
+    for (int c = 0; c < NUM_COLS; ++c)
+        if ((hc->prog.col_mask & (1u << c)) && !t.resident(c)) {
+            set_error(std::string("WHERE references column '") + kCols[c].name + "' which is not resident on the device");
+            return false;
+        }
+    hc->tile_counter = 0;
+    hc->pad0 = 0;
+    hc->out_count = 0;
+
+    // ---- path rule of the reference ----
+    SegmentPlan segs[kMaxSegments];
+    int n_seg = 0;
+    if (!force_scan && !invert) {
+        bool too_many = false;
+        n_seg = plan_segments(g, wc, segs, kMaxSegments, &too_many);
+        if (too_many) {
+            set_error("too many (condition x index) segments in one WHERE clause");
+            return false;
+        }
+    }
+
+    int64_t bytes_per_row = 0;
+    for (int c = 0; c < NUM_COLS; ++c)
+        if (hc->prog.col_mask & (1u << c)) bytes_per_row += t.col[c].width;
+
+    if (!cuda_ok(cudaMemcpyAsync(g->d_ctl, hc, sizeof(QueryCtl), cudaMemcpyHostToDevice, g->stream), "upload query"))
+        return false;
+
+    if (n_seg == 0) {
+        // ===== full-scan path: linearSearchRecords over the table (:464-467) =====
+        st.path = 0;
+        st.rows_scanned = t.n;
+        ScanGeometry geo{};
+        const char *why = nullptr;
+        const bool staged = scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, &geo, &why);
+        if (staged) {
+            if (!ensure_desc(g, geo.n_tiles)) return false;
+            if (!count_only && !engine_ensure_ids(g, t.n)) return false;
+            const int64_t bm_words = geo.n_tiles * (geo.tile_rows / 32);
+            if (want_bitmap && !ensure_bitmap(g, bm_words)) return false;
+            ScanLaunch L{};
+            L.table = &t;
+            L.d_ctl = g->d_ctl;
+            L.h_prog = &hc->prog;
+            L.tile_desc = g->d_tile_desc;
+            L.epoch = next_epoch(g);
+            L.out_ids = count_only ? nullptr : g->d_ids;
+            L.out_bitmap = want_bitmap ? g->d_bitmap : nullptr;
+            L.force_tile_rows = g->force_tile_rows;
+            L.force_stages = g->force_stages;
+            cudaEventRecord(g->ev0, g->stream);
+            if (!cuda_ok(scan_launch(L, geo, g->stream), "scan kernel launch")) return false;
+            cudaEventRecord(g->ev1, g->stream);
+            st.launches = 1;
+            st.tile_rows = geo.tile_rows;
+            st.stages = geo.stages;
+            st.grid = geo.grid;
+        } else {
+            // a tile of this WHERE's columns does not fit shared memory: evaluate with gathered
+            // loads over the identity candidate list (still on the device, still ordered)
+            if (want_bitmap) {
+                set_error(std::string("match mask unavailable: ") + (why ? why : "scan cannot be staged"));
+                return false;
+            }
+            CandSegments cs{};
+            cs.n_seg = 1;
+            cs.perm[0] = nullptr;
+            cs.first[0] = 0;
+            cs.vstart[0] = 0;
+            cs.vstart[1] = t.n;
+            if (!ensure_desc(g, filter_tiles(t.n))) return false;
+            if (!count_only && !engine_ensure_ids(g, t.n)) return false;
+            cudaEventRecord(g->ev0, g->stream);
+            if (!cuda_ok(filter_launch(t, g->d_ctl, cs, g->d_tile_desc, next_epoch(g), count_only ? nullptr : g->d_ids,
+                                       g->stream),
+                         "filter kernel launch"))
+                return false;
+            cudaEventRecord(g->ev1, g->stream);
+            st.launches = t.n > 0 ? 1 : 0;
+        }
+    } else {
+        // ===== index path: candidates from findRange per segment, then the whole WHERE (:469-474) =====
+        st.path = 1;
+        if (want_bitmap) {
+            set_error("match mask is only defined on the full-scan path");
+            return false;
+        }
+        int launches = 0;
+        for (int s = 0; s < n_seg; ++s)
+            if (!ensure_index(g, &g->idx[segs[s].index_slot], &launches)) return false;
+        cudaEventRecord(g->ev0, g->stream);
+        for (int s = 0; s < n_seg; ++s) {
+            if (segs[s].is_u64) {
+                g->h_probe_keys[s] = segs[s].lo_u64;
+                g->h_probe_keys[kMaxSegments + s] = segs[s].hi_u64;
+            } else {
+                int32_t lo = segs[s].lo_i32, hi = segs[s].hi_i32;
+                g->h_probe_keys[s] = 0;
+                g->h_probe_keys[kMaxSegments + s] = 0;
+                std::memcpy(&g->h_probe_keys[s], &lo, 4);
+                std::memcpy(&g->h_probe_keys[kMaxSegments + s], &hi, 4);
+            }
+        }
+        if (!cuda_ok(cudaMemcpyAsync(g->d_probe_lo, g->h_probe_keys, sizeof(unsigned long long) * n_seg,
+                                     cudaMemcpyHostToDevice, g->stream),
+                     "upload probe keys") ||
+            !cuda_ok(cudaMemcpyAsync(g->d_probe_hi, g->h_probe_keys + kMaxSegments, sizeof(unsigned long long) * n_seg,
+                                     cudaMemcpyHostToDevice, g->stream),
+                     "upload probe keys"))
+            return false;
+        for (int s = 0; s < n_seg; ++s) {
+            // keys of segment s sit in 8-byte slots: int keys use the low 4 bytes of their slot
+            const DevIndex &ix = g->idx[segs[s].index_slot];
+            if (!cuda_ok(index_probe(ix, g->d_probe_lo + s, g->d_probe_hi + s, 1, g->d_probe_first + s,
+                                     g->d_probe_count + s, g->stream),
+                         "probe kernel launch"))
+                return false;
+            ++launches;
+        }
+        if (!cuda_ok(cudaMemcpyAsync(g->h_probe_out, g->d_probe_first, sizeof(uint32_t) * n_seg, cudaMemcpyDeviceToHost,
+                                     g->stream),
+                     "download probe") ||
+            !cuda_ok(cudaMemcpyAsync(g->h_probe_out + kMaxSegments, g->d_probe_count, sizeof(uint32_t) * n_seg,
+                                     cudaMemcpyDeviceToHost, g->stream),
+                     "download probe") ||
+            !cuda_ok(cudaStreamSynchronize(g->stream), "probe sync"))
+            return false;
+        CandSegments cs{};
+        cs.n_seg = n_seg;
+        cs.vstart[0] = 0;
+        for (int s = 0; s < n_seg; ++s) {
+            const DevIndex &ix = g->idx[segs[s].index_slot];
+            cs.perm[s] = ix.perm;
+            cs.first[s] = g->h_probe_out[s];
+            cs.vstart[s + 1] = cs.vstart[s] + g->h_probe_out[kMaxSegments + s];
+        }
+        const long long n_cand = cs.vstart[n_seg];
+        st.candidates = n_cand;
+        st.rows_scanned = n_cand;
+        if (!ensure_desc(g, filter_tiles(n_cand))) return false;
+        if (!count_only && !engine_ensure_ids(g, n_cand)) return false;
+        if (!cuda_ok(filter_launch(t, g->d_ctl, cs, g->d_tile_desc, next_epoch(g), count_only ? nullptr : g->d_ids,
+                                   g->stream),
+                     "filter kernel launch"))
+            return false;
+        if (n_cand > 0) ++launches;
+        cudaEventRecord(g->ev1, g->stream);
+        st.launches = launches;
+    }
+
+    if (!cuda_ok(cudaMemcpyAsync(&hc->out_count, &g->d_ctl->out_count, sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, g->stream),
+                 "download count") ||
+        !cuda_ok(cudaStreamSynchronize(g->stream), "match sync"))
+        return false;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g->ev0, g->ev1);
+    st.kernel_ms = ms;
+    st.matches = static_cast<int64_t>(hc->out_count);
+    st.algo_bytes = st.rows_scanned * bytes_per_row + (count_only ? 0 : 4 * st.matches) +
+                    (st.path == 1 ? 4 * st.candidates : 0);
+    st.total_ms = now_ms() - t_begin;
+    g->last = st;
+    if (count) *count = hc->out_count;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// downloads
+// ------------------------------------------------------------------------------------------
+bool engine_fetch_rows(GpuEngine *g, int col, const uint32_t *d_ids, int64_t n, std::vector<uint8_t> *out) {
+    cudaSetDevice(g->device);
+    const DevColumn &c = g->table.col[col];
+    out->assign(static_cast<size_t>(n) * c.width, 0);
+    if (n == 0) return true;
+    if (!c.d) {
+        set_error(std::string("column '") + kCols[col].name + "' is not resident on the device");
+        return false;
+    }
+    uint8_t *d_tmp = nullptr;
+    if (!cuda_ok(cudaMalloc(&d_tmp, static_cast<size_t>(n) * c.width), "cudaMalloc gather")) return false;
+    bool ok = cuda_ok(gather_launch(c.d, c.width, d_ids, n, d_tmp, g->stream), "gather kernel launch");
+    ok = ok && cuda_ok(cudaMemcpyAsync(out->data(), d_tmp, out->size(), cudaMemcpyDeviceToHost, g->stream),
+                       "download gather");
+    ok = cuda_ok(cudaStreamSynchronize(g->stream), "gather sync") && ok;
+    cudaFree(d_tmp);
+    return ok;
+}
+
+bool engine_download_all(GpuEngine *g, HostColumns *out) {
+    cudaSetDevice(g->device);
+    out->n = g->table.n;
+    for (int c = 0; c < NUM_COLS; ++c) {
+        const DevColumn &dc = g->table.col[c];
+        out->width[c] = dc.width;
+        out->data[c].assign(static_cast<size_t>(g->table.n) * dc.width, 0);
+        if (g->table.n == 0) continue;
+        if (!dc.d) {
+            set_error(std::string("column '") + kCols[c].name + "' is not resident on the device");
+            return false;
+        }
+        if (!cuda_ok(cudaMemcpyAsync(out->data[c].data(), dc.d, out->data[c].size(), cudaMemcpyDeviceToHost, g->stream),
+                     "download column"))
+            return false;
+    }
+    return cuda_ok(cudaStreamSynchronize(g->stream), "download sync");
+}
+
+// ------------------------------------------------------------------------------------------
+// DELETE: stable compaction of every column by the keep list (K1 with the inverted program)
+// ------------------------------------------------------------------------------------------
+bool engine_delete(GpuEngine *g, const struct whereClauseS *wc, int64_t *deleted) {
+    cudaSetDevice(g->device);
+    uint64_t kept = 0;
+    // executeQueryDeleteSerial never uses an index (:646-677): force the scan path; invert = keep list
+    if (!engine_match(g, wc, true, true, false, false, &kept)) return false;
+    const int64_t n_old = g->table.n;
+    *deleted = n_old - static_cast<int64_t>(kept);
+    if (*deleted == 0) return true;
+    for (int c = 0; c < NUM_COLS; ++c) {
+        DevColumn &dc = g->table.col[c];
+        if (!dc.d) continue;
+        DevColumn nc;
+        if (!column_alloc(&nc, dc.width, dc.cap, g->stream)) return false;
+        if (!cuda_ok(gather_launch(dc.d, dc.width, g->d_ids, static_cast<int64_t>(kept), nc.d, g->stream),
+                     "compaction kernel launch"))
+            return false;
+        if (!cuda_ok(cudaStreamSynchronize(g->stream), "compaction sync")) return false;
+        cudaFree(dc.d);
+        dc = nc;
+    }
+    g->table.n = static_cast<int64_t>(kept);
+    g->head.num_records = static_cast<int>(kept);
+    for (auto &ix : g->idx) ix.dirty = true;  // (key ASC, pos DESC) is a pure function of the table
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// INSERT: append one row (widening string columns when the new text needs it)
+// ------------------------------------------------------------------------------------------
+static bool grow_column(GpuEngine *g, int c, uint32_t new_width, int64_t new_cap) {
+    DevColumn &dc = g->table.col[c];
+    DevColumn nc;
+    if (!column_alloc(&nc, new_width, new_cap, g->stream)) return false;
+    if (g->table.n > 0) {
+        if (new_width == dc.width) {
+            if (!cuda_ok(cudaMemcpyAsync(nc.d, dc.d, static_cast<size_t>(g->table.n) * dc.width,
+                                         cudaMemcpyDeviceToDevice, g->stream),
+                         "grow column"))
+                return false;
+        } else if (!cuda_ok(restride_launch(dc.d, dc.width, nc.d, new_width, g->table.n, g->stream),
+                            "restride kernel launch"))
+            return false;
+    }
+    if (!cuda_ok(cudaStreamSynchronize(g->stream), "grow sync")) return false;
+    cudaFree(dc.d);
+    dc = nc;
+    return true;
+}
+
+bool engine_append(GpuEngine *g, const record &r) {
+    cudaSetDevice(g->device);
+    const uint8_t *rb = reinterpret_cast<const uint8_t *>(&r);
+    const int64_t n = g->table.n;
+    for (int c = 0; c < NUM_COLS; ++c) {
+        DevColumn &dc = g->table.col[c];
+        if (!dc.d) {
+            set_error("INSERT needs every column resident on the device");
+            return false;
+        }
+        uint32_t need_w = dc.width;
+        size_t len = 0;
+        if (kCols[c].type == T_STR) {
+            len = strnlen(reinterpret_cast<const char *>(rb + kCols[c].rec_offset), kCols[c].field_bytes - 1);
+            const uint32_t w = round_up16(static_cast<uint32_t>(len) + 1);
+            if (w > need_w) need_w = w;
+        }
+        // keep one full tile of slack behind the last row (bulk copies read whole tiles)
+        const bool need_cap = n + 1 + kRowPad > dc.cap;
+        if (need_w != dc.width || need_cap) {
+            if (!grow_column(g, c, need_w, need_cap ? cap_for(n + 1) : dc.cap)) return false;
+        }
+        uint8_t cell[512 + 16];
+        std::memset(cell, 0, sizeof cell);
+        if (kCols[c].type == T_STR)
+            std::memcpy(cell, rb + kCols[c].rec_offset, len);
+        else if (kCols[c].type == T_BOOL)
+            cell[0] = r.sudo_used ? 1 : 0;
+        else
+            std::memcpy(cell, rb + kCols[c].rec_offset, dc.width);
+        if (!cuda_ok(cudaMemcpyAsync(g->table.col[c].d + static_cast<size_t>(n) * g->table.col[c].width, cell,
+                                     g->table.col[c].width, cudaMemcpyHostToDevice, g->stream),
+                     "append cell"))
+            return false;
+        if (!cuda_ok(cudaStreamSynchronize(g->stream), "append sync")) return false;  // cell is a stack buffer
+    }
+    g->table.n = n + 1;
+    g->head.num_records = static_cast<int>(n + 1);
+    for (auto &ix : g->idx) ix.dirty = true;
+    return true;
+}
+
+}  // namespace qpe

@@ -1,0 +1,78 @@
+// engine.cuh -- the engine object behind `struct engineS *` and its internal operations
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "qpe_internal.h"
+#include "scan_kernels.cuh"
+#include "index.cuh"
+#include "qpe_gpu.h"
+
+namespace qpe {
+
+constexpr uint64_t kEngineMagic = 0x5150454750553031ull;  // "QPEGPU01"
+constexpr uint64_t kResultMagic = 0x5150455245533031ull;  // "QPERES01"
+
+struct GpuEngine {
+    struct engineS head;  // MUST stay first: callers hold `struct engineS *`
+    uint64_t magic = kEngineMagic;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    DevTable table;
+    std::vector<DevIndex> idx;  // parallel to head.indexed_attributes
+    int idx_slots = 0;          // capacity of the head's index arrays
+
+    // per-query scratch
+    QueryCtl *d_ctl = nullptr;
+    QueryCtl *h_ctl = nullptr;  // pinned
+    unsigned long long *d_tile_desc = nullptr;
+    int64_t desc_cap = 0;
+    uint32_t epoch = 0;
+    uint32_t *d_ids = nullptr;
+    int64_t ids_cap = 0;
+    uint32_t *d_bitmap = nullptr;
+    int64_t bitmap_cap_words = 0;
+    // probe scratch (device + pinned host), kMaxSegments entries each
+    unsigned long long *d_probe_lo = nullptr, *d_probe_hi = nullptr;
+    uint32_t *d_probe_first = nullptr, *d_probe_count = nullptr;
+    unsigned long long *h_probe_keys = nullptr;  // pinned: lo[kMaxSegments], hi[kMaxSegments]
+    uint32_t *h_probe_out = nullptr;             // pinned: first[kMaxSegments], count[kMaxSegments]
+
+    int force_tile_rows = 0, force_stages = 0;
+    ScanStats last;
+};
+
+GpuEngine *as_engine(struct engineS *e);  // nullptr (and error set) if e is not one of ours
+void set_error(const std::string &msg);
+bool cuda_ok(cudaError_t e, const char *what);
+
+// create an engine with an empty table; nullptr if no device
+GpuEngine *engine_create(const char *tableName, const char *datafile, int index_slots);
+void engine_destroy(GpuEngine *g);
+int device_count();
+const char *last_error_cstr();
+bool column_alloc(DevColumn *col, uint32_t width, int64_t cap_rows, cudaStream_t stream);
+// DELETE (stable compaction of every column) and INSERT (append one row); indexes go dirty
+bool engine_delete(GpuEngine *g, const struct whereClauseS *wc, int64_t *deleted);
+bool engine_append(GpuEngine *g, const record &r);
+bool engine_upload(GpuEngine *g, const HostColumns &hc);  // replaces the table
+bool engine_add_index(GpuEngine *g, const char *name, int attributeType);
+bool engine_ensure_ids(GpuEngine *g, int64_t n);
+
+// match phase. On success the ids are in g->d_ids[0 .. *count) (unless count_only).
+bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, bool invert, bool count_only,
+                  bool want_bitmap, uint64_t *count);
+
+// download helpers
+bool engine_fetch_rows(GpuEngine *g, int col, const uint32_t *d_ids, int64_t n, std::vector<uint8_t> *out);
+bool engine_download_all(GpuEngine *g, HostColumns *out);
+
+int64_t load_csv_columns(const char *path, HostColumns *out);
+void parse_csv_chunk(const char *chunk, size_t len, record *r);
+
+}  // namespace qpe

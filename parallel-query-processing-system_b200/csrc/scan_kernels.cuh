@@ -1,0 +1,73 @@
+// scan_kernels.cuh -- launch interface of the SELECT/WHERE kernels (sm_100a)
+#pragma once
+
+#include <cuda_runtime.h>
+#include "qpe_internal.h"
+
+namespace qpe {
+
+// Device-resident control block of one query: the compiled predicate plus the words the
+// kernels need zeroed at launch.  Uploaded with ONE cudaMemcpyAsync per query.
+struct QueryCtl {
+    Program prog;
+    unsigned int tile_counter;      // dynamic tile claim
+    unsigned int pad0;
+    unsigned long long out_count;   // total matches (written by the kernel)
+};
+
+struct ScanLaunch {
+    const DevTable *table;
+    const QueryCtl *d_ctl;          // device copy (prog already uploaded)
+    const Program *h_prog;          // host copy (for col_mask / sizing)
+    unsigned long long *tile_desc;  // >= n_tiles 64-bit look-back descriptors
+    uint32_t epoch;                 // launch epoch stamped into descriptors (never 0)
+    uint32_t *out_ids;              // device, may be null (count / mask only)
+    uint32_t *out_bitmap;           // device, may be null; one bit per row, tile-padded
+    int force_tile_rows;            // 0 = choose
+    int force_stages;               // 0 = choose
+};
+
+struct ScanGeometry {
+    int tile_rows;
+    int stages;
+    int grid;
+    size_t smem_bytes;
+    int64_t n_tiles;
+    int64_t bytes_per_row;
+};
+
+// K1: TMA-staged predicate evaluation + order-preserving compaction over the whole table.
+// Returns false (and sets *why) if the query cannot be staged (row too wide for shared memory):
+// the caller then uses the gather path below with an identity candidate list.
+bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages,
+               ScanGeometry *geo, const char **why);
+cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream_t stream);
+
+// K1g: evaluate the predicate on a list of candidate rows (concatenated index segments, or the
+// identity list when perm == nullptr) and compact the survivors in list order.
+constexpr int kMaxSegments = 32;
+struct CandSegments {
+    int n_seg;
+    const uint32_t *perm[kMaxSegments];  // nullptr => identity
+    long long first[kMaxSegments];       // first entry of the slice within perm
+    long long vstart[kMaxSegments + 1];  // prefix of slice lengths (virtual candidate index)
+};
+cudaError_t filter_launch(const DevTable &t, const QueryCtl *d_ctl, const CandSegments &segs,
+                          unsigned long long *tile_desc, uint32_t epoch, uint32_t *out_ids,
+                          cudaStream_t stream);
+int64_t filter_tiles(long long n_candidates);
+
+// K2: projection gather  out[k] = column[ids[k]]  (width bytes per row)
+cudaError_t gather_launch(const uint8_t *col, uint32_t width, const uint32_t *ids, int64_t n_ids,
+                          uint8_t *out, cudaStream_t stream);
+// same, but ids come from a bitmap-free "keep list" and output goes to a new column (DELETE)
+// -- identical kernel; alias kept for readability at call sites.
+
+// widen / re-stride a fixed-width column (INSERT of a longer string): dst width >= src width
+cudaError_t restride_launch(const uint8_t *src, uint32_t src_w, uint8_t *dst, uint32_t dst_w, int64_t n,
+                            cudaStream_t stream);
+
+// ids[k] += base (sharded tables: local -> global row id), 64-bit output optional
+cudaError_t add_base_launch(uint32_t *ids, int64_t n, uint32_t base, cudaStream_t stream);
+
+}  // namespace qpe
