@@ -212,7 +212,7 @@ PROBE_WHERES = [
     'command_id != 7',
     'user_id <= 1003',
     'exit_code >= 127',
-    'risk_level < 2 AND exit_code = 0 AND sudo_used = FALSE AND shell_type = "fish"',
+    'risk_level > 3 AND exit_code = 130 AND sudo_used = FALSE AND shell_type = "bash"',
     '((risk_level = 1 OR risk_level = 2) AND (shell_type = "zsh")) OR (exit_code = 130)',
     'command_id = 1234',
     'command_id > 1995',

@@ -109,7 +109,7 @@ def test_insert_delete_sequence(pkg, tmp_path):
     ]
     checks = ['SELECT * FROM Commands WHERE risk_level = 5',
               'SELECT command_id, raw_command FROM Commands WHERE user_id = 1001',
-              'SELECT command_id FROM Commands WHERE command_id <= 800 AND command_id >= 5',
+              'SELECT command_id FROM Commands WHERE command_id <= 800 AND command_id >= 1900',
               'SELECT command_id, working_directory FROM Commands WHERE (risk_level > 3)']
     import io, contextlib
     for s in stmts:
