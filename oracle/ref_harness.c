@@ -144,6 +144,45 @@ double ref_time_select(struct engineS *e, const char *sql, int reps, int *matche
     return t1 - t0;
 }
 
+/* the whereClauseS list the reference's tokenizer + parser + convert_conditions build for `sql`,
+ * rendered as text (same rendering as qpe_sql_where_to_text in the product's front end);
+ * also reports the parsed command. Caller frees. */
+static void render_where(const struct whereClauseS *w, char *out, size_t cap) {
+    for (; w; w = w->next) {
+        size_t n = strlen(out);
+        if (w->sub) {
+            snprintf(out + n, cap - n, "( ");
+            render_where(w->sub, out, cap);
+            n = strlen(out);
+            snprintf(out + n, cap - n, " )");
+        } else {
+            snprintf(out + n, cap - n, "%s %s %s", w->attribute ? w->attribute : "<null>",
+                     w->operator ? w->operator : "<null>", w->value ? w->value : "<null>");
+        }
+        if (w->next) {
+            n = strlen(out);
+            snprintf(out + n, cap - n, " %s ", w->logical_op ? w->logical_op : "<none>");
+        }
+    }
+}
+
+char *ref_where_text(const char *sql, int *command_out) {
+    Token tokens[MAX_TOKENS];
+    memset(tokens, 0, sizeof tokens);
+    char *out = calloc(1, 8192);
+    if (command_out) *command_out = -1;
+    if (tokenize(sql, tokens, MAX_TOKENS) <= 0) return out;
+    ParsedSQL parsed = parse_tokens(tokens);
+    if (command_out) *command_out = (int)parsed.command;
+    if (parsed.command != CMD_SELECT && parsed.command != CMD_DELETE) return out;
+    struct whereClauseS *wc = convert_conditions(&parsed);
+    render_where(wc, out, 8192);
+    free_where_clause_list(wc);
+    return out;
+}
+
+void ref_free(void *p) { free(p); }
+
 #ifdef REF_HARNESS_MAIN
 /* qpe_ref_dump <csv> <query-file> [max_rows=0] [num_indexes=5]
  * Same statement splitting as QPESeq.c:74-82 (strtok on ';', leading-space trim). */

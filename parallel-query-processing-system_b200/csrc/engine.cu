@@ -373,7 +373,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
             return false;
         }
     hc->tile_counter = 0;
-    hc->pad0 = 0;
+    hc->chunk_counter = 0;
     hc->out_count = 0;
 
     // ---- path rule of the reference ----
@@ -403,24 +403,31 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
         const char *why = nullptr;
         const bool staged = scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, &geo, &why);
         if (staged) {
-            if (!ensure_desc(g, geo.n_tiles)) return false;
-            if (!count_only && !engine_ensure_ids(g, t.n)) return false;
             const int64_t bm_words = geo.n_tiles * (geo.tile_rows / 32);
-            if (want_bitmap && !ensure_bitmap(g, bm_words)) return false;
+            const int64_t n_chunks = compact_chunks(bm_words);
+            if (!count_only || want_bitmap) {
+                if (!ensure_bitmap(g, bm_words)) return false;
+            }
+            if (!count_only && (!ensure_desc(g, n_chunks) || !engine_ensure_ids(g, t.n))) return false;
             ScanLaunch L{};
             L.table = &t;
             L.d_ctl = g->d_ctl;
             L.h_prog = &hc->prog;
-            L.tile_desc = g->d_tile_desc;
-            L.epoch = next_epoch(g);
-            L.out_ids = count_only ? nullptr : g->d_ids;
-            L.out_bitmap = want_bitmap ? g->d_bitmap : nullptr;
+            L.out_bitmap = (!count_only || want_bitmap) ? g->d_bitmap : nullptr;
             L.force_tile_rows = g->force_tile_rows;
             L.force_stages = g->force_stages;
             cudaEventRecord(g->ev0, g->stream);
             if (!cuda_ok(scan_launch(L, geo, g->stream), "scan kernel launch")) return false;
-            cudaEventRecord(g->ev1, g->stream);
             st.launches = 1;
+            if (!count_only && t.n > 0) {
+                // K1c: ordered compaction of the match bitmap (decoupled look-back per 64 Ki rows)
+                if (!cuda_ok(compact_launch(g->d_bitmap, bm_words, g->d_ctl, g->d_tile_desc, next_epoch(g), g->d_ids,
+                                            g->stream),
+                             "compaction kernel launch"))
+                    return false;
+                st.launches = 2;
+            }
+            cudaEventRecord(g->ev1, g->stream);
             st.tile_rows = geo.tile_rows;
             st.stages = geo.stages;
             st.grid = geo.grid;

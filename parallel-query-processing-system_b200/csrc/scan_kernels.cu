@@ -1,21 +1,28 @@
 // scan_kernels.cu -- SELECT/WHERE hot path for B200 (sm_100a)
 //
-// K1  scan_tma_kernel      full-table predicate evaluation + order-preserving compaction.
+// K1  scan_tma_kernel      full-table predicate evaluation -> match bitmap + match count.
 //       Replaces linearSearchRecords/evaluateWhereClause/checkCondition
 //       (engine/serial/executeEngine-serial.c:854-878, :292-316, :251-289).
-//       Warp-specialised persistent CTAs:
-//         P  (1 warp, 1 lane)  claims tiles from an atomic counter and streams every referenced
-//                              column's slice of the tile into shared memory with 1-D TMA bulk
-//                              copies (cp.async.bulk + mbarrier complete_tx), S stages deep;
-//         E  (kEvalWarps)      evaluate the compiled WHERE program on the staged tile, one
-//                              R-bit match mask per lane, __ballot_sync -> tile bitmap in smem,
-//                              publish the tile's match count (look-back "aggregate");
-//         W  (kWriteWarps)     decoupled look-back over the tile descriptors to get the tile's
-//                              global offset, then expand the bitmap into row ids with
-//                              popc-ranked coalesced stores -- rows come out in table order.
-//       E never waits on a look-back, so HBM streaming is not stalled by the scan chain.
-// K1g filter_kernel        same program on a gathered candidate list (index path), same
-//                          ordered compaction (single-pass, decoupled look-back).
+//       Warp-specialised persistent CTAs, one per SM:
+//         P  (1 warp, 1 lane)  streams every referenced column's slice of a tile into shared
+//                              memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier
+//                              complete_tx), S stages deep;
+//         E  (kEvalWarps)      evaluate the compiled WHERE program on the staged tile, one R-bit
+//                              match mask per lane (the operator dispatch happens once per tile,
+//                              the per-row work is load / compare / predicated OR), transpose it
+//                              with __ballot_sync into bitmap words (bit b of word w = row 32w+b)
+//                              and store them.  The bitmap is 1 bit per row: 1/104 of the
+//                              narrowest scan's input traffic.
+//       Nothing in K1 waits on another CTA, so HBM streaming is never stalled by a scan chain.
+// K1c compact_kernel       order-preserving stream compaction of the bitmap into row ids:
+//       popc per word, block scan, single-pass DECOUPLED LOOK-BACK over 64 Ki-row chunks
+//       (status flag + aggregate / inclusive prefix per chunk), ids staged in shared memory and
+//       written with coalesced stores -- rows come out in exactly table order.  The same bitmap
+//       is DELETE's match mask.  (A first version ran the look-back per 4 Ki-row tile inside K1:
+//       at HBM speed that is >100 descriptors/us, more than a 32-wide look-back window can
+//       follow at L2 latency, and the chain fell behind; see DESIGN.md.)
+// K1g filter_kernel        same program on a gathered candidate list (index path), ordered
+//                          single-pass compaction with decoupled look-back per 1 Ki candidates.
 // K2  gather_kernel        projection / column compaction gather.
 //
 // HBM-bound integer/byte work: no tensor cores by design.
@@ -23,6 +30,7 @@
 #include "scan_kernels.cuh"
 
 #include <cstdint>
+#include <cstdlib>
 
 namespace qpe {
 
@@ -131,12 +139,11 @@ __device__ __forceinline__ uint32_t str_cmp3(RowPtr row, const uint4 *lit, int n
 // K1: TMA-staged scan
 // ------------------------------------------------------------------------------------------
 constexpr int kEvalWarps = 8;
-constexpr int kWriteWarps = 4;
-constexpr int kBmSlots = kWriteWarps;  // one bitmap slot per writer warp
 constexpr int kMaxStages = 8;
-constexpr int kScanThreads = 32 * (1 + kWriteWarps + kEvalWarps);
-constexpr int kMaxTileRows = 8192;  // == kRowPad: a full tile is always inside the allocation
-constexpr int kRowsPerGroup = 32 * kEvalWarps;  // tile_rows is a multiple of this
+constexpr int kScanThreads = 32 * (1 + kEvalWarps);
+constexpr int kRowsPerGroup = 32 * kEvalWarps;   // rows one "row group" covers: a tile is R groups
+constexpr int kMaxR = 16;                        // rows per lane per tile: 1, 2, 4, 8 or 16
+constexpr int kMaxTileRows = kRowsPerGroup * kMaxR;  // 4096 (<= kRowPad: a full tile is always inside the allocation)
 
 struct ScanParams {
     const uint8_t *col[NUM_COLS];
@@ -147,78 +154,120 @@ struct ScanParams {
     uint32_t stage_bytes;
     int32_t tile_rows;
     int32_t n_stages;
-    uint32_t epoch;
+    int32_t dynamic_tiles;  // 1: claim tiles from the global counter; 0: tile = cta + k * grid
     long long n_rows;
     long long n_tiles;
     QueryCtl *ctl;
-    unsigned long long *tile_desc;
-    uint32_t *out_ids;
-    uint32_t *out_bitmap;
+    uint32_t *out_bitmap;   // n_tiles * tile_rows / 32 words, or null (count only)
 };
 
 struct ScanSmemHeader {
     Program prog;
     alignas(8) uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
-    uint64_t bm_full[kBmSlots];
-    uint64_t bm_empty[kBmSlots];
     long long tile_of_stage[kMaxStages];
-    long long tile_of_bm[kBmSlots];
-    uint32_t agg[kBmSlots];
-    alignas(16) uint32_t bm[kBmSlots][kMaxTileRows / 32];
+    unsigned long long cta_count;
 };
 
-// evaluate one leaf for the R rows of this lane (rows lrow, lrow+32, ...) out of a staged tile
-__device__ __forceinline__ uint32_t eval_leaf_tile(const PLeaf &lf, const Program *sp, const uint8_t *stage,
-                                                   const ScanParams &p, int lrow, int R) {
+// R-bit mask of a per-row predicate, fully unrolled so every shift is an immediate
+template <int R, typename F>
+__device__ __forceinline__ uint32_t rows_mask(F pred) {
     uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) m |= pred(j) ? (1u << j) : 0u;
+    return m;
+}
+
+// numeric leaf: the operator is warp-uniform, so it is dispatched ONCE per tile and each case is
+// a straight run of R (load, compare, predicated OR) triples
+template <int R, typename T>
+__device__ __forceinline__ uint32_t cmp_numeric(const T *c, const T lit, const uint32_t tt) {
+    switch (tt) {
+        case 0b010: return rows_mask<R>([&](int j) { return c[j * 32] == lit; });
+        case 0b101: return rows_mask<R>([&](int j) { return c[j * 32] != lit; });
+        case 0b100: return rows_mask<R>([&](int j) { return c[j * 32] > lit; });
+        case 0b001: return rows_mask<R>([&](int j) { return c[j * 32] < lit; });
+        case 0b110: return rows_mask<R>([&](int j) { return c[j * 32] >= lit; });
+        case 0b011: return rows_mask<R>([&](int j) { return c[j * 32] <= lit; });
+        case 0b111: return (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
+        default: return 0u;
+    }
+}
+
+__device__ __forceinline__ uint32_t diff16(const uint4 v, const uint4 l) {
+    return (v.x ^ l.x) | (v.y ^ l.y) | (v.z ^ l.z) | (v.w ^ l.w);
+}
+
+// evaluate one leaf for the R rows of this lane (rows lrow, lrow+32, ...) out of a staged tile
+template <int R>
+__device__ __forceinline__ uint32_t eval_leaf_tile(const PLeaf &lf, const Program *sp, const uint8_t *stage,
+                                                   const ScanParams &p, int lrow) {
     const uint8_t *base = stage + p.smem_off[lf.col];
     const uint32_t tt = lf.tt;
+    constexpr uint32_t kAll = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
     switch (lf.type) {
-        case T_I32: {
-            const int32_t *c = reinterpret_cast<const int32_t *>(base) + lrow;
-            const int32_t lit = lf.lit_i32;
-#pragma unroll 4
-            for (int j = 0; j < R; ++j) {
-                const int32_t v = c[j * 32];
-                m |= tt_bit(tt, v < lit, v == lit) << j;
-            }
-            break;
-        }
-        case T_U64: {
-            const unsigned long long *c = reinterpret_cast<const unsigned long long *>(base) + lrow;
-            const unsigned long long lit = lf.lit_u64;
-#pragma unroll 4
-            for (int j = 0; j < R; ++j) {
-                const unsigned long long v = c[j * 32];
-                m |= tt_bit(tt, v < lit, v == lit) << j;
-            }
-            break;
-        }
+        case T_I32:
+            return cmp_numeric<R, int32_t>(reinterpret_cast<const int32_t *>(base) + lrow, lf.lit_i32, tt);
+        case T_U64:
+            return cmp_numeric<R, unsigned long long>(reinterpret_cast<const unsigned long long *>(base) + lrow,
+                                                      lf.lit_u64, tt);
         case T_BOOL: {
+            // only = and != exist; (cell != 0) == want
             const uint8_t *c = base + lrow;
-            const uint32_t lit = static_cast<uint32_t>(lf.lit_i32) & 1u;
-#pragma unroll 4
-            for (int j = 0; j < R; ++j) {
-                const uint32_t v = c[j * 32] != 0 ? 1u : 0u;
-                m |= tt_bit(tt, v < lit, v == lit) << j;
-            }
-            break;
+            const bool want = ((tt == 0b010u) == ((lf.lit_i32 & 1) != 0));
+            const uint32_t nz = rows_mask<R>([&](int j) { return c[j * 32] != 0; });
+            return want ? nz : (~nz & kAll);
         }
-        default: {  // T_STR
+        default: {  // T_STR: strcmp order == unsigned byte order over the NUL-padded cell
             const uint32_t w = p.width[lf.col];
             const int nch = static_cast<int>(w >> 4);
             const uint4 *lit = reinterpret_cast<const uint4 *>(sp->lit_pool + lf.lit_off);
             const uint8_t *c = base + static_cast<size_t>(lrow) * w;
-            for (int j = 0; j < R; ++j) {
-                const uint4 *row = reinterpret_cast<const uint4 *>(c + static_cast<size_t>(j) * 32u * w);
-                const uint32_t r = str_cmp3(row, lit, nch);
-                m |= ((tt >> r) & 1u) << j;
+            const size_t jstride = static_cast<size_t>(32u) * w;
+            if (tt == 0b010u || tt == 0b101u) {
+                // equality only: OR of XORs, no byte swapping
+                uint32_t ne = 0;
+                if (nch == 1) {
+                    const uint4 l0 = lit[0];
+                    ne = rows_mask<R>([&](int j) {
+                        return diff16(*reinterpret_cast<const uint4 *>(c + j * jstride), l0) != 0u;
+                    });
+                } else {
+                    for (int k = 0; k < nch; ++k) {
+                        const uint4 lk = lit[k];
+                        ne |= rows_mask<R>([&](int j) {
+                            return diff16(reinterpret_cast<const uint4 *>(c + j * jstride)[k], lk) != 0u;
+                        });
+                        if (__all_sync(0xffffffffu, ne == kAll)) break;  // warp-uniform early exit
+                    }
+                }
+                return (tt == 0b010u) ? (~ne & kAll) : ne;
             }
-            break;
+            // ordering: three-way compare chunk by chunk, first differing chunk decides
+            uint32_t lt = 0, decided = 0;
+            for (int k = 0; k < nch; ++k) {
+                const uint4 lk = lit[k];
+                const uint32_t b0 = bswap32(lk.x), b1 = bswap32(lk.y), b2 = bswap32(lk.z), b3 = bswap32(lk.w);
+                uint32_t dk = 0, ltk = 0;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const uint4 v = reinterpret_cast<const uint4 *>(c + j * jstride)[k];
+                    const uint32_t a0 = bswap32(v.x), a1 = bswap32(v.y), a2 = bswap32(v.z), a3 = bswap32(v.w);
+                    const bool d0 = a0 != b0, d1 = a1 != b1, d2 = a2 != b2, d3 = a3 != b3;
+                    const bool l = d0 ? (a0 < b0) : d1 ? (a1 < b1) : d2 ? (a2 < b2) : (a3 < b3);
+                    dk |= (d0 | d1 | d2 | d3) ? (1u << j) : 0u;
+                    ltk |= l ? (1u << j) : 0u;
+                }
+                const uint32_t fresh = dk & ~decided;
+                lt |= ltk & fresh;
+                decided |= dk;
+                if (__all_sync(0xffffffffu, decided == kAll)) break;
+            }
+            const uint32_t eq = ~decided & kAll;
+            const uint32_t gt = decided & ~lt;
+            return ((tt & 1u) ? lt : 0u) | ((tt & 2u) ? eq : 0u) | ((tt & 4u) ? gt : 0u);
         }
     }
-    return m;
 }
 
 // run the compiled WHERE program; returns the R-bit match mask of this lane's rows
@@ -279,12 +328,13 @@ __device__ __forceinline__ uint32_t warp_lookback(const unsigned long long *desc
         const long long mine = idx - static_cast<long long>(lane);
         uint32_t state = kStatePrefix, val = 0;
         if (mine >= 0) {
-            unsigned long long d;
-            uint32_t flag;
-            do {
+            unsigned long long d = ld_desc(desc + mine);
+            uint32_t flag = static_cast<uint32_t>(d >> 32);
+            while ((flag >> 2) != epoch) {
+                __nanosleep(64);  // predecessor not published yet: back off instead of hammering L2
                 d = ld_desc(desc + mine);
                 flag = static_cast<uint32_t>(d >> 32);
-            } while ((flag >> 2) != epoch);
+            }
             state = flag & 3u;
             val = static_cast<uint32_t>(d);
         }
@@ -302,38 +352,7 @@ __device__ __forceinline__ uint32_t warp_lookback(const unsigned long long *desc
     return excl;
 }
 
-// expand `nwords` bitmap words (32 rows each, row id of bit b in word w = row0 + 32*w + b) into
-// ids at out[excl...], in row order.  Whole warp cooperates; stores are popc-ranked.
-__device__ __forceinline__ void warp_expand_bitmap(const uint32_t *words, int nwords, long long row0, uint32_t *out,
-                                                   uint32_t excl, uint32_t lane) {
-    uint32_t running = excl;
-    for (int wb = 0; wb < nwords; wb += 32) {
-        const int wi = wb + static_cast<int>(lane);
-        const uint32_t word = (wi < nwords) ? words[wi] : 0u;
-        const uint32_t pc = __popc(word);
-        // inclusive scan of pc over lanes
-        uint32_t inc = pc;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= static_cast<uint32_t>(d)) inc += t;
-        }
-        const uint32_t woff = running + inc - pc;
-        uint32_t nz = __ballot_sync(0xffffffffu, word != 0u);
-        while (nz) {
-            const int src = __ffs(nz) - 1;
-            nz &= nz - 1;
-            const uint32_t w = __shfl_sync(0xffffffffu, word, src);
-            const uint32_t o = __shfl_sync(0xffffffffu, woff, src);
-            if ((w >> lane) & 1u) {
-                out[o + __popc(w & lanemask_lt())] =
-                    static_cast<uint32_t>(row0 + 32ll * (wb + src) + static_cast<long long>(lane));
-            }
-        }
-        running += __shfl_sync(0xffffffffu, inc, 31);
-    }
-}
-
+template <int R>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     ScanSmemHeader *sh = reinterpret_cast<ScanSmemHeader *>(smem_raw);
@@ -343,9 +362,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const __grid_
     const uint32_t warp = tid >> 5;
     const uint32_t lane = tid & 31u;
     const int S = p.n_stages;
-    const int T = p.tile_rows;
-    const int R = T / kRowsPerGroup;   // rows per lane per tile (<= 32)
-    const int WPT = T >> 5;            // bitmap words per tile
+    constexpr int T = kRowsPerGroup * R;  // rows per tile
+    constexpr int WPT = T >> 5;           // bitmap words per tile
 
     // program -> shared memory (uniform reads afterwards), barrier init
     {
@@ -358,11 +376,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const __grid_
             mbar_init(&sh->full[s], 1);
             mbar_init(&sh->empty[s], kEvalWarps);
         }
-        for (int b = 0; b < kBmSlots; ++b) {
-            mbar_init(&sh->bm_full[b], kEvalWarps);
-            mbar_init(&sh->bm_empty[b], 1);
-            sh->agg[b] = 0;
-        }
+        sh->cta_count = 0;
         fence_mbar_init();
     }
     __syncthreads();
@@ -371,11 +385,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const __grid_
     if (warp == 0) {
         // ===== P: tile claim + TMA producer =====
         if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
             for (long long k = 0;; ++k) {
-                const int s = static_cast<int>(k % S);
-                const uint32_t u = static_cast<uint32_t>(k / S);
-                mbar_wait(&sh->empty[s], (u & 1u) ^ 1u);
-                const long long tile = static_cast<long long>(atomicAdd(&p.ctl->tile_counter, 1u));
+                mbar_wait(&sh->empty[s], phase ^ 1u);
+                // static round-robin keeps the claim off the critical path (a global atomic costs a
+                // full round trip per tile); every CTA is resident (grid <= SM count) and walks its
+                // tiles in increasing order, so the look-back chain always makes progress.
+                const long long tile = p.dynamic_tiles ? static_cast<long long>(atomicAdd(&p.ctl->tile_counter, 1u))
+                                                       : static_cast<long long>(blockIdx.x) + k * gridDim.x;
                 if (tile >= p.n_tiles) {
                     sh->tile_of_stage[s] = -1;
                     mbar_arrive(&sh->full[s]);
@@ -390,87 +408,57 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const __grid_
                     tma_bulk_g2s(dst + p.smem_off[c], p.col[c] + static_cast<size_t>(tile) * T * w,
                                  static_cast<uint32_t>(T) * w, &sh->full[s]);
                 }
-            }
-        }
-    } else if (warp <= kWriteWarps) {
-        // ===== W: look-back + ordered id expansion =====
-        const int w = static_cast<int>(warp) - 1;  // == bitmap slot
-        for (long long k = w;; k += kWriteWarps) {
-            const uint32_t u = static_cast<uint32_t>(k / kBmSlots);
-            mbar_wait(&sh->bm_full[w], u & 1u);
-            const long long tile = sh->tile_of_bm[w];
-            if (tile < 0) break;
-            const uint32_t total = sh->agg[w] & 0xffffffu;
-            const uint32_t excl = warp_lookback(p.tile_desc, tile, p.epoch, lane);
-            if (lane == 0) {
-                st_desc(p.tile_desc + tile, make_desc(p.epoch, kStatePrefix, excl + total));
-                if (tile == p.n_tiles - 1) p.ctl->out_count = static_cast<unsigned long long>(excl) + total;
-            }
-            const uint32_t *words = sh->bm[w];
-            if (p.out_bitmap) {
-                uint32_t *dstw = p.out_bitmap + tile * WPT;
-                for (int i = static_cast<int>(lane); i < WPT; i += 32) dstw[i] = words[i];
-            }
-            if (p.out_ids && total) warp_expand_bitmap(words, WPT, tile * T, p.out_ids, excl, lane);
-            __syncwarp();
-            if (lane == 0) {
-                sh->agg[w] = 0;
-                mbar_arrive(&sh->bm_empty[w]);
+                if (++s == S) {
+                    s = 0;
+                    phase ^= 1u;
+                }
             }
         }
     } else {
         // ===== E: predicate evaluation =====
-        const int ew = static_cast<int>(warp) - 1 - kWriteWarps;
-        const uint32_t all_mask = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
+        const int ew = static_cast<int>(warp) - 1;
+        constexpr uint32_t all_mask = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
         const int lrow = ew * (32 * R) + static_cast<int>(lane);  // first row of this lane inside a tile
-        long long k = 0;
-        for (;; ++k) {
-            const int s = static_cast<int>(k % S);
-            const uint32_t us = static_cast<uint32_t>(k / S);
-            mbar_wait(&sh->full[s], us & 1u);
+        int s = 0;
+        uint32_t sphase = 0;
+        uint32_t my_count = 0;  // matches seen by this lane's rows (summed per CTA at the end)
+        for (;;) {
+            mbar_wait(&sh->full[s], sphase);
             const long long tile = sh->tile_of_stage[s];
             if (tile < 0) break;
-            const int b = static_cast<int>(k % kBmSlots);
-            const uint32_t ub = static_cast<uint32_t>(k / kBmSlots);
-            mbar_wait(&sh->bm_empty[b], (ub & 1u) ^ 1u);
 
             const uint8_t *stage = stages + static_cast<size_t>(s) * p.stage_bytes;
-            const uint32_t acc = run_program(sp, all_mask, [&](const PLeaf &lf) {
-                return eval_leaf_tile(lf, sp, stage, p, lrow, R);
+            uint32_t acc = run_program(sp, all_mask, [&](const PLeaf &lf) {
+                return eval_leaf_tile<R>(lf, sp, stage, p, lrow);
             });
+            // the stage can be refilled as soon as every evaluator has read it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh->empty[s]);
 
             const long long row_base = tile * T + lrow;  // global row of this lane's j = 0
-            uint32_t myword = 0, cnt = 0;
-            for (int j = 0; j < R; ++j) {
-                const bool hit = ((acc >> j) & 1u) && (row_base + 32ll * j < p.n_rows);
-                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-                if (static_cast<int>(lane) == j) myword = bal;
-                cnt += __popc(bal);
-            }
-            if (static_cast<int>(lane) < R) sh->bm[b][ew * R + lane] = myword;
-            __syncwarp();
-            if (lane == 0) {
-                const uint32_t old = atomicAdd(&sh->agg[b], (1u << 24) | cnt);
-                if ((old >> 24) == kEvalWarps - 1) {  // last evaluator of this tile: publish aggregate
-                    const uint32_t total = (old & 0xffffffu) + cnt;
-                    sh->tile_of_bm[b] = tile;
-                    st_desc(p.tile_desc + tile, make_desc(p.epoch, tile == 0 ? kStatePrefix : kStateAgg, total));
+            if (tile * T + T > p.n_rows)                 // last (partial) tile: drop the padding rows
+                acc &= rows_mask<R>([&](int j) { return row_base + 32ll * j < p.n_rows; });
+            my_count += static_cast<uint32_t>(__popc(acc));
+            if (p.out_bitmap) {
+                // transpose: lane j ends up with the word of rows [32 j, 32 j + 32) of this warp's slice
+                uint32_t myword = 0;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const uint32_t bal = __ballot_sync(0xffffffffu, (acc >> j) & 1u);
+                    if (static_cast<int>(lane) == j) myword = bal;
                 }
-                mbar_arrive(&sh->bm_full[b]);
-                mbar_arrive(&sh->empty[s]);
+                if (static_cast<int>(lane) < R) p.out_bitmap[tile * WPT + ew * R + lane] = myword;
+            }
+            if (++s == S) {
+                s = 0;
+                sphase ^= 1u;
             }
         }
-        // termination: hand one sentinel to every writer warp (next kWriteWarps slots in sequence)
-        for (int t = 0; t < kWriteWarps; ++t, ++k) {
-            const int b = static_cast<int>(k % kBmSlots);
-            const uint32_t ub = static_cast<uint32_t>(k / kBmSlots);
-            mbar_wait(&sh->bm_empty[b], (ub & 1u) ^ 1u);
-            if (lane == 0) {
-                if (ew == 0) sh->tile_of_bm[b] = -1;
-                mbar_arrive(&sh->bm_full[b]);
-            }
-        }
+        const uint32_t warp_total = __reduce_add_sync(0xffffffffu, my_count);
+        if (lane == 0) atomicAdd(&sh->cta_count, static_cast<unsigned long long>(warp_total));
     }
+    __syncthreads();
+    if (tid == 0 && sh->cta_count) atomicAdd(&p.ctl->out_count, sh->cta_count);
 }
 
 bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages, ScanGeometry *geo,
@@ -493,35 +481,51 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
             bpr += t.col[c].width;
         }
     const size_t header = (sizeof(ScanSmemHeader) + 127) & ~size_t(127);
-    const size_t budget = static_cast<size_t>(max_smem) - header - 1024;
+    const size_t budget = static_cast<size_t>(max_smem) - header - 256;
+
+    auto stage_bytes_for = [&](int T) {
+        size_t sb = 0;
+        for (int c = 0; c < NUM_COLS; ++c)
+            if (prog.col_mask & (1u << c)) sb += (static_cast<size_t>(T) * t.col[c].width + 127) & ~size_t(127);
+        return sb;
+    };
 
     int T = force_tile_rows;
     int S = force_stages;
     if (bpr == 0) {  // no column referenced (NULL where / constants): nothing to stage
-        T = T ? T : 4096;
+        T = T ? T : kMaxTileRows;
         S = S ? S : 2;
-    } else {
-        if (!T) {
-            // aim at ~48 KB per stage, 4 stages; shrink for wide rows
-            int64_t rows = (48 * 1024) / bpr;
-            rows = (rows / kRowsPerGroup) * kRowsPerGroup;
-            if (rows < kRowsPerGroup) rows = kRowsPerGroup;
-            if (rows > kMaxTileRows) rows = kMaxTileRows;
-            T = static_cast<int>(rows);
+    } else if (!T) {
+        // largest tile that still leaves >= 3 stages in flight; else the largest with 2; else 1
+        int best_T = 0, best_S = 0;
+        for (int want = 3; want >= 1 && !best_T; --want)
+            for (int R = kMaxR; R >= 1; R >>= 1) {
+                const size_t sb = stage_bytes_for(kRowsPerGroup * R);
+                int fit = static_cast<int>(budget / (sb ? sb : 1));
+                if (fit > 4) fit = 4;
+                if (fit >= want) {
+                    best_T = kRowsPerGroup * R;
+                    best_S = fit;
+                    break;
+                }
+            }
+        if (!best_T) {
+            if (why) *why = "row too wide to stage a tile in shared memory";
+            return false;
         }
-        if (!S) {
-            S = 4;
-            while (S > 2 && static_cast<size_t>(S) * (static_cast<size_t>(T) * bpr + 128 * NUM_COLS) > budget) --S;
-        }
+        T = best_T;
+        if (!S) S = best_S;
+    } else if (!S) {
+        const size_t sb = stage_bytes_for(T);
+        S = static_cast<int>(budget / (sb ? sb : 1));
+        if (S > 4) S = 4;
     }
-    if (T % kRowsPerGroup != 0 || T > kMaxTileRows || T <= 0 || S < 1 || S > kMaxStages) {
-        if (why) *why = "invalid tile geometry";
+    const int R = T / kRowsPerGroup;
+    if (T % kRowsPerGroup != 0 || (R != 1 && R != 2 && R != 4 && R != 8 && R != 16) || S < 1 || S > kMaxStages) {
+        if (why) *why = "invalid tile geometry (tile rows must be 256 x {1,2,4,8,16})";
         return false;
     }
-    // stage layout: each referenced column 128-byte aligned
-    size_t stage_bytes = 0;
-    for (int c = 0; c < NUM_COLS; ++c)
-        if (prog.col_mask & (1u << c)) stage_bytes += (static_cast<size_t>(T) * t.col[c].width + 127) & ~size_t(127);
+    const size_t stage_bytes = stage_bytes_for(T);
     if (stage_bytes * S > budget || stage_bytes >= (1u << 20)) {
         if (why) *why = "row too wide to stage a tile in shared memory";
         return false;
@@ -535,6 +539,15 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
     if (grid < 1) grid = 1;
     geo->grid = static_cast<int>(grid);
     return true;
+}
+
+template <int R>
+static cudaError_t launch_scan_r(const ScanParams &p, const ScanGeometry &geo, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(geo.smem_bytes));
+    if (e != cudaSuccess) return e;
+    scan_tma_kernel<R><<<geo.grid, kScanThreads, geo.smem_bytes, stream>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream_t stream) {
@@ -552,31 +565,177 @@ cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream
             off += (static_cast<size_t>(geo.tile_rows) * t.col[c].width + 127) & ~size_t(127);
         }
     }
-    // expect_tx counts the bytes actually copied (unpadded)
+    // the barrier of a stage is armed with the bytes actually copied; tile_rows is a multiple of
+    // 256 and widths are 1, 4, 8 or 16k, so every column slice is already a 128-byte multiple
     uint32_t tx = 0;
     for (int r = 0; r < p.n_ref; ++r) tx += static_cast<uint32_t>(geo.tile_rows) * p.width[p.ref_col[r]];
-    // stage stride must cover the padded layout; tx is what the barrier waits for
     p.stage_bytes = static_cast<uint32_t>(off);
+    if (tx != p.stage_bytes) return cudaErrorInvalidValue;
     p.tile_rows = geo.tile_rows;
     p.n_stages = geo.stages;
-    p.epoch = L.epoch;
+    {
+        static const int dyn = [] {
+            const char *e = std::getenv("QPE_SCAN_DYNAMIC");
+            return (e && e[0] == '1') ? 1 : 0;
+        }();
+        p.dynamic_tiles = dyn;
+    }
     p.n_rows = t.n;
     p.n_tiles = geo.n_tiles;
     p.ctl = const_cast<QueryCtl *>(L.d_ctl);
-    p.tile_desc = L.tile_desc;
-    p.out_ids = L.out_ids;
     p.out_bitmap = L.out_bitmap;
-    // the kernel arms each barrier with stage_bytes: make them equal by construction
-    if (tx != p.stage_bytes) {
-        // padded layout differs from copied bytes: pass tx through a second field
-        // (columns are 128-byte multiples whenever tile_rows*width is, which holds for
-        // tile_rows % 256 == 0 and width in {1,4,8,16k}) -- so this cannot happen.
-        return cudaErrorInvalidValue;
+    switch (geo.tile_rows / kRowsPerGroup) {
+        case 1: return launch_scan_r<1>(p, geo, stream);
+        case 2: return launch_scan_r<2>(p, geo, stream);
+        case 4: return launch_scan_r<4>(p, geo, stream);
+        case 8: return launch_scan_r<8>(p, geo, stream);
+        case 16: return launch_scan_r<16>(p, geo, stream);
+        default: return cudaErrorInvalidValue;
     }
-    cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(geo.smem_bytes));
-    if (e != cudaSuccess) return e;
-    scan_tma_kernel<<<geo.grid, kScanThreads, geo.smem_bytes, stream>>>(p);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1c: order-preserving compaction of the match bitmap into row ids
+//
+// One CTA per chunk of kChunkWords bitmap words (64 Ki rows), chunks claimed in order from an
+// atomic counter (so a chunk's predecessors are always resident or finished: the look-back
+// cannot deadlock).  Thread t owns words t, t + 256, ... of the chunk (coalesced loads); popc,
+// warp shuffles and one shared-memory pass give every word its offset inside the chunk; warp 0
+// publishes the chunk aggregate, looks back for the exclusive prefix and publishes the inclusive
+// prefix; ids are scattered into a shared-memory stage and copied out with coalesced stores.
+// ------------------------------------------------------------------------------------------
+constexpr int kCompactThreads = 256;
+constexpr int kCompactRounds = 8;                                    // words per thread
+constexpr int kChunkWords = kCompactThreads * kCompactRounds;        // 2048 words = 65536 rows
+constexpr int kStageIds = 8192;                                      // ids staged per copy-out (32 KB)
+
+struct CompactParams {
+    const uint32_t *bitmap;
+    long long n_words;
+    long long n_chunks;
+    QueryCtl *ctl;
+    unsigned long long *desc;
+    uint32_t epoch;
+    uint32_t *out_ids;
+};
+
+__global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_constant__ CompactParams p) {
+    __shared__ uint32_t s_stage[kStageIds];
+    __shared__ uint32_t s_warp_tot[kCompactRounds][kCompactThreads / 32];
+    __shared__ uint32_t s_round_base[kCompactRounds + 1];
+    __shared__ long long s_chunk;
+    __shared__ uint32_t s_excl;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    constexpr int kWarps = kCompactThreads / 32;
+    if (tid == 0) s_chunk = static_cast<long long>(atomicAdd(&p.ctl->chunk_counter, 1u));
+    __syncthreads();
+    const long long chunk = s_chunk;
+    if (chunk >= p.n_chunks) return;
+
+    // 1. load this thread's words, popc, warp-inclusive scan per round
+    uint32_t word[kCompactRounds], off[kCompactRounds];
+    const long long w0 = chunk * kChunkWords;
+#pragma unroll
+    for (int r = 0; r < kCompactRounds; ++r) {
+        const long long wi = w0 + r * kCompactThreads + tid;
+        word[r] = wi < p.n_words ? __ldg(p.bitmap + wi) : 0u;
+        const uint32_t pc = __popc(word[r]);
+        uint32_t inc = pc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= static_cast<uint32_t>(d)) inc += t;
+        }
+        off[r] = inc - pc;  // exclusive within the warp
+        if (lane == 31) s_warp_tot[r][warp] = inc;
+    }
+    __syncthreads();
+    // 2. per-round bases (thread r of warp 0 sums round r), then chunk total + look-back
+    if (warp == 0) {
+        uint32_t rt = 0;
+        if (lane < kCompactRounds) {
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) rt += s_warp_tot[lane][w];
+        }
+        uint32_t inc = rt;
+#pragma unroll
+        for (int d = 1; d < kCompactRounds; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= static_cast<uint32_t>(d)) inc += t;
+        }
+        if (lane < kCompactRounds) s_round_base[lane] = inc - rt;
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, kCompactRounds - 1);
+        if (lane == 0) {
+            s_round_base[kCompactRounds] = total;
+            st_desc(p.desc + chunk, make_desc(p.epoch, chunk == 0 ? kStatePrefix : kStateAgg, total));
+        }
+        const uint32_t excl = warp_lookback(p.desc, chunk, p.epoch, lane);
+        if (lane == 0) {
+            st_desc(p.desc + chunk, make_desc(p.epoch, kStatePrefix, excl + total));
+            s_excl = excl;
+        }
+    }
+    __syncthreads();
+    const uint32_t total = s_round_base[kCompactRounds];
+    if (total == 0) return;
+    const uint32_t excl = s_excl;
+    // offsets inside the chunk: round base + earlier warps of the round + earlier lanes of the warp
+#pragma unroll
+    for (int r = 0; r < kCompactRounds; ++r) {
+        uint32_t o = s_round_base[r] + off[r];
+        for (uint32_t w = 0; w < warp; ++w) o += s_warp_tot[r][w];
+        off[r] = o;
+    }
+    uint32_t *out = p.out_ids + excl;
+    if (total <= kStageIds) {
+        // sparse chunk: everything fits the stage -> one scatter, one coalesced copy
+#pragma unroll
+        for (int r = 0; r < kCompactRounds; ++r) {
+            uint32_t w = word[r], o = off[r];
+            const uint32_t row0 = static_cast<uint32_t>((w0 + r * kCompactThreads + tid) * 32);
+            while (w) {
+                const int b = __ffs(w) - 1;
+                w &= w - 1;
+                s_stage[o++] = row0 + static_cast<uint32_t>(b);
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < total; i += kCompactThreads) out[i] = s_stage[i];
+    } else {
+        // dense chunk: a round (256 words, <= 8192 ids) at a time
+        for (int r = 0; r < kCompactRounds; ++r) {
+            const uint32_t base = s_round_base[r];
+            const uint32_t cnt = (r + 1 < kCompactRounds ? s_round_base[r + 1] : total) - base;
+            if (cnt == 0) continue;  // block-uniform
+            uint32_t w = word[r], o = off[r] - base;
+            const uint32_t row0 = static_cast<uint32_t>((w0 + r * kCompactThreads + tid) * 32);
+            while (w) {
+                const int b = __ffs(w) - 1;
+                w &= w - 1;
+                s_stage[o++] = row0 + static_cast<uint32_t>(b);
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < cnt; i += kCompactThreads) out[base + i] = s_stage[i];
+            __syncthreads();
+        }
+    }
+}
+
+int64_t compact_chunks(long long n_words) { return (n_words + kChunkWords - 1) / kChunkWords; }
+
+cudaError_t compact_launch(const uint32_t *bitmap, long long n_words, const QueryCtl *d_ctl, unsigned long long *desc,
+                           uint32_t epoch, uint32_t *out_ids, cudaStream_t stream) {
+    CompactParams p{};
+    p.bitmap = bitmap;
+    p.n_words = n_words;
+    p.n_chunks = compact_chunks(n_words);
+    p.ctl = const_cast<QueryCtl *>(d_ctl);
+    p.desc = desc;
+    p.epoch = epoch;
+    p.out_ids = out_ids;
+    if (p.n_chunks == 0) return cudaSuccess;
+    compact_kernel<<<static_cast<unsigned>(p.n_chunks), kCompactThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -10,8 +10,8 @@ namespace qpe {
 // kernels need zeroed at launch.  Uploaded with ONE cudaMemcpyAsync per query.
 struct QueryCtl {
     Program prog;
-    unsigned int tile_counter;      // dynamic tile claim
-    unsigned int pad0;
+    unsigned int tile_counter;      // dynamic tile claim (K1, K1g)
+    unsigned int chunk_counter;     // ordered chunk claim (K1c)
     unsigned long long out_count;   // total matches (written by the kernel)
 };
 
@@ -19,10 +19,7 @@ struct ScanLaunch {
     const DevTable *table;
     const QueryCtl *d_ctl;          // device copy (prog already uploaded)
     const Program *h_prog;          // host copy (for col_mask / sizing)
-    unsigned long long *tile_desc;  // >= n_tiles 64-bit look-back descriptors
-    uint32_t epoch;                 // launch epoch stamped into descriptors (never 0)
-    uint32_t *out_ids;              // device, may be null (count / mask only)
-    uint32_t *out_bitmap;           // device, may be null; one bit per row, tile-padded
+    uint32_t *out_bitmap;           // device, may be null (count only); one bit per row, tile-padded
     int force_tile_rows;            // 0 = choose
     int force_stages;               // 0 = choose
 };
@@ -36,12 +33,20 @@ struct ScanGeometry {
     int64_t bytes_per_row;
 };
 
-// K1: TMA-staged predicate evaluation + order-preserving compaction over the whole table.
+// K1: TMA-staged predicate evaluation over the whole table -> match bitmap + count (ctl->out_count).
 // Returns false (and sets *why) if the query cannot be staged (row too wide for shared memory):
 // the caller then uses the gather path below with an identity candidate list.
 bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages,
                ScanGeometry *geo, const char **why);
 cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream_t stream);
+
+// K1c: order-preserving compaction of a match bitmap (bit b of word w = row 32 w + b) into row
+// ids, single pass with decoupled look-back over 64 Ki-row chunks.  desc needs
+// compact_chunks(n_words) descriptors; epoch is stamped into them (never 0).  The match count is
+// NOT produced here (K1 already accumulated it into ctl->out_count).
+int64_t compact_chunks(long long n_words);
+cudaError_t compact_launch(const uint32_t *bitmap, long long n_words, const QueryCtl *d_ctl, unsigned long long *desc,
+                           uint32_t epoch, uint32_t *out_ids, cudaStream_t stream);
 
 // K1g: evaluate the predicate on a list of candidate rows (concatenated index segments, or the
 // identity list when perm == nullptr) and compact the survivors in list order.

@@ -220,3 +220,239 @@ PROBE_WHERES = [
     'raw_command > "z"',
     'timestamp < "2025"',
 ]
+
+
+# ---------------------------------------------------------------------------------------------
+# C oracle (oracle/liboracle.so) -- the CPU restatement, used ONLY as a checker
+# ---------------------------------------------------------------------------------------------
+ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle.so")
+COLUMNS = ("command_id", "raw_command", "base_command", "shell_type", "exit_code", "timestamp", "sudo_used",
+           "working_directory", "user_id", "user_name", "host_name", "risk_level")
+DEFAULT_INDEXES = (("command_id", 0), ("user_id", 1), ("risk_level", 1), ("exit_code", 1), ("sudo_used", 3))
+
+
+class WhereNode(C.Structure):
+    """struct whereClauseS (include/executeEngine-serial.h:48-56)"""
+
+
+WhereNode._fields_ = [("attribute", C.c_char_p), ("operator", C.c_char_p), ("value", C.c_char_p),
+                      ("value_type", C.c_int), ("next", C.POINTER(WhereNode)), ("logical_op", C.c_char_p),
+                      ("sub", C.POINTER(WhereNode))]
+
+
+class OracleTable(C.Structure):
+    _fields_ = [("n", C.c_longlong), ("col", C.c_void_p * 12), ("width", C.c_uint * 12)]
+
+
+_WTOK = re.compile(r'\s*(?:(\()|(\))|(AND\b)|([oO][rR]\b)|(>=|<=|!=|=|>|<)|"([^"]*)"|\'([^\']*)\'|(-?\d+)|(\w+))')
+
+
+def parse_where(text):
+    """WHERE text (well-formed subset of the reference grammar) -> nested list form:
+    [item, op, item, op, ...] with item = (col, op, value) or a nested list.  Follows the
+    tokenizer's literal rules (tokenizer.c:47-107): quotes dropped, digits only, TRUE/FALSE upper."""
+    pos = 0
+    toks = []
+    while pos < len(text):
+        if text[pos:].strip() == "":
+            break
+        m = _WTOK.match(text, pos)
+        assert m, f"cannot tokenise WHERE at: {text[pos:]!r}"
+        pos = m.end()
+        if m.group(1): toks.append(("(", None))
+        elif m.group(2): toks.append((")", None))
+        elif m.group(3): toks.append(("AND", None))
+        elif m.group(4): toks.append(("OR", None))
+        elif m.group(5): toks.append(("op", m.group(5)))
+        elif m.group(6) is not None: toks.append(("val", m.group(6)))
+        elif m.group(7) is not None: toks.append(("val", m.group(7)))
+        elif m.group(8): toks.append(("val", m.group(8).lstrip("-")))
+        else:
+            w = m.group(9)
+            toks.append(("val", w.upper()) if w.upper() in ("TRUE", "FALSE") else ("id", w))
+    i = 0
+
+    def level():
+        nonlocal i
+        items = []
+        while i < len(toks) and toks[i][0] != ")":
+            if toks[i][0] == "(":
+                i += 1
+                items.append(level())
+                assert toks[i][0] == ")"
+                i += 1
+            else:
+                assert toks[i][0] == "id" and toks[i + 1][0] == "op" and toks[i + 2][0] == "val", toks[i:i + 3]
+                items.append((toks[i][1], toks[i + 1][1], toks[i + 2][1]))
+                i += 3
+            if i < len(toks) and toks[i][0] in ("AND", "OR"):
+                items.append(toks[i][0])
+                i += 1
+        return items
+
+    return level()
+
+
+def render_where_tree(tree):
+    """same rendering as ref_where_text / qpe_sql_where_to_text"""
+    out = []
+    for it in tree:
+        if isinstance(it, str):
+            out.append(it)
+        elif isinstance(it, list):
+            out.append("( " + render_where_tree(it) + " )")
+        else:
+            out.append(f"{it[0]} {it[1]} {it[2]}")
+    return " ".join(out)
+
+
+def build_where_nodes(tree, keep):
+    """nested list form -> whereClauseS linked list (convert_conditions, connectEngine.c:65-113)"""
+    items = [it for it in tree if not isinstance(it, str)]
+    ops = [it for it in tree if isinstance(it, str)]
+    head = None
+    prev = None
+    for k, it in enumerate(items):
+        n = WhereNode()
+        keep.append(n)
+        if isinstance(it, list):
+            sub = build_where_nodes(it, keep)
+            if sub is not None:
+                n.sub = C.pointer(sub)
+        else:
+            n.attribute, n.operator, n.value = it[0].encode(), it[1].encode(), it[2].encode()
+        if k < len(items) - 1:
+            n.logical_op = (ops[k] if k < len(ops) else "AND").encode()
+        if head is None:
+            head = n
+        else:
+            prev.next = C.pointer(n)
+        prev = n
+    return head
+
+
+class Oracle:
+    """CPU restatement over a columnar table built from a CSV (oracle loader) or numpy columns."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            lib = C.CDLL(ORACLE_LIB)
+            pt = C.POINTER(OracleTable)
+            pw = C.POINTER(WhereNode)
+            lib.oracle_load_csv.restype = C.c_void_p
+            lib.oracle_load_csv.argtypes = [C.c_char_p, C.POINTER(C.c_longlong)]
+            lib.oracle_table_from_records.restype = pt
+            lib.oracle_table_from_records.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p]
+            lib.oracle_table_free.argtypes = [pt]
+            lib.oracle_free.argtypes = [C.c_void_p]
+            lib.oracle_eval_row.argtypes = [pt, C.c_longlong, pw]
+            lib.oracle_scan.restype = C.c_longlong
+            lib.oracle_scan.argtypes = [pt, pw, C.c_void_p]
+            lib.oracle_scan_range.restype = C.c_longlong
+            lib.oracle_scan_range.argtypes = [pt, C.c_longlong, C.c_longlong, pw, C.c_void_p]
+            lib.oracle_index_order.argtypes = [pt, C.c_int, C.c_void_p]
+            lib.oracle_index_order_by_insertion.argtypes = [pt, C.c_int, C.c_void_p]
+            lib.oracle_select.restype = C.c_longlong
+            lib.oracle_select.argtypes = [pt, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), pw,
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+            lib.oracle_cell_text.argtypes = [pt, C.c_longlong, C.c_char_p, C.c_char_p, C.c_size_t]
+            lib.oracle_col_by_name.argtypes = [C.c_char_p]
+            cls._lib = lib
+        return cls._lib
+
+    @staticmethod
+    def available():
+        return os.path.exists(ORACLE_LIB)
+
+    def __init__(self, table_ptr=None, owned=True, keep=None):
+        self.t = table_ptr
+        self.owned = owned
+        self._keep = keep
+
+    @classmethod
+    def from_csv(cls, path):
+        lib = cls.lib()
+        n = C.c_longlong()
+        rows = lib.oracle_load_csv(path.encode(), C.byref(n))
+        assert rows, "cannot read " + path
+        t = lib.oracle_table_from_records(rows, n.value, None)
+        lib.oracle_free(rows)
+        return cls(t, True)
+
+    @classmethod
+    def from_columns(cls, cols):
+        """cols: {name: numpy array}; numeric arrays 1-D of the column dtype, text arrays (n, width) uint8."""
+        import numpy as np
+        tab = OracleTable()
+        keep = []
+        n = None
+        for c, name in enumerate(COLUMNS):
+            if name not in cols:
+                continue
+            a = np.ascontiguousarray(cols[name])
+            keep.append(a)
+            n = a.shape[0] if n is None else n
+            assert a.shape[0] == n
+            tab.col[c] = a.ctypes.data
+            tab.width[c] = a.shape[1] if a.ndim == 2 else a.dtype.itemsize
+        tab.n = n or 0
+        keep.append(tab)
+        return cls(C.pointer(tab), False, keep)
+
+    def close(self):
+        if self.t is not None and self.owned:
+            self.lib().oracle_table_free(self.t)
+        self.t = None
+
+    @property
+    def num_rows(self):
+        return self.t.contents.n
+
+    @staticmethod
+    def where(where_text_or_tree):
+        tree = parse_where(where_text_or_tree) if isinstance(where_text_or_tree, str) else where_text_or_tree
+        keep = []
+        head = build_where_nodes(tree, keep)
+        return (C.pointer(head) if head is not None else None), keep
+
+    def scan(self, where, first=None, n=None):
+        import numpy as np
+        wc, keep = self.where(where) if where is not None else (None, None)
+        total = self.num_rows
+        first = 0 if first is None else first
+        n = total - first if n is None else n
+        ids = np.zeros(max(n, 1), dtype=np.uint32)
+        m = self.lib().oracle_scan_range(self.t, first, n, wc, ids.ctypes.data)
+        return ids[:m]
+
+    def select_ids(self, where, indexes=DEFAULT_INDEXES):
+        import numpy as np
+        wc, keep = self.where(where) if where is not None else (None, None)
+        nidx = len(indexes)
+        names = (C.c_char_p * max(nidx, 1))(*[a.encode() for a, _ in indexes])
+        types = (C.c_int * max(nidx, 1))(*[t for _, t in indexes])
+        out = C.c_void_p()
+        used = C.c_int()
+        m = self.lib().oracle_select(self.t, nidx, names, types, wc, C.byref(out), C.byref(used))
+        assert m >= 0
+        ids = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint32)), shape=(max(m, 1),))[:m].copy()
+        self.lib().oracle_free(out)
+        return ids, bool(used.value)
+
+    def index_order(self, attribute, by_insertion=False):
+        import numpy as np
+        perm = np.zeros(max(self.num_rows, 1), dtype=np.uint32)
+        c = self.lib().oracle_col_by_name(attribute.encode())
+        fn = self.lib().oracle_index_order_by_insertion if by_insertion else self.lib().oracle_index_order
+        assert fn(self.t, c, perm.ctypes.data) == 0
+        return perm[:self.num_rows]
+
+    def cell(self, row, attribute):
+        buf = C.create_string_buffer(1024)
+        self.lib().oracle_cell_text(self.t, row, attribute.encode(), buf, 1024)
+        return buf.value.decode(errors="replace")
+
+    def rows(self, ids, attributes):
+        return [[self.cell(int(i), a) for a in attributes] for i in ids]
