@@ -34,6 +34,8 @@ typedef struct qpe_scan_stats {
     int stages;
     int grid;
     int reserved;
+    double scan_ms;         /* K1 (scan_tma_kernel) alone; 0 on the index path */
+    double compact_ms;      /* K1c (compact_kernel) alone; 0 when not launched */
 } qpe_scan_stats;
 
 /* 1 when a CUDA device is usable by this process, else 0 (then every engine call fails loudly). */
@@ -66,9 +68,10 @@ int qpe_gpu_select_ids(struct engineS *engine, struct whereClauseS *whereClause,
 
 /* Same match phase, result left in HBM (device pointer valid until the next call on this
  * engine).  flags: bit0 = force the full-scan path even if an index applies;
- * bit1 = count only (no ids written). */
+ * bit1 = count only (no ids written); bit2 = global row ids (see QPE_SCAN_GLOBAL_IDS). */
 #define QPE_SCAN_FORCE 1
 #define QPE_SCAN_COUNT_ONLY 2
+#define QPE_SCAN_GLOBAL_IDS 4 /* sharded table: add the shard's first global row to every id */
 int qpe_gpu_select_ids_device(struct engineS *engine, struct whereClauseS *whereClause, int flags,
                               unsigned long long *count_out, const unsigned int **d_ids_out,
                               qpe_scan_stats *stats);

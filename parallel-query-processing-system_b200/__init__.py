@@ -35,6 +35,7 @@ NUMERIC_DTYPES = {"command_id": np.uint64, "exit_code": np.int32, "user_id": np.
 
 SCAN_FORCE = 1
 SCAN_COUNT_ONLY = 2
+SCAN_GLOBAL_IDS = 4
 
 
 class QpeError(RuntimeError):
@@ -45,7 +46,7 @@ class ScanStats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("total_ms", C.c_double), ("rows_scanned", C.c_longlong),
                 ("candidates", C.c_longlong), ("matches", C.c_longlong), ("algo_bytes", C.c_longlong),
                 ("path", C.c_int), ("launches", C.c_int), ("tile_rows", C.c_int), ("stages", C.c_int),
-                ("grid", C.c_int), ("reserved", C.c_int)]
+                ("grid", C.c_int), ("reserved", C.c_int), ("scan_ms", C.c_double), ("compact_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -252,12 +253,14 @@ class Engine:
         self._check(rc, "select_ids_into")
         return int(n.value), st.as_dict()
 
-    def select_ids_device(self, statement: str, force_scan: bool = False, count_only: bool = False):
+    def select_ids_device(self, statement: str, force_scan: bool = False, count_only: bool = False,
+                          global_ids: bool = False):
         """Match phase, result left in HBM: (count, device pointer, stats)."""
         cnt = C.c_ulonglong()
         dptr = C.c_void_p()
         st = ScanStats()
-        flags = (SCAN_FORCE if force_scan else 0) | (SCAN_COUNT_ONLY if count_only else 0)
+        flags = ((SCAN_FORCE if force_scan else 0) | (SCAN_COUNT_ONLY if count_only else 0) |
+                 (SCAN_GLOBAL_IDS if global_ids else 0))
         rc = self._lib.qpe_sql_select_ids_device(self._h, statement.encode(), flags, C.byref(cnt), C.byref(dptr),
                                                  C.byref(st))
         self._check(rc, "select_ids_device")

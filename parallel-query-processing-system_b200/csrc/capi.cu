@@ -82,6 +82,8 @@ void fill_stats(const GpuEngine *g, qpe_scan_stats *s) {
     s->stages = a.stages;
     s->grid = a.grid;
     s->reserved = 0;
+    s->scan_ms = a.scan_ms;
+    s->compact_ms = a.compact_ms;
 }
 
 // SELECT projection: get_attribute_string_value (executeEngine-serial.c:216-248) for every
@@ -453,6 +455,19 @@ int qpe_gpu_select_ids_device(struct engineS *engine, struct whereClauseS *where
     uint64_t m = 0;
     const bool count_only = (flags & QPE_SCAN_COUNT_ONLY) != 0;
     if (!engine_match(g, whereClause, (flags & QPE_SCAN_FORCE) != 0, false, count_only, false, &m)) return -2;
+    if ((flags & QPE_SCAN_GLOBAL_IDS) && !count_only && m > 0 && g->table.row_base != 0) {
+        // sharded table: local position -> position in the whole table (this shard starts at row_base)
+        if (g->table.row_base + static_cast<uint64_t>(g->table.n) > 0xffffffffull) {
+            set_error("global row ids do not fit 32 bits");
+            return -5;
+        }
+        if (!cuda_ok(add_base_launch(g->d_ids, static_cast<int64_t>(m), static_cast<uint32_t>(g->table.row_base),
+                                     g->stream),
+                     "add_base kernel launch") ||
+            !cuda_ok(cudaStreamSynchronize(g->stream), "add_base sync"))
+            return -4;
+        g->last.launches += 1;
+    }
     if (count_out) *count_out = m;
     if (d_ids_out) *d_ids_out = count_only ? nullptr : g->d_ids;
     fill_stats(g, stats);

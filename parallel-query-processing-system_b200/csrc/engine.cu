@@ -105,6 +105,7 @@ GpuEngine *engine_create(const char *tableName, const char *datafile, int index_
     bool ok = cuda_ok(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking), "cudaStreamCreate");
     ok = ok && cuda_ok(cudaEventCreate(&g->ev0), "cudaEventCreate");
     ok = ok && cuda_ok(cudaEventCreate(&g->ev1), "cudaEventCreate");
+    ok = ok && cuda_ok(cudaEventCreate(&g->ev_mid), "cudaEventCreate");
     ok = ok && cuda_ok(cudaMalloc(&g->d_ctl, sizeof(QueryCtl)), "cudaMalloc ctl");
     ok = ok && cuda_ok(cudaMallocHost(&g->h_ctl, sizeof(QueryCtl)), "cudaMallocHost ctl");
     ok = ok && cuda_ok(cudaMalloc(&g->d_probe_lo, sizeof(unsigned long long) * kMaxSegments), "cudaMalloc probe");
@@ -148,6 +149,7 @@ void engine_destroy(GpuEngine *g) {
     if (g->h_probe_out) cudaFreeHost(g->h_probe_out);
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
+    if (g->ev_mid) cudaEventDestroy(g->ev_mid);
     if (g->stream) cudaStreamDestroy(g->stream);
     for (int i = 0; i < g->head.num_indexes; ++i) std::free(g->head.indexed_attributes[i]);
     std::free(g->head.indexed_attributes);
@@ -419,6 +421,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
             cudaEventRecord(g->ev0, g->stream);
             if (!cuda_ok(scan_launch(L, geo, g->stream), "scan kernel launch")) return false;
             st.launches = 1;
+            cudaEventRecord(g->ev_mid, g->stream);
             if (!count_only && t.n > 0) {
                 // K1c: ordered compaction of the match bitmap (decoupled look-back per 64 Ki rows)
                 if (!cuda_ok(compact_launch(g->d_bitmap, bm_words, g->d_ctl, g->d_tile_desc, next_epoch(g), g->d_ids,
@@ -532,6 +535,13 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     float ms = 0.f;
     cudaEventElapsedTime(&ms, g->ev0, g->ev1);
     st.kernel_ms = ms;
+    if (st.path == 0 && st.tile_rows > 0) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, g->ev0, g->ev_mid);
+        cudaEventElapsedTime(&b, g->ev_mid, g->ev1);
+        st.scan_ms = a;
+        st.compact_ms = st.launches > 1 ? b : 0.0;
+    }
     st.matches = static_cast<int64_t>(hc->out_count);
     st.algo_bytes = st.rows_scanned * bytes_per_row + (count_only ? 0 : 4 * st.matches) +
                     (st.path == 1 ? 4 * st.candidates : 0);

@@ -21,7 +21,7 @@ struct GpuEngine {
     uint64_t magic = kEngineMagic;
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
 
     DevTable table;
     std::vector<DevIndex> idx;  // parallel to head.indexed_attributes

@@ -175,6 +175,8 @@ struct ScanStats {
     int32_t stages = 0;
     int32_t grid = 0;
     int32_t pad = 0;
+    double scan_ms = 0;       // K1 alone
+    double compact_ms = 0;    // K1c alone
 };
 
 }  // namespace qpe
