@@ -138,12 +138,14 @@ __device__ __forceinline__ uint32_t str_cmp3(RowPtr row, const uint4 *lit, int n
 // ------------------------------------------------------------------------------------------
 // K1: TMA-staged scan
 // ------------------------------------------------------------------------------------------
-constexpr int kEvalWarps = 8;
+constexpr int kEvalWarps = 16;                   // evaluator warps per CTA (4 per scheduler: latency hiding)
+constexpr int kEvalWarpsWide = 8;                // variant for very wide rows (256-row tiles)
 constexpr int kMaxStages = 8;
 constexpr int kScanThreads = 32 * (1 + kEvalWarps);
 constexpr int kRowsPerGroup = 32 * kEvalWarps;   // rows one "row group" covers: a tile is R groups
-constexpr int kMaxR = 16;                        // rows per lane per tile: 1, 2, 4, 8 or 16
+constexpr int kMaxR = 8;                         // rows per lane per tile: 1, 2, 4 or 8
 constexpr int kMaxTileRows = kRowsPerGroup * kMaxR;  // 4096 (<= kRowPad: a full tile is always inside the allocation)
+constexpr int kMinTileRows = 32 * kEvalWarpsWide;    // 256
 
 struct ScanParams {
     const uint8_t *col[NUM_COLS];
@@ -278,10 +280,13 @@ __device__ __forceinline__ uint32_t run_program(const Program *sp, uint32_t all_
     const int n = sp->n_instr;
     for (int i = 0; i < n; ++i) {
         const PInstr in = sp->instr[i];
+        if (in.op <= P_LEAF_OR) {
+            // one inlined copy of the (large, unrolled) leaf evaluator for all three leaf ops
+            const uint32_t v = leaf_fn(sp->leaf[in.arg]);
+            acc = (in.op == P_LEAF_SET) ? v : (in.op == P_LEAF_AND) ? (acc & v) : (acc | v);
+            continue;
+        }
         switch (in.op) {
-            case P_LEAF_SET: acc = leaf_fn(sp->leaf[in.arg]); break;
-            case P_LEAF_AND: acc &= leaf_fn(sp->leaf[in.arg]); break;
-            case P_LEAF_OR: acc |= leaf_fn(sp->leaf[in.arg]); break;
             case P_PUSH:
                 switch (in.arg) {
                     case 0: s0 = acc; break;
@@ -352,8 +357,8 @@ __device__ __forceinline__ uint32_t warp_lookback(const unsigned long long *desc
     return excl;
 }
 
-template <int R>
-__global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const __grid_constant__ ScanParams p) {
+template <int EW, int R>
+__global__ void __launch_bounds__(32 * (1 + EW), 1) scan_tma_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     ScanSmemHeader *sh = reinterpret_cast<ScanSmemHeader *>(smem_raw);
     uint8_t *stages = smem_raw + ((sizeof(ScanSmemHeader) + 127) & ~size_t(127));
@@ -362,19 +367,20 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tma_kernel(const __grid_
     const uint32_t warp = tid >> 5;
     const uint32_t lane = tid & 31u;
     const int S = p.n_stages;
-    constexpr int T = kRowsPerGroup * R;  // rows per tile
+    constexpr int T = 32 * EW * R;        // rows per tile
     constexpr int WPT = T >> 5;           // bitmap words per tile
+    constexpr uint32_t kThreads = 32 * (1 + EW);
 
     // program -> shared memory (uniform reads afterwards), barrier init
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(&p.ctl->prog);
         uint4 *dst = reinterpret_cast<uint4 *>(&sh->prog);
-        for (uint32_t i = tid; i < sizeof(Program) / 16; i += kScanThreads) dst[i] = src[i];
+        for (uint32_t i = tid; i < sizeof(Program) / 16; i += kThreads) dst[i] = src[i];
     }
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&sh->full[s], 1);
-            mbar_init(&sh->empty[s], kEvalWarps);
+            mbar_init(&sh->empty[s], EW);
         }
         sh->cta_count = 0;
         fence_mbar_init();
@@ -497,14 +503,15 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
         S = S ? S : 2;
     } else if (!T) {
         // largest tile that still leaves >= 3 stages in flight; else the largest with 2; else 1
+        static const int kTiles[] = {4096, 2048, 1024, 512, 256};
         int best_T = 0, best_S = 0;
         for (int want = 3; want >= 1 && !best_T; --want)
-            for (int R = kMaxR; R >= 1; R >>= 1) {
-                const size_t sb = stage_bytes_for(kRowsPerGroup * R);
+            for (int cand : kTiles) {
+                const size_t sb = stage_bytes_for(cand);
                 int fit = static_cast<int>(budget / (sb ? sb : 1));
                 if (fit > 4) fit = 4;
                 if (fit >= want) {
-                    best_T = kRowsPerGroup * R;
+                    best_T = cand;
                     best_S = fit;
                     break;
                 }
@@ -520,9 +527,8 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
         S = static_cast<int>(budget / (sb ? sb : 1));
         if (S > 4) S = 4;
     }
-    const int R = T / kRowsPerGroup;
-    if (T % kRowsPerGroup != 0 || (R != 1 && R != 2 && R != 4 && R != 8 && R != 16) || S < 1 || S > kMaxStages) {
-        if (why) *why = "invalid tile geometry (tile rows must be 256 x {1,2,4,8,16})";
+    if ((T != 256 && T != 512 && T != 1024 && T != 2048 && T != 4096) || S < 1 || S > kMaxStages) {
+        if (why) *why = "invalid tile geometry (tile rows must be 256, 512, 1024, 2048 or 4096)";
         return false;
     }
     const size_t stage_bytes = stage_bytes_for(T);
@@ -541,12 +547,12 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
     return true;
 }
 
-template <int R>
+template <int EW, int R>
 static cudaError_t launch_scan_r(const ScanParams &p, const ScanGeometry &geo, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(geo.smem_bytes));
     if (e != cudaSuccess) return e;
-    scan_tma_kernel<R><<<geo.grid, kScanThreads, geo.smem_bytes, stream>>>(p);
+    scan_tma_kernel<EW, R><<<geo.grid, 32 * (1 + EW), geo.smem_bytes, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -584,12 +590,12 @@ cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream
     p.n_tiles = geo.n_tiles;
     p.ctl = const_cast<QueryCtl *>(L.d_ctl);
     p.out_bitmap = L.out_bitmap;
-    switch (geo.tile_rows / kRowsPerGroup) {
-        case 1: return launch_scan_r<1>(p, geo, stream);
-        case 2: return launch_scan_r<2>(p, geo, stream);
-        case 4: return launch_scan_r<4>(p, geo, stream);
-        case 8: return launch_scan_r<8>(p, geo, stream);
-        case 16: return launch_scan_r<16>(p, geo, stream);
+    switch (geo.tile_rows) {
+        case 256: return launch_scan_r<kEvalWarpsWide, 1>(p, geo, stream);
+        case 512: return launch_scan_r<kEvalWarps, 1>(p, geo, stream);
+        case 1024: return launch_scan_r<kEvalWarps, 2>(p, geo, stream);
+        case 2048: return launch_scan_r<kEvalWarps, 4>(p, geo, stream);
+        case 4096: return launch_scan_r<kEvalWarps, 8>(p, geo, stream);
         default: return cudaErrorInvalidValue;
     }
 }

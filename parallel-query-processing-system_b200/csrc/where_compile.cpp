@@ -144,7 +144,15 @@ struct Compiler {
             const bool last = (j == n - 1);
             // join between node j and j+1 is node j's logical_op; "OR" => or, anything else => and (:307-315)
             const bool is_or = !last && nd->logical_op && std::strcmp(nd->logical_op, "OR") == 0;
+            // a group holding exactly one plain condition evaluates like that condition
+            // ("(a < 5) AND ..." == "a < 5 AND ..."): no accumulator save / restore needed
+            const struct whereClauseS *single = nullptr;
             if (nd->sub != nullptr) {
+                const struct whereClauseS *x = nd->sub;
+                while (x->sub != nullptr && x->next == nullptr) x = x->sub;  // ((a < 5)) unwraps too
+                if (x->sub == nullptr && x->next == nullptr) single = x;
+            }
+            if (nd->sub != nullptr && single == nullptr) {
                 if (last) {
                     if (!emit_list(nd->sub, depth)) return false;
                 } else {
@@ -157,7 +165,8 @@ struct Compiler {
                     if (!emit(is_or ? P_POP_OR : P_POP_AND, static_cast<uint8_t>(depth))) return false;
                 }
             } else {
-                const int lf = nd->attribute ? make_leaf(nd) : -1;
+                const struct whereClauseS *cond = single ? single : nd;
+                const int lf = cond->attribute ? make_leaf(cond) : -1;
                 if (lf == -2) return false;
                 if (lf == -1) {
                     // constant-false condition
