@@ -68,6 +68,9 @@ def parse_args():
     ap.add_argument("--selectivity", type=float, default=0.01)
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = K1c stores the ids straight into rank 0's buffer over NVLink (CUDA IPC "
+                         "mapping); 'nccl' = compact locally, then grouped NCCL send/recv")
     return ap.parse_args()
 
 
@@ -290,14 +293,17 @@ def run_ours(args):
     t_gen = time.perf_counter() - t0
 
     # result buffers: device buffer on rank 0 for the gathered ids, pinned host buffer for e2e
+    from importlib import import_module
+    sharding = import_module("pqps_b200.sharding")
     cnt0, _, _ = eng.select_ids_device(sql, force_scan=True)
-    counts_dev = torch.zeros(world, dtype=torch.int64, device=dev)
     if world > 1:
-        dist.all_gather_into_tensor(counts_dev, torch.tensor([cnt0], dtype=torch.int64, device=dev))
-        total_matches = int(counts_dev.sum().item())
+        total_matches = sum(sharding.exchange_counts(cnt0, dev))
     else:
         total_matches = cnt0
-    gathered = torch.empty(max(total_matches, 1), dtype=torch.int32, device=dev) if rank == 0 else None
+    use_peer = world > 1 and args.gather == "peer"
+    pg = sharding.PeerGather(pkg, capacity_ids=total_matches + 1024) if use_peer else None
+    gathered = (torch.empty(max(total_matches, 1), dtype=torch.int32, device=dev)
+                if (rank == 0 and world > 1 and not use_peer) else None)
     pinned = torch.empty(max(total_matches, 1), dtype=torch.int32).pin_memory() if rank == 0 else None
     pinned_np = pinned.numpy().view(np.uint32) if rank == 0 else None
     launches = [0]
@@ -305,30 +311,20 @@ def run_ours(args):
 
     def step_device(record=False):
         """scan + ordered compaction on every GPU, count exchange, ordered gather to rank 0 (device)"""
-        cnt, dptr, st = eng.select_ids_device(sql, force_scan=True, global_ids=(world > 1))
+        if use_peer:
+            total_n, counts, st = pg.run(eng, sql, dev)
+        else:
+            cnt, dptr, st = eng.select_ids_device(sql, force_scan=True, global_ids=(world > 1))
+            total_n = cnt
+            if world > 1:
+                mine = torch.as_tensor(DevArray(dptr, max(cnt, 1)), device=dev)[:cnt]
+                total_n, counts, _ = sharding.ordered_gather(mine, gathered)
         launches[0] += st["launches"]
         if record:
             scan_ms.append(st["scan_ms"])
             compact_ms.append(st["compact_ms"])
             kernel_ms.append(st["kernel_ms"])
-        if world == 1:
-            return cnt
-        mine = torch.as_tensor(DevArray(dptr, max(cnt, 1)), device=dev)[:cnt]
-        dist.all_gather_into_tensor(counts_dev, torch.tensor([cnt], dtype=torch.int64, device=dev))
-        counts = counts_dev.tolist()
-        offs = np.concatenate([[0], np.cumsum(counts)]).tolist()
-        ops = []
-        if rank == 0:
-            gathered[offs[0]:offs[1]].copy_(mine)
-            for r in range(1, world):
-                if counts[r]:
-                    ops.append(dist.P2POp(dist.irecv, gathered[offs[r]:offs[r + 1]], r))
-        elif cnt:
-            ops.append(dist.P2POp(dist.isend, mine, 0))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        return offs[-1]
+        return total_n
 
     def step_e2e():
         """host-facing call: SQL text in host memory -> row ids in pinned host memory"""
@@ -338,8 +334,11 @@ def run_ours(args):
             return n
         n = step_device()
         if rank == 0:
-            pinned[:n].copy_(gathered[:n], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            if use_peer:
+                pg.buffer.to_host(n, out=pinned_np)
+            else:
+                pinned[:n].copy_(gathered[:n], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
         return n
 
     def timed(fn, steps, sampler=None, **kw):
@@ -405,7 +404,9 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"synthetic {total}-row command-log table (device generator, seed 12345), "
-                                   f"row-range sharded over {world} GPU(s); {args.query} full-scan SELECT/WHERE, "
+                                   f"row-range sharded over {world} GPU(s)"
+                                   + (f", ordered gather = {'K1c stores into rank 0 over NVLink peer memory' if use_peer else 'NCCL send/recv'}" if world > 1 else "")
+                                   + f"; {args.query} full-scan SELECT/WHERE, "
                                    f"{args.selectivity:g} selectivity; inputs ({shard_rows * bpr / 1e9:.1f} GB/GPU) "
                                    f"larger than L2, no flush needed",
                        "rows": total, "rows_per_gpu": shard_rows, "query": sql, "bytes_per_row": bpr,
@@ -427,6 +428,8 @@ def run_ours(args):
                 out["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": 1, "kind": "reference",
                                        "sample": f"failed: {e}"}
         print(json.dumps(out))
+    if pg is not None:
+        pg.close()
     eng.close()
     if world > 1:
         dist.destroy_process_group()

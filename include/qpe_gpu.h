@@ -81,6 +81,26 @@ int qpe_gpu_select_ids_device(struct engineS *engine, struct whereClauseS *where
 int qpe_gpu_select_ids_into(struct engineS *engine, struct whereClauseS *whereClause, int flags, unsigned int *ids,
                             size_t cap, size_t *n_out, qpe_scan_stats *stats);
 
+/* Split full scan for sharded tables.  qpe_gpu_scan_count runs K1 only (match bitmap + count,
+ * always the full-scan path); qpe_gpu_compact_to then runs K1c on that bitmap and writes the row
+ * ids to dst_device, which may be memory of ANOTHER GPU mapped with qpe_gpu_ipc_open: the
+ * ordered gather of a sharded table is then the compaction kernel's own coalesced stores over
+ * NVLink (each rank writes at the exclusive prefix of the lower ranks' counts).  global_ids != 0
+ * adds the shard's first global row to every id. */
+int qpe_gpu_scan_count(struct engineS *engine, struct whereClauseS *whereClause, unsigned long long *count_out,
+                       qpe_scan_stats *stats);
+int qpe_gpu_compact_to(struct engineS *engine, unsigned int *dst_device, int global_ids, qpe_scan_stats *stats);
+int qpe_sql_scan_count(struct engineS *engine, const char *statement, unsigned long long *count_out,
+                       qpe_scan_stats *stats);
+
+/* Raw device buffers shareable between the processes (one per GPU) of one box through CUDA IPC. */
+void *qpe_gpu_device_alloc(size_t bytes);
+void qpe_gpu_device_free(void *p);
+int qpe_gpu_ipc_export(void *device_ptr, unsigned char handle_out[64]);
+void *qpe_gpu_ipc_open(const unsigned char handle[64]);
+void qpe_gpu_ipc_close(void *mapped_ptr);
+int qpe_gpu_copy_to_host(void *dst_host, const void *src_device, size_t bytes);
+
 /* cudaMemcpy device -> host for pointers handed out by the *_device calls. 0 on success. */
 int qpe_gpu_copy_from_device(void *dst_host, const void *src_device, size_t bytes);
 

@@ -105,6 +105,14 @@ def load_library() -> C.CDLL:
         "qpe_sql_select_ids_device": (i, [vp, cp, i, C.POINTER(ull), C.POINTER(vp), pstats]),
         "qpe_sql_select_ids_into": (i, [vp, cp, i, vp, sz, C.POINTER(sz), pstats]),
         "qpe_sql_match_mask": (i, [vp, cp, vp, sz, C.POINTER(ull), pstats]),
+        "qpe_sql_scan_count": (i, [vp, cp, C.POINTER(ull), pstats]),
+        "qpe_gpu_compact_to": (i, [vp, vp, i, pstats]),
+        "qpe_gpu_device_alloc": (vp, [sz]),
+        "qpe_gpu_device_free": (None, [vp]),
+        "qpe_gpu_ipc_export": (i, [vp, C.c_char_p]),
+        "qpe_gpu_ipc_open": (vp, [C.c_char_p]),
+        "qpe_gpu_ipc_close": (None, [vp]),
+        "qpe_gpu_copy_to_host": (i, [vp, vp, sz]),
         "qpe_sql_select": (C.POINTER(ResultSet), [vp, cp]),
         "qpe_sql_where_to_text": (vp, [cp]),
     }
@@ -114,6 +122,48 @@ def load_library() -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+class DeviceBuffer:
+    """Raw device memory of this process's GPU that the other ranks of the box can map (CUDA IPC)."""
+
+    def __init__(self, n_bytes: int):
+        self._lib = load_library()
+        self.ptr = self._lib.qpe_gpu_device_alloc(n_bytes)
+        if not self.ptr:
+            raise QpeError("device allocation failed: " + (self._lib.qpe_gpu_last_error() or b"").decode())
+        self.n_bytes = n_bytes
+
+    def export_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        if self._lib.qpe_gpu_ipc_export(self.ptr, buf) != 0:
+            raise QpeError("cudaIpcGetMemHandle failed: " + (self._lib.qpe_gpu_last_error() or b"").decode())
+        return buf.raw
+
+    def to_host(self, n_items: int, dtype=np.uint32, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(n_items, dtype=dtype)
+        if n_items and self._lib.qpe_gpu_copy_to_host(out.ctypes.data, self.ptr, n_items * out.itemsize) != 0:
+            raise QpeError("copy to host failed")
+        return out[:n_items]
+
+    def free(self):
+        if self.ptr:
+            self._lib.qpe_gpu_device_free(self.ptr)
+            self.ptr = None
+
+
+def ipc_open(handle: bytes) -> int:
+    """Map another rank's DeviceBuffer into this process; returns the device pointer."""
+    lib = load_library()
+    p = lib.qpe_gpu_ipc_open(handle)
+    if not p:
+        raise QpeError("cudaIpcOpenMemHandle failed: " + (lib.qpe_gpu_last_error() or b"").decode())
+    return p
+
+
+def ipc_close(ptr: int):
+    load_library().qpe_gpu_ipc_close(ptr)
 
 
 def gpu_available() -> bool:
@@ -265,6 +315,21 @@ class Engine:
                                                  C.byref(st))
         self._check(rc, "select_ids_device")
         return int(cnt.value), dptr.value, st.as_dict()
+
+    def scan_count(self, statement: str) -> Tuple[int, dict]:
+        """First half of a split full scan: K1 only -> match count (the bitmap stays in HBM)."""
+        cnt = C.c_ulonglong()
+        st = ScanStats()
+        self._check(self._lib.qpe_sql_scan_count(self._h, statement.encode(), C.byref(cnt), C.byref(st)), "scan_count")
+        return int(cnt.value), st.as_dict()
+
+    def compact_to(self, dst_device_ptr: int, global_ids: bool = False) -> dict:
+        """Second half: K1c writes the row ids of the last scan_count to `dst_device_ptr`, which may be
+        another GPU's buffer mapped through CUDA IPC (the ids then cross NVLink as the kernel's stores)."""
+        st = ScanStats()
+        self._check(self._lib.qpe_gpu_compact_to(self._h, dst_device_ptr, 1 if global_ids else 0, C.byref(st)),
+                    "compact_to")
+        return st.as_dict()
 
     def copy_from_device(self, dptr: int, n_items: int, dtype=np.uint32) -> np.ndarray:
         out = np.empty(n_items, dtype=dtype)

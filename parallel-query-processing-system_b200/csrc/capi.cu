@@ -662,6 +662,67 @@ int qpe_gpu_fetch_column(struct engineS *engine, const char *attribute, long lon
     return 0;
 }
 
+// ---- split scan: count first, compaction later to a caller-chosen (possibly peer) destination ----
+int qpe_gpu_scan_count(struct engineS *engine, struct whereClauseS *whereClause, unsigned long long *count_out,
+                       qpe_scan_stats *stats) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    uint64_t m = 0;
+    if (!engine_match(g, whereClause, true, false, true, true, &m)) return -2;
+    if (count_out) *count_out = m;
+    fill_stats(g, stats);
+    return 0;
+}
+
+int qpe_gpu_compact_to(struct engineS *engine, unsigned int *dst_device, int global_ids, qpe_scan_stats *stats) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    uint32_t base = 0;
+    if (global_ids) {
+        if (g->table.row_base + static_cast<uint64_t>(g->table.n) > 0xffffffffull) {
+            set_error("global row ids do not fit 32 bits");
+            return -5;
+        }
+        base = static_cast<uint32_t>(g->table.row_base);
+    }
+    if (!engine_compact_to(g, dst_device, base)) return -2;
+    fill_stats(g, stats);
+    return 0;
+}
+
+// ---- raw device buffers that can be shared with the other ranks of the box (CUDA IPC) ----
+void *qpe_gpu_device_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (!cuda_ok(cudaMalloc(&p, bytes ? bytes : 16), "cudaMalloc")) return nullptr;
+    return p;
+}
+void qpe_gpu_device_free(void *p) {
+    if (p) cudaFree(p);
+}
+int qpe_gpu_ipc_export(void *device_ptr, unsigned char handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    if (!cuda_ok(cudaIpcGetMemHandle(&h, device_ptr), "cudaIpcGetMemHandle")) return -4;
+    std::memcpy(handle_out, &h, 64);
+    return 0;
+}
+void *qpe_gpu_ipc_open(const unsigned char handle[64]) {
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void *p = nullptr;
+    if (!cuda_ok(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return nullptr;
+    return p;
+}
+void qpe_gpu_ipc_close(void *mapped_ptr) {
+    if (mapped_ptr) cudaIpcCloseMemHandle(mapped_ptr);
+}
+int qpe_gpu_copy_to_host(void *dst_host, const void *src_device, size_t bytes) {
+    if (bytes == 0) return 0;
+    return cuda_ok(cudaMemcpy(dst_host, src_device, bytes, cudaMemcpyDeviceToHost), "copy to host") ? 0 : -4;
+}
+
 int qpe_gpu_copy_from_device(void *dst_host, const void *src_device, size_t bytes) {
     if (bytes == 0) return 0;
     return cuda_ok(cudaMemcpy(dst_host, src_device, bytes, cudaMemcpyDeviceToHost), "copy from device") ? 0 : -4;

@@ -360,6 +360,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     const double t_begin = now_ms();
     ScanStats st;
     const DevTable &t = g->table;
+    g->last_bm_words = 0;
 
     uint32_t widths[NUM_COLS];
     for (int c = 0; c < NUM_COLS; ++c) widths[c] = t.col[c].width;
@@ -424,7 +425,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
             cudaEventRecord(g->ev_mid, g->stream);
             if (!count_only && t.n > 0) {
                 // K1c: ordered compaction of the match bitmap (decoupled look-back per 64 Ki rows)
-                if (!cuda_ok(compact_launch(g->d_bitmap, bm_words, g->d_ctl, g->d_tile_desc, next_epoch(g), g->d_ids,
+                if (!cuda_ok(compact_launch(g->d_bitmap, bm_words, g->d_ctl, g->d_tile_desc, next_epoch(g), g->d_ids, 0u,
                                             g->stream),
                              "compaction kernel launch"))
                     return false;
@@ -434,6 +435,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
             st.tile_rows = geo.tile_rows;
             st.stages = geo.stages;
             st.grid = geo.grid;
+            g->last_bm_words = L.out_bitmap ? bm_words : 0;
         } else {
             // a tile of this WHERE's columns does not fit shared memory: evaluate with gathered
             // loads over the identity candidate list (still on the device, still ordered)
@@ -547,7 +549,44 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
                     (st.path == 1 ? 4 * st.candidates : 0);
     st.total_ms = now_ms() - t_begin;
     g->last = st;
+    g->last_bm_count = hc->out_count;
     if (count) *count = hc->out_count;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1c on its own: the second half of a split scan (count first, then compaction to a caller
+// chosen destination -- possibly another GPU's buffer, so the ordered gather of a sharded
+// table is done by the compaction kernel's own stores over NVLink)
+// ------------------------------------------------------------------------------------------
+bool engine_compact_to(GpuEngine *g, uint32_t *dst, uint32_t id_base) {
+    cudaSetDevice(g->device);
+    if (g->last_bm_words <= 0 && g->table.n > 0) {
+        set_error("no match bitmap to compact: run a full-scan match with a bitmap first");
+        return false;
+    }
+    if (g->table.n == 0 || g->last_bm_count == 0) {
+        g->last.compact_ms = 0;
+        return true;
+    }
+    const int64_t n_chunks = compact_chunks(g->last_bm_words);
+    if (!ensure_desc(g, n_chunks)) return false;
+    // the chunk claim counter lives in the control block: reset it for this launch
+    if (!cuda_ok(cudaMemsetAsync(&g->d_ctl->chunk_counter, 0, sizeof(unsigned int), g->stream), "reset chunk counter"))
+        return false;
+    cudaEventRecord(g->ev_mid, g->stream);
+    if (!cuda_ok(compact_launch(g->d_bitmap, g->last_bm_words, g->d_ctl, g->d_tile_desc, next_epoch(g), dst, id_base,
+                                g->stream),
+                 "compaction kernel launch"))
+        return false;
+    cudaEventRecord(g->ev1, g->stream);
+    if (!cuda_ok(cudaStreamSynchronize(g->stream), "compaction sync")) return false;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g->ev_mid, g->ev1);
+    g->last.compact_ms = ms;
+    g->last.kernel_ms = g->last.scan_ms + ms;
+    g->last.launches += 1;
+    g->last.algo_bytes += 4 * static_cast<int64_t>(g->last_bm_count);
     return true;
 }
 

@@ -37,6 +37,8 @@ struct GpuEngine {
     int64_t ids_cap = 0;
     uint32_t *d_bitmap = nullptr;
     int64_t bitmap_cap_words = 0;
+    int64_t last_bm_words = 0;   // words of the bitmap the last full-scan match left in d_bitmap (0 = none)
+    uint64_t last_bm_count = 0;  // its match count
     // probe scratch (device + pinned host), kMaxSegments entries each
     unsigned long long *d_probe_lo = nullptr, *d_probe_hi = nullptr;
     uint32_t *d_probe_first = nullptr, *d_probe_count = nullptr;
@@ -67,6 +69,10 @@ bool engine_ensure_ids(GpuEngine *g, int64_t n);
 // match phase. On success the ids are in g->d_ids[0 .. *count) (unless count_only).
 bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, bool invert, bool count_only,
                   bool want_bitmap, uint64_t *count);
+
+// K1c alone: compact the bitmap left by the last count-only full-scan match into `dst` (device
+// memory of this GPU or a peer mapping), adding id_base to every id
+bool engine_compact_to(GpuEngine *g, uint32_t *dst, uint32_t id_base);
 
 // download helpers
 bool engine_fetch_rows(GpuEngine *g, int col, const uint32_t *d_ids, int64_t n, std::vector<uint8_t> *out);

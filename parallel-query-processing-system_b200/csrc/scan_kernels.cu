@@ -622,7 +622,8 @@ struct CompactParams {
     QueryCtl *ctl;
     unsigned long long *desc;
     uint32_t epoch;
-    uint32_t *out_ids;
+    uint32_t id_base;   // added to every row id (a shard's first global row); 0 for a whole table
+    uint32_t *out_ids;  // may be PEER memory (another GPU's buffer mapped through CUDA IPC / NVLink)
 };
 
 __global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_constant__ CompactParams p) {
@@ -699,7 +700,7 @@ __global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_c
 #pragma unroll
         for (int r = 0; r < kCompactRounds; ++r) {
             uint32_t w = word[r], o = off[r];
-            const uint32_t row0 = static_cast<uint32_t>((w0 + r * kCompactThreads + tid) * 32);
+            const uint32_t row0 = static_cast<uint32_t>((w0 + r * kCompactThreads + tid) * 32) + p.id_base;
             while (w) {
                 const int b = __ffs(w) - 1;
                 w &= w - 1;
@@ -715,7 +716,7 @@ __global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_c
             const uint32_t cnt = (r + 1 < kCompactRounds ? s_round_base[r + 1] : total) - base;
             if (cnt == 0) continue;  // block-uniform
             uint32_t w = word[r], o = off[r] - base;
-            const uint32_t row0 = static_cast<uint32_t>((w0 + r * kCompactThreads + tid) * 32);
+            const uint32_t row0 = static_cast<uint32_t>((w0 + r * kCompactThreads + tid) * 32) + p.id_base;
             while (w) {
                 const int b = __ffs(w) - 1;
                 w &= w - 1;
@@ -731,7 +732,7 @@ __global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_c
 int64_t compact_chunks(long long n_words) { return (n_words + kChunkWords - 1) / kChunkWords; }
 
 cudaError_t compact_launch(const uint32_t *bitmap, long long n_words, const QueryCtl *d_ctl, unsigned long long *desc,
-                           uint32_t epoch, uint32_t *out_ids, cudaStream_t stream) {
+                           uint32_t epoch, uint32_t *out_ids, uint32_t id_base, cudaStream_t stream) {
     CompactParams p{};
     p.bitmap = bitmap;
     p.n_words = n_words;
@@ -739,6 +740,7 @@ cudaError_t compact_launch(const uint32_t *bitmap, long long n_words, const Quer
     p.ctl = const_cast<QueryCtl *>(d_ctl);
     p.desc = desc;
     p.epoch = epoch;
+    p.id_base = id_base;
     p.out_ids = out_ids;
     if (p.n_chunks == 0) return cudaSuccess;
     compact_kernel<<<static_cast<unsigned>(p.n_chunks), kCompactThreads, 0, stream>>>(p);

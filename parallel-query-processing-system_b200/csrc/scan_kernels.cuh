@@ -45,8 +45,10 @@ cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream
 // compact_chunks(n_words) descriptors; epoch is stamped into them (never 0).  The match count is
 // NOT produced here (K1 already accumulated it into ctl->out_count).
 int64_t compact_chunks(long long n_words);
+// out_ids may point into ANOTHER GPU's memory (peer mapping): the ids then travel over NVLink as
+// the coalesced stores of the compaction itself; id_base is added to every id (shard -> table).
 cudaError_t compact_launch(const uint32_t *bitmap, long long n_words, const QueryCtl *d_ctl, unsigned long long *desc,
-                           uint32_t epoch, uint32_t *out_ids, cudaStream_t stream);
+                           uint32_t epoch, uint32_t *out_ids, uint32_t id_base, cudaStream_t stream);
 
 // K1g: evaluate the predicate on a list of candidate rows (concatenated index segments, or the
 // identity list when perm == nullptr) and compact the survivors in list order.

@@ -561,6 +561,13 @@ int qpe_sql_select_ids_into(struct engineS *engine, const char *statement, int f
     return qpe_gpu_select_ids_into(engine, pw.wc, flags, ids, cap, n_out, stats);
 }
 
+int qpe_sql_scan_count(struct engineS *engine, const char *statement, unsigned long long *count_out,
+                       qpe_scan_stats *stats) {
+    ParsedWhere pw(statement);
+    if (!pw.ok) return -7;
+    return qpe_gpu_scan_count(engine, pw.wc, count_out, stats);
+}
+
 int qpe_sql_match_mask(struct engineS *engine, const char *statement, unsigned int *bitmap, size_t n_words,
                        unsigned long long *count_out, qpe_scan_stats *stats) {
     ParsedWhere pw(statement);

@@ -24,11 +24,24 @@ def shard_range(total_rows: int, world: int, rank: int) -> Tuple[int, int]:
     return start, n
 
 
+_count_bufs = {}
+
+
 def exchange_counts(local_count: int, device, group=None) -> List[int]:
-    """every rank learns every rank's match count (one 8-byte all-gather)"""
+    """every rank learns every rank's match count (one 8-byte all-gather; NCCL over NVLink on GPUs)"""
     world = dist.get_world_size(group)
-    mine = torch.tensor([int(local_count)], dtype=torch.int64, device=device)
-    parts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    device = torch.device(device)
+    if device.type == "cuda":
+        key = (device, world, id(group))
+        if key not in _count_bufs:
+            _count_bufs[key] = (torch.zeros(1, dtype=torch.int64, device=device),
+                                torch.zeros(world, dtype=torch.int64, device=device))
+        mine, every = _count_bufs[key]
+        mine.fill_(int(local_count))
+        dist.all_gather_into_tensor(every, mine, group=group)
+        return every.tolist()
+    mine = torch.tensor([int(local_count)], dtype=torch.int64)
+    parts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)
     return [int(p.item()) for p in parts]
 
@@ -65,3 +78,51 @@ def ordered_gather(local_ids: torch.Tensor, out: Optional[torch.Tensor] = None, 
         for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local_ids.contiguous(), dst, group)]):
             w.wait()
     return total, counts, None
+
+
+class PeerGather:
+    """Ordered gather of a sharded full scan WITHOUT a separate transfer step: rank `dst` owns the
+    result buffer, every other rank maps it through CUDA IPC, and each rank's compaction kernel
+    (K1c) stores its (global) row ids straight into that buffer at the exclusive prefix of the lower
+    ranks' counts -- over NVLink for the non-owners.  The only collectives are the 8-byte count
+    all-gather and a barrier; there is no send/recv of the ids."""
+
+    def __init__(self, pkg, capacity_ids: int, dst: int = 0, group=None):
+        self.pkg = pkg
+        self.dst = dst
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.capacity = int(capacity_ids)
+        self.buffer = None
+        handle = [None]
+        if self.rank == dst:
+            self.buffer = pkg.DeviceBuffer(4 * max(self.capacity, 1))
+            self.ptr = self.buffer.ptr
+            handle[0] = self.buffer.export_handle()
+        dist.broadcast_object_list(handle, src=dst, group=group)
+        if self.rank != dst:
+            self.ptr = pkg.ipc_open(handle[0])
+        dist.barrier(group=group)
+
+    def run(self, engine, statement: str, counts_device) -> Tuple[int, List[int], dict]:
+        """One sharded SELECT: K1 everywhere, count exchange, K1c into the owner's buffer, barrier.
+        Returns (total matches, per-rank counts, this rank's stats)."""
+        cnt, _ = engine.scan_count(statement)
+        counts = exchange_counts(cnt, counts_device, self.group)
+        off = sum(counts[:self.rank])
+        total = sum(counts)
+        if total > self.capacity:
+            raise RuntimeError(f"gather buffer too small: {total} ids > capacity {self.capacity}")
+        st = engine.compact_to(self.ptr + 4 * off, global_ids=True)
+        dist.barrier(group=self.group)  # every rank's stores have landed (each compact_to synchronised its stream)
+        return total, counts, st
+
+    def close(self):
+        dist.barrier(group=self.group)
+        if self.rank != self.dst:
+            self.pkg.ipc_close(self.ptr)
+        dist.barrier(group=self.group)
+        if self.buffer is not None:
+            self.buffer.free()
+            self.buffer = None
