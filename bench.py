@@ -57,6 +57,15 @@ ALL_COLUMNS = ["command_id", "raw_command", "base_command", "shell_type", "exit_
                "working_directory", "user_id", "user_name", "host_name", "risk_level"]
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    f = _REAL_STDOUT or sys.stdout
+    f.write(line + "\n")
+    f.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,7 +218,7 @@ def run_reference(args):
     import multiprocessing as mp
     import support
     if not support.Ref.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libqpe_ref.so was not built"}))
+        emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libqpe_ref.so was not built"}))
         return 0
     pkg = support.load_pkg()
     sql_t, cols, bpr = QUERIES[args.query]
@@ -248,7 +257,7 @@ def run_reference(args):
     for p, _ in workers:
         p.join(timeout=10)
     value = procs * rows * args.steps / dt
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "select_where_rows_per_s", "value": value, "unit": "rows/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -301,7 +310,9 @@ def run_ours(args):
     else:
         total_matches = cnt0
     use_peer = world > 1 and args.gather == "peer"
-    pg = sharding.PeerGather(pkg, capacity_ids=total_matches + 1024) if use_peer else None
+    if world > 1:
+        seg_cap = int(max(sharding.exchange_counts(cnt0, dev)) * 1.25) + 4096
+    pg = sharding.PeerGather(pkg, segment_capacity=seg_cap) if use_peer else None
     gathered = (torch.empty(max(total_matches, 1), dtype=torch.int32, device=dev)
                 if (rank == 0 and world > 1 and not use_peer) else None)
     pinned = torch.empty(max(total_matches, 1), dtype=torch.int32).pin_memory() if rank == 0 else None
@@ -309,10 +320,10 @@ def run_ours(args):
     launches = [0]
     scan_ms, compact_ms, kernel_ms = [], [], []
 
-    def step_device(record=False):
+    def step_device(record=False, pack="device"):
         """scan + ordered compaction on every GPU, count exchange, ordered gather to rank 0 (device)"""
         if use_peer:
-            total_n, counts, st = pg.run(eng, sql, dev)
+            total_n, counts, st = pg.run(eng, sql, dev, pack=pack, host_out=pinned_np)
         else:
             cnt, dptr, st = eng.select_ids_device(sql, force_scan=True, global_ids=(world > 1))
             total_n = cnt
@@ -332,10 +343,10 @@ def run_ours(args):
             n, st = eng.select_ids_into(sql, pinned_np, force_scan=True)
             launches[0] += st["launches"]
             return n
-        n = step_device()
+        n = step_device(pack="host")
         if rank == 0:
             if use_peer:
-                pg.buffer.to_host(n, out=pinned_np)
+                pass  # the owner copied every segment straight into the pinned host buffer
             else:
                 pinned[:n].copy_(gathered[:n], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
@@ -427,7 +438,7 @@ def run_ours(args):
             except Exception as e:  # the baseline is reported, never required
                 out["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": 1, "kind": "reference",
                                        "sample": f"failed: {e}"}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if pg is not None:
         pg.close()
     eng.close()
@@ -438,6 +449,11 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -90,6 +90,15 @@ int qpe_gpu_select_ids_into(struct engineS *engine, struct whereClauseS *whereCl
 int qpe_gpu_scan_count(struct engineS *engine, struct whereClauseS *whereClause, unsigned long long *count_out,
                        qpe_scan_stats *stats);
 int qpe_gpu_compact_to(struct engineS *engine, unsigned int *dst_device, int global_ids, qpe_scan_stats *stats);
+/* K1 + K1c in one call, ids written to dst_device (this GPU's memory or a peer mapping) which holds
+ * dst_capacity ids.  *count_out always receives the match count; if it exceeds dst_capacity the call
+ * returns -5 and nothing was stored at or beyond the capacity. */
+int qpe_gpu_select_ids_to(struct engineS *engine, struct whereClauseS *whereClause, unsigned int *dst_device,
+                          unsigned long long dst_capacity, int global_ids, unsigned long long *count_out,
+                          qpe_scan_stats *stats);
+int qpe_sql_select_ids_to(struct engineS *engine, const char *statement, unsigned int *dst_device,
+                          unsigned long long dst_capacity, int global_ids, unsigned long long *count_out,
+                          qpe_scan_stats *stats);
 int qpe_sql_scan_count(struct engineS *engine, const char *statement, unsigned long long *count_out,
                        qpe_scan_stats *stats);
 
@@ -100,6 +109,7 @@ int qpe_gpu_ipc_export(void *device_ptr, unsigned char handle_out[64]);
 void *qpe_gpu_ipc_open(const unsigned char handle[64]);
 void qpe_gpu_ipc_close(void *mapped_ptr);
 int qpe_gpu_copy_to_host(void *dst_host, const void *src_device, size_t bytes);
+int qpe_gpu_copy_device(void *dst_device, const void *src_device, size_t bytes);
 
 /* cudaMemcpy device -> host for pointers handed out by the *_device calls. 0 on success. */
 int qpe_gpu_copy_from_device(void *dst_host, const void *src_device, size_t bytes);

@@ -107,6 +107,8 @@ def load_library() -> C.CDLL:
         "qpe_sql_match_mask": (i, [vp, cp, vp, sz, C.POINTER(ull), pstats]),
         "qpe_sql_scan_count": (i, [vp, cp, C.POINTER(ull), pstats]),
         "qpe_gpu_compact_to": (i, [vp, vp, i, pstats]),
+        "qpe_sql_select_ids_to": (i, [vp, cp, vp, ull, i, C.POINTER(ull), pstats]),
+        "qpe_gpu_copy_device": (i, [vp, vp, sz]),
         "qpe_gpu_device_alloc": (vp, [sz]),
         "qpe_gpu_device_free": (None, [vp]),
         "qpe_gpu_ipc_export": (i, [vp, C.c_char_p]),
@@ -322,6 +324,17 @@ class Engine:
         st = ScanStats()
         self._check(self._lib.qpe_sql_scan_count(self._h, statement.encode(), C.byref(cnt), C.byref(st)), "scan_count")
         return int(cnt.value), st.as_dict()
+
+    def select_ids_to(self, statement: str, dst_device_ptr: int, capacity: int, global_ids: bool = False):
+        """Full scan (K1 + K1c) with the ids stored at `dst_device_ptr` (own or peer memory, `capacity` ids).
+        Returns (count, stats, fits): when the result does not fit nothing is stored past the capacity."""
+        cnt = C.c_ulonglong()
+        st = ScanStats()
+        rc = self._lib.qpe_sql_select_ids_to(self._h, statement.encode(), dst_device_ptr, capacity,
+                                             1 if global_ids else 0, C.byref(cnt), C.byref(st))
+        if rc not in (0, -5):
+            self._check(rc, "select_ids_to")
+        return int(cnt.value), st.as_dict(), rc == 0
 
     def compact_to(self, dst_device_ptr: int, global_ids: bool = False) -> dict:
         """Second half: K1c writes the row ids of the last scan_count to `dst_device_ptr`, which may be

@@ -675,6 +675,39 @@ int qpe_gpu_scan_count(struct engineS *engine, struct whereClauseS *whereClause,
     return 0;
 }
 
+// K1 + K1c in one call with the ids written to a caller-chosen destination (this GPU or a peer)
+int qpe_gpu_select_ids_to(struct engineS *engine, struct whereClauseS *whereClause, unsigned int *dst_device,
+                          unsigned long long dst_capacity, int global_ids, unsigned long long *count_out,
+                          qpe_scan_stats *stats) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    uint32_t base = 0;
+    if (global_ids) {
+        if (g->table.row_base + static_cast<uint64_t>(g->table.n) > 0xffffffffull) {
+            set_error("global row ids do not fit 32 bits");
+            return -5;
+        }
+        base = static_cast<uint32_t>(g->table.row_base);
+    }
+    g->out_override = dst_device;
+    g->out_override_cap = dst_capacity;
+    g->id_base_override = base;
+    uint64_t m = 0;
+    const bool ok = engine_match(g, whereClause, true, false, false, false, &m);
+    g->out_override = nullptr;
+    g->out_override_cap = 0;
+    g->id_base_override = 0;
+    if (!ok) return -2;
+    if (count_out) *count_out = m;
+    fill_stats(g, stats);
+    if (m > dst_capacity) {
+        set_error("destination too small for the result (nothing was written past it)");
+        return -5;
+    }
+    return 0;
+}
+
 int qpe_gpu_compact_to(struct engineS *engine, unsigned int *dst_device, int global_ids, qpe_scan_stats *stats) {
     std::lock_guard<std::mutex> lk(g_api_mutex);
     GpuEngine *g = as_engine(engine);
@@ -687,7 +720,7 @@ int qpe_gpu_compact_to(struct engineS *engine, unsigned int *dst_device, int glo
         }
         base = static_cast<uint32_t>(g->table.row_base);
     }
-    if (!engine_compact_to(g, dst_device, base)) return -2;
+    if (!engine_compact_to(g, dst_device, base, ~0ull)) return -2;
     fill_stats(g, stats);
     return 0;
 }
@@ -717,6 +750,10 @@ void *qpe_gpu_ipc_open(const unsigned char handle[64]) {
 }
 void qpe_gpu_ipc_close(void *mapped_ptr) {
     if (mapped_ptr) cudaIpcCloseMemHandle(mapped_ptr);
+}
+int qpe_gpu_copy_device(void *dst_device, const void *src_device, size_t bytes) {
+    if (bytes == 0) return 0;
+    return cuda_ok(cudaMemcpy(dst_device, src_device, bytes, cudaMemcpyDeviceToDevice), "device copy") ? 0 : -4;
 }
 int qpe_gpu_copy_to_host(void *dst_host, const void *src_device, size_t bytes) {
     if (bytes == 0) return 0;

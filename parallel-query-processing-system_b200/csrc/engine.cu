@@ -411,7 +411,8 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
             if (!count_only || want_bitmap) {
                 if (!ensure_bitmap(g, bm_words)) return false;
             }
-            if (!count_only && (!ensure_desc(g, n_chunks) || !engine_ensure_ids(g, t.n))) return false;
+            if (!count_only && !ensure_desc(g, n_chunks)) return false;
+            if (!count_only && !g->out_override && !engine_ensure_ids(g, t.n)) return false;
             ScanLaunch L{};
             L.table = &t;
             L.d_ctl = g->d_ctl;
@@ -425,8 +426,10 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
             cudaEventRecord(g->ev_mid, g->stream);
             if (!count_only && t.n > 0) {
                 // K1c: ordered compaction of the match bitmap (decoupled look-back per 64 Ki rows)
-                if (!cuda_ok(compact_launch(g->d_bitmap, bm_words, g->d_ctl, g->d_tile_desc, next_epoch(g), g->d_ids, 0u,
-                                            g->stream),
+                uint32_t *dst = g->out_override ? g->out_override : g->d_ids;
+                const unsigned long long cap = g->out_override ? g->out_override_cap : static_cast<unsigned long long>(g->ids_cap);
+                if (!cuda_ok(compact_launch(g->d_bitmap, bm_words, g->d_ctl, g->d_tile_desc, next_epoch(g), dst,
+                                            g->out_override ? g->id_base_override : 0u, cap, g->stream),
                              "compaction kernel launch"))
                     return false;
                 st.launches = 2;
@@ -559,7 +562,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
 // chosen destination -- possibly another GPU's buffer, so the ordered gather of a sharded
 // table is done by the compaction kernel's own stores over NVLink)
 // ------------------------------------------------------------------------------------------
-bool engine_compact_to(GpuEngine *g, uint32_t *dst, uint32_t id_base) {
+bool engine_compact_to(GpuEngine *g, uint32_t *dst, uint32_t id_base, uint64_t cap) {
     cudaSetDevice(g->device);
     if (g->last_bm_words <= 0 && g->table.n > 0) {
         set_error("no match bitmap to compact: run a full-scan match with a bitmap first");
@@ -576,7 +579,7 @@ bool engine_compact_to(GpuEngine *g, uint32_t *dst, uint32_t id_base) {
         return false;
     cudaEventRecord(g->ev_mid, g->stream);
     if (!cuda_ok(compact_launch(g->d_bitmap, g->last_bm_words, g->d_ctl, g->d_tile_desc, next_epoch(g), dst, id_base,
-                                g->stream),
+                                cap, g->stream),
                  "compaction kernel launch"))
         return false;
     cudaEventRecord(g->ev1, g->stream);

@@ -37,6 +37,11 @@ struct GpuEngine {
     int64_t ids_cap = 0;
     uint32_t *d_bitmap = nullptr;
     int64_t bitmap_cap_words = 0;
+    // destination override for the next full-scan match (qpe_gpu_select_ids_to): ids go to out_override
+    // (this GPU's or a peer's memory, out_override_cap ids at most) with id_base_override added
+    uint32_t *out_override = nullptr;
+    uint64_t out_override_cap = 0;
+    uint32_t id_base_override = 0;
     int64_t last_bm_words = 0;   // words of the bitmap the last full-scan match left in d_bitmap (0 = none)
     uint64_t last_bm_count = 0;  // its match count
     // probe scratch (device + pinned host), kMaxSegments entries each
@@ -72,7 +77,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
 
 // K1c alone: compact the bitmap left by the last count-only full-scan match into `dst` (device
 // memory of this GPU or a peer mapping), adding id_base to every id
-bool engine_compact_to(GpuEngine *g, uint32_t *dst, uint32_t id_base);
+bool engine_compact_to(GpuEngine *g, uint32_t *dst, uint32_t id_base, uint64_t cap);
 
 // download helpers
 bool engine_fetch_rows(GpuEngine *g, int col, const uint32_t *d_ids, int64_t n, std::vector<uint8_t> *out);

@@ -624,6 +624,7 @@ struct CompactParams {
     uint32_t epoch;
     uint32_t id_base;   // added to every row id (a shard's first global row); 0 for a whole table
     uint32_t *out_ids;  // may be PEER memory (another GPU's buffer mapped through CUDA IPC / NVLink)
+    unsigned long long out_cap;  // ids the destination can hold: nothing is ever stored at or beyond it
 };
 
 __global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_constant__ CompactParams p) {
@@ -687,6 +688,8 @@ __global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_c
     const uint32_t total = s_round_base[kCompactRounds];
     if (total == 0) return;
     const uint32_t excl = s_excl;
+    // destination too small (the caller learns it from the match count): never store out of bounds
+    if (static_cast<unsigned long long>(excl) + total > p.out_cap) return;
     // offsets inside the chunk: round base + earlier warps of the round + earlier lanes of the warp
 #pragma unroll
     for (int r = 0; r < kCompactRounds; ++r) {
@@ -732,7 +735,8 @@ __global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_c
 int64_t compact_chunks(long long n_words) { return (n_words + kChunkWords - 1) / kChunkWords; }
 
 cudaError_t compact_launch(const uint32_t *bitmap, long long n_words, const QueryCtl *d_ctl, unsigned long long *desc,
-                           uint32_t epoch, uint32_t *out_ids, uint32_t id_base, cudaStream_t stream) {
+                           uint32_t epoch, uint32_t *out_ids, uint32_t id_base, unsigned long long out_cap,
+                           cudaStream_t stream) {
     CompactParams p{};
     p.bitmap = bitmap;
     p.n_words = n_words;
@@ -742,6 +746,7 @@ cudaError_t compact_launch(const uint32_t *bitmap, long long n_words, const Quer
     p.epoch = epoch;
     p.id_base = id_base;
     p.out_ids = out_ids;
+    p.out_cap = out_cap;
     if (p.n_chunks == 0) return cudaSuccess;
     compact_kernel<<<static_cast<unsigned>(p.n_chunks), kCompactThreads, 0, stream>>>(p);
     return cudaGetLastError();

@@ -48,7 +48,8 @@ int64_t compact_chunks(long long n_words);
 // out_ids may point into ANOTHER GPU's memory (peer mapping): the ids then travel over NVLink as
 // the coalesced stores of the compaction itself; id_base is added to every id (shard -> table).
 cudaError_t compact_launch(const uint32_t *bitmap, long long n_words, const QueryCtl *d_ctl, unsigned long long *desc,
-                           uint32_t epoch, uint32_t *out_ids, uint32_t id_base, cudaStream_t stream);
+                           uint32_t epoch, uint32_t *out_ids, uint32_t id_base, unsigned long long out_cap,
+                           cudaStream_t stream);
 
 // K1g: evaluate the predicate on a list of candidate rows (concatenated index segments, or the
 // identity list when perm == nullptr) and compact the survivors in list order.

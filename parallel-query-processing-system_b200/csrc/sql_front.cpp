@@ -568,6 +568,14 @@ int qpe_sql_scan_count(struct engineS *engine, const char *statement, unsigned l
     return qpe_gpu_scan_count(engine, pw.wc, count_out, stats);
 }
 
+int qpe_sql_select_ids_to(struct engineS *engine, const char *statement, unsigned int *dst_device,
+                          unsigned long long dst_capacity, int global_ids, unsigned long long *count_out,
+                          qpe_scan_stats *stats) {
+    ParsedWhere pw(statement);
+    if (!pw.ok) return -7;
+    return qpe_gpu_select_ids_to(engine, pw.wc, dst_device, dst_capacity, global_ids, count_out, stats);
+}
+
 int qpe_sql_match_mask(struct engineS *engine, const char *statement, unsigned int *bitmap, size_t n_words,
                        unsigned long long *count_out, qpe_scan_stats *stats) {
     ParsedWhere pw(statement);

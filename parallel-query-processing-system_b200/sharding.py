@@ -81,23 +81,30 @@ def ordered_gather(local_ids: torch.Tensor, out: Optional[torch.Tensor] = None, 
 
 
 class PeerGather:
-    """Ordered gather of a sharded full scan WITHOUT a separate transfer step: rank `dst` owns the
+    """Ordered gather of a sharded full scan WITHOUT a transfer step of its own: rank `dst` owns the
     result buffer, every other rank maps it through CUDA IPC, and each rank's compaction kernel
-    (K1c) stores its (global) row ids straight into that buffer at the exclusive prefix of the lower
-    ranks' counts -- over NVLink for the non-owners.  The only collectives are the 8-byte count
-    all-gather and a barrier; there is no send/recv of the ids."""
+    (K1c) stores its (global) row ids straight into its segment of that buffer -- over NVLink for
+    the non-owners.  One stream synchronisation and ONE collective per query (the 8-byte count
+    all-gather, which also orders the stores before the owner reads); no send/recv of ids.
+    The owner then packs the segments (device-to-device, or straight into host memory)."""
 
-    def __init__(self, pkg, capacity_ids: int, dst: int = 0, group=None):
+    def __init__(self, pkg, segment_capacity: int, dst: int = 0, group=None):
         self.pkg = pkg
         self.dst = dst
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        self.capacity = int(capacity_ids)
-        self.buffer = None
+        self.seg_cap = int(max(segment_capacity, 1))
+        self.parity = 0
+        self.buffer = None   # owner: 2 x world segments of seg_cap ids
+        self.dense = None    # owner: packed result
         handle = [None]
         if self.rank == dst:
-            self.buffer = pkg.DeviceBuffer(4 * max(self.capacity, 1))
+            # two sets of segments, used alternately: a rank can run at most one query ahead of the
+            # owner (the next count all-gather needs the owner), so the set the owner is still
+            # packing is never the one being written
+            self.buffer = pkg.DeviceBuffer(4 * self.seg_cap * self.world * 2)
+            self.dense = pkg.DeviceBuffer(4 * self.seg_cap * self.world)
             self.ptr = self.buffer.ptr
             handle[0] = self.buffer.export_handle()
         dist.broadcast_object_list(handle, src=dst, group=group)
@@ -105,18 +112,34 @@ class PeerGather:
             self.ptr = pkg.ipc_open(handle[0])
         dist.barrier(group=group)
 
-    def run(self, engine, statement: str, counts_device) -> Tuple[int, List[int], dict]:
-        """One sharded SELECT: K1 everywhere, count exchange, K1c into the owner's buffer, barrier.
+    def run(self, engine, statement: str, counts_device, pack: str = "device", host_out=None):
+        """One sharded SELECT.  pack = "device": the owner packs the segments into self.dense;
+        "host": the owner copies them into host_out (numpy uint32, ideally pinned); "none": leave them.
         Returns (total matches, per-rank counts, this rank's stats)."""
-        cnt, _ = engine.scan_count(statement)
+        set_off = 4 * self.seg_cap * self.world * self.parity
+        self.parity ^= 1
+        seg = self.ptr + set_off + 4 * self.seg_cap * self.rank
+        cnt, st, _ = engine.select_ids_to(statement, seg, self.seg_cap, global_ids=True)
         counts = exchange_counts(cnt, counts_device, self.group)
-        off = sum(counts[:self.rank])
+        if max(counts) > self.seg_cap:
+            raise RuntimeError(f"segment too small: {max(counts)} ids > capacity {self.seg_cap}")
         total = sum(counts)
-        if total > self.capacity:
-            raise RuntimeError(f"gather buffer too small: {total} ids > capacity {self.capacity}")
-        st = engine.compact_to(self.ptr + 4 * off, global_ids=True)
-        dist.barrier(group=self.group)  # every rank's stores have landed (each compact_to synchronised its stream)
+        if self.rank == self.dst and pack != "none":
+            lib = self.pkg.load_library()
+            off = 0
+            for r, c in enumerate(counts):
+                if c:
+                    src = self.buffer.ptr + set_off + 4 * self.seg_cap * r
+                    if pack == "host":
+                        lib.qpe_gpu_copy_to_host(host_out.ctypes.data + 4 * off, src, 4 * c)
+                    else:
+                        lib.qpe_gpu_copy_device(self.dense.ptr + 4 * off, src, 4 * c)
+                off += c
         return total, counts, st
+
+    def result(self, total: int):
+        """owner: the packed result on the host (for checks)"""
+        return self.dense.to_host(total)
 
     def close(self):
         dist.barrier(group=self.group)
@@ -125,4 +148,5 @@ class PeerGather:
         dist.barrier(group=self.group)
         if self.buffer is not None:
             self.buffer.free()
+            self.dense.free()
             self.buffer = None

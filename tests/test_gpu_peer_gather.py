@@ -41,12 +41,19 @@ def _worker(rank, world, port, ret):
     sharding = import_module("pqps_b200.sharding")
     start, n = sharding.shard_range(TOTAL, world, rank)
     eng = pkg.Engine.from_synth(TOTAL, n_rows=n, row_base=start, columns=COLS)
-    pg = sharding.PeerGather(pkg, capacity_ids=TOTAL)
+    pg = sharding.PeerGather(pkg, segment_capacity=n + 1)
     out = []
-    for q in QUERIES:
-        total, counts, st = pg.run(eng, q, torch.device("cpu"))
+    host = np.zeros(TOTAL, dtype=np.uint32)
+    for k, q in enumerate(QUERIES):
+        if k % 2 == 0:
+            total, counts, st = pg.run(eng, q, torch.device("cpu"))
+            ids = pg.result(total).copy() if rank == 0 else None
+        else:
+            total, counts, st = pg.run(eng, q, torch.device("cpu"), pack="host", host_out=host)
+            ids = host[:total].copy()
         if rank == 0:
-            out.append((total, counts, pg.buffer.to_host(total).copy()))
+            out.append((total, counts, ids))
+        # no barrier needed: segments are double-buffered (see PeerGather)
     pg.close()
     eng.close()
     if rank == 0:
