@@ -312,7 +312,7 @@ def run_ours(args):
     use_peer = world > 1 and args.gather == "peer"
     if world > 1:
         seg_cap = int(max(sharding.exchange_counts(cnt0, dev)) * 1.25) + 4096
-    pg = sharding.PeerGather(pkg, segment_capacity=seg_cap) if use_peer else None
+    pg = sharding.PeerGather(pkg, segment_capacity=seg_cap, counts_device=dev) if use_peer else None
     gathered = (torch.empty(max(total_matches, 1), dtype=torch.int32, device=dev)
                 if (rank == 0 and world > 1 and not use_peer) else None)
     pinned = torch.empty(max(total_matches, 1), dtype=torch.int32).pin_memory() if rank == 0 else None

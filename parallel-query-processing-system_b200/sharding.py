@@ -88,13 +88,14 @@ class PeerGather:
     all-gather, which also orders the stores before the owner reads); no send/recv of ids.
     The owner then packs the segments (device-to-device, or straight into host memory)."""
 
-    def __init__(self, pkg, segment_capacity: int, dst: int = 0, group=None):
+    def __init__(self, pkg, segment_capacity: int, counts_device="cpu", dst: int = 0, group=None):
         self.pkg = pkg
         self.dst = dst
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        self.seg_cap = int(max(segment_capacity, 1))
+        # every rank must lay the segments out identically: agree on the largest request
+        self.seg_cap = max(exchange_counts(int(max(segment_capacity, 1)), counts_device, group))
         self.parity = 0
         self.buffer = None   # owner: 2 x world segments of seg_cap ids
         self.dense = None    # owner: packed result
