@@ -102,6 +102,20 @@ int qpe_sql_select_ids_to(struct engineS *engine, const char *statement, unsigne
 int qpe_sql_scan_count(struct engineS *engine, const char *statement, unsigned long long *count_out,
                        qpe_scan_stats *stats);
 
+/* Index path of a SHARDED table.  For every (top-level condition x index) segment of the WHERE, in the
+ * reference's generation order (executeEngine-serial.c:358-459), the rows of THIS shard that pass the
+ * whole WHERE, in (key ASC, local position DESC) order, with their keys (u64 keys as long long bits,
+ * int keys sign-extended).  The caller merges the shards per segment: concatenate from the highest
+ * rank to the lowest and sort stably by key = (key ASC, global position DESC), the reference's order.
+ * *used_index_out = 0 when no index applies (use the scan path).  keys_out / ids_out are malloc'ed
+ * (qpe_gpu_free), concatenated over the segments; seg_counts_out[s] = rows of segment s (<= 32). */
+int qpe_gpu_select_segments(struct engineS *engine, struct whereClauseS *whereClause, int global_ids,
+                            int *used_index_out, int *n_segments_out, size_t seg_counts_out[32], long long **keys_out,
+                            unsigned int **ids_out);
+int qpe_sql_select_segments(struct engineS *engine, const char *statement, int global_ids, int *used_index_out,
+                            int *n_segments_out, size_t seg_counts_out[32], long long **keys_out,
+                            unsigned int **ids_out);
+
 /* Raw device buffers shareable between the processes (one per GPU) of one box through CUDA IPC. */
 void *qpe_gpu_device_alloc(size_t bytes);
 void qpe_gpu_device_free(void *p);

@@ -106,6 +106,8 @@ def load_library() -> C.CDLL:
         "qpe_sql_select_ids_into": (i, [vp, cp, i, vp, sz, C.POINTER(sz), pstats]),
         "qpe_sql_match_mask": (i, [vp, cp, vp, sz, C.POINTER(ull), pstats]),
         "qpe_sql_scan_count": (i, [vp, cp, C.POINTER(ull), pstats]),
+        "qpe_sql_select_segments": (i, [vp, cp, i, C.POINTER(i), C.POINTER(i), C.POINTER(sz), C.POINTER(vp),
+                                        C.POINTER(vp)]),
         "qpe_gpu_compact_to": (i, [vp, vp, i, pstats]),
         "qpe_sql_select_ids_to": (i, [vp, cp, vp, ull, i, C.POINTER(ull), pstats]),
         "qpe_gpu_copy_device": (i, [vp, vp, sz]),
@@ -317,6 +319,30 @@ class Engine:
                                                  C.byref(st))
         self._check(rc, "select_ids_device")
         return int(cnt.value), dptr.value, st.as_dict()
+
+    def select_segments(self, statement: str, global_ids: bool = True):
+        """Index path of one shard, per segment: (used_index, [(keys int64, ids uint32), ...]).
+        Used by sharding.sharded_select to merge shards into the reference's (key ASC, position DESC) order."""
+        used = C.c_int()
+        nseg = C.c_int()
+        counts = (C.c_size_t * 32)()
+        keys = C.c_void_p()
+        ids = C.c_void_p()
+        rc = self._lib.qpe_sql_select_segments(self._h, statement.encode(), 1 if global_ids else 0, C.byref(used),
+                                               C.byref(nseg), counts, C.byref(keys), C.byref(ids))
+        self._check(rc, "select_segments")
+        try:
+            total = sum(counts[s] for s in range(nseg.value))
+            k = np.ctypeslib.as_array(C.cast(keys, C.POINTER(C.c_int64)), shape=(max(total, 1),))[:total].copy()
+            d = np.ctypeslib.as_array(C.cast(ids, C.POINTER(C.c_uint32)), shape=(max(total, 1),))[:total].copy()
+        finally:
+            self._lib.qpe_gpu_free(keys)
+            self._lib.qpe_gpu_free(ids)
+        out, o = [], 0
+        for s in range(nseg.value):
+            out.append((k[o:o + counts[s]], d[o:o + counts[s]]))
+            o += counts[s]
+        return bool(used.value), out
 
     def scan_count(self, statement: str) -> Tuple[int, dict]:
         """First half of a split full scan: K1 only -> match count (the bitmap stays in HBM)."""

@@ -725,6 +725,43 @@ int qpe_gpu_compact_to(struct engineS *engine, unsigned int *dst_device, int glo
     return 0;
 }
 
+// ---- index path of a sharded table: per-segment (key, id) lists for the cross-shard merge ----
+int qpe_gpu_select_segments(struct engineS *engine, struct whereClauseS *whereClause, int global_ids,
+                            int *used_index_out, int *n_segments_out, size_t seg_counts_out[32], long long **keys_out,
+                            unsigned int **ids_out) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    std::vector<SegmentResult> segs;
+    bool used = false;
+    if (!engine_match_segments(g, whereClause, &segs, &used)) return -2;
+    if (used_index_out) *used_index_out = used ? 1 : 0;
+    if (n_segments_out) *n_segments_out = static_cast<int>(segs.size());
+    size_t total = 0;
+    for (size_t s = 0; s < segs.size(); ++s) {
+        if (seg_counts_out) seg_counts_out[s] = segs[s].ids.size();
+        total += segs[s].ids.size();
+    }
+    long long *keys = static_cast<long long *>(std::malloc(sizeof(long long) * (total ? total : 1)));
+    unsigned int *ids = static_cast<unsigned int *>(std::malloc(sizeof(unsigned int) * (total ? total : 1)));
+    if (!keys || !ids) {
+        std::free(keys);
+        std::free(ids);
+        set_error("out of host memory");
+        return -3;
+    }
+    const uint32_t base = global_ids ? static_cast<uint32_t>(g->table.row_base) : 0u;
+    size_t o = 0;
+    for (const SegmentResult &r : segs)
+        for (size_t k = 0; k < r.ids.size(); ++k, ++o) {
+            keys[o] = r.keys[k];
+            ids[o] = r.ids[k] + base;
+        }
+    if (keys_out) *keys_out = keys; else std::free(keys);
+    if (ids_out) *ids_out = ids; else std::free(ids);
+    return 0;
+}
+
 // ---- raw device buffers that can be shared with the other ranks of the box (CUDA IPC) ----
 void *qpe_gpu_device_alloc(size_t bytes) {
     void *p = nullptr;

@@ -594,6 +594,114 @@ bool engine_compact_to(GpuEngine *g, uint32_t *dst, uint32_t id_base, uint64_t c
 }
 
 // ------------------------------------------------------------------------------------------
+// index path, one segment at a time, with the keys of the survivors: what a SHARDED table needs.
+// The global result of segment S(w, i) is ordered (key ASC, GLOBAL position DESC); a shard can
+// only produce (key ASC, local position DESC).  Handing out (key, id) per segment lets the caller
+// merge the shards: concatenate them from the highest rank to the lowest and sort stably by key
+// (sharding.py).  Single-GPU queries never come here.
+// ------------------------------------------------------------------------------------------
+bool engine_match_segments(GpuEngine *g, const struct whereClauseS *wc, std::vector<SegmentResult> *out,
+                           bool *used_index) {
+    cudaSetDevice(g->device);
+    out->clear();
+    const DevTable &t = g->table;
+    uint32_t widths[NUM_COLS];
+    for (int c = 0; c < NUM_COLS; ++c) widths[c] = t.col[c].width;
+    QueryCtl *hc = g->h_ctl;
+    const std::string err = compile_where(wc, widths, &hc->prog, false);
+    if (!err.empty()) {
+        set_error(err);
+        return false;
+    }
+    for (int c = 0; c < NUM_COLS; ++c)
+        if ((hc->prog.col_mask & (1u << c)) && !t.resident(c)) {
+            set_error(std::string("WHERE references column '") + kCols[c].name + "' which is not resident on the device");
+            return false;
+        }
+    SegmentPlan segs[kMaxSegments];
+    bool too_many = false;
+    const int n_seg = plan_segments(g, wc, segs, kMaxSegments, &too_many);
+    if (too_many) {
+        set_error("too many (condition x index) segments in one WHERE clause");
+        return false;
+    }
+    *used_index = n_seg > 0;
+    if (n_seg == 0) return true;
+    int launches = 0;
+    for (int s = 0; s < n_seg; ++s) {
+        DevIndex &ix = g->idx[segs[s].index_slot];
+        if (!ensure_index(g, &ix, &launches)) return false;
+        // probe this segment
+        unsigned long long lo = 0, hi = 0;
+        if (segs[s].is_u64) {
+            lo = segs[s].lo_u64;
+            hi = segs[s].hi_u64;
+        } else {
+            std::memcpy(&lo, &segs[s].lo_i32, 4);
+            std::memcpy(&hi, &segs[s].hi_i32, 4);
+        }
+        g->h_probe_keys[0] = lo;
+        g->h_probe_keys[kMaxSegments] = hi;
+        if (!cuda_ok(cudaMemcpyAsync(g->d_probe_lo, g->h_probe_keys, 8, cudaMemcpyHostToDevice, g->stream), "probe h2d") ||
+            !cuda_ok(cudaMemcpyAsync(g->d_probe_hi, g->h_probe_keys + kMaxSegments, 8, cudaMemcpyHostToDevice, g->stream),
+                     "probe h2d") ||
+            !cuda_ok(index_probe(ix, g->d_probe_lo, g->d_probe_hi, 1, g->d_probe_first, g->d_probe_count, g->stream),
+                     "probe kernel launch") ||
+            !cuda_ok(cudaMemcpyAsync(g->h_probe_out, g->d_probe_first, 4, cudaMemcpyDeviceToHost, g->stream), "probe d2h") ||
+            !cuda_ok(cudaMemcpyAsync(g->h_probe_out + kMaxSegments, g->d_probe_count, 4, cudaMemcpyDeviceToHost, g->stream),
+                     "probe d2h") ||
+            !cuda_ok(cudaStreamSynchronize(g->stream), "probe sync"))
+            return false;
+        CandSegments cs{};
+        cs.n_seg = 1;
+        cs.perm[0] = ix.perm;
+        cs.first[0] = g->h_probe_out[0];
+        cs.vstart[0] = 0;
+        cs.vstart[1] = g->h_probe_out[kMaxSegments];
+        const long long n_cand = cs.vstart[1];
+        SegmentResult r;
+        r.key_col = ix.col;
+        if (n_cand > 0) {
+            hc->tile_counter = 0;
+            hc->chunk_counter = 0;
+            hc->out_count = 0;
+            if (!cuda_ok(cudaMemcpyAsync(g->d_ctl, hc, sizeof(QueryCtl), cudaMemcpyHostToDevice, g->stream), "upload query"))
+                return false;
+            if (!ensure_desc(g, filter_tiles(n_cand)) || !engine_ensure_ids(g, n_cand)) return false;
+            if (!cuda_ok(filter_launch(t, g->d_ctl, cs, g->d_tile_desc, next_epoch(g), g->d_ids, g->stream),
+                         "filter kernel launch") ||
+                !cuda_ok(cudaMemcpyAsync(&hc->out_count, &g->d_ctl->out_count, 8, cudaMemcpyDeviceToHost, g->stream),
+                         "download count") ||
+                !cuda_ok(cudaStreamSynchronize(g->stream), "filter sync"))
+                return false;
+            const int64_t m = static_cast<int64_t>(hc->out_count);
+            r.ids.resize(static_cast<size_t>(m));
+            if (m > 0) {
+                if (!cuda_ok(cudaMemcpy(r.ids.data(), g->d_ids, static_cast<size_t>(m) * 4, cudaMemcpyDeviceToHost),
+                             "download ids"))
+                    return false;
+                std::vector<uint8_t> raw;
+                if (!engine_fetch_rows(g, ix.col, g->d_ids, m, &raw)) return false;
+                r.keys.resize(static_cast<size_t>(m));
+                for (int64_t k = 0; k < m; ++k) {
+                    if (ix.type == T_U64) {
+                        unsigned long long v;
+                        std::memcpy(&v, raw.data() + 8 * k, 8);
+                        r.keys[k] = static_cast<long long>(v);
+                    } else {
+                        int v;
+                        std::memcpy(&v, raw.data() + 4 * k, 4);
+                        r.keys[k] = v;
+                    }
+                }
+            }
+        }
+        out->push_back(std::move(r));
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
 // downloads
 // ------------------------------------------------------------------------------------------
 bool engine_fetch_rows(GpuEngine *g, int col, const uint32_t *d_ids, int64_t n, std::vector<uint8_t> *out) {

@@ -79,6 +79,15 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
 // memory of this GPU or a peer mapping), adding id_base to every id
 bool engine_compact_to(GpuEngine *g, uint32_t *dst, uint32_t id_base, uint64_t cap);
 
+// index path per segment with keys (sharded tables; see engine.cu)
+struct SegmentResult {
+    int key_col = -1;
+    std::vector<long long> keys;  // key of every surviving row (u64 keys reinterpreted; int keys sign-extended)
+    std::vector<uint32_t> ids;    // local row ids, (key ASC, local position DESC)
+};
+bool engine_match_segments(GpuEngine *g, const struct whereClauseS *wc, std::vector<SegmentResult> *out,
+                           bool *used_index);
+
 // download helpers
 bool engine_fetch_rows(GpuEngine *g, int col, const uint32_t *d_ids, int64_t n, std::vector<uint8_t> *out);
 bool engine_download_all(GpuEngine *g, HostColumns *out);

@@ -576,6 +576,15 @@ int qpe_sql_select_ids_to(struct engineS *engine, const char *statement, unsigne
     return qpe_gpu_select_ids_to(engine, pw.wc, dst_device, dst_capacity, global_ids, count_out, stats);
 }
 
+int qpe_sql_select_segments(struct engineS *engine, const char *statement, int global_ids, int *used_index_out,
+                            int *n_segments_out, size_t seg_counts_out[32], long long **keys_out,
+                            unsigned int **ids_out) {
+    ParsedWhere pw(statement);
+    if (!pw.ok) return -7;
+    return qpe_gpu_select_segments(engine, pw.wc, global_ids, used_index_out, n_segments_out, seg_counts_out, keys_out,
+                                   ids_out);
+}
+
 int qpe_sql_match_mask(struct engineS *engine, const char *statement, unsigned int *bitmap, size_t n_words,
                        unsigned long long *count_out, qpe_scan_stats *stats) {
     ParsedWhere pw(statement);

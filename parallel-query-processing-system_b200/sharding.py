@@ -80,6 +80,54 @@ def ordered_gather(local_ids: torch.Tensor, out: Optional[torch.Tensor] = None, 
     return total, counts, None
 
 
+def merge_index_segments(local_segments, device="cpu", dst: int = 0, group=None):
+    """Cross-shard merge of an index-path SELECT.  `local_segments` = this rank's
+    [(keys int64, global ids), ...] per segment, each (key ASC, local position DESC).  For every
+    segment the shards are concatenated from the HIGHEST rank to the lowest and sorted stably by
+    key, which yields (key ASC, global position DESC): exactly the leaf-chain order of one B+ tree
+    over the whole table (engine/bplus.c:282-358).  Segments are then concatenated in
+    WHERE order, duplicates kept.  Returns the merged global ids on rank `dst` (numpy), None elsewhere."""
+    import numpy as np
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    device = torch.device(device)
+    merged = []
+    for keys, ids in local_segments:
+        k = torch.from_numpy(np.ascontiguousarray(keys, dtype=np.int64)).to(device)
+        i = torch.from_numpy(np.ascontiguousarray(ids).astype(np.int64)).to(device)
+        tot_k, counts, all_k = ordered_gather(k, None, dst, group)
+        _, _, all_i = ordered_gather(i, None, dst, group)
+        if rank == dst:
+            offs = [0]
+            for c in counts:
+                offs.append(offs[-1] + c)
+            # highest rank first: among equal keys rows of later shards (larger global positions) come first
+            order = [r for r in range(world - 1, -1, -1)]
+            kk = torch.cat([all_k[offs[r]:offs[r + 1]] for r in order]) if tot_k else all_k[:0]
+            ii = torch.cat([all_i[offs[r]:offs[r + 1]] for r in order]) if tot_k else all_i[:0]
+            perm = torch.sort(kk, stable=True).indices
+            merged.append(ii[perm].cpu().numpy().astype(np.uint32))
+    if rank != dst:
+        return None
+    return np.concatenate(merged) if merged else np.zeros(0, dtype=np.uint32)
+
+
+def sharded_select(engine, statement: str, device="cpu", dst: int = 0, group=None):
+    """SELECT on a row-range sharded table with the reference's path rule and result order:
+    index path (per-segment merge) when a top-level condition names a u64/int index, else the
+    full-scan path (ordered gather).  Returns the global row ids on rank `dst` (numpy), None elsewhere."""
+    import numpy as np
+    used, segs = engine.select_segments(statement, global_ids=True)
+    if used:
+        return merge_index_segments(segs, device, dst, group)
+    cnt, dptr, _ = engine.select_ids_device(statement, force_scan=True, global_ids=True)
+    local = engine.copy_from_device(dptr, cnt).astype(np.int64)
+    total, _, out = ordered_gather(torch.from_numpy(local).to(torch.device(device)), None, dst, group)
+    if dist.get_rank(group) != dst:
+        return None
+    return out[:total].cpu().numpy().astype(np.uint32)
+
+
 class PeerGather:
     """Ordered gather of a sharded full scan WITHOUT a transfer step of its own: rank `dst` owns the
     result buffer, every other rank maps it through CUDA IPC, and each rank's compaction kernel

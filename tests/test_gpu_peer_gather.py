@@ -81,3 +81,59 @@ def test_peer_gather_equals_single_engine(world):
         assert total == len(want) and len(counts) == world and sum(counts) == total
         assert np.array_equal(ids, want), q
     whole.close()
+
+
+# ---- sharded SELECT with the reference's path rule (index path merged across shards) ------------
+SHARDED_QUERIES = [
+    'SELECT command_id FROM Commands WHERE risk_level > 3 AND shell_type != "bash"',
+    'SELECT command_id FROM Commands WHERE user_id = 1001 OR (exit_code = 127)',
+    'SELECT command_id FROM Commands WHERE exit_code > 126 AND risk_level < 2',
+    'SELECT command_id FROM Commands WHERE command_id >= 400000 AND command_id <= 700000',
+    'SELECT command_id FROM Commands WHERE (risk_level > 3) AND (shell_type = "zsh")',   # groups only: scan path
+    'SELECT command_id FROM Commands WHERE user_id = 999999',
+]
+SH_TOTAL = 1_000_003
+SH_COLS = ["command_id", "sudo_used", "risk_level", "exit_code", "user_id", "shell_type"]
+SH_IDX = (("command_id", 0), ("user_id", 1), ("risk_level", 1), ("exit_code", 1), ("sudo_used", 3))
+
+
+def _sharded_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["QPE_GPU_DEVICE"] = "0"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = support.load_pkg()
+    from importlib import import_module
+    sharding = import_module("pqps_b200.sharding")
+    start, n = sharding.shard_range(SH_TOTAL, world, rank)
+    eng = pkg.Engine.from_synth(SH_TOTAL, n_rows=n, row_base=start, columns=SH_COLS, indexes=SH_IDX)
+    out = []
+    for q in SHARDED_QUERIES:
+        ids = sharding.sharded_select(eng, q)
+        if rank == 0:
+            out.append(ids)
+    eng.close()
+    if rank == 0:
+        ret.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_select_equals_single_engine(world):
+    pkg = support.load_pkg()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = ret.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    whole = pkg.Engine.from_synth(SH_TOTAL, columns=SH_COLS, indexes=SH_IDX)
+    for q, ids in zip(SHARDED_QUERIES, results):
+        want, _ = whole.select_ids(q)
+        assert np.array_equal(ids, want), q
+    whole.close()

@@ -86,3 +86,64 @@ def test_shard_range_is_the_mpi_block_partition():
                 assert n == base + (1 if r < rem else 0)   # executeEngine-mpi.c:703-715
                 covered += n
             assert covered == total
+
+
+# ---- index path across shards: per-segment merge == one B+ tree over the whole table -----------
+INDEX_QUERIES = [
+    # (where, [(key column, lo, hi)] = the segments the reference generates, in order)
+    ('risk_level > 3 AND shell_type != "bash"', [("risk_level", 4, 2**31 - 1)]),
+    ('user_id = 1001 OR (exit_code = 127)', [("user_id", 1001, 1001)]),
+    ('exit_code > 126 AND risk_level < 2', [("exit_code", 127, 2**31 - 1), ("risk_level", -2**31, 1)]),
+    ('command_id >= 500 AND command_id <= 1500', [("command_id", 500, 2**63 - 1), ("command_id", 0, 1500)]),
+    ('risk_level = 5 OR user_id = 1003', [("risk_level", 5, 5), ("user_id", 1003, 1003)]),
+]
+
+
+def _merge_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    support.load_pkg()
+    from importlib import import_module
+    sharding = import_module("pqps_b200.sharding")
+    o = Oracle.from_csv(CSV_2K)
+    total = o.num_rows
+    start, n = sharding.shard_range(total, world, rank)
+    pos = np.arange(start, start + n)
+    out = []
+    for where, segments in INDEX_QUERIES:
+        passing = np.zeros(total, dtype=bool)
+        passing[o.scan(where, first=start, n=n)] = True          # this shard's rows that pass the whole WHERE
+        local = []
+        for col, lo, hi in segments:
+            key = np.array([int(o.cell(int(p), col)) for p in pos], dtype=np.int64)
+            cand = (key >= lo) & (key <= hi)
+            order = np.lexsort((-pos, key))                        # (key ASC, position DESC) within the shard
+            order = order[cand[order] & passing[pos[order]]]
+            local.append((key[order], pos[order].astype(np.uint32)))
+        merged = sharding.merge_index_segments(local)
+        if rank == 0:
+            out.append(merged.tolist())
+    if rank == 0:
+        ret.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_index_path_merge_across_shards(world):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_merge_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = ret.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = Oracle.from_csv(CSV_2K)
+    for (where, _), got in zip(INDEX_QUERIES, results):
+        want, used = o.select_ids(where)
+        assert used
+        assert got == want.tolist(), where
