@@ -238,11 +238,21 @@ struct engineS *initializeEngineGPU(int num_indexes, const char *indexed_attribu
     if (!datafile) datafile = "../data/commands_50k.csv";  // the reference's default (executeEngine-serial.c:757)
     GpuEngine *g = engine_create(tableName ? tableName : "", datafile, num_indexes);
     if (!g) return nullptr;
-    HostColumns hc;
-    if (load_csv_columns(datafile, &hc) < 0) hc.init_widths_minimal();  // unreadable file: empty table
-    if (!engine_upload(g, hc)) {
+    // ingest: parsed on the device (K6); the host loader handles what K6 declines (unreadable or
+    // empty file, a line the reference's fgets(1024) would split) and QPE_INGEST=host forces it
+    const char *mode = std::getenv("QPE_INGEST");
+    int r = (mode && std::strcmp(mode, "host") == 0) ? 0 : ingest_csv_gpu(g, datafile, nullptr);
+    if (r < 0) {
         engine_destroy(g);
         return nullptr;
+    }
+    if (r == 0) {
+        HostColumns hc;
+        if (load_csv_columns(datafile, &hc) < 0) hc.init_widths_minimal();  // unreadable file: empty table
+        if (!engine_upload(g, hc)) {
+            engine_destroy(g);
+            return nullptr;
+        }
     }
     engine_load_indexes(g, num_indexes, indexed_attributes, attribute_types);
     return &g->head;

@@ -93,6 +93,8 @@ bool engine_fetch_rows(GpuEngine *g, int col, const uint32_t *d_ids, int64_t n, 
 bool engine_download_all(GpuEngine *g, HostColumns *out);
 
 int64_t load_csv_columns(const char *path, HostColumns *out);
+// K6: parse the CSV on the device straight into columns. 1 = done, 0 = use the host loader, -1 = CUDA error
+int ingest_csv_gpu(GpuEngine *g, const char *path, int *launches_out);
 void parse_csv_chunk(const char *chunk, size_t len, record *r);
 
 }  // namespace qpe

@@ -23,47 +23,20 @@
 #include <unistd.h>
 
 #include "qpe_internal.h"
+#include "csv_rules.h"
 #include "buildEngine-gpu.h"
 
 namespace qpe {
 
 namespace {
 
-// parse one field starting at *cur (bounded by end); writes the unescaped text to buf
-// (NUL-terminated) and returns false when the field is absent.
+// one field through the shared rules (csv_rules.h); text is NUL-terminated in buf
 inline bool next_field(const char *&cur, const char *end, char *buf, size_t *len_out) {
-    const char *s = cur;
-    if (s >= end || *s == '\0' || *s == '\n' || *s == '\r') return false;
-    size_t i = 0;
-    bool in_quotes = false;
-    if (*s == '"') {
-        in_quotes = true;
-        ++s;
-    }
-    while (s < end && *s != '\0' && *s != '\n' && *s != '\r') {
-        if (in_quotes) {
-            if (*s == '"') {
-                if (s + 1 < end && s[1] == '"') {
-                    buf[i++] = '"';
-                    s += 2;
-                } else {
-                    in_quotes = false;
-                    ++s;
-                }
-            } else {
-                buf[i++] = *s++;
-            }
-        } else {
-            if (*s == ',') {
-                ++s;
-                break;
-            }
-            buf[i++] = *s++;
-        }
-    }
-    buf[i] = '\0';
-    *len_out = i;
-    cur = s;
+    int len = 0;
+    if (!csv::next_field(cur, end, buf, 1031, &len)) return false;
+    if (len > 1031) len = 1031;
+    buf[len] = '\0';
+    *len_out = static_cast<size_t>(len);
     return true;
 }
 
