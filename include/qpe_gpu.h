@@ -158,6 +158,10 @@ int qpe_gpu_fetch_column(struct engineS *engine, const char *attribute, long lon
 
 /* Tuning override for the scan kernel (0 = automatic). */
 int qpe_gpu_set_tile(struct engineS *engine, int tile_rows, int stages);
+/* Pipelined full scan: the table is cut into `segments` pieces of whole 64 Ki-row chunks and K1c of
+ * piece i runs beside K1 of piece i+1 (two streams), so the ordered ids leave the GPU during the
+ * scan.  0 = automatic (one piece per 32 Mi rows, at most 8), 1 = never pipeline, up to 16. */
+int qpe_gpu_set_pipeline(struct engineS *engine, int segments);
 
 /* SQL front end (same grammar and quirks as the reference's tokenizer/src/tokenizer.c +
  * connectEngine.c bridge).  qpe_sql_run executes one statement and writes what the

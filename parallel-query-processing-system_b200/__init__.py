@@ -96,6 +96,7 @@ def load_library() -> C.CDLL:
         "qpe_gpu_index_slice": (i, [vp, cp, C.c_uint, C.c_uint, vp]),
         "qpe_gpu_fetch_column": (i, [vp, cp, ll, ll, vp, C.POINTER(C.c_uint)]),
         "qpe_gpu_set_tile": (i, [vp, i, i]),
+        "qpe_gpu_set_pipeline": (i, [vp, i]),
         "qpe_gpu_copy_from_device": (i, [vp, vp, sz]),
         "qpe_gpu_last_stats": (i, [vp, pstats]),
         "qpe_gpu_write_csv": (i, [vp, cp]),
@@ -252,6 +253,10 @@ class Engine:
 
     def set_tile(self, tile_rows: int = 0, stages: int = 0):
         self._check(self._lib.qpe_gpu_set_tile(self._h, tile_rows, stages), "set_tile")
+
+    def set_pipeline(self, segments: int = 0):
+        """0 = automatic, 1 = one K1 + one K1c launch, n = n table segments with K1c(i) beside K1(i+1)"""
+        self._check(self._lib.qpe_gpu_set_pipeline(self._h, segments), "set_pipeline")
 
     def last_stats(self) -> dict:
         st = ScanStats()

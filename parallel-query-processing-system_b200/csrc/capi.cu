@@ -513,7 +513,22 @@ int qpe_gpu_select_ids(struct engineS *engine, struct whereClauseS *whereClause,
     return 0;
 }
 
-// same as qpe_gpu_select_ids but into a caller-provided (ideally pinned) host buffer of `cap` ids
+// Device-visible alias of a host pointer, or nullptr: pinned (cudaHostAlloc / cudaHostRegister)
+// memory is mapped into the device's address space, so a kernel can store to it directly.
+static unsigned int *device_alias_of_host(void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    return static_cast<unsigned int *>(a.devicePointer);
+}
+
+// same as qpe_gpu_select_ids but into a caller-provided host buffer of `cap` ids.  When the buffer is
+// PINNED and the query takes the full-scan path, K1c stores the row ids straight into it (zero copy:
+// the ids cross PCIe as the compaction kernel's own coalesced stores, overlapped with the rest of
+// the scan when the scan is pipelined); otherwise the ids are compacted in HBM and copied.
 int qpe_gpu_select_ids_into(struct engineS *engine, struct whereClauseS *whereClause, int flags, unsigned int *ids,
                             size_t cap, size_t *n_out, qpe_scan_stats *stats) {
     std::lock_guard<std::mutex> lk(g_api_mutex);
@@ -521,16 +536,29 @@ int qpe_gpu_select_ids_into(struct engineS *engine, struct whereClauseS *whereCl
     if (!g) return -1;
     const double t0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     uint64_t m = 0;
-    if (!engine_match(g, whereClause, (flags & QPE_SCAN_FORCE) != 0, false, false, false, &m)) return -2;
+    cudaSetDevice(g->device);
+    unsigned int *alias = (ids && cap) ? device_alias_of_host(ids) : nullptr;
+    if (alias) {
+        g->out_override = alias;
+        g->out_override_cap = cap;
+        g->id_base_override = 0;
+    }
+    const bool ok = engine_match(g, whereClause, (flags & QPE_SCAN_FORCE) != 0, false, false, false, &m);
+    const bool direct = alias && g->last.path == 0 && g->last.tile_rows > 0;  // K1c wrote into `ids`
+    g->out_override = nullptr;
+    g->out_override_cap = 0;
+    if (!ok) return -2;
     if (n_out) *n_out = static_cast<size_t>(m);
     if (m > cap) {
         set_error("id buffer too small");
         return -5;
     }
-    if (m && !cuda_ok(cudaMemcpyAsync(ids, g->d_ids, sizeof(unsigned int) * m, cudaMemcpyDeviceToHost, g->stream),
-                      "download ids"))
-        return -4;
-    if (!cuda_ok(cudaStreamSynchronize(g->stream), "download ids")) return -4;
+    if (!direct) {
+        if (m && !cuda_ok(cudaMemcpyAsync(ids, g->d_ids, sizeof(unsigned int) * m, cudaMemcpyDeviceToHost, g->stream),
+                          "download ids"))
+            return -4;
+        if (!cuda_ok(cudaStreamSynchronize(g->stream), "download ids")) return -4;
+    }
     fill_stats(g, stats);
     if (stats)
         stats->total_ms =
@@ -875,6 +903,18 @@ int qpe_gpu_write_csv(struct engineS *engine, const char *path) {
         std::fputs("\r\n", f);
     }
     std::fclose(f);
+    return 0;
+}
+
+int qpe_gpu_set_pipeline(struct engineS *engine, int segments) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    if (segments < 0 || segments > kMaxPipeSegments) {
+        set_error("pipeline segments must be 0 (automatic) .. 16");
+        return -5;
+    }
+    g->pipe_segments = segments;
     return 0;
 }
 

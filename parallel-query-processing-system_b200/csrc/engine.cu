@@ -37,6 +37,9 @@ bool cuda_ok(cudaError_t e, const char *what) {
     return false;
 }
 
+// automatic pipelining: one segment per this many 64 Ki-row chunks (32 Mi rows), at most 8
+constexpr int64_t kAutoSegmentChunks = 512;
+
 static double now_ms() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
@@ -102,7 +105,13 @@ GpuEngine *engine_create(const char *tableName, const char *datafile, int index_
     g->head.record_block = nullptr;
     g->head.num_records = 0;
 
-    bool ok = cuda_ok(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    bool ok = cuda_ok(cudaStreamCreateWithPriority(&g->stream, cudaStreamNonBlocking, prio_greatest), "cudaStreamCreate");
+    ok = ok && cuda_ok(cudaStreamCreateWithPriority(&g->stream2, cudaStreamNonBlocking, prio_least), "cudaStreamCreate");
+    for (int i = 0; ok && i < kMaxPipeSegments; ++i)
+        ok = cuda_ok(cudaEventCreateWithFlags(&g->ev_seg[i], cudaEventDisableTiming), "cudaEventCreate");
+    if (const char *e = std::getenv("QPE_PIPE_SEGMENTS")) g->pipe_segments = std::atoi(e);
     ok = ok && cuda_ok(cudaEventCreate(&g->ev0), "cudaEventCreate");
     ok = ok && cuda_ok(cudaEventCreate(&g->ev1), "cudaEventCreate");
     ok = ok && cuda_ok(cudaEventCreate(&g->ev_mid), "cudaEventCreate");
@@ -134,6 +143,7 @@ void engine_destroy(GpuEngine *g) {
     if (!g) return;
     cudaSetDevice(g->device);
     if (g->stream) cudaStreamSynchronize(g->stream);
+    if (g->stream2) cudaStreamSynchronize(g->stream2);
     free_table(&g->table);
     for (auto &ix : g->idx) index_free(&ix);
     if (g->d_ctl) cudaFree(g->d_ctl);
@@ -150,6 +160,9 @@ void engine_destroy(GpuEngine *g) {
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
     if (g->ev_mid) cudaEventDestroy(g->ev_mid);
+    for (int i = 0; i < kMaxPipeSegments; ++i)
+        if (g->ev_seg[i]) cudaEventDestroy(g->ev_seg[i]);
+    if (g->stream2) cudaStreamDestroy(g->stream2);
     if (g->stream) cudaStreamDestroy(g->stream);
     for (int i = 0; i < g->head.num_indexes; ++i) std::free(g->head.indexed_attributes[i]);
     std::free(g->head.indexed_attributes);
@@ -404,7 +417,25 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
         st.rows_scanned = t.n;
         ScanGeometry geo{};
         const char *why = nullptr;
-        const bool staged = scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, &geo, &why);
+        bool staged = scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, 4, &geo, &why);
+        // Pipelined scan: the table is cut into P segments of whole 64 Ki-row chunks; K1 of segment
+        // i+1 (stream, high priority) runs while K1c of segment i (stream2, low priority) compacts
+        // and stores its ids -- possibly straight into pinned host memory or a peer GPU -- so the
+        // ordered output leaves the GPU during the scan instead of after it.  K1 then runs with at
+        // most 3 stages so that a K1c CTA (33 KB of shared memory) fits beside it on every SM.
+        int P = 1;
+        if (staged && !count_only && !want_bitmap && t.n > 0) {
+            const int64_t chunks = compact_chunks(geo.n_tiles * (geo.tile_rows / 32));
+            P = g->pipe_segments > 0 ? g->pipe_segments : static_cast<int>(chunks / kAutoSegmentChunks);
+            if (P > kMaxPipeSegments) P = kMaxPipeSegments;
+            if (g->pipe_segments <= 0 && P > 8) P = 8;
+            if (P > chunks) P = static_cast<int>(chunks);
+            if (P < 1) P = 1;
+            if (P > 1 && !g->force_stages && geo.stages > 3) {
+                ScanGeometry g3{};
+                if (scan_plan(t, hc->prog, geo.tile_rows, 0, 3, &g3, &why)) geo = g3;
+            }
+        }
         if (staged) {
             const int64_t bm_words = geo.n_tiles * (geo.tile_rows / 32);
             const int64_t n_chunks = compact_chunks(bm_words);
@@ -420,21 +451,49 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
             L.out_bitmap = (!count_only || want_bitmap) ? g->d_bitmap : nullptr;
             L.force_tile_rows = g->force_tile_rows;
             L.force_stages = g->force_stages;
+            uint32_t *dst = g->out_override ? g->out_override : g->d_ids;
+            const unsigned long long cap =
+                g->out_override ? g->out_override_cap : static_cast<unsigned long long>(g->ids_cap);
+            const uint32_t id_base = g->out_override ? g->id_base_override : 0u;
             cudaEventRecord(g->ev0, g->stream);
-            if (!cuda_ok(scan_launch(L, geo, g->stream), "scan kernel launch")) return false;
-            st.launches = 1;
-            cudaEventRecord(g->ev_mid, g->stream);
-            if (!count_only && t.n > 0) {
-                // K1c: ordered compaction of the match bitmap (decoupled look-back per 64 Ki rows)
-                uint32_t *dst = g->out_override ? g->out_override : g->d_ids;
-                const unsigned long long cap = g->out_override ? g->out_override_cap : static_cast<unsigned long long>(g->ids_cap);
-                if (!cuda_ok(compact_launch(g->d_bitmap, bm_words, g->d_ctl, g->d_tile_desc, next_epoch(g), dst,
-                                            g->out_override ? g->id_base_override : 0u, cap, g->stream),
-                             "compaction kernel launch"))
-                    return false;
-                st.launches = 2;
+            if (P == 1) {
+                if (!cuda_ok(scan_launch(L, geo, g->stream), "scan kernel launch")) return false;
+                st.launches = 1;
+                cudaEventRecord(g->ev_mid, g->stream);
+                if (!count_only && t.n > 0) {
+                    // K1c: ordered compaction of the match bitmap (decoupled look-back per 64 Ki rows)
+                    if (!cuda_ok(compact_launch(g->d_bitmap, bm_words, g->d_ctl, g->d_tile_desc, next_epoch(g), dst,
+                                                id_base, cap, g->stream),
+                                 "compaction kernel launch"))
+                        return false;
+                    st.launches = 2;
+                }
+                cudaEventRecord(g->ev1, g->stream);
+            } else {
+                const uint32_t epoch = next_epoch(g);
+                const int64_t tiles_per_chunk = kCompactChunkRows / geo.tile_rows;
+                const int64_t seg_chunks = (n_chunks + P - 1) / P;
+                int launched = 0;
+                for (int i = 0; i < P; ++i) {
+                    const int64_t c0 = static_cast<int64_t>(i) * seg_chunks;
+                    const int64_t c1 = (c0 + seg_chunks < n_chunks) ? c0 + seg_chunks : n_chunks;
+                    if (c0 >= c1) break;
+                    L.tile_begin = c0 * tiles_per_chunk;
+                    L.tile_end = (c1 * tiles_per_chunk < geo.n_tiles) ? c1 * tiles_per_chunk : geo.n_tiles;
+                    if (!cuda_ok(scan_launch(L, geo, g->stream), "scan kernel launch")) return false;
+                    cudaEventRecord(g->ev_seg[i], g->stream);
+                    cudaStreamWaitEvent(g->stream2, g->ev_seg[i], 0);
+                    if (!cuda_ok(compact_launch(g->d_bitmap, bm_words, g->d_ctl, g->d_tile_desc, epoch, dst, id_base, cap,
+                                                g->stream2, c1 - c0),
+                                 "compaction kernel launch"))
+                        return false;
+                    launched += 2;
+                }
+                cudaEventRecord(g->ev_mid, g->stream);   // the last K1 is done
+                cudaEventRecord(g->ev1, g->stream2);     // the last K1c is done
+                cudaStreamWaitEvent(g->stream, g->ev1, 0);
+                st.launches = launched;
             }
-            cudaEventRecord(g->ev1, g->stream);
             st.tile_rows = geo.tile_rows;
             st.stages = geo.stages;
             st.grid = geo.grid;

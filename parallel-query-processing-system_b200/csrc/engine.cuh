@@ -13,6 +13,7 @@
 
 namespace qpe {
 
+constexpr int kMaxPipeSegments = 16;
 constexpr uint64_t kEngineMagic = 0x5150454750553031ull;  // "QPEGPU01"
 constexpr uint64_t kResultMagic = 0x5150455245533031ull;  // "QPERES01"
 
@@ -20,8 +21,11 @@ struct GpuEngine {
     struct engineS head;  // MUST stay first: callers hold `struct engineS *`
     uint64_t magic = kEngineMagic;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // K1 and everything else (highest priority)
+    cudaStream_t stream2 = nullptr;  // K1c of a pipelined scan (lowest priority: fills the SMs beside K1)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
+    cudaEvent_t ev_seg[kMaxPipeSegments] = {nullptr};  // K1 of segment i done -> K1c of segment i may start
+    int pipe_segments = 0;           // 0 = automatic, 1 = never pipeline, else the segment count to use
 
     DevTable table;
     std::vector<DevIndex> idx;  // parallel to head.indexed_attributes

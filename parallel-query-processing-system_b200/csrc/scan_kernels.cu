@@ -158,7 +158,8 @@ struct ScanParams {
     int32_t n_stages;
     int32_t dynamic_tiles;  // 1: claim tiles from the global counter; 0: tile = cta + k * grid
     long long n_rows;
-    long long n_tiles;
+    long long tile_begin;   // this launch covers tiles [tile_begin, n_tiles): a pipelined scan launches
+    long long n_tiles;      // K1 once per table segment so that K1c of segment i overlaps K1 of segment i+1
     QueryCtl *ctl;
     uint32_t *out_bitmap;   // n_tiles * tile_rows / 32 words, or null (count only)
 };
@@ -398,8 +399,9 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_tma_kernel(const __grid
                 // static round-robin keeps the claim off the critical path (a global atomic costs a
                 // full round trip per tile); every CTA is resident (grid <= SM count) and walks its
                 // tiles in increasing order, so the look-back chain always makes progress.
-                const long long tile = p.dynamic_tiles ? static_cast<long long>(atomicAdd(&p.ctl->tile_counter, 1u))
-                                                       : static_cast<long long>(blockIdx.x) + k * gridDim.x;
+                const long long tile = p.tile_begin +
+                                       (p.dynamic_tiles ? static_cast<long long>(atomicAdd(&p.ctl->tile_counter, 1u))
+                                                        : static_cast<long long>(blockIdx.x) + k * gridDim.x);
                 if (tile >= p.n_tiles) {
                     sh->tile_of_stage[s] = -1;
                     mbar_arrive(&sh->full[s]);
@@ -467,8 +469,9 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_tma_kernel(const __grid
     if (tid == 0 && sh->cta_count) atomicAdd(&p.ctl->out_count, sh->cta_count);
 }
 
-bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages, ScanGeometry *geo,
-               const char **why) {
+bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages, int max_stages,
+               ScanGeometry *geo, const char **why) {
+    if (max_stages < 1 || max_stages > 4) max_stages = 4;
     int dev = 0;
     cudaGetDevice(&dev);
     int max_smem = 0, n_sm = 0;
@@ -509,7 +512,7 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
             for (int cand : kTiles) {
                 const size_t sb = stage_bytes_for(cand);
                 int fit = static_cast<int>(budget / (sb ? sb : 1));
-                if (fit > 4) fit = 4;
+                if (fit > max_stages) fit = max_stages;
                 if (fit >= want) {
                     best_T = cand;
                     best_S = fit;
@@ -525,7 +528,7 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
     } else if (!S) {
         const size_t sb = stage_bytes_for(T);
         S = static_cast<int>(budget / (sb ? sb : 1));
-        if (S > 4) S = 4;
+        if (S > max_stages) S = max_stages;
     }
     if ((T != 256 && T != 512 && T != 1024 && T != 2048 && T != 4096) || S < 1 || S > kMaxStages) {
         if (why) *why = "invalid tile geometry (tile rows must be 256, 512, 1024, 2048 or 4096)";
@@ -552,7 +555,10 @@ static cudaError_t launch_scan_r(const ScanParams &p, const ScanGeometry &geo, c
     cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(geo.smem_bytes));
     if (e != cudaSuccess) return e;
-    scan_tma_kernel<EW, R><<<geo.grid, 32 * (1 + EW), geo.smem_bytes, stream>>>(p);
+    long long grid = p.n_tiles - p.tile_begin;  // tiles of this launch
+    if (grid > geo.grid) grid = geo.grid;
+    if (grid < 1) grid = 1;
+    scan_tma_kernel<EW, R><<<static_cast<unsigned>(grid), 32 * (1 + EW), geo.smem_bytes, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -587,7 +593,9 @@ cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream
         p.dynamic_tiles = dyn;
     }
     p.n_rows = t.n;
-    p.n_tiles = geo.n_tiles;
+    p.tile_begin = L.tile_begin;
+    p.n_tiles = L.tile_end > 0 ? L.tile_end : geo.n_tiles;
+    if (p.tile_begin != 0 || p.n_tiles != geo.n_tiles) p.dynamic_tiles = 0;  // segments use the static walk
     p.ctl = const_cast<QueryCtl *>(L.d_ctl);
     p.out_bitmap = L.out_bitmap;
     switch (geo.tile_rows) {
@@ -614,6 +622,7 @@ constexpr int kCompactThreads = 256;
 constexpr int kCompactRounds = 8;                                    // words per thread
 constexpr int kChunkWords = kCompactThreads * kCompactRounds;        // 2048 words = 65536 rows
 constexpr int kStageIds = 8192;                                      // ids staged per copy-out (32 KB)
+static_assert(kChunkWords * 32 == kCompactChunkRows, "chunk size is part of the launch interface");
 
 struct CompactParams {
     const uint32_t *bitmap;
@@ -736,7 +745,7 @@ int64_t compact_chunks(long long n_words) { return (n_words + kChunkWords - 1) /
 
 cudaError_t compact_launch(const uint32_t *bitmap, long long n_words, const QueryCtl *d_ctl, unsigned long long *desc,
                            uint32_t epoch, uint32_t *out_ids, uint32_t id_base, unsigned long long out_cap,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, long long launch_chunks) {
     CompactParams p{};
     p.bitmap = bitmap;
     p.n_words = n_words;
@@ -748,7 +757,11 @@ cudaError_t compact_launch(const uint32_t *bitmap, long long n_words, const Quer
     p.out_ids = out_ids;
     p.out_cap = out_cap;
     if (p.n_chunks == 0) return cudaSuccess;
-    compact_kernel<<<static_cast<unsigned>(p.n_chunks), kCompactThreads, 0, stream>>>(p);
+    // chunks are claimed from ctl->chunk_counter, which keeps counting across the launches of one
+    // query: a pipelined scan launches the chunks of one table segment at a time (launch_chunks of
+    // them), in order, on one stream -- the look-back of a later launch finds the earlier ones done
+    const long long blocks = launch_chunks > 0 ? launch_chunks : p.n_chunks;
+    compact_kernel<<<static_cast<unsigned>(blocks), kCompactThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,8 @@ struct ScanLaunch {
     uint32_t *out_bitmap;           // device, may be null (count only); one bit per row, tile-padded
     int force_tile_rows;            // 0 = choose
     int force_stages;               // 0 = choose
+    long long tile_begin;           // tiles [tile_begin, tile_end) of the table; tile_end 0 = to the last tile
+    long long tile_end;
 };
 
 struct ScanGeometry {
@@ -36,7 +38,8 @@ struct ScanGeometry {
 // K1: TMA-staged predicate evaluation over the whole table -> match bitmap + count (ctl->out_count).
 // Returns false (and sets *why) if the query cannot be staged (row too wide for shared memory):
 // the caller then uses the gather path below with an identity candidate list.
-bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages,
+// max_stages (1..4) caps the pipeline depth: 3 leaves room for a K1c CTA beside K1's on every SM.
+bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages, int max_stages,
                ScanGeometry *geo, const char **why);
 cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream_t stream);
 
@@ -47,9 +50,11 @@ cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream
 int64_t compact_chunks(long long n_words);
 // out_ids may point into ANOTHER GPU's memory (peer mapping): the ids then travel over NVLink as
 // the coalesced stores of the compaction itself; id_base is added to every id (shard -> table).
+// launch_chunks > 0: launch only the next launch_chunks chunks (pipelined scan; see compact_launch).
+constexpr int kCompactChunkRows = 65536;
 cudaError_t compact_launch(const uint32_t *bitmap, long long n_words, const QueryCtl *d_ctl, unsigned long long *desc,
                            uint32_t epoch, uint32_t *out_ids, uint32_t id_base, unsigned long long out_cap,
-                           cudaStream_t stream);
+                           cudaStream_t stream, long long launch_chunks = 0);
 
 // K1g: evaluate the predicate on a list of candidate rows (concatenated index segments, or the
 // identity list when perm == nullptr) and compact the survivors in list order.
