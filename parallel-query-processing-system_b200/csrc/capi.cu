@@ -525,10 +525,10 @@ static unsigned int *device_alias_of_host(void *p) {
     return static_cast<unsigned int *>(a.devicePointer);
 }
 
-// same as qpe_gpu_select_ids but into a caller-provided host buffer of `cap` ids.  When the buffer is
-// PINNED and the query takes the full-scan path, K1c stores the row ids straight into it (zero copy:
-// the ids cross PCIe as the compaction kernel's own coalesced stores, overlapped with the rest of
-// the scan when the scan is pipelined); otherwise the ids are compacted in HBM and copied.
+// same as qpe_gpu_select_ids but into a caller-provided host buffer of `cap` ids (pinned memory makes
+// the copies asynchronous).  On the full-scan path the fused kernel K1f reports every finished table
+// segment through a progress word in mapped host memory and the segment's ids are copied out by the
+// copy engine while the scan of the following segments is still running.
 int qpe_gpu_select_ids_into(struct engineS *engine, struct whereClauseS *whereClause, int flags, unsigned int *ids,
                             size_t cap, size_t *n_out, qpe_scan_stats *stats) {
     std::lock_guard<std::mutex> lk(g_api_mutex);
@@ -537,16 +537,22 @@ int qpe_gpu_select_ids_into(struct engineS *engine, struct whereClauseS *whereCl
     const double t0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     uint64_t m = 0;
     cudaSetDevice(g->device);
-    unsigned int *alias = (ids && cap) ? device_alias_of_host(ids) : nullptr;
+    // K1 then K1c (pipeline setting 1) with a pinned destination: K1c stores straight into `ids`
+    unsigned int *alias = (ids && cap && g->pipe_segments == 1) ? device_alias_of_host(ids) : nullptr;
     if (alias) {
         g->out_override = alias;
         g->out_override_cap = cap;
         g->id_base_override = 0;
+    } else {
+        g->host_out = ids;   // fused scan: finished table segments are copied out during the scan
+        g->host_out_cap = cap;
     }
     const bool ok = engine_match(g, whereClause, (flags & QPE_SCAN_FORCE) != 0, false, false, false, &m);
-    const bool direct = alias && g->last.path == 0 && g->last.tile_rows > 0;  // K1c wrote into `ids`
+    const bool direct = (alias && g->last.path == 0 && g->last.tile_rows > 0) || g->host_out_done;
     g->out_override = nullptr;
     g->out_override_cap = 0;
+    g->host_out = nullptr;
+    g->host_out_cap = 0;
     if (!ok) return -2;
     if (n_out) *n_out = static_cast<size_t>(m);
     if (m > cap) {
@@ -911,7 +917,7 @@ int qpe_gpu_set_pipeline(struct engineS *engine, int segments) {
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     if (segments < 0 || segments > kMaxPipeSegments) {
-        set_error("pipeline segments must be 0 (automatic) .. 16");
+        set_error("pipeline setting must be 0 (fused K1f), 1 (K1 then K1c) or 2..16 (pipelined table segments)");
         return -5;
     }
     g->pipe_segments = segments;

@@ -37,9 +37,6 @@ bool cuda_ok(cudaError_t e, const char *what) {
     return false;
 }
 
-// automatic pipelining: one segment per this many 64 Ki-row chunks (32 Mi rows), at most 8
-constexpr int64_t kAutoSegmentChunks = 512;
-
 static double now_ms() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
@@ -112,6 +109,13 @@ GpuEngine *engine_create(const char *tableName, const char *datafile, int index_
     for (int i = 0; ok && i < kMaxPipeSegments; ++i)
         ok = cuda_ok(cudaEventCreateWithFlags(&g->ev_seg[i], cudaEventDisableTiming), "cudaEventCreate");
     if (const char *e = std::getenv("QPE_PIPE_SEGMENTS")) g->pipe_segments = std::atoi(e);
+    ok = ok && cuda_ok(cudaHostAlloc(&g->h_progress, sizeof(unsigned long long) * kMaxProgressSegments,
+                                     cudaHostAllocMapped),
+                       "cudaHostAlloc progress");
+    if (ok) {
+        std::memset(g->h_progress, 0, sizeof(unsigned long long) * kMaxProgressSegments);
+        ok = cuda_ok(cudaHostGetDevicePointer(&g->d_progress, g->h_progress, 0), "cudaHostGetDevicePointer");
+    }
     ok = ok && cuda_ok(cudaEventCreate(&g->ev0), "cudaEventCreate");
     ok = ok && cuda_ok(cudaEventCreate(&g->ev1), "cudaEventCreate");
     ok = ok && cuda_ok(cudaEventCreate(&g->ev_mid), "cudaEventCreate");
@@ -148,6 +152,7 @@ void engine_destroy(GpuEngine *g) {
     for (auto &ix : g->idx) index_free(&ix);
     if (g->d_ctl) cudaFree(g->d_ctl);
     if (g->h_ctl) cudaFreeHost(g->h_ctl);
+    if (g->h_progress) cudaFreeHost(g->h_progress);
     if (g->d_tile_desc) cudaFree(g->d_tile_desc);
     if (g->d_ids) cudaFree(g->d_ids);
     if (g->d_bitmap) cudaFree(g->d_bitmap);
@@ -391,6 +396,8 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     hc->tile_counter = 0;
     hc->chunk_counter = 0;
     hc->out_count = 0;
+    std::memset(hc->seg_stored, 0, sizeof(hc->seg_stored));
+    g->host_out_done = false;
 
     // ---- path rule of the reference ----
     SegmentPlan segs[kMaxSegments];
@@ -423,12 +430,84 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
         // and stores its ids -- possibly straight into pinned host memory or a peer GPU -- so the
         // ordered output leaves the GPU during the scan instead of after it.  K1 then runs with at
         // most 3 stages so that a K1c CTA (33 KB of shared memory) fits beside it on every SM.
+        // Default for a SELECT's id list: K1f, scan + ordered compaction fused in one launch.
+        bool fused_done = false;
+        if (staged && !count_only && !want_bitmap && t.n > 0 && g->pipe_segments == 0) {
+            ScanGeometry fg{};
+            const char *fwhy = nullptr;
+            if (scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, 4, &fg, &fwhy, true)) {
+                if (!ensure_desc(g, fg.n_chunks)) return false;
+                if (!g->out_override && !engine_ensure_ids(g, t.n)) return false;
+                FusedLaunch F{};
+                F.scan.table = &t;
+                F.scan.d_ctl = g->d_ctl;
+                F.scan.h_prog = &hc->prog;
+                F.scan.out_bitmap = nullptr;
+                F.desc = g->d_tile_desc;
+                F.epoch = next_epoch(g);
+                F.id_base = g->out_override ? g->id_base_override : 0u;
+                F.out_ids = g->out_override ? g->out_override : g->d_ids;
+                F.out_cap = g->out_override ? g->out_override_cap : static_cast<unsigned long long>(g->ids_cap);
+                // progress segments only when the ids are wanted on the host: ~16 Mi rows each, at most 16
+                int n_prog = 0;
+                if (g->host_out && !g->out_override) {
+                    n_prog = static_cast<int>(t.n / (16ll << 20));
+                    if (n_prog > kMaxProgressSegments) n_prog = kMaxProgressSegments;
+                    if (n_prog < 1) n_prog = 1;
+                    if (n_prog > fg.n_chunks) n_prog = static_cast<int>(fg.n_chunks);
+                    F.seg_chunks = (fg.n_chunks + n_prog - 1) / n_prog;
+                    n_prog = static_cast<int>((fg.n_chunks + F.seg_chunks - 1) / F.seg_chunks);
+                    F.progress = g->d_progress;
+                }
+                cudaEventRecord(g->ev0, g->stream);
+                if (!cuda_ok(fused_launch(F, fg, g->stream), "fused scan kernel launch")) return false;
+                cudaEventRecord(g->ev_mid, g->stream);
+                cudaEventRecord(g->ev1, g->stream);
+                st.launches = 1;
+                st.tile_rows = fg.tile_rows;
+                st.stages = fg.stages;
+                st.grid = fg.grid;
+                if (n_prog > 0) {
+                    // copy each finished table segment's ids to the host while the scan goes on
+                    volatile unsigned long long *hp = g->h_progress;
+                    uint64_t prev = 0;
+                    bool kernel_over = false;
+                    for (int sgi = 0; sgi < n_prog; ++sgi) {
+                        uint32_t spins = 0;
+                        while ((hp[sgi] >> 32) != F.epoch) {
+                            if (kernel_over) {
+                                set_error("fused scan finished without publishing its progress");
+                                return false;
+                            }
+                            if ((++spins & 0x3ffu) == 0) {
+                                const cudaError_t q = cudaStreamQuery(g->stream);
+                                if (q == cudaSuccess)
+                                    kernel_over = true;  // one more look at the word, then give up
+                                else if (q != cudaErrorNotReady)
+                                    return cuda_ok(q, "fused scan kernel");
+                            }
+                        }
+                        uint64_t cum = hp[sgi] & 0xffffffffull;
+                        if (cum > g->host_out_cap) cum = g->host_out_cap;  // the caller reports the overflow
+                        if (cum > prev) {
+                            if (!cuda_ok(cudaMemcpyAsync(g->host_out + prev, g->d_ids + prev, (cum - prev) * 4,
+                                                         cudaMemcpyDeviceToHost, g->stream2),
+                                         "download ids"))
+                                return false;
+                            prev = cum;
+                        }
+                    }
+                    cudaEventRecord(g->ev_seg[0], g->stream2);
+                    cudaStreamWaitEvent(g->stream, g->ev_seg[0], 0);
+                    g->host_out_done = true;
+                }
+                fused_done = true;
+            }
+        }
         int P = 1;
-        if (staged && !count_only && !want_bitmap && t.n > 0) {
+        if (staged && !fused_done && !count_only && !want_bitmap && t.n > 0) {
             const int64_t chunks = compact_chunks(geo.n_tiles * (geo.tile_rows / 32));
-            P = g->pipe_segments > 0 ? g->pipe_segments : static_cast<int>(chunks / kAutoSegmentChunks);
-            if (P > kMaxPipeSegments) P = kMaxPipeSegments;
-            if (g->pipe_segments <= 0 && P > 8) P = 8;
+            P = g->pipe_segments;
             if (P > chunks) P = static_cast<int>(chunks);
             if (P < 1) P = 1;
             if (P > 1 && !g->force_stages && geo.stages > 3) {
@@ -436,7 +515,9 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
                 if (scan_plan(t, hc->prog, geo.tile_rows, 0, 3, &g3, &why)) geo = g3;
             }
         }
-        if (staged) {
+        if (fused_done) {
+            g->last_bm_words = 0;
+        } else if (staged) {
             const int64_t bm_words = geo.n_tiles * (geo.tile_rows / 32);
             const int64_t n_chunks = compact_chunks(bm_words);
             if (!count_only || want_bitmap) {

@@ -25,7 +25,16 @@ struct GpuEngine {
     cudaStream_t stream2 = nullptr;  // K1c of a pipelined scan (lowest priority: fills the SMs beside K1)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     cudaEvent_t ev_seg[kMaxPipeSegments] = {nullptr};  // K1 of segment i done -> K1c of segment i may start
-    int pipe_segments = 0;           // 0 = automatic, 1 = never pipeline, else the segment count to use
+    int pipe_segments = 0;           // 0 = fused K1f (default), 1 = K1 then K1c, n >= 2 = n pipelined table segments
+    // K1f progress words (mapped pinned host memory): the kernel publishes "ids of table segment s are
+    // complete in HBM" so the host can copy that segment out while the scan is still running
+    unsigned long long *h_progress = nullptr;
+    unsigned long long *d_progress = nullptr;  // device alias of h_progress
+    // host destination for the ids of the next full-scan match (qpe_gpu_select_ids_into): copied segment
+    // by segment on stream2 during the scan
+    uint32_t *host_out = nullptr;
+    uint64_t host_out_cap = 0;
+    bool host_out_done = false;      // the match phase delivered the ids to host_out
 
     DevTable table;
     std::vector<DevIndex> idx;  // parallel to head.indexed_attributes

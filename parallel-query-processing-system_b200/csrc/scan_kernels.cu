@@ -61,9 +61,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Every spin in this file is bounded: a protocol bug (or a peer that never arrives) ends in a trapped
+// kernel and a CUDA error on the host, never in a hung GPU.  2^31 polls are minutes of waiting.
+constexpr uint32_t kSpinLimit = 0x7fffffffu;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins == kSpinLimit) __trap();
     }
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -336,8 +344,10 @@ __device__ __forceinline__ uint32_t warp_lookback(const unsigned long long *desc
         if (mine >= 0) {
             unsigned long long d = ld_desc(desc + mine);
             uint32_t flag = static_cast<uint32_t>(d >> 32);
+            uint32_t spins = 0;
             while ((flag >> 2) != epoch) {
                 __nanosleep(64);  // predecessor not published yet: back off instead of hammering L2
+                if (++spins == (kSpinLimit >> 6)) __trap();
                 d = ld_desc(desc + mine);
                 flag = static_cast<uint32_t>(d >> 32);
             }
@@ -469,8 +479,311 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_tma_kernel(const __grid
     if (tid == 0 && sh->cta_count) atomicAdd(&p.ctl->out_count, sh->cta_count);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K1f: fused scan + ordered compaction (one launch, ids leave the SM while the scan is running)
+//
+// Same producer / evaluator roles as K1, plus kFuseCompactWarps COMPACTION warps per CTA.  Work is
+// handed out in CHUNKS of chunk_tiles consecutive tiles (<= 64 Ki rows), chunk c to CTA c % grid, in
+// increasing order.  The evaluators leave the chunk's match bitmap in shared memory (double
+// buffered); the compaction warps popc/scan it, publish the chunk aggregate, run the DECOUPLED
+// LOOK-BACK over the chunk descriptors of the other CTAs (all resident: grid <= SM count, every
+// CTA walks its chunks in increasing order, so the smallest unfinished chunk never waits), expand
+// the bits into row ids in shared memory and store them coalesced at out_ids + prefix -- while the
+// evaluators are already two chunks ahead.  Compared with K1 -> K1c: no second launch, no bitmap
+// round trip through HBM, no barrier-bound compaction pass after the scan (K1c: 7.5 % of a step).
+// The look-back granularity stays one descriptor per chunk (a per-tile chain cannot keep up with
+// HBM), but the chain now advances beside the scan instead of after it.
+// Optional progress words in pinned host memory tell the host when a table segment's ids are
+// complete in HBM, so it can start the device->host copy of that segment during the scan.
+// ------------------------------------------------------------------------------------------
+constexpr int kFuseCompactWarps = 4;
+constexpr int kFuseCompactThreads = 32 * kFuseCompactWarps;          // 128
+constexpr int kFuseChunkWords = kFuseMaxChunkRows / 32;              // 2048 words
+constexpr int kFuseRounds = kFuseChunkWords / kFuseCompactThreads;   // 16 words per compaction thread
+constexpr int kFuseStageIds = 32 * kFuseCompactThreads;              // 4096: a round never holds more ids
+static_assert(kFuseReserveBytes == 2 * kFuseChunkWords * 4 + kFuseStageIds * 4, "smem reserve");
+
+struct FusedParams {
+    ScanParams s;
+    int32_t chunk_tiles;            // tiles per chunk; chunk_tiles * tile_rows <= kFuseMaxChunkRows
+    int32_t pad;
+    long long n_chunks;
+    unsigned long long *desc;       // one look-back descriptor per chunk
+    uint32_t epoch;
+    uint32_t id_base;
+    uint32_t *out_ids;              // HBM of this GPU, a peer mapping, or mapped pinned host memory
+    unsigned long long out_cap;
+    long long seg_chunks;           // progress: chunks per table segment (0 = no progress words)
+    unsigned long long *progress;   // mapped pinned host memory: [seg] = epoch << 32 | ids complete through seg
+};
+
+struct FusedSmemHeader {
+    Program prog;
+    alignas(8) uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    uint64_t cb_full[2];
+    uint64_t cb_empty[2];
+    long long tile_of_stage[kMaxStages];
+    unsigned long long cta_count;
+    uint32_t warp_tot[kFuseRounds][kFuseCompactWarps];
+    uint32_t round_base[kFuseRounds + 1];
+    uint32_t excl;
+};
+
+template <int EW, int R>
+__global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
+    scan_fused_kernel(const __grid_constant__ FusedParams fp) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const ScanParams &p = fp.s;
+    FusedSmemHeader *sh = reinterpret_cast<FusedSmemHeader *>(smem_raw);
+    uint8_t *stages = smem_raw + ((sizeof(FusedSmemHeader) + 127) & ~size_t(127));
+    const int S = p.n_stages;
+    uint32_t *cbuf = reinterpret_cast<uint32_t *>(stages + static_cast<size_t>(S) * p.stage_bytes);  // [2][2048]
+    uint32_t *id_stage = cbuf + 2 * kFuseChunkWords;                                                    // [4096]
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5;
+    const uint32_t lane = tid & 31u;
+    constexpr int T = 32 * EW * R;   // rows per tile
+    constexpr int WPT = T >> 5;      // bitmap words per tile
+    constexpr uint32_t kThreads = 32 * (1 + EW + kFuseCompactWarps);
+    const int CT = fp.chunk_tiles;
+
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(&p.ctl->prog);
+        uint4 *dst = reinterpret_cast<uint4 *>(&sh->prog);
+        for (uint32_t i = tid; i < sizeof(Program) / 16; i += kThreads) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&sh->full[s], 1);
+            mbar_init(&sh->empty[s], EW);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&sh->cb_full[b], EW);
+            mbar_init(&sh->cb_empty[b], 1);
+        }
+        sh->cta_count = 0;
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const Program *sp = &sh->prog;
+
+    if (warp == 0) {
+        // ===== P: TMA producer, tiles of this CTA's chunks in order =====
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            for (long long chunk = blockIdx.x;; chunk += gridDim.x) {
+                const bool done = chunk >= fp.n_chunks;
+                const long long t0 = chunk * CT;
+                const int nt = done ? 1 : static_cast<int>((p.n_tiles - t0 < CT) ? (p.n_tiles - t0) : CT);
+                for (int j = 0; j < nt; ++j) {
+                    mbar_wait(&sh->empty[s], phase ^ 1u);
+                    if (done) {
+                        sh->tile_of_stage[s] = -1;
+                        mbar_arrive(&sh->full[s]);
+                    } else {
+                        const long long tile = t0 + j;
+                        sh->tile_of_stage[s] = tile;
+                        mbar_arrive_expect_tx(&sh->full[s], p.stage_bytes);
+                        uint8_t *dst = stages + static_cast<size_t>(s) * p.stage_bytes;
+                        for (int r = 0; r < p.n_ref; ++r) {
+                            const int c = p.ref_col[r];
+                            const uint32_t w = p.width[c];
+                            tma_bulk_g2s(dst + p.smem_off[c], p.col[c] + static_cast<size_t>(tile) * T * w,
+                                         static_cast<uint32_t>(T) * w, &sh->full[s]);
+                        }
+                    }
+                    if (++s == S) {
+                        s = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if (done) break;
+            }
+        }
+    } else if (warp <= EW) {
+        // ===== E: predicate evaluation, bitmap words into the chunk buffer =====
+        const int ew = static_cast<int>(warp) - 1;
+        constexpr uint32_t all_mask = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
+        const int lrow = ew * (32 * R) + static_cast<int>(lane);
+        int s = 0;
+        uint32_t sphase = 0;
+        uint32_t my_count = 0;
+        uint32_t k = 0;  // k-th chunk of this CTA
+        for (long long chunk = blockIdx.x; chunk < fp.n_chunks; chunk += gridDim.x, ++k) {
+            const uint32_t buf = k & 1u;
+            // the compaction warps must have read this buffer's previous chunk (k - 2)
+            mbar_wait(&sh->cb_empty[buf], ((k >> 1) & 1u) ^ 1u);
+            uint32_t *cb = cbuf + buf * kFuseChunkWords;
+            const long long t0 = chunk * CT;
+            const int nt = static_cast<int>((p.n_tiles - t0 < CT) ? (p.n_tiles - t0) : CT);
+            for (int j = 0; j < nt; ++j) {
+                mbar_wait(&sh->full[s], sphase);
+                const long long tile = t0 + j;
+                const uint8_t *stage = stages + static_cast<size_t>(s) * p.stage_bytes;
+                uint32_t acc = run_program(sp, all_mask, [&](const PLeaf &lf) {
+                    return eval_leaf_tile<R>(lf, sp, stage, p, lrow);
+                });
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh->empty[s]);
+
+                const long long row_base = tile * T + lrow;
+                if (tile * T + T > p.n_rows)
+                    acc &= rows_mask<R>([&](int jj) { return row_base + 32ll * jj < p.n_rows; });
+                my_count += static_cast<uint32_t>(__popc(acc));
+                uint32_t myword = 0;
+#pragma unroll
+                for (int jj = 0; jj < R; ++jj) {
+                    const uint32_t bal = __ballot_sync(0xffffffffu, (acc >> jj) & 1u);
+                    if (static_cast<int>(lane) == jj) myword = bal;
+                }
+                if (static_cast<int>(lane) < R) {
+                    cb[j * WPT + ew * R + lane] = myword;
+                    if (p.out_bitmap) p.out_bitmap[tile * WPT + ew * R + lane] = myword;
+                }
+                if (++s == S) {
+                    s = 0;
+                    sphase ^= 1u;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh->cb_full[buf]);  // release: this warp's words of the chunk are in cb
+        }
+        // consume the producer's end marker so that every barrier phase is balanced
+        mbar_wait(&sh->full[s], sphase);
+        const uint32_t warp_total = __reduce_add_sync(0xffffffffu, my_count);
+        if (lane == 0) atomicAdd(&sh->cta_count, static_cast<unsigned long long>(warp_total));
+    } else {
+        // ===== C: ordered compaction of finished chunks =====
+        const uint32_t ct = tid - 32u * (1 + EW);
+        const uint32_t cw = ct >> 5;
+        const uint32_t chunk_rows = static_cast<uint32_t>(CT) * T;
+        uint32_t k = 0;
+        for (long long chunk = blockIdx.x; chunk < fp.n_chunks; chunk += gridDim.x, ++k) {
+            const uint32_t buf = k & 1u;
+            const long long t0 = chunk * CT;
+            const int nt = static_cast<int>((p.n_tiles - t0 < CT) ? (p.n_tiles - t0) : CT);
+            const uint32_t nw = static_cast<uint32_t>(nt) * WPT;
+            mbar_wait(&sh->cb_full[buf], (k >> 1) & 1u);
+            const uint32_t *cb = cbuf + buf * kFuseChunkWords;
+            // 1. words -> registers, popc, warp-inclusive scan per round
+            uint32_t word[kFuseRounds], off[kFuseRounds];
+#pragma unroll
+            for (int r = 0; r < kFuseRounds; ++r) {
+                const uint32_t wi = r * kFuseCompactThreads + ct;
+                word[r] = wi < nw ? cb[wi] : 0u;
+                const uint32_t pc = __popc(word[r]);
+                uint32_t inc = pc;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= static_cast<uint32_t>(d)) inc += t;
+                }
+                off[r] = inc - pc;
+                if (lane == 31) sh->warp_tot[r][cw] = inc;
+            }
+            named_bar_sync(1, kFuseCompactThreads);
+            if (ct == 0) mbar_arrive(&sh->cb_empty[buf]);  // the evaluators may refill this buffer
+            // 2. round bases, chunk aggregate, look-back
+            if (cw == 0) {
+                uint32_t rt = 0;
+                if (lane < kFuseRounds) {
+#pragma unroll
+                    for (int w = 0; w < kFuseCompactWarps; ++w) rt += sh->warp_tot[lane][w];
+                }
+                uint32_t inc = rt;
+#pragma unroll
+                for (int d = 1; d < kFuseRounds; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= static_cast<uint32_t>(d)) inc += t;
+                }
+                if (lane < kFuseRounds) sh->round_base[lane] = inc - rt;
+                const uint32_t total = __shfl_sync(0xffffffffu, inc, kFuseRounds - 1);
+                if (lane == 0) {
+                    sh->round_base[kFuseRounds] = total;
+                    st_desc(fp.desc + chunk, make_desc(fp.epoch, chunk == 0 ? kStatePrefix : kStateAgg, total));
+                }
+                const uint32_t excl = warp_lookback(fp.desc, chunk, fp.epoch, lane);
+                if (lane == 0) {
+                    st_desc(fp.desc + chunk, make_desc(fp.epoch, kStatePrefix, excl + total));
+                    sh->excl = excl;
+                }
+            }
+            named_bar_sync(1, kFuseCompactThreads);
+            const uint32_t total = sh->round_base[kFuseRounds];
+            const uint32_t excl = sh->excl;
+            // 3. expand the bits into row ids, staged in shared memory, coalesced stores
+            if (total != 0 && static_cast<unsigned long long>(excl) + total <= fp.out_cap) {
+                uint32_t *out = fp.out_ids + excl;
+                const uint32_t row_chunk = static_cast<uint32_t>(chunk) * chunk_rows + fp.id_base;
+                if (total <= kFuseStageIds) {
+#pragma unroll
+                    for (int r = 0; r < kFuseRounds; ++r) {
+                        uint32_t w = word[r];
+                        if (w) {
+                            uint32_t o = sh->round_base[r] + off[r];
+                            for (uint32_t q = 0; q < cw; ++q) o += sh->warp_tot[r][q];
+                            const uint32_t row0 = row_chunk + (r * kFuseCompactThreads + ct) * 32u;
+                            while (w) {
+                                const int b = __ffs(w) - 1;
+                                w &= w - 1;
+                                id_stage[o++] = row0 + static_cast<uint32_t>(b);
+                            }
+                        }
+                    }
+                    named_bar_sync(1, kFuseCompactThreads);
+                    for (uint32_t i = ct; i < total; i += kFuseCompactThreads) out[i] = id_stage[i];
+                } else {
+                    // dense chunk: a round (128 words, <= 4096 ids) at a time through the stage.  (Expanding
+                    // word by word with lane-parallel direct stores was measured slower: 2.4 x the
+                    // instructions, and they compete with the evaluators for issue slots.)
+#pragma unroll
+                    for (int r = 0; r < kFuseRounds; ++r) {
+                        const uint32_t base = sh->round_base[r];
+                        const uint32_t cnt = sh->round_base[r + 1] - base;
+                        if (cnt == 0) continue;  // uniform over the compaction warps
+                        uint32_t w = word[r];
+                        uint32_t o = off[r];
+                        for (uint32_t q = 0; q < cw; ++q) o += sh->warp_tot[r][q];
+                        const uint32_t row0 = row_chunk + (r * kFuseCompactThreads + ct) * 32u;
+                        while (w) {
+                            const int b = __ffs(w) - 1;
+                            w &= w - 1;
+                            id_stage[o++] = row0 + static_cast<uint32_t>(b);
+                        }
+                        named_bar_sync(1, kFuseCompactThreads);
+                        for (uint32_t i = ct; i < cnt; i += kFuseCompactThreads) out[base + i] = id_stage[i];
+                        named_bar_sync(1, kFuseCompactThreads);
+                    }
+                }
+            }
+            named_bar_sync(1, kFuseCompactThreads);  // stage / scan scratch are free again; this chunk's stores are issued
+            // 4. progress: the last chunk of a table segment to finish publishes the segment to the host
+            if (fp.seg_chunks > 0 && ct == 0) {
+                __threadfence();
+                const long long seg = chunk / fp.seg_chunks;
+                const long long first = seg * fp.seg_chunks;
+                const long long last = (first + fp.seg_chunks < fp.n_chunks ? first + fp.seg_chunks : fp.n_chunks) - 1;
+                const unsigned int stored = atomicAdd(&p.ctl->seg_stored[seg], 1u) + 1u;
+                if (stored == static_cast<unsigned int>(last - first + 1)) {
+                    __threadfence();
+                    const unsigned long long d = ld_desc(fp.desc + last);  // PREFIX: that chunk has finished
+                    __threadfence_system();
+                    *reinterpret_cast<volatile unsigned long long *>(fp.progress + seg) =
+                        (static_cast<unsigned long long>(fp.epoch) << 32) | static_cast<uint32_t>(d);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && sh->cta_count) atomicAdd(&p.ctl->out_count, sh->cta_count);
+}
+
 bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages, int max_stages,
-               ScanGeometry *geo, const char **why) {
+               ScanGeometry *geo, const char **why, bool fused) {
     if (max_stages < 1 || max_stages > 4) max_stages = 4;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -489,8 +802,8 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
             }
             bpr += t.col[c].width;
         }
-    const size_t header = (sizeof(ScanSmemHeader) + 127) & ~size_t(127);
-    const size_t budget = static_cast<size_t>(max_smem) - header - 256;
+    const size_t header = ((fused ? sizeof(FusedSmemHeader) : sizeof(ScanSmemHeader)) + 127) & ~size_t(127);
+    const size_t budget = static_cast<size_t>(max_smem) - header - 256 - (fused ? kFuseReserveBytes : 0);
 
     auto stage_bytes_for = [&](int T) {
         size_t sb = 0;
@@ -543,10 +856,36 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
     geo->stages = S;
     geo->n_tiles = (t.n + T - 1) / T;
     geo->bytes_per_row = bpr;
-    geo->smem_bytes = header + stage_bytes * S + 128;
+    geo->smem_bytes = header + stage_bytes * S + 128 + (fused ? kFuseReserveBytes : 0);
     int64_t grid = geo->n_tiles < n_sm ? geo->n_tiles : n_sm;
     if (grid < 1) grid = 1;
     geo->grid = static_cast<int>(grid);
+    geo->chunk_tiles = 0;
+    geo->n_chunks = 0;
+    if (fused) {
+        // chunk = the largest power-of-two run of tiles (<= 64 Ki rows) whose last, partly filled round of
+        // CTAs costs < 3 %; halving stops at 8 Ki rows (shorter chunks publish descriptors faster than
+        // a look-back window can follow at HBM speed)
+        int ct = kFuseMaxChunkRows / T;
+        int best_ct = ct;
+        double best_loss = 1e9;
+        for (; ct >= 1 && static_cast<long long>(ct) * T >= 8192; ct >>= 1) {
+            const int64_t nc = (geo->n_tiles + ct - 1) / ct;
+            const int64_t g = nc < n_sm ? nc : n_sm;
+            const int64_t rounds = (nc + g - 1) / (g > 0 ? g : 1);
+            const double loss = nc > 0 ? static_cast<double>(rounds * g) / static_cast<double>(nc) - 1.0 : 0.0;
+            if (loss < best_loss - 1e-9) {
+                best_loss = loss;
+                best_ct = ct;
+            }
+            if (loss < 0.03) break;
+        }
+        geo->chunk_tiles = best_ct;
+        geo->n_chunks = (geo->n_tiles + best_ct - 1) / best_ct;
+        int64_t g = geo->n_chunks < n_sm ? geo->n_chunks : n_sm;
+        if (g < 1) g = 1;
+        geo->grid = static_cast<int>(g);
+    }
     return true;
 }
 
@@ -562,8 +901,7 @@ static cudaError_t launch_scan_r(const ScanParams &p, const ScanGeometry &geo, c
     return cudaGetLastError();
 }
 
-cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream_t stream) {
-    ScanParams p{};
+static cudaError_t fill_scan_params(const ScanLaunch &L, const ScanGeometry &geo, ScanParams &p) {
     const DevTable &t = *L.table;
     size_t off = 0;
     p.n_ref = 0;
@@ -598,12 +936,55 @@ cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream
     if (p.tile_begin != 0 || p.n_tiles != geo.n_tiles) p.dynamic_tiles = 0;  // segments use the static walk
     p.ctl = const_cast<QueryCtl *>(L.d_ctl);
     p.out_bitmap = L.out_bitmap;
+    return cudaSuccess;
+}
+
+cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream_t stream) {
+    ScanParams p{};
+    const cudaError_t e = fill_scan_params(L, geo, p);
+    if (e != cudaSuccess) return e;
     switch (geo.tile_rows) {
         case 256: return launch_scan_r<kEvalWarpsWide, 1>(p, geo, stream);
         case 512: return launch_scan_r<kEvalWarps, 1>(p, geo, stream);
         case 1024: return launch_scan_r<kEvalWarps, 2>(p, geo, stream);
         case 2048: return launch_scan_r<kEvalWarps, 4>(p, geo, stream);
         case 4096: return launch_scan_r<kEvalWarps, 8>(p, geo, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int EW, int R>
+static cudaError_t launch_fused_r(const FusedParams &fp, const ScanGeometry &geo, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(scan_fused_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(geo.smem_bytes));
+    if (e != cudaSuccess) return e;
+    scan_fused_kernel<EW, R><<<geo.grid, 32 * (1 + EW + kFuseCompactWarps), geo.smem_bytes, stream>>>(fp);
+    return cudaGetLastError();
+}
+
+cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStream_t stream) {
+    FusedParams fp{};
+    const cudaError_t e = fill_scan_params(L.scan, geo, fp.s);
+    if (e != cudaSuccess) return e;
+    if (geo.chunk_tiles < 1 || static_cast<long long>(geo.chunk_tiles) * geo.tile_rows > kFuseMaxChunkRows)
+        return cudaErrorInvalidValue;
+    fp.s.dynamic_tiles = 0;
+    fp.chunk_tiles = geo.chunk_tiles;
+    fp.n_chunks = geo.n_chunks;
+    fp.desc = L.desc;
+    fp.epoch = L.epoch;
+    fp.id_base = L.id_base;
+    fp.out_ids = L.out_ids;
+    fp.out_cap = L.out_cap;
+    fp.seg_chunks = L.progress ? L.seg_chunks : 0;
+    fp.progress = L.progress;
+    if (fp.n_chunks == 0) return cudaSuccess;
+    switch (geo.tile_rows) {
+        case 256: return launch_fused_r<kEvalWarpsWide, 1>(fp, geo, stream);
+        case 512: return launch_fused_r<kEvalWarps, 1>(fp, geo, stream);
+        case 1024: return launch_fused_r<kEvalWarps, 2>(fp, geo, stream);
+        case 2048: return launch_fused_r<kEvalWarps, 4>(fp, geo, stream);
+        case 4096: return launch_fused_r<kEvalWarps, 8>(fp, geo, stream);
         default: return cudaErrorInvalidValue;
     }
 }

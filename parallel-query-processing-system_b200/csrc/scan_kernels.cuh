@@ -6,6 +6,8 @@
 
 namespace qpe {
 
+constexpr int kMaxProgressSegments = 16;
+
 // Device-resident control block of one query: the compiled predicate plus the words the
 // kernels need zeroed at launch.  Uploaded with ONE cudaMemcpyAsync per query.
 struct QueryCtl {
@@ -13,7 +15,13 @@ struct QueryCtl {
     unsigned int tile_counter;      // dynamic tile claim (K1, K1g)
     unsigned int chunk_counter;     // ordered chunk claim (K1c)
     unsigned long long out_count;   // total matches (written by the kernel)
+    unsigned int seg_stored[kMaxProgressSegments];  // K1f: chunks of table segment s whose ids are stored
 };
+
+// K1f (fused scan + compaction): chunk = consecutive tiles, at most this many rows; the kernel keeps
+// two chunk bitmaps and one id stage in shared memory beside the TMA stages
+constexpr int kFuseMaxChunkRows = 65536;
+constexpr int kFuseReserveBytes = 2 * (kFuseMaxChunkRows / 32) * 4 + 4096 * 4;
 
 struct ScanLaunch {
     const DevTable *table;
@@ -33,14 +41,32 @@ struct ScanGeometry {
     size_t smem_bytes;
     int64_t n_tiles;
     int64_t bytes_per_row;
+    int chunk_tiles;      // K1f only
+    int64_t n_chunks;     // K1f only
 };
 
 // K1: TMA-staged predicate evaluation over the whole table -> match bitmap + count (ctl->out_count).
 // Returns false (and sets *why) if the query cannot be staged (row too wide for shared memory):
 // the caller then uses the gather path below with an identity candidate list.
 // max_stages (1..4) caps the pipeline depth: 3 leaves room for a K1c CTA beside K1's on every SM.
+// fused: plan for K1f (larger header, kFuseReserveBytes of shared memory set aside; geo->chunk_tiles and
+// geo->n_chunks are filled in).
 bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages, int max_stages,
-               ScanGeometry *geo, const char **why);
+               ScanGeometry *geo, const char **why, bool fused = false);
+
+// K1f: scan + ordered compaction in one launch.  desc needs geo.n_chunks descriptors; progress (may be
+// null) points to mapped pinned host memory with one word per table segment of seg_chunks chunks.
+struct FusedLaunch {
+    ScanLaunch scan;
+    unsigned long long *desc;
+    uint32_t epoch;
+    uint32_t id_base;
+    uint32_t *out_ids;
+    unsigned long long out_cap;
+    long long seg_chunks;
+    unsigned long long *progress;
+};
+cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStream_t stream);
 cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream_t stream);
 
 // K1c: order-preserving compaction of a match bitmap (bit b of word w = row 32 w + b) into row
