@@ -77,9 +77,11 @@ def parse_args():
     ap.add_argument("--selectivity", type=float, default=0.01)
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: 'peer' = K1c stores the ids straight into rank 0's buffer over NVLink (CUDA IPC "
-                         "mapping); 'nccl' = compact locally, then grouped NCCL send/recv")
+    ap.add_argument("--gather", default="native", choices=["native", "peer", "nccl"],
+                    help="N > 1: 'native' = csrc/shard.cu: ids stored into rank 0's buffer by the scan kernel over "
+                         "NVLink peer memory, counts exchanged by kernel stores, no host collective per query; "
+                         "'peer' = same stores, count exchange through an NCCL all-gather; 'nccl' = compact "
+                         "locally, then grouped NCCL send/recv")
     return ap.parse_args()
 
 
@@ -310,19 +312,27 @@ def run_ours(args):
     else:
         total_matches = cnt0
     use_peer = world > 1 and args.gather == "peer"
+    use_native = world > 1 and args.gather == "native"
     if world > 1:
         seg_cap = int(max(sharding.exchange_counts(cnt0, dev)) * 1.25) + 4096
     pg = sharding.PeerGather(pkg, segment_capacity=seg_cap, counts_device=dev) if use_peer else None
+    sg = (sharding.ShardGroup(pkg, eng, segment_capacity=seg_cap, host_capacity=total_matches + 4096,
+                              counts_device=dev) if use_native else None)
     gathered = (torch.empty(max(total_matches, 1), dtype=torch.int32, device=dev)
                 if (rank == 0 and world > 1 and not use_peer) else None)
     pinned = torch.empty(max(total_matches, 1), dtype=torch.int32).pin_memory() if rank == 0 else None
     pinned_np = pinned.numpy().view(np.uint32) if rank == 0 else None
     launches = [0]
     scan_ms, compact_ms, kernel_ms = [], [], []
+    eng_stream = torch.cuda.ExternalStream(eng.stream, device=dev)
 
     def step_device(record=False, pack="device"):
         """scan + ordered compaction on every GPU, count exchange, ordered gather to rank 0 (device)"""
-        if use_peer:
+        if use_native:
+            total_n, counts, sst = sg.select(sql, to_host=(pack == "host"))
+            st = {"launches": sst.launches, "scan_ms": sst.scan_ms, "compact_ms": sst.compact_ms,
+                  "kernel_ms": sst.kernel_ms}
+        elif use_peer:
             total_n, counts, st = pg.run(eng, sql, dev, pack=pack, host_out=pinned_np)
         else:
             cnt, dptr, st = eng.select_ids_device(sql, force_scan=True, global_ids=(world > 1))
@@ -345,8 +355,9 @@ def run_ours(args):
             return n
         n = step_device(pack="host")
         if rank == 0:
-            if use_peer:
-                pass  # the owner copied every segment straight into the pinned host buffer
+            if use_peer or use_native:
+                pass  # peer: the owner copied every segment straight into the pinned host buffer;
+                      # native: every rank delivered its piece into the shared pinned buffer over its own PCIe link
             else:
                 pinned[:n].copy_(gathered[:n], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
@@ -360,11 +371,11 @@ def run_ours(args):
         if sampler:
             sampler.start()
         t0 = time.perf_counter()
-        ev0.record()
+        ev0.record(eng_stream)      # the engine launches on its own stream: time THERE
         n = 0
         for _ in range(steps):
             n = fn(**kw)
-        ev1.record()
+        ev1.record(eng_stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         clocks = sampler.stop() if sampler else None
@@ -419,7 +430,13 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"synthetic {total}-row command-log table (device generator, seed 12345), "
                                    f"row-range sharded over {world} GPU(s)"
-                                   + (f", ordered gather = {'K1c stores into rank 0 over NVLink peer memory' if use_peer else 'NCCL send/recv'}" if world > 1 else "")
+                                   + (", ordered gather = " + {"native": "scan kernel stores into rank 0 over NVLink peer memory, "
+                                                                       "counts exchanged by kernel stores (no host "
+                                                                       "collective per query)",
+                                                             "peer": "K1c stores into rank 0 over NVLink peer memory, "
+                                                                     "NCCL count all-gather",
+                                                             "nccl": "NCCL send/recv"}[args.gather]
+                                      if world > 1 else "")
                                    + f"; {args.query} full-scan SELECT/WHERE, "
                                    f"{args.selectivity:g} selectivity; inputs ({shard_rows * bpr / 1e9:.1f} GB/GPU) "
                                    f"larger than L2, no flush needed",
@@ -445,6 +462,8 @@ def run_ours(args):
         emit(json.dumps(out))
     if pg is not None:
         pg.close()
+    if sg is not None:
+        sg.close()
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -125,6 +125,33 @@ void qpe_gpu_ipc_close(void *mapped_ptr);
 int qpe_gpu_copy_to_host(void *dst_host, const void *src_device, size_t bytes);
 int qpe_gpu_copy_device(void *dst_device, const void *src_device, size_t bytes);
 
+/* ---- Row-range sharded table, one process per GPU of one box (csrc/shard.cu) ----------------------
+ * What the reference's MPI mode does with MPI_Allreduce / MPI_Allgather(v) (engine/mpi/executeEngine-mpi.c:
+ * 703-770), done by the kernels themselves over NVLink peer memory: every rank's scan stores its (global)
+ * row ids into its segment of the owner's result buffer, a one-thread-per-rank kernel stores (epoch, count)
+ * into every rank's comm block, and the owner packs the segments in partition order = table order.  No
+ * host collective and no NCCL call per query; the caller only passes the 64-byte IPC handles around once.
+ *   qpe_shard_init(engine, rank, world, handle_out)      allocate this rank's comm block, export it
+ *   qpe_shard_connect(engine, all_handles)               world x 64 bytes in rank order
+ *   qpe_shard_set_device_result(engine, owner, segments, cap)  segments = 2 x world x cap ids in the OWNER's
+ *                                                        memory (own pointer / qpe_gpu_ipc_open mapping)
+ *   qpe_shard_open_host_result(engine, name, cap, create) POSIX shared-memory id buffer all ranks write
+ *                                                        their piece into over their own PCIe link
+ *   qpe_shard_select / qpe_sql_shard_select              one full-scan SELECT; every rank calls it with the
+ *                                                        same statement in the same order */
+int qpe_shard_init(struct engineS *engine, int rank, int world, unsigned char comm_handle_out[64]);
+int qpe_shard_connect(struct engineS *engine, const unsigned char *all_handles);
+int qpe_shard_set_device_result(struct engineS *engine, int owner_rank, unsigned int *segments,
+                                unsigned long long segment_capacity);
+unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *name, unsigned long long capacity,
+                                         int create);
+const unsigned int *qpe_shard_device_result(struct engineS *engine);
+void qpe_shard_close(struct engineS *engine);
+int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, int to_host,
+                     unsigned long long *counts_out, qpe_scan_stats *stats);
+int qpe_sql_shard_select(struct engineS *engine, const char *statement, int to_host,
+                         unsigned long long *counts_out, qpe_scan_stats *stats);
+
 /* cudaMemcpy device -> host for pointers handed out by the *_device calls. 0 on success. */
 int qpe_gpu_copy_from_device(void *dst_host, const void *src_device, size_t bytes);
 
@@ -155,6 +182,10 @@ int qpe_gpu_index_slice(struct engineS *engine, const char *attribute, unsigned 
  * out == NULL to query the width only. */
 int qpe_gpu_fetch_column(struct engineS *engine, const char *attribute, long long first_row, long long n_rows,
                          void *out, unsigned int *width_out);
+
+/* The CUDA stream (cudaStream_t) every kernel of this engine is launched on, so a caller can bracket
+ * calls with its own CUDA events for device-side timing. */
+void *qpe_gpu_stream(struct engineS *engine);
 
 /* Tuning override for the scan kernel (0 = automatic). */
 int qpe_gpu_set_tile(struct engineS *engine, int tile_rows, int stages);

@@ -97,6 +97,7 @@ def load_library() -> C.CDLL:
         "qpe_gpu_fetch_column": (i, [vp, cp, ll, ll, vp, C.POINTER(C.c_uint)]),
         "qpe_gpu_set_tile": (i, [vp, i, i]),
         "qpe_gpu_set_pipeline": (i, [vp, i]),
+        "qpe_gpu_stream": (vp, [vp]),
         "qpe_gpu_copy_from_device": (i, [vp, vp, sz]),
         "qpe_gpu_last_stats": (i, [vp, pstats]),
         "qpe_gpu_write_csv": (i, [vp, cp]),
@@ -118,6 +119,13 @@ def load_library() -> C.CDLL:
         "qpe_gpu_ipc_open": (vp, [C.c_char_p]),
         "qpe_gpu_ipc_close": (None, [vp]),
         "qpe_gpu_copy_to_host": (i, [vp, vp, sz]),
+        "qpe_shard_init": (i, [vp, i, i, C.c_char_p]),
+        "qpe_shard_connect": (i, [vp, C.c_char_p]),
+        "qpe_shard_set_device_result": (i, [vp, i, vp, ull]),
+        "qpe_shard_open_host_result": (vp, [vp, cp, ull, i]),
+        "qpe_shard_device_result": (vp, [vp]),
+        "qpe_shard_close": (None, [vp]),
+        "qpe_sql_shard_select": (i, [vp, cp, i, C.POINTER(ull), pstats]),
         "qpe_sql_select": (C.POINTER(ResultSet), [vp, cp]),
         "qpe_sql_where_to_text": (vp, [cp]),
     }
@@ -257,6 +265,11 @@ class Engine:
     def set_pipeline(self, segments: int = 0):
         """0 = automatic, 1 = one K1 + one K1c launch, n = n table segments with K1c(i) beside K1(i+1)"""
         self._check(self._lib.qpe_gpu_set_pipeline(self._h, segments), "set_pipeline")
+
+    @property
+    def stream(self) -> int:
+        """cudaStream_t of the engine (all its kernels run there)"""
+        return int(self._lib.qpe_gpu_stream(self._h))
 
     def last_stats(self) -> dict:
         st = ScanStats()

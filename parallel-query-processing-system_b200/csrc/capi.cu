@@ -18,7 +18,6 @@ using namespace qpe;
 
 namespace {
 
-std::mutex g_api_mutex;  // the engine is not re-entrant (one stream, one scratch set)
 
 // results produced by this library keep their cells in one arena; freeResultSet recognises them
 struct ResultArena {
@@ -910,6 +909,11 @@ int qpe_gpu_write_csv(struct engineS *engine, const char *path) {
     }
     std::fclose(f);
     return 0;
+}
+
+void *qpe_gpu_stream(struct engineS *engine) {
+    GpuEngine *g = as_engine(engine);
+    return g ? static_cast<void *>(g->stream) : nullptr;
 }
 
 int qpe_gpu_set_pipeline(struct engineS *engine, int segments) {

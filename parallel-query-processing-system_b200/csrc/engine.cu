@@ -22,6 +22,9 @@
 
 namespace qpe {
 
+std::mutex g_api_mutex;
+
+
 // ------------------------------------------------------------------------------------------
 // errors
 // ------------------------------------------------------------------------------------------
@@ -148,6 +151,7 @@ void engine_destroy(GpuEngine *g) {
     cudaSetDevice(g->device);
     if (g->stream) cudaStreamSynchronize(g->stream);
     if (g->stream2) cudaStreamSynchronize(g->stream2);
+    shard_destroy(g);
     free_table(&g->table);
     for (auto &ix : g->idx) index_free(&ix);
     if (g->d_ctl) cudaFree(g->d_ctl);
@@ -445,7 +449,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
                 F.scan.out_bitmap = nullptr;
                 F.desc = g->d_tile_desc;
                 F.epoch = next_epoch(g);
-                F.id_base = g->out_override ? g->id_base_override : 0u;
+                F.id_base = (g->out_override || g->id_base_always) ? g->id_base_override : 0u;
                 F.out_ids = g->out_override ? g->out_override : g->d_ids;
                 F.out_cap = g->out_override ? g->out_override_cap : static_cast<unsigned long long>(g->ids_cap);
                 // progress segments only when the ids are wanted on the host: ~16 Mi rows each, at most 16
@@ -535,7 +539,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
             uint32_t *dst = g->out_override ? g->out_override : g->d_ids;
             const unsigned long long cap =
                 g->out_override ? g->out_override_cap : static_cast<unsigned long long>(g->ids_cap);
-            const uint32_t id_base = g->out_override ? g->id_base_override : 0u;
+            const uint32_t id_base = (g->out_override || g->id_base_always) ? g->id_base_override : 0u;
             cudaEventRecord(g->ev0, g->stream);
             if (P == 1) {
                 if (!cuda_ok(scan_launch(L, geo, g->stream), "scan kernel launch")) return false;
@@ -672,6 +676,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
         st.launches = launches;
     }
 
+    if (g->post_match && !g->post_match()) return false;
     if (!cuda_ok(cudaMemcpyAsync(&hc->out_count, &g->d_ctl->out_count, sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, g->stream),
                  "download count") ||

@@ -3,6 +3,8 @@
 
 #include <cuda_runtime.h>
 
+#include <functional>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -55,6 +57,11 @@ struct GpuEngine {
     uint32_t *out_override = nullptr;
     uint64_t out_override_cap = 0;
     uint32_t id_base_override = 0;
+    bool id_base_always = false;     // add id_base_override even when the ids go to d_ids (sharded host result)
+    // sharded table (shard.cu): kernels enqueued on `stream` right after the match kernels, before the
+    // single stream synchronisation of engine_match (count exchange + pack over peer memory)
+    std::function<bool()> post_match;
+    void *shard = nullptr;           // ShardState of shard.cu
     int64_t last_bm_words = 0;   // words of the bitmap the last full-scan match left in d_bitmap (0 = none)
     uint64_t last_bm_count = 0;  // its match count
     // probe scratch (device + pinned host), kMaxSegments entries each
@@ -67,6 +74,7 @@ struct GpuEngine {
     ScanStats last;
 };
 
+extern std::mutex g_api_mutex;  // the engine is not re-entrant (one stream, one scratch set)
 GpuEngine *as_engine(struct engineS *e);  // nullptr (and error set) if e is not one of ours
 void set_error(const std::string &msg);
 bool cuda_ok(cudaError_t e, const char *what);
@@ -74,6 +82,7 @@ bool cuda_ok(cudaError_t e, const char *what);
 // create an engine with an empty table; nullptr if no device
 GpuEngine *engine_create(const char *tableName, const char *datafile, int index_slots);
 void engine_destroy(GpuEngine *g);
+void shard_destroy(GpuEngine *g);  // shard.cu: releases the peer mappings / shared host buffer, if any
 int device_count();
 const char *last_error_cstr();
 bool column_alloc(DevColumn *col, uint32_t width, int64_t cap_rows, cudaStream_t stream);

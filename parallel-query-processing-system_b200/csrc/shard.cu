@@ -1,0 +1,391 @@
+// shard.cu -- a row-range sharded table: one process per GPU, full-scan SELECT with the ordered
+// gather fused into the kernels over peer memory.
+//
+// What the reference does in MPI mode (engine/mpi/executeEngine-mpi.c:703-770): block partition of
+// the rows, every rank evaluates its slice, MPI_Allreduce / MPI_Allgather of the per-rank counts,
+// MPI_Allgatherv of the per-rank pieces in partition order.  Here, per query (no host collective,
+// no NCCL call, no send/recv on the data path):
+//
+//   every rank      K1f scans its shard; the ids (already global: + first row of the shard) are
+//                   stored by the compaction warps either into the rank's segment of the OWNER's
+//                   result buffer -- peer memory mapped through CUDA IPC, so the ids cross NVLink
+//                   as the kernel's own coalesced stores, during the scan -- or into the rank's own
+//                   HBM (host result);
+//   every rank      publish_kernel: one system-scope release store of (epoch, match count) into
+//                   EVERY rank's comm block (peer stores) = the count exchange;
+//   owner           pack_kernel: waits for all counts of this epoch (acquire loads of its own comm
+//                   block), then packs the segments into one dense id list in partition order,
+//                   which is table order;
+//   host result     each rank learns the counts of the lower ranks the same way and copies its ids
+//                   over ITS OWN PCIe link to its exact offset in a host buffer shared by all ranks
+//                   (POSIX shared memory, registered with CUDA in every process).
+//
+// Slots are double buffered by epoch parity: no rank finishes query e before every rank has
+// published its count of e, so a rank is never more than one query ahead of another.
+// Every wait is bounded (trap, never a hung GPU).  NCCL / torch.distributed is only used by the
+// caller to hand the IPC handles around at start-up.
+
+#include "engine.cuh"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstring>
+#include <mutex>
+
+namespace qpe {
+
+constexpr int kMaxRanks = 16;
+
+struct ShardComm {                      // device memory of one rank, mapped by all the others
+    unsigned long long count[2][kMaxRanks];  // [epoch parity][source rank] = epoch << 32 | match count
+};
+
+struct ShardHostHeader {                // start of the shared host buffer
+    volatile unsigned long long done[kMaxRanks][8];  // [rank][0] = epoch whose ids rank has delivered (64 B apart)
+};
+
+struct ShardState {
+    int rank = 0, world = 1;
+    ShardComm *comm[kMaxRanks] = {nullptr};  // [rank] = own allocation, others = IPC mappings
+    uint32_t epoch = 0;
+    // device result: segments in the owner's memory (own pointer on the owner, IPC mapping elsewhere)
+    int owner = 0;
+    uint32_t *seg_base = nullptr;       // 2 parities x world segments x seg_cap ids
+    uint64_t seg_cap = 0;
+    uint32_t *dense = nullptr;          // owner: packed result (world * seg_cap ids)
+    // host result
+    void *host_map = nullptr;           // shared mapping: ShardHostHeader, then the ids
+    size_t host_bytes = 0;
+    uint64_t host_cap = 0;              // ids
+    char host_name[96] = {0};
+    bool host_creator = false;
+    // per-query counts as seen by this rank (mapped pinned host memory, written by wait_counts_kernel)
+    unsigned long long *h_counts = nullptr;
+    unsigned long long *d_counts = nullptr;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// wait until the slot carries `epoch`; bounded (about 20 s), then trap
+__device__ __forceinline__ unsigned long long wait_slot(const unsigned long long *slot, uint32_t epoch) {
+    unsigned long long v = ld_acquire_sys(slot);
+    uint32_t spins = 0;
+    while (static_cast<uint32_t>(v >> 32) != epoch) {
+        __nanosleep(200);
+        if (++spins == 100000000u) __trap();
+        v = ld_acquire_sys(slot);
+    }
+    return v;
+}
+
+struct PeerPtrs {
+    ShardComm *comm[kMaxRanks];
+};
+
+// the count exchange: (epoch, this rank's match count) into every rank's comm block
+__global__ void publish_kernel(const QueryCtl *ctl, PeerPtrs peers, int rank, int world, uint32_t epoch) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    const unsigned long long cnt = *reinterpret_cast<const volatile unsigned long long *>(&ctl->out_count);
+    __threadfence_system();  // this rank's id stores (peer memory included) are visible before the count is
+    st_release_sys(&peers.comm[r]->count[epoch & 1u][rank],
+                   (static_cast<unsigned long long>(epoch) << 32) | (cnt & 0xffffffffull));
+}
+
+// every rank: the counts of this epoch -> mapped host memory (the host reads them after its stream sync)
+__global__ void wait_counts_kernel(const ShardComm *mine, int world, uint32_t epoch, unsigned long long *out) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    out[r] = wait_slot(&mine->count[epoch & 1u][r], epoch) & 0xffffffffull;
+}
+
+// owner: wait for every rank's count, then pack the segments in partition order
+__global__ void __launch_bounds__(256) pack_kernel(const ShardComm *mine, int world, uint32_t epoch,
+                                                   const uint32_t *seg_base, unsigned long long seg_cap,
+                                                   uint32_t *dense) {
+    __shared__ unsigned long long s_off[kMaxRanks + 1];
+    if (threadIdx.x == 0) {
+        unsigned long long o = 0;
+        for (int r = 0; r < world; ++r) {
+            s_off[r] = o;
+            o += wait_slot(&mine->count[epoch & 1u][r], epoch) & 0xffffffffull;
+        }
+        s_off[world] = o;
+    }
+    __syncthreads();
+    const uint32_t *set = seg_base + static_cast<size_t>(epoch & 1u) * world * seg_cap;
+    for (int r = 0; r < world; ++r) {
+        const unsigned long long n = s_off[r + 1] - s_off[r];
+        if (n > seg_cap) continue;  // the host reports the overflow
+        const uint32_t *src = set + static_cast<size_t>(r) * seg_cap;
+        uint32_t *dst = dense + s_off[r];
+        for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < n;
+             i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+            dst[i] = src[i];
+    }
+}
+
+static ShardState *shard_of(GpuEngine *g) { return static_cast<ShardState *>(g->shard); }
+
+void shard_destroy(GpuEngine *g) {
+    ShardState *s = shard_of(g);
+    if (!s) return;
+    cudaSetDevice(g->device);
+    cudaStreamSynchronize(g->stream);
+    for (int r = 0; r < s->world; ++r) {
+        if (!s->comm[r]) continue;
+        if (r == s->rank)
+            cudaFree(s->comm[r]);
+        else
+            cudaIpcCloseMemHandle(s->comm[r]);
+    }
+    if (s->dense) cudaFree(s->dense);
+    if (s->h_counts) cudaFreeHost(s->h_counts);
+    if (s->host_map) {
+        cudaHostUnregister(s->host_map);
+        munmap(s->host_map, s->host_bytes);
+        if (s->host_creator) shm_unlink(s->host_name);
+    }
+    delete s;
+    g->shard = nullptr;
+}
+
+}  // namespace qpe
+
+using namespace qpe;
+
+extern "C" {
+
+int qpe_shard_init(struct engineS *engine, int rank, int world, unsigned char comm_handle_out[64]) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) {
+        set_error("qpe_shard_init: rank / world out of range (at most 16 ranks)");
+        return -5;
+    }
+    if (g->shard) shard_destroy(g);
+    cudaSetDevice(g->device);
+    ShardState *s = new ShardState();
+    s->rank = rank;
+    s->world = world;
+    bool ok = cuda_ok(cudaMalloc(&s->comm[rank], sizeof(ShardComm)), "cudaMalloc comm") &&
+              cuda_ok(cudaMemset(s->comm[rank], 0, sizeof(ShardComm)), "cudaMemset comm") &&
+              cuda_ok(cudaHostAlloc(&s->h_counts, sizeof(unsigned long long) * kMaxRanks, cudaHostAllocMapped),
+                      "cudaHostAlloc counts") &&
+              cuda_ok(cudaHostGetDevicePointer(&s->d_counts, s->h_counts, 0), "cudaHostGetDevicePointer");
+    cudaIpcMemHandle_t h;
+    ok = ok && cuda_ok(cudaIpcGetMemHandle(&h, s->comm[rank]), "cudaIpcGetMemHandle");
+    g->shard = s;
+    if (!ok) {
+        shard_destroy(g);
+        return -4;
+    }
+    std::memcpy(comm_handle_out, &h, 64);
+    return 0;
+}
+
+/* all_handles: world x 64 bytes, in rank order (what every rank's qpe_shard_init returned) */
+int qpe_shard_connect(struct engineS *engine, const unsigned char *all_handles) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    if (!s) {
+        set_error("qpe_shard_connect: call qpe_shard_init first");
+        return -1;
+    }
+    cudaSetDevice(g->device);
+    for (int r = 0; r < s->world; ++r) {
+        if (r == s->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, all_handles + 64 * r, 64);
+        void *p = nullptr;
+        if (!cuda_ok(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle comm")) return -4;
+        s->comm[r] = static_cast<ShardComm *>(p);
+    }
+    return 0;
+}
+
+/* Device result: `segments` = 2 x world x segment_capacity ids in the OWNER's memory (the owner passes
+ * its own allocation, the other ranks their IPC mapping of it). */
+int qpe_shard_set_device_result(struct engineS *engine, int owner_rank, unsigned int *segments,
+                                unsigned long long segment_capacity) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    if (!s) {
+        set_error("qpe_shard_set_device_result: call qpe_shard_init first");
+        return -1;
+    }
+    cudaSetDevice(g->device);
+    s->owner = owner_rank;
+    s->seg_base = segments;
+    s->seg_cap = segment_capacity;
+    if (s->dense) cudaFree(s->dense);
+    s->dense = nullptr;
+    if (s->rank == owner_rank &&
+        !cuda_ok(cudaMalloc(&s->dense, sizeof(uint32_t) * (segment_capacity * s->world + 16)), "cudaMalloc dense"))
+        return -4;
+    return 0;
+}
+
+/* Host result: a buffer of `capacity` ids shared by all ranks of the box.  create != 0 on exactly one
+ * rank (it creates /dev/shm/<name>), the others open it afterwards.  Returns the host pointer of the
+ * id array in this process (NULL on failure). */
+unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *name, unsigned long long capacity,
+                                         int create) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    if (!s || !name || std::strlen(name) >= sizeof(s->host_name)) {
+        set_error("qpe_shard_open_host_result: call qpe_shard_init first / bad name");
+        return nullptr;
+    }
+    cudaSetDevice(g->device);
+    const size_t bytes = sizeof(ShardHostHeader) + sizeof(uint32_t) * (capacity + 16);
+    const int fd = shm_open(name, create ? (O_CREAT | O_RDWR | O_TRUNC) : O_RDWR, 0600);
+    if (fd < 0) {
+        set_error(std::string("shm_open failed for ") + name);
+        return nullptr;
+    }
+    if (create && ftruncate(fd, static_cast<off_t>(bytes)) != 0) {
+        close(fd);
+        set_error("ftruncate failed on the shared result buffer");
+        return nullptr;
+    }
+    void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) {
+        set_error("mmap failed on the shared result buffer");
+        return nullptr;
+    }
+    if (create) std::memset(p, 0, sizeof(ShardHostHeader));
+    if (!cuda_ok(cudaHostRegister(p, bytes, cudaHostRegisterPortable), "cudaHostRegister shared result")) {
+        munmap(p, bytes);
+        return nullptr;
+    }
+    s->host_map = p;
+    s->host_bytes = bytes;
+    s->host_cap = capacity;
+    s->host_creator = create != 0;
+    std::strncpy(s->host_name, name, sizeof(s->host_name) - 1);
+    return reinterpret_cast<unsigned int *>(static_cast<uint8_t *>(p) + sizeof(ShardHostHeader));
+}
+
+const unsigned int *qpe_shard_device_result(struct engineS *engine) {
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    return s ? s->dense : nullptr;
+}
+
+void qpe_shard_close(struct engineS *engine) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (g) shard_destroy(g);
+}
+
+/* One sharded full-scan SELECT; every rank of the group calls it with the same statement, in the same
+ * order.  to_host == 0: the ids end up packed in the owner's HBM (qpe_shard_device_result);
+ * to_host != 0: in the shared host buffer.  counts_out[world] = per-rank match counts (partition
+ * order); the result is their concatenation = table order.  Returns -5 if a rank's ids did not fit. */
+int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, int to_host,
+                     unsigned long long *counts_out, qpe_scan_stats *stats) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    if (!s) {
+        set_error("qpe_shard_select: call qpe_shard_init / qpe_shard_connect first");
+        return -1;
+    }
+    if (to_host ? !s->host_map : !s->seg_base) {
+        set_error(to_host ? "qpe_shard_select: no host result buffer" : "qpe_shard_select: no device result segments");
+        return -1;
+    }
+    if (g->table.row_base + static_cast<uint64_t>(g->table.n) > 0xffffffffull) {
+        set_error("global row ids do not fit 32 bits");
+        return -5;
+    }
+    cudaSetDevice(g->device);
+    if (++s->epoch == 0) s->epoch = 1;
+    const uint32_t epoch = s->epoch;
+    PeerPtrs peers{};
+    for (int r = 0; r < s->world; ++r) peers.comm[r] = s->comm[r];
+
+    // kernels that follow the scan on the engine's stream, before its single synchronisation
+    g->post_match = [&]() -> bool {
+        publish_kernel<<<1, 32, 0, g->stream>>>(g->d_ctl, peers, s->rank, s->world, epoch);
+        if (!to_host && s->rank == s->owner)
+            pack_kernel<<<148 * 2, 256, 0, g->stream>>>(s->comm[s->rank], s->world, epoch, s->seg_base, s->seg_cap,
+                                                        s->dense);
+        wait_counts_kernel<<<1, 32, 0, g->stream>>>(s->comm[s->rank], s->world, epoch, s->d_counts);
+        return cuda_ok(cudaGetLastError(), "shard kernels launch");
+    };
+    if (!to_host) {
+        g->out_override = s->seg_base + (static_cast<size_t>(epoch & 1u) * s->world + s->rank) * s->seg_cap;
+        g->out_override_cap = s->seg_cap;
+    }
+    g->id_base_override = static_cast<uint32_t>(g->table.row_base);
+    g->id_base_always = true;
+    uint64_t m = 0;
+    const bool ok = engine_match(g, whereClause, true, false, false, false, &m);
+    g->post_match = nullptr;
+    g->out_override = nullptr;
+    g->out_override_cap = 0;
+    g->id_base_override = 0;
+    g->id_base_always = false;
+    if (!ok) return -2;
+    if (g->last.path != 0 || (g->table.n > 0 && g->last.tile_rows == 0)) {
+        // every rank takes the same branch (same statement, same column widths), so nobody is left waiting
+        set_error("qpe_shard_select: this WHERE cannot be staged by the scan kernel (too wide for shared memory)");
+        return -6;
+    }
+    g->last.launches += (!to_host && s->rank == s->owner) ? 3 : 2;
+
+    int rc = 0;
+    unsigned long long before = 0;
+    for (int r = 0; r < s->world; ++r) {
+        const unsigned long long c = s->h_counts[r];
+        if (counts_out) counts_out[r] = c;
+        if (r < s->rank) before += c;
+        if (!to_host && c > s->seg_cap) rc = -5;
+    }
+    if (to_host) {
+        ShardHostHeader *hh = static_cast<ShardHostHeader *>(s->host_map);
+        uint32_t *ids = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(s->host_map) + sizeof(ShardHostHeader));
+        if (before + m > s->host_cap) {
+            rc = -5;
+        } else if (m && !cuda_ok(cudaMemcpyAsync(ids + before, g->d_ids, m * 4, cudaMemcpyDeviceToHost, g->stream),
+                                 "download ids")) {
+            return -4;
+        }
+        if (!cuda_ok(cudaStreamSynchronize(g->stream), "download ids")) return -4;
+        __atomic_store_n(&hh->done[s->rank][0], static_cast<unsigned long long>(epoch), __ATOMIC_RELEASE);
+        if (s->rank == s->owner) {
+            // the result is complete when every rank has delivered its piece
+            for (int r = 0; r < s->world; ++r) {
+                unsigned long long spins = 0;
+                while (__atomic_load_n(&hh->done[r][0], __ATOMIC_ACQUIRE) != epoch) {
+                    if (++spins > 4000000000ull) {
+                        set_error("qpe_shard_select: a rank never delivered its ids");
+                        return -4;
+                    }
+                }
+            }
+        }
+    }
+    if (rc == -5) set_error("a rank's ids did not fit the result buffer (nothing was written past it)");
+    if (stats) qpe_gpu_last_stats(engine, stats);
+    return rc;
+}
+
+}  // extern "C"

@@ -576,6 +576,13 @@ int qpe_sql_select_ids_to(struct engineS *engine, const char *statement, unsigne
     return qpe_gpu_select_ids_to(engine, pw.wc, dst_device, dst_capacity, global_ids, count_out, stats);
 }
 
+int qpe_sql_shard_select(struct engineS *engine, const char *statement, int to_host,
+                         unsigned long long *counts_out, qpe_scan_stats *stats) {
+    ParsedWhere pw(statement);
+    if (!pw.ok) return -7;
+    return qpe_shard_select(engine, pw.wc, to_host, counts_out, stats);
+}
+
 int qpe_sql_select_segments(struct engineS *engine, const char *statement, int global_ids, int *used_index_out,
                             int *n_segments_out, size_t seg_counts_out[32], long long **keys_out,
                             unsigned int **ids_out) {

@@ -199,3 +199,83 @@ class PeerGather:
             self.buffer.free()
             self.dense.free()
             self.buffer = None
+
+
+class ShardGroup:
+    """A row-range sharded table driven natively (csrc/shard.cu): per query NO host collective and no NCCL
+    call.  Every rank's scan kernel stores its global row ids into the owner's result buffer over NVLink
+    peer memory, a tiny kernel stores (epoch, count) into every rank's comm block, the owner packs the
+    segments in partition order.  `torch.distributed` is used once, here, to pass the IPC handles around."""
+
+    def __init__(self, pkg, engine, segment_capacity: int, host_capacity: int = 0, owner: int = 0, group=None,
+                 counts_device="cpu"):
+        import ctypes as C
+        import os
+        self.pkg, self.engine, self.owner, self.group = pkg, engine, owner, group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.lib = pkg.load_library()
+        lib, h = self.lib, engine._h
+        buf = C.create_string_buffer(64)
+        engine._check(lib.qpe_shard_init(h, self.rank, self.world, buf), "qpe_shard_init")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, buf.raw, group=group)
+        engine._check(lib.qpe_shard_connect(h, b"".join(handles)), "qpe_shard_connect")
+        # device result: 2 parities x world segments in the owner's memory
+        self.seg_cap = max(exchange_counts(int(max(segment_capacity, 1)), counts_device, group))
+        self.buffer = None
+        obj = [None]
+        if self.rank == owner:
+            self.buffer = pkg.DeviceBuffer(4 * self.seg_cap * self.world * 2 + 64)
+            self.seg_ptr = self.buffer.ptr
+            obj[0] = self.buffer.export_handle()
+        dist.broadcast_object_list(obj, src=owner, group=group)
+        if self.rank != owner:
+            self.seg_ptr = pkg.ipc_open(obj[0])
+        engine._check(lib.qpe_shard_set_device_result(h, owner, self.seg_ptr, self.seg_cap), "set_device_result")
+        # host result: one shared-memory id buffer, every rank delivers its piece over its own PCIe link
+        self.host_ids = None
+        self.host_cap = max(exchange_counts(int(host_capacity), counts_device, group))
+        if self.host_cap > 0:
+            name = [f"/qpe_shard_{os.getpid()}_{id(self) & 0xffff:x}" if self.rank == owner else None]
+            dist.broadcast_object_list(name, src=owner, group=group)
+            if self.rank == owner:
+                p = lib.qpe_shard_open_host_result(h, name[0].encode(), self.host_cap, 1)
+            dist.barrier(group=group)
+            if self.rank != owner:
+                p = lib.qpe_shard_open_host_result(h, name[0].encode(), self.host_cap, 0)
+            if not p:
+                raise pkg.QpeError("shared host result: " + (lib.qpe_gpu_last_error() or b"").decode())
+            import numpy as np
+            self.host_ids = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(self.host_cap,))
+        self._counts = (C.c_ulonglong * 16)()
+        self._stats = pkg.ScanStats()
+        self._C = C
+        dist.barrier(group=group)
+
+    def select(self, statement: str, to_host: bool = False):
+        """One sharded full-scan SELECT (every rank calls it).  Returns (total, per-rank counts, stats dict).
+        to_host=False: ids packed in the owner's HBM (`device_result`); True: in `host_ids` on every rank."""
+        rc = self.lib.qpe_sql_shard_select(self.engine._h, statement.encode(), 1 if to_host else 0, self._counts,
+                                           self._C.byref(self._stats))
+        self.engine._check(rc, "qpe_shard_select")
+        counts = [int(self._counts[r]) for r in range(self.world)]
+        return sum(counts), counts, self._stats
+
+    def device_result_ptr(self) -> int:
+        return self.lib.qpe_shard_device_result(self.engine._h)
+
+    def device_result(self, total: int):
+        """owner: the packed device result copied to the host (checks)"""
+        return self.engine.copy_from_device(self.device_result_ptr(), total)
+
+    def close(self):
+        dist.barrier(group=self.group)
+        self.host_ids = None
+        self.lib.qpe_shard_close(self.engine._h)
+        if self.rank != self.owner:
+            self.pkg.ipc_close(self.seg_ptr)
+        dist.barrier(group=self.group)
+        if self.buffer is not None:
+            self.buffer.free()
+            self.buffer = None
