@@ -323,7 +323,7 @@ def run_ours(args):
     pinned = torch.empty(max(total_matches, 1), dtype=torch.int32).pin_memory() if rank == 0 else None
     pinned_np = pinned.numpy().view(np.uint32) if rank == 0 else None
     launches = [0]
-    scan_ms, compact_ms, kernel_ms = [], [], []
+    scan_ms, compact_ms, kernel_ms, traces = [], [], [], []
     eng_stream = torch.cuda.ExternalStream(eng.stream, device=dev)
 
     def step_device(record=False, pack="device"):
@@ -342,6 +342,7 @@ def run_ours(args):
                 total_n, counts, _ = sharding.ordered_gather(mine, gathered)
         launches[0] += st["launches"]
         if record:
+            traces.append(eng.last_trace())
             scan_ms.append(st["scan_ms"])
             compact_ms.append(st["compact_ms"])
             kernel_ms.append(st["kernel_ms"])
@@ -395,6 +396,10 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     ms_step, wall_step, n_matches, clocks = timed(step_device, args.steps, sampler, record=True)
     gpu_launches = launches[0]
+    tr = [statistics.mean(x[k] for x in traces) for k in range(4)]
+    sys.stderr.write(f"[rank {rank}] per step: wall {wall_step:.4f} ms, device events {ms_step:.4f} ms; inside the call: "
+                     f"compile {tr[0]:.4f}, enqueue {tr[1]:.4f}, sync {tr[2]:.4f} ms; device: K1f "
+                     f"{statistics.mean(scan_ms):.4f}, post-scan kernels {tr[3]:.4f} ms\n")
     ms_e2e, wall_e2e, n_e2e, _ = timed(step_e2e, args.steps)
     assert n_e2e == n_matches
 

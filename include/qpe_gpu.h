@@ -133,14 +133,17 @@ int qpe_gpu_copy_device(void *dst_device, const void *src_device, size_t bytes);
  * host collective and no NCCL call per query; the caller only passes the 64-byte IPC handles around once.
  *   qpe_shard_init(engine, rank, world, handle_out)      allocate this rank's comm block, export it
  *   qpe_shard_connect(engine, all_handles)               world x 64 bytes in rank order
- *   qpe_shard_set_device_result(engine, owner, segments, cap)  segments = 2 x world x cap ids in the OWNER's
- *                                                        memory (own pointer / qpe_gpu_ipc_open mapping)
+ *   qpe_shard_set_device_result(engine, owner, segments, cap)  segments = qpe_shard_result_ids(world, cap) ids
+ *                                                        in the OWNER's memory (own pointer / qpe_gpu_ipc_open
+ *                                                        mapping); the first shard stores straight into the
+ *                                                        dense result (its offset is always 0)
  *   qpe_shard_open_host_result(engine, name, cap, create) POSIX shared-memory id buffer all ranks write
  *                                                        their piece into over their own PCIe link
  *   qpe_shard_select / qpe_sql_shard_select              one full-scan SELECT; every rank calls it with the
  *                                                        same statement in the same order */
 int qpe_shard_init(struct engineS *engine, int rank, int world, unsigned char comm_handle_out[64]);
 int qpe_shard_connect(struct engineS *engine, const unsigned char *all_handles);
+unsigned long long qpe_shard_result_ids(int world, unsigned long long segment_capacity);
 int qpe_shard_set_device_result(struct engineS *engine, int owner_rank, unsigned int *segments,
                                 unsigned long long segment_capacity);
 unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *name, unsigned long long capacity,
@@ -157,6 +160,10 @@ int qpe_gpu_copy_from_device(void *dst_host, const void *src_device, size_t byte
 
 /* Statistics of the engine's most recent match phase. */
 int qpe_gpu_last_stats(struct engineS *engine, qpe_scan_stats *stats);
+
+/* Host-side breakdown of the most recent match phase, in ms: [0] WHERE compile, [1] enqueue (copies +
+ * launches), [2] stream synchronisation, [3] device time of the post-scan kernels of a sharded SELECT. */
+int qpe_gpu_last_trace(struct engineS *engine, double out[4]);
 
 /* Write the whole table as a CSV in the data generator's format (header line, QUOTE_MINIMAL
  * quoting, \r\n line ends, sudo_used as true/false: data-generation/generate_commands.py:812-816)

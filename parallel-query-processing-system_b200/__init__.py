@@ -98,6 +98,7 @@ def load_library() -> C.CDLL:
         "qpe_gpu_set_tile": (i, [vp, i, i]),
         "qpe_gpu_set_pipeline": (i, [vp, i]),
         "qpe_gpu_stream": (vp, [vp]),
+        "qpe_gpu_last_trace": (i, [vp, C.POINTER(C.c_double)]),
         "qpe_gpu_copy_from_device": (i, [vp, vp, sz]),
         "qpe_gpu_last_stats": (i, [vp, pstats]),
         "qpe_gpu_write_csv": (i, [vp, cp]),
@@ -122,6 +123,7 @@ def load_library() -> C.CDLL:
         "qpe_shard_init": (i, [vp, i, i, C.c_char_p]),
         "qpe_shard_connect": (i, [vp, C.c_char_p]),
         "qpe_shard_set_device_result": (i, [vp, i, vp, ull]),
+        "qpe_shard_result_ids": (ull, [i, ull]),
         "qpe_shard_open_host_result": (vp, [vp, cp, ull, i]),
         "qpe_shard_device_result": (vp, [vp]),
         "qpe_shard_close": (None, [vp]),
@@ -270,6 +272,12 @@ class Engine:
     def stream(self) -> int:
         """cudaStream_t of the engine (all its kernels run there)"""
         return int(self._lib.qpe_gpu_stream(self._h))
+
+    def last_trace(self) -> list:
+        """[compile, enqueue, sync, post-kernel] ms of the most recent match phase"""
+        out = (C.c_double * 4)()
+        self._check(self._lib.qpe_gpu_last_trace(self._h, out), "last_trace")
+        return list(out)
 
     def last_stats(self) -> dict:
         st = ScanStats()

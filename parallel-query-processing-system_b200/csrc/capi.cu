@@ -852,6 +852,13 @@ int qpe_gpu_last_stats(struct engineS *engine, qpe_scan_stats *stats) {
     return 0;
 }
 
+int qpe_gpu_last_trace(struct engineS *engine, double out[4]) {
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    for (int k = 0; k < 4; ++k) out[k] = g->trace[k];
+    return 0;
+}
+
 int qpe_gpu_write_csv(struct engineS *engine, const char *path) {
     std::lock_guard<std::mutex> lk(g_api_mutex);
     GpuEngine *g = as_engine(engine);

@@ -122,6 +122,7 @@ GpuEngine *engine_create(const char *tableName, const char *datafile, int index_
     ok = ok && cuda_ok(cudaEventCreate(&g->ev0), "cudaEventCreate");
     ok = ok && cuda_ok(cudaEventCreate(&g->ev1), "cudaEventCreate");
     ok = ok && cuda_ok(cudaEventCreate(&g->ev_mid), "cudaEventCreate");
+    ok = ok && cuda_ok(cudaEventCreate(&g->ev_post), "cudaEventCreate");
     ok = ok && cuda_ok(cudaMalloc(&g->d_ctl, sizeof(QueryCtl)), "cudaMalloc ctl");
     ok = ok && cuda_ok(cudaMallocHost(&g->h_ctl, sizeof(QueryCtl)), "cudaMallocHost ctl");
     ok = ok && cuda_ok(cudaMalloc(&g->d_probe_lo, sizeof(unsigned long long) * kMaxSegments), "cudaMalloc probe");
@@ -169,6 +170,7 @@ void engine_destroy(GpuEngine *g) {
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
     if (g->ev_mid) cudaEventDestroy(g->ev_mid);
+    if (g->ev_post) cudaEventDestroy(g->ev_post);
     for (int i = 0; i < kMaxPipeSegments; ++i)
         if (g->ev_seg[i]) cudaEventDestroy(g->ev_seg[i]);
     if (g->stream2) cudaStreamDestroy(g->stream2);
@@ -383,6 +385,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     ScanStats st;
     const DevTable &t = g->table;
     g->last_bm_words = 0;
+    bool post_done = false;
 
     uint32_t widths[NUM_COLS];
     for (int c = 0; c < NUM_COLS; ++c) widths[c] = t.col[c].width;
@@ -397,6 +400,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
             set_error(std::string("WHERE references column '") + kCols[c].name + "' which is not resident on the device");
             return false;
         }
+    const double t_compiled = now_ms();
     hc->tile_counter = 0;
     hc->chunk_counter = 0;
     hc->out_count = 0;
@@ -467,6 +471,13 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
                 if (!cuda_ok(fused_launch(F, fg, g->stream), "fused scan kernel launch")) return false;
                 cudaEventRecord(g->ev_mid, g->stream);
                 cudaEventRecord(g->ev1, g->stream);
+                if (g->post_match) {
+                    // sharded table: the count exchange follows the scan at once (before the host starts
+                    // copying finished segments out), so the other ranks never wait for this rank's copies
+                    if (!g->post_match()) return false;
+                    cudaEventRecord(g->ev_post, g->stream);
+                    post_done = true;
+                }
                 st.launches = 1;
                 st.tile_rows = fg.tile_rows;
                 st.stages = fg.stages;
@@ -676,12 +687,27 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
         st.launches = launches;
     }
 
-    if (g->post_match && !g->post_match()) return false;
-    if (!cuda_ok(cudaMemcpyAsync(&hc->out_count, &g->d_ctl->out_count, sizeof(unsigned long long),
-                                 cudaMemcpyDeviceToHost, g->stream),
-                 "download count") ||
-        !cuda_ok(cudaStreamSynchronize(g->stream), "match sync"))
+    if (g->post_match && !post_done) {
+        if (!g->post_match()) return false;
+        cudaEventRecord(g->ev_post, g->stream);
+    }
+    if (!g->count_mapped && !cuda_ok(cudaMemcpyAsync(&hc->out_count, &g->d_ctl->out_count, sizeof(unsigned long long),
+                                                     cudaMemcpyDeviceToHost, g->stream),
+                                     "download count"))
         return false;
+    const double t_enq = now_ms();
+    if (!cuda_ok(cudaStreamSynchronize(g->stream), "match sync")) return false;
+    if (g->count_mapped) hc->out_count = *static_cast<const volatile unsigned long long *>(g->count_mapped);
+    const double t_sync = now_ms();
+    g->trace[0] = t_compiled - t_begin;
+    g->trace[1] = t_enq - t_compiled;
+    g->trace[2] = t_sync - t_enq;
+    g->trace[3] = 0;
+    if (g->post_match) {
+        float pm = 0.f;
+        cudaEventElapsedTime(&pm, g->ev1, g->ev_post);
+        g->trace[3] = pm;
+    }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, g->ev0, g->ev1);
     st.kernel_ms = ms;

@@ -61,6 +61,7 @@ struct GpuEngine {
     // sharded table (shard.cu): kernels enqueued on `stream` right after the match kernels, before the
     // single stream synchronisation of engine_match (count exchange + pack over peer memory)
     std::function<bool()> post_match;
+    const unsigned long long *count_mapped = nullptr;  // set: post_match's kernel writes the match count here (mapped pinned)
     void *shard = nullptr;           // ShardState of shard.cu
     int64_t last_bm_words = 0;   // words of the bitmap the last full-scan match left in d_bitmap (0 = none)
     uint64_t last_bm_count = 0;  // its match count
@@ -70,6 +71,10 @@ struct GpuEngine {
     unsigned long long *h_probe_keys = nullptr;  // pinned: lo[kMaxSegments], hi[kMaxSegments]
     uint32_t *h_probe_out = nullptr;             // pinned: first[kMaxSegments], count[kMaxSegments]
 
+    // host-side breakdown of the last match phase (ms): [0] parse/compile, [1] enqueue (copies + launches),
+    // [2] stream synchronisation, [3] device time ev1 -> end of the post-match kernels
+    double trace[4] = {0, 0, 0, 0};
+    cudaEvent_t ev_post = nullptr;
     int force_tile_rows = 0, force_stages = 0;
     ScanStats last;
 };

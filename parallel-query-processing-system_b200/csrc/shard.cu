@@ -11,11 +11,12 @@
 //                   result buffer -- peer memory mapped through CUDA IPC, so the ids cross NVLink
 //                   as the kernel's own coalesced stores, during the scan -- or into the rank's own
 //                   HBM (host result);
-//   every rank      publish_kernel: one system-scope release store of (epoch, match count) into
+//   every rank      post_kernel: one system-scope release store of (epoch, match count) into
 //                   EVERY rank's comm block (peer stores) = the count exchange;
-//   owner           pack_kernel: waits for all counts of this epoch (acquire loads of its own comm
-//                   block), then packs the segments into one dense id list in partition order,
-//                   which is table order;
+//   owner           post_kernel: waits for all counts of this epoch (acquire loads of its own comm
+//                   block), then moves the segments of ranks 1.. behind rank 0's ids -- rank 0's
+//                   offset is always 0, so ITS scan stores straight into the dense result and is never
+//                   moved -- giving one dense id list in partition order, which is table order;
 //   host result     each rank learns the counts of the lower ranks the same way and copies its ids
 //                   over ITS OWN PCIe link to its exact offset in a host buffer shared by all ranks
 //                   (POSIX shared memory, registered with CUDA in every process).
@@ -53,16 +54,18 @@ struct ShardState {
     uint32_t epoch = 0;
     // device result: segments in the owner's memory (own pointer on the owner, IPC mapping elsewhere)
     int owner = 0;
-    uint32_t *seg_base = nullptr;       // 2 parities x world segments x seg_cap ids
+    // result memory (owner's; own pointer on the owner, IPC mapping elsewhere), per epoch parity:
+    //   [ dense result: world x seg_cap ids | segments of ranks 1 .. world-1: seg_cap ids each ]
+    uint32_t *seg_base = nullptr;
     uint64_t seg_cap = 0;
-    uint32_t *dense = nullptr;          // owner: packed result (world * seg_cap ids)
+    uint32_t last_parity = 0;           // parity of the most recent device-result query
     // host result
     void *host_map = nullptr;           // shared mapping: ShardHostHeader, then the ids
     size_t host_bytes = 0;
     uint64_t host_cap = 0;              // ids
     char host_name[96] = {0};
     bool host_creator = false;
-    // per-query counts as seen by this rank (mapped pinned host memory, written by wait_counts_kernel)
+    // per-query counts as seen by this rank (mapped pinned host memory, written by post_kernel)
     unsigned long long *h_counts = nullptr;
     unsigned long long *d_counts = nullptr;
 };
@@ -92,46 +95,63 @@ struct PeerPtrs {
     ShardComm *comm[kMaxRanks];
 };
 
-// the count exchange: (epoch, this rank's match count) into every rank's comm block
-__global__ void publish_kernel(const QueryCtl *ctl, PeerPtrs peers, int rank, int world, uint32_t epoch) {
-    const int r = threadIdx.x;
-    if (r >= world) return;
-    const unsigned long long cnt = *reinterpret_cast<const volatile unsigned long long *>(&ctl->out_count);
-    __threadfence_system();  // this rank's id stores (peer memory included) are visible before the count is
-    st_release_sys(&peers.comm[r]->count[epoch & 1u][rank],
-                   (static_cast<unsigned long long>(epoch) << 32) | (cnt & 0xffffffffull));
+// ids per parity set: the dense area, then one segment per rank >= 1
+__host__ __device__ inline unsigned long long set_ids(int world, unsigned long long seg_cap) {
+    return static_cast<unsigned long long>(2 * world - 1) * seg_cap;
 }
 
-// every rank: the counts of this epoch -> mapped host memory (the host reads them after its stream sync)
-__global__ void wait_counts_kernel(const ShardComm *mine, int world, uint32_t epoch, unsigned long long *out) {
-    const int r = threadIdx.x;
-    if (r >= world) return;
-    out[r] = wait_slot(&mine->count[epoch & 1u][r], epoch) & 0xffffffffull;
-}
-
-// owner: wait for every rank's count, then pack the segments in partition order
-__global__ void __launch_bounds__(256) pack_kernel(const ShardComm *mine, int world, uint32_t epoch,
-                                                   const uint32_t *seg_base, unsigned long long seg_cap,
-                                                   uint32_t *dense) {
+// The ONE kernel that follows the scan on every rank (same stream):
+//   1. count exchange: thread r of CTA 0 stores (epoch, this rank's match count) into rank r's comm block;
+//   2. every CTA waits (thread 0, acquire loads of this rank's own comm block) for all counts of the epoch;
+//      CTA 0 also hands them to the host through mapped pinned memory;
+//   3. pack != 0 (owner, device result): the segments of ranks 1.. are moved to their offsets in the dense
+//      result, 4 independent loads in flight per thread (the move is latency-bound otherwise).
+__global__ void __launch_bounds__(256) post_kernel(const QueryCtl *ctl, PeerPtrs peers, int rank, int world,
+                                                   uint32_t epoch, unsigned long long *host_counts, int pack,
+                                                   uint32_t *set, unsigned long long seg_cap) {
     __shared__ unsigned long long s_off[kMaxRanks + 1];
+    const unsigned long long my = *reinterpret_cast<const volatile unsigned long long *>(&ctl->out_count);
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        __threadfence_system();  // this rank's id stores (peer memory included) are visible before the count is
+        st_release_sys(&peers.comm[threadIdx.x]->count[epoch & 1u][rank],
+                       (static_cast<unsigned long long>(epoch) << 32) | (my & 0xffffffffull));
+    }
+    if (threadIdx.x < world) {
+        const int r = threadIdx.x;
+        const unsigned long long c =
+            (r == rank) ? (my & 0xffffffffull) : (wait_slot(&peers.comm[rank]->count[epoch & 1u][r], epoch) & 0xffffffffull);
+        s_off[r + 1] = c;
+        if (blockIdx.x == 0) host_counts[r] = c;
+    }
+    __syncthreads();
+    if (!pack) return;
     if (threadIdx.x == 0) {
         unsigned long long o = 0;
         for (int r = 0; r < world; ++r) {
+            const unsigned long long c = s_off[r + 1];
             s_off[r] = o;
-            o += wait_slot(&mine->count[epoch & 1u][r], epoch) & 0xffffffffull;
+            o += c;
         }
         s_off[world] = o;
     }
     __syncthreads();
-    const uint32_t *set = seg_base + static_cast<size_t>(epoch & 1u) * world * seg_cap;
-    for (int r = 0; r < world; ++r) {
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    const unsigned long long t0 = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    for (int r = 1; r < world; ++r) {
         const unsigned long long n = s_off[r + 1] - s_off[r];
-        if (n > seg_cap) continue;  // the host reports the overflow
-        const uint32_t *src = set + static_cast<size_t>(r) * seg_cap;
-        uint32_t *dst = dense + s_off[r];
-        for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < n;
-             i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
-            dst[i] = src[i];
+        if (n > seg_cap || s_off[r] + n > static_cast<unsigned long long>(world) * seg_cap) continue;  // host reports it
+        const uint32_t *__restrict__ src = set + (static_cast<unsigned long long>(world) + (r - 1)) * seg_cap;
+        uint32_t *__restrict__ dst = set + s_off[r];
+        unsigned long long i = t0;
+        for (; i + 3 * stride < n; i += 4 * stride) {
+            const uint32_t a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride),
+                           d = __ldcs(src + i + 3 * stride);
+            dst[i] = a;
+            dst[i + stride] = b;
+            dst[i + 2 * stride] = c;
+            dst[i + 3 * stride] = d;
+        }
+        for (; i < n; i += stride) dst[i] = src[i];
     }
 }
 
@@ -149,7 +169,6 @@ void shard_destroy(GpuEngine *g) {
         else
             cudaIpcCloseMemHandle(s->comm[r]);
     }
-    if (s->dense) cudaFree(s->dense);
     if (s->h_counts) cudaFreeHost(s->h_counts);
     if (s->host_map) {
         cudaHostUnregister(s->host_map);
@@ -216,8 +235,14 @@ int qpe_shard_connect(struct engineS *engine, const unsigned char *all_handles) 
     return 0;
 }
 
-/* Device result: `segments` = 2 x world x segment_capacity ids in the OWNER's memory (the owner passes
- * its own allocation, the other ranks their IPC mapping of it). */
+/* Device result memory, in the OWNER's HBM (the owner passes its own allocation, the other ranks their IPC
+ * mapping of it): qpe_shard_result_ids(world, segment_capacity) ids.  Per epoch parity it holds the dense
+ * result (world x segment_capacity ids; the first shard's scan stores straight into it, at offset 0) and
+ * one segment of segment_capacity ids for every other rank. */
+unsigned long long qpe_shard_result_ids(int world, unsigned long long segment_capacity) {
+    return 2ull * set_ids(world, segment_capacity) + 16;
+}
+
 int qpe_shard_set_device_result(struct engineS *engine, int owner_rank, unsigned int *segments,
                                 unsigned long long segment_capacity) {
     std::lock_guard<std::mutex> lk(g_api_mutex);
@@ -227,15 +252,9 @@ int qpe_shard_set_device_result(struct engineS *engine, int owner_rank, unsigned
         set_error("qpe_shard_set_device_result: call qpe_shard_init first");
         return -1;
     }
-    cudaSetDevice(g->device);
     s->owner = owner_rank;
     s->seg_base = segments;
     s->seg_cap = segment_capacity;
-    if (s->dense) cudaFree(s->dense);
-    s->dense = nullptr;
-    if (s->rank == owner_rank &&
-        !cuda_ok(cudaMalloc(&s->dense, sizeof(uint32_t) * (segment_capacity * s->world + 16)), "cudaMalloc dense"))
-        return -4;
     return 0;
 }
 
@@ -285,7 +304,7 @@ unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *nam
 const unsigned int *qpe_shard_device_result(struct engineS *engine) {
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
-    return s ? s->dense : nullptr;
+    return (s && s->seg_base) ? s->seg_base + s->last_parity * set_ids(s->world, s->seg_cap) : nullptr;
 }
 
 void qpe_shard_close(struct engineS *engine) {
@@ -321,24 +340,37 @@ int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, i
     PeerPtrs peers{};
     for (int r = 0; r < s->world; ++r) peers.comm[r] = s->comm[r];
 
-    // kernels that follow the scan on the engine's stream, before its single synchronisation
+    // the kernel that follows the scan on the engine's stream, before its single synchronisation
+    uint32_t *set = to_host ? nullptr : s->seg_base + (epoch & 1u) * set_ids(s->world, s->seg_cap);
+    const int pack = (!to_host && s->rank == s->owner && s->world > 1) ? 1 : 0;
     g->post_match = [&]() -> bool {
-        publish_kernel<<<1, 32, 0, g->stream>>>(g->d_ctl, peers, s->rank, s->world, epoch);
-        if (!to_host && s->rank == s->owner)
-            pack_kernel<<<148 * 2, 256, 0, g->stream>>>(s->comm[s->rank], s->world, epoch, s->seg_base, s->seg_cap,
-                                                        s->dense);
-        wait_counts_kernel<<<1, 32, 0, g->stream>>>(s->comm[s->rank], s->world, epoch, s->d_counts);
-        return cuda_ok(cudaGetLastError(), "shard kernels launch");
+        post_kernel<<<pack ? 148 * 8 : 1, 256, 0, g->stream>>>(g->d_ctl, peers, s->rank, s->world, epoch, s->d_counts,
+                                                               pack, set, s->seg_cap);
+        return cuda_ok(cudaGetLastError(), "shard post-scan kernel launch");
     };
     if (!to_host) {
-        g->out_override = s->seg_base + (static_cast<size_t>(epoch & 1u) * s->world + s->rank) * s->seg_cap;
+        // the first shard's offset in the result is always 0: its scan writes the dense result in place
+        g->out_override = s->rank == 0 ? set : set + (static_cast<size_t>(s->world) + (s->rank - 1)) * s->seg_cap;
         g->out_override_cap = s->seg_cap;
+        s->last_parity = epoch & 1u;
+    }
+    uint32_t *host_ids =
+        to_host ? reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(s->host_map) + sizeof(ShardHostHeader)) : nullptr;
+    if (to_host && s->rank == 0) {
+        // the first shard's offset is always 0: its ids are copied out segment by segment DURING the scan
+        g->host_out = host_ids;
+        g->host_out_cap = s->host_cap;
     }
     g->id_base_override = static_cast<uint32_t>(g->table.row_base);
     g->id_base_always = true;
+    g->count_mapped = &s->h_counts[s->rank];  // the post kernel hands the count over: no separate download
     uint64_t m = 0;
     const bool ok = engine_match(g, whereClause, true, false, false, false, &m);
     g->post_match = nullptr;
+    g->count_mapped = nullptr;
+    const bool delivered = g->host_out != nullptr && g->host_out_done;
+    g->host_out = nullptr;
+    g->host_out_cap = 0;
     g->out_override = nullptr;
     g->out_override_cap = 0;
     g->id_base_override = 0;
@@ -349,7 +381,7 @@ int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, i
         set_error("qpe_shard_select: this WHERE cannot be staged by the scan kernel (too wide for shared memory)");
         return -6;
     }
-    g->last.launches += (!to_host && s->rank == s->owner) ? 3 : 2;
+    g->last.launches += 1;
 
     int rc = 0;
     unsigned long long before = 0;
@@ -361,14 +393,14 @@ int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, i
     }
     if (to_host) {
         ShardHostHeader *hh = static_cast<ShardHostHeader *>(s->host_map);
-        uint32_t *ids = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(s->host_map) + sizeof(ShardHostHeader));
         if (before + m > s->host_cap) {
             rc = -5;
-        } else if (m && !cuda_ok(cudaMemcpyAsync(ids + before, g->d_ids, m * 4, cudaMemcpyDeviceToHost, g->stream),
-                                 "download ids")) {
-            return -4;
+        } else if (m && !delivered) {
+            if (!cuda_ok(cudaMemcpyAsync(host_ids + before, g->d_ids, m * 4, cudaMemcpyDeviceToHost, g->stream),
+                         "download ids") ||
+                !cuda_ok(cudaStreamSynchronize(g->stream), "download ids"))
+                return -4;
         }
-        if (!cuda_ok(cudaStreamSynchronize(g->stream), "download ids")) return -4;
         __atomic_store_n(&hh->done[s->rank][0], static_cast<unsigned long long>(epoch), __ATOMIC_RELEASE);
         if (s->rank == s->owner) {
             // the result is complete when every rank has delivered its piece

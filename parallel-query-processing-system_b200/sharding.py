@@ -221,12 +221,12 @@ class ShardGroup:
         handles = [None] * self.world
         dist.all_gather_object(handles, buf.raw, group=group)
         engine._check(lib.qpe_shard_connect(h, b"".join(handles)), "qpe_shard_connect")
-        # device result: 2 parities x world segments in the owner's memory
+        # device result memory in the owner's HBM (dense result + one segment per rank >= 1, two parities)
         self.seg_cap = max(exchange_counts(int(max(segment_capacity, 1)), counts_device, group))
         self.buffer = None
         obj = [None]
         if self.rank == owner:
-            self.buffer = pkg.DeviceBuffer(4 * self.seg_cap * self.world * 2 + 64)
+            self.buffer = pkg.DeviceBuffer(4 * int(lib.qpe_shard_result_ids(self.world, self.seg_cap)))
             self.seg_ptr = self.buffer.ptr
             obj[0] = self.buffer.export_handle()
         dist.broadcast_object_list(obj, src=owner, group=group)
