@@ -327,32 +327,33 @@ def run_ours(args):
     eng_stream = torch.cuda.ExternalStream(eng.stream, device=dev)
 
     def step_device(record=False, pack="device"):
-        """scan + ordered compaction on every GPU, count exchange, ordered gather to rank 0 (device)"""
+        """scan + ordered compaction on every GPU, count exchange, ordered gather to rank 0 (device).
+        record=False: no statistics asked for (the engine's CUDA events stay unresolved and are summed after the
+        loop: Engine.timing_totals); record="trace": host-side breakdown of the call (diagnostic pass)."""
+        want = bool(record)
         if use_native:
-            total_n, counts, sst = sg.select(sql, to_host=(pack == "host"))
-            st = {"launches": sst.launches, "scan_ms": sst.scan_ms, "compact_ms": sst.compact_ms,
-                  "kernel_ms": sst.kernel_ms}
+            total_n, counts, st = sg.select(sql, to_host=(pack == "host"), stats=want)
+            n_launch = st.launches if want else 0
         elif use_peer:
             total_n, counts, st = pg.run(eng, sql, dev, pack=pack, host_out=pinned_np)
+            n_launch = st["launches"]
         else:
-            cnt, dptr, st = eng.select_ids_device(sql, force_scan=True, global_ids=(world > 1))
+            cnt, dptr, st = eng.select_ids_device(sql, force_scan=True, global_ids=(world > 1), stats=want or world > 1)
             total_n = cnt
+            n_launch = st["launches"] if st else 0
             if world > 1:
                 mine = torch.as_tensor(DevArray(dptr, max(cnt, 1)), device=dev)[:cnt]
                 total_n, counts, _ = sharding.ordered_gather(mine, gathered)
-        launches[0] += st["launches"]
-        if record:
+        if want:
+            launches[0] = n_launch      # kernels per step (the same every step)
+        if record == "trace":
             traces.append(eng.last_trace())
-            scan_ms.append(st["scan_ms"])
-            compact_ms.append(st["compact_ms"])
-            kernel_ms.append(st["kernel_ms"])
         return total_n
 
     def step_e2e():
         """host-facing call: SQL text in host memory -> row ids in pinned host memory"""
         if world == 1:
-            n, st = eng.select_ids_into(sql, pinned_np, force_scan=True)
-            launches[0] += st["launches"]
+            n, _ = eng.select_ids_into(sql, pinned_np, force_scan=True, stats=False)
             return n
         n = step_device(pack="host")
         if rank == 0:
@@ -390,16 +391,24 @@ def run_ours(args):
         return t[0].item() / steps, t[1].item() / steps, n, clocks
 
     for _ in range(max(args.warmup, 3)):
-        step_device()
+        step_device(record=True)
         step_e2e()
-    launches[0] = 0
     sampler = ClockSampler(local_rank)
-    ms_step, wall_step, n_matches, clocks = timed(step_device, args.steps, sampler, record=True)
-    gpu_launches = launches[0]
-    tr = [statistics.mean(x[k] for x in traces) for k in range(4)]
+    eng.set_timing(True)   # sum the CUDA-event times of every call of the timed loop, resolved after it
+    ms_step, wall_step, n_matches, clocks = timed(step_device, args.steps, sampler)
+    tot = eng.timing_totals()
+    eng.set_timing(False)
+    assert tot["calls"] == args.steps, tot
+    scan_ms.append(tot["scan_ms"] / tot["calls"])
+    compact_ms.append(tot["compact_ms"] / tot["calls"])
+    gpu_launches = launches[0] * args.steps
+    for _ in range(10):  # diagnostic pass (not timed): where a step's time goes inside the call
+        step_device(record="trace")
+    tr = [statistics.mean(x[k] for x in traces) for k in range(6)]
     sys.stderr.write(f"[rank {rank}] per step: wall {wall_step:.4f} ms, device events {ms_step:.4f} ms; inside the call: "
-                     f"compile {tr[0]:.4f}, enqueue {tr[1]:.4f}, sync {tr[2]:.4f} ms; device: K1f "
-                     f"{statistics.mean(scan_ms):.4f}, post-scan kernels {tr[3]:.4f} ms\n")
+                     f"compile {tr[0]:.4f}, enqueue {tr[1]:.4f}, sync {tr[2]:.4f}, tail {tr[4]:.4f}, whole call {tr[5]:.4f} ms; device: K1f "
+                     f"{statistics.mean(scan_ms):.4f}, post-scan kernel {tot['post_ms'] / tot['calls']:.4f} ms "
+                     f"(means over the timed loop)\n")
     ms_e2e, wall_e2e, n_e2e, _ = timed(step_e2e, args.steps)
     assert n_e2e == n_matches
 

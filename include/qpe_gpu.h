@@ -161,9 +161,18 @@ int qpe_gpu_copy_from_device(void *dst_host, const void *src_device, size_t byte
 /* Statistics of the engine's most recent match phase. */
 int qpe_gpu_last_stats(struct engineS *engine, qpe_scan_stats *stats);
 
+/* Device timing is taken with CUDA events on the engine's stream around every match phase and resolved
+ * lazily (only when a qpe_scan_stats is asked for).  qpe_gpu_set_timing(engine, 1) additionally sums the
+ * times of EVERY call since then (up to 512 calls are held unresolved, older ones are folded in as their slot
+ * is reused); qpe_gpu_timing_totals returns {match kernels, scan kernel, compaction kernel, post-scan kernel}
+ * ms and the number of calls, so a benchmark can time a loop without paying for event queries inside it. */
+int qpe_gpu_set_timing(struct engineS *engine, int accumulate);
+int qpe_gpu_timing_totals(struct engineS *engine, double totals_ms[4], long long *calls_out);
+
 /* Host-side breakdown of the most recent match phase, in ms: [0] WHERE compile, [1] enqueue (copies +
- * launches), [2] stream synchronisation, [3] device time of the post-scan kernels of a sharded SELECT. */
-int qpe_gpu_last_trace(struct engineS *engine, double out[4]);
+ * launches), [2] stream synchronisation, [3] device time of the post-scan kernel of a sharded SELECT,
+ * [4] tail of the match phase after the synchronisation, [5] whole qpe_sql_shard_select call, [6..7] 0. */
+int qpe_gpu_last_trace(struct engineS *engine, double out[8]);
 
 /* Write the whole table as a CSV in the data generator's format (header line, QUOTE_MINIMAL
  * quoting, \r\n line ends, sudo_used as true/false: data-generation/generate_commands.py:812-816)

@@ -99,6 +99,8 @@ def load_library() -> C.CDLL:
         "qpe_gpu_set_pipeline": (i, [vp, i]),
         "qpe_gpu_stream": (vp, [vp]),
         "qpe_gpu_last_trace": (i, [vp, C.POINTER(C.c_double)]),
+        "qpe_gpu_set_timing": (i, [vp, i]),
+        "qpe_gpu_timing_totals": (i, [vp, C.POINTER(C.c_double), C.POINTER(ll)]),
         "qpe_gpu_copy_from_device": (i, [vp, vp, sz]),
         "qpe_gpu_last_stats": (i, [vp, pstats]),
         "qpe_gpu_write_csv": (i, [vp, cp]),
@@ -273,9 +275,20 @@ class Engine:
         """cudaStream_t of the engine (all its kernels run there)"""
         return int(self._lib.qpe_gpu_stream(self._h))
 
+    def set_timing(self, accumulate: bool):
+        """start (and reset) / stop summing the device time of every match phase (see timing_totals)"""
+        self._check(self._lib.qpe_gpu_set_timing(self._h, 1 if accumulate else 0), "set_timing")
+
+    def timing_totals(self) -> dict:
+        """CUDA-event times summed over the calls since set_timing(True), resolved after the fact"""
+        t = (C.c_double * 4)()
+        n = C.c_longlong()
+        self._check(self._lib.qpe_gpu_timing_totals(self._h, t, C.byref(n)), "timing_totals")
+        return {"kernel_ms": t[0], "scan_ms": t[1], "compact_ms": t[2], "post_ms": t[3], "calls": int(n.value)}
+
     def last_trace(self) -> list:
         """[compile, enqueue, sync, post-kernel] ms of the most recent match phase"""
-        out = (C.c_double * 4)()
+        out = (C.c_double * 8)()
         self._check(self._lib.qpe_gpu_last_trace(self._h, out), "last_trace")
         return list(out)
 
@@ -324,27 +337,29 @@ class Engine:
             self._lib.qpe_gpu_free(ids)
         return out, st.as_dict()
 
-    def select_ids_into(self, statement: str, out: np.ndarray, force_scan: bool = False) -> Tuple[int, dict]:
+    def select_ids_into(self, statement: str, out: np.ndarray, force_scan: bool = False,
+                        stats: bool = True) -> Tuple[int, dict]:
         """Match phase with the ids copied into a caller-owned (ideally pinned) uint32 buffer."""
         n = C.c_size_t()
-        st = ScanStats()
+        st = ScanStats() if stats else None
         rc = self._lib.qpe_sql_select_ids_into(self._h, statement.encode(), SCAN_FORCE if force_scan else 0,
-                                               out.ctypes.data, out.size, C.byref(n), C.byref(st))
+                                               out.ctypes.data, out.size, C.byref(n), C.byref(st) if stats else None)
         self._check(rc, "select_ids_into")
-        return int(n.value), st.as_dict()
+        return int(n.value), (st.as_dict() if stats else None)
 
     def select_ids_device(self, statement: str, force_scan: bool = False, count_only: bool = False,
-                          global_ids: bool = False):
-        """Match phase, result left in HBM: (count, device pointer, stats)."""
+                          global_ids: bool = False, stats: bool = True):
+        """Match phase, result left in HBM: (count, device pointer, stats).  stats=False skips the statistics
+        (the event times then stay unresolved: see set_timing / timing_totals) and returns None for them."""
         cnt = C.c_ulonglong()
         dptr = C.c_void_p()
-        st = ScanStats()
+        st = ScanStats() if stats else None
         flags = ((SCAN_FORCE if force_scan else 0) | (SCAN_COUNT_ONLY if count_only else 0) |
                  (SCAN_GLOBAL_IDS if global_ids else 0))
         rc = self._lib.qpe_sql_select_ids_device(self._h, statement.encode(), flags, C.byref(cnt), C.byref(dptr),
-                                                 C.byref(st))
+                                                 C.byref(st) if stats else None)
         self._check(rc, "select_ids_device")
-        return int(cnt.value), dptr.value, st.as_dict()
+        return int(cnt.value), dptr.value, (st.as_dict() if stats else None)
 
     def select_segments(self, statement: str, global_ids: bool = True):
         """Index path of one shard, per segment: (used_index, [(keys int64, ids uint32), ...]).

@@ -66,8 +66,9 @@ inline size_t fmt_i32(int v, char *out) {  // "%d"
     return fmt_u64(static_cast<unsigned long long>(v), out);
 }
 
-void fill_stats(const GpuEngine *g, qpe_scan_stats *s) {
+void fill_stats(GpuEngine *g, qpe_scan_stats *s) {
     if (!s) return;
+    engine_resolve_timing(g);
     const ScanStats &a = g->last;
     s->kernel_ms = a.kernel_ms;
     s->total_ms = a.total_ms;
@@ -625,6 +626,7 @@ int qpe_gpu_probe_batch(struct engineS *engine, const char *attribute, const KEY
     const auto t0 = std::chrono::steady_clock::now();
     ok = ok && cuda_ok(cudaMemcpyAsync(dlo, hlo.data(), n_queries * ksz, cudaMemcpyHostToDevice, g->stream), "probe h2d");
     ok = ok && cuda_ok(cudaMemcpyAsync(dhi, hhi.data(), n_queries * ksz, cudaMemcpyHostToDevice, g->stream), "probe h2d");
+    engine_resolve_timing(g);  // ev0 / ev1 belong to the last match phase's slot: settle it before reuse
     if (ok) cudaEventRecord(g->ev0, g->stream);
     ok = ok && cuda_ok(index_probe(ix, dlo, dhi, static_cast<long long>(n_queries), dfirst, dcount, g->stream),
                        "probe kernel launch");
@@ -852,10 +854,40 @@ int qpe_gpu_last_stats(struct engineS *engine, qpe_scan_stats *stats) {
     return 0;
 }
 
-int qpe_gpu_last_trace(struct engineS *engine, double out[4]) {
+int qpe_gpu_set_timing(struct engineS *engine, int accumulate) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
-    for (int k = 0; k < 4; ++k) out[k] = g->trace[k];
+    engine_resolve_all(g);
+    g->accumulate_timing = accumulate != 0;
+    g->acc_kernel_ms = g->acc_scan_ms = g->acc_compact_ms = g->acc_post_ms = 0;
+    g->acc_calls = 0;
+    return 0;
+}
+
+int qpe_gpu_timing_totals(struct engineS *engine, double totals_ms[4], long long *calls_out) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    engine_resolve_all(g);
+    totals_ms[0] = g->acc_kernel_ms;
+    totals_ms[1] = g->acc_scan_ms;
+    totals_ms[2] = g->acc_compact_ms;
+    totals_ms[3] = g->acc_post_ms;
+    if (calls_out) *calls_out = g->acc_calls;
+    return 0;
+}
+
+void qpe_gpu_trace_put(struct engineS *engine, int slot, double ms) {
+    GpuEngine *g = as_engine(engine);
+    if (g && slot >= 0 && slot < 8) g->trace[slot] = ms;
+}
+
+int qpe_gpu_last_trace(struct engineS *engine, double out[8]) {
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    engine_resolve_timing(g);
+    for (int k = 0; k < 8; ++k) out[k] = g->trace[k];
     return 0;
 }
 

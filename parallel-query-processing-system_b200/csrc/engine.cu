@@ -40,7 +40,7 @@ bool cuda_ok(cudaError_t e, const char *what) {
     return false;
 }
 
-static double now_ms() {
+double now_ms() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
@@ -119,10 +119,14 @@ GpuEngine *engine_create(const char *tableName, const char *datafile, int index_
         std::memset(g->h_progress, 0, sizeof(unsigned long long) * kMaxProgressSegments);
         ok = cuda_ok(cudaHostGetDevicePointer(&g->d_progress, g->h_progress, 0), "cudaHostGetDevicePointer");
     }
-    ok = ok && cuda_ok(cudaEventCreate(&g->ev0), "cudaEventCreate");
-    ok = ok && cuda_ok(cudaEventCreate(&g->ev1), "cudaEventCreate");
-    ok = ok && cuda_ok(cudaEventCreate(&g->ev_mid), "cudaEventCreate");
-    ok = ok && cuda_ok(cudaEventCreate(&g->ev_post), "cudaEventCreate");
+    for (int i = 0; i < GpuEngine::kTimingRing && ok; ++i)
+        for (int k = 0; k < 4 && ok; ++k) ok = cuda_ok(cudaEventCreate(&g->ring[i].ev[k]), "cudaEventCreate");
+    if (ok) {
+        g->ev0 = g->ring[0].ev[0];
+        g->ev_mid = g->ring[0].ev[1];
+        g->ev1 = g->ring[0].ev[2];
+        g->ev_post = g->ring[0].ev[3];
+    }
     ok = ok && cuda_ok(cudaMalloc(&g->d_ctl, sizeof(QueryCtl)), "cudaMalloc ctl");
     ok = ok && cuda_ok(cudaMallocHost(&g->h_ctl, sizeof(QueryCtl)), "cudaMallocHost ctl");
     ok = ok && cuda_ok(cudaMalloc(&g->d_probe_lo, sizeof(unsigned long long) * kMaxSegments), "cudaMalloc probe");
@@ -167,10 +171,9 @@ void engine_destroy(GpuEngine *g) {
     if (g->d_probe_count) cudaFree(g->d_probe_count);
     if (g->h_probe_keys) cudaFreeHost(g->h_probe_keys);
     if (g->h_probe_out) cudaFreeHost(g->h_probe_out);
-    if (g->ev0) cudaEventDestroy(g->ev0);
-    if (g->ev1) cudaEventDestroy(g->ev1);
-    if (g->ev_mid) cudaEventDestroy(g->ev_mid);
-    if (g->ev_post) cudaEventDestroy(g->ev_post);
+    for (int i = 0; i < GpuEngine::kTimingRing; ++i)
+        for (int k = 0; k < 4; ++k)
+            if (g->ring[i].ev[k]) cudaEventDestroy(g->ring[i].ev[k]);
     for (int i = 0; i < kMaxPipeSegments; ++i)
         if (g->ev_seg[i]) cudaEventDestroy(g->ev_seg[i]);
     if (g->stream2) cudaStreamDestroy(g->stream2);
@@ -376,6 +379,48 @@ static int plan_segments(const GpuEngine *g, const struct whereClauseS *wc, Segm
 }
 
 // ------------------------------------------------------------------------------------------
+// lazy event timing
+// ------------------------------------------------------------------------------------------
+static void resolve_slot(GpuEngine *g, GpuEngine::TimingSlot *slot, ScanStats *into) {
+    float ms = 0.f, a = 0.f, b = 0.f, pm = 0.f;
+    cudaEventElapsedTime(&ms, slot->ev[0], slot->ev[2]);
+    if (slot->staged) {
+        cudaEventElapsedTime(&a, slot->ev[0], slot->ev[1]);
+        if (slot->two_kernels) cudaEventElapsedTime(&b, slot->ev[1], slot->ev[2]);
+    }
+    if (slot->has_post) cudaEventElapsedTime(&pm, slot->ev[2], slot->ev[3]);
+    slot->pending = false;
+    if (into) {
+        into->kernel_ms = ms;
+        into->scan_ms = a;
+        into->compact_ms = b;
+        g->trace[3] = pm;
+    }
+    if (g->accumulate_timing) {
+        g->acc_kernel_ms += ms;
+        g->acc_scan_ms += a;
+        g->acc_compact_ms += b;
+        g->acc_post_ms += pm;
+        g->acc_calls += 1;
+    }
+}
+
+void engine_resolve_timing(GpuEngine *g) {
+    if (g->cur_slot && g->cur_slot->pending) {
+        cudaSetDevice(g->device);
+        resolve_slot(g, g->cur_slot, &g->last);
+    }
+}
+
+void engine_resolve_all(GpuEngine *g) {
+    cudaSetDevice(g->device);
+    for (int i = 0; i < GpuEngine::kTimingRing; ++i) {
+        GpuEngine::TimingSlot *slot = &g->ring[i];
+        if (slot->pending) resolve_slot(g, slot, slot == g->cur_slot ? &g->last : nullptr);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // match phase
 // ------------------------------------------------------------------------------------------
 bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, bool invert, bool count_only,
@@ -386,6 +431,18 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     const DevTable &t = g->table;
     g->last_bm_words = 0;
     bool post_done = false;
+    {
+        GpuEngine::TimingSlot *slot = &g->ring[g->ring_head];
+        g->ring_head = (g->ring_head + 1) % GpuEngine::kTimingRing;
+        if (slot->pending && g->accumulate_timing) resolve_slot(g, slot, nullptr);
+        slot->pending = false;
+        if (g->cur_slot && g->cur_slot->pending && !g->accumulate_timing) g->cur_slot->pending = false;  // never asked for
+        g->cur_slot = slot;
+        g->ev0 = slot->ev[0];
+        g->ev_mid = slot->ev[1];
+        g->ev1 = slot->ev[2];
+        g->ev_post = slot->ev[3];
+    }
 
     uint32_t widths[NUM_COLS];
     for (int c = 0; c < NUM_COLS; ++c) widths[c] = t.col[c].width;
@@ -703,25 +760,16 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     g->trace[1] = t_enq - t_compiled;
     g->trace[2] = t_sync - t_enq;
     g->trace[3] = 0;
-    if (g->post_match) {
-        float pm = 0.f;
-        cudaEventElapsedTime(&pm, g->ev1, g->ev_post);
-        g->trace[3] = pm;
-    }
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, g->ev0, g->ev1);
-    st.kernel_ms = ms;
-    if (st.path == 0 && st.tile_rows > 0) {
-        float a = 0.f, b = 0.f;
-        cudaEventElapsedTime(&a, g->ev0, g->ev_mid);
-        cudaEventElapsedTime(&b, g->ev_mid, g->ev1);
-        st.scan_ms = a;
-        st.compact_ms = st.launches > 1 ? b : 0.0;
-    }
+    // kernel_ms / scan_ms / compact_ms: resolved lazily from the slot's events (engine_resolve_timing)
+    g->cur_slot->pending = true;
+    g->cur_slot->staged = st.path == 0 && st.tile_rows > 0;
+    g->cur_slot->two_kernels = st.launches > 1;
+    g->cur_slot->has_post = static_cast<bool>(g->post_match);
     st.matches = static_cast<int64_t>(hc->out_count);
     st.algo_bytes = st.rows_scanned * bytes_per_row + (count_only ? 0 : 4 * st.matches) +
                     (st.path == 1 ? 4 * st.candidates : 0);
     st.total_ms = now_ms() - t_begin;
+    g->trace[4] = now_ms() - t_sync;  // tail of the call: event queries + statistics
     g->last = st;
     g->last_bm_count = hc->out_count;
     if (count) *count = hc->out_count;
@@ -735,6 +783,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
 // ------------------------------------------------------------------------------------------
 bool engine_compact_to(GpuEngine *g, uint32_t *dst, uint32_t id_base, uint64_t cap) {
     cudaSetDevice(g->device);
+    engine_resolve_timing(g);  // this call re-records two of the slot's events
     if (g->last_bm_words <= 0 && g->table.n > 0) {
         set_error("no match bitmap to compact: run a full-scan match with a bitmap first");
         return false;

@@ -25,7 +25,22 @@ struct GpuEngine {
     int device = 0;
     cudaStream_t stream = nullptr;   // K1 and everything else (highest priority)
     cudaStream_t stream2 = nullptr;  // K1c of a pipelined scan (lowest priority: fills the SMs beside K1)
+    // Events of the CURRENT match phase: handles borrowed from `ring` (one slot per call).  Elapsed times are
+    // resolved lazily -- when statistics are asked for (qpe_scan_stats / qpe_gpu_last_stats), or, with
+    // accumulate_timing, when the slot comes round again / qpe_gpu_timing_totals is called -- because four
+    // cudaEventElapsedTime calls cost ~11 us of host time per query, which a sharded 125 M-row scan notices.
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
+    struct TimingSlot {
+        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // ev0, ev_mid, ev1, ev_post
+        bool pending = false, staged = false, two_kernels = false, has_post = false;
+    };
+    static constexpr int kTimingRing = 512;
+    TimingSlot ring[kTimingRing];
+    int ring_head = 0;
+    TimingSlot *cur_slot = nullptr;      // slot of the most recent match phase (pending = not resolved yet)
+    bool accumulate_timing = false;
+    double acc_kernel_ms = 0, acc_scan_ms = 0, acc_compact_ms = 0, acc_post_ms = 0;
+    long long acc_calls = 0;
     cudaEvent_t ev_seg[kMaxPipeSegments] = {nullptr};  // K1 of segment i done -> K1c of segment i may start
     int pipe_segments = 0;           // 0 = fused K1f (default), 1 = K1 then K1c, n >= 2 = n pipelined table segments
     // K1f progress words (mapped pinned host memory): the kernel publishes "ids of table segment s are
@@ -72,8 +87,9 @@ struct GpuEngine {
     uint32_t *h_probe_out = nullptr;             // pinned: first[kMaxSegments], count[kMaxSegments]
 
     // host-side breakdown of the last match phase (ms): [0] parse/compile, [1] enqueue (copies + launches),
-    // [2] stream synchronisation, [3] device time ev1 -> end of the post-match kernels
-    double trace[4] = {0, 0, 0, 0};
+    // [2] stream synchronisation, [3] device time ev1 -> end of the post-match kernels, [4] tail of the
+    // match phase after the synchronisation, [5] whole C-ABI call of a sharded SELECT (parse included)
+    double trace[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev_post = nullptr;
     int force_tile_rows = 0, force_stages = 0;
     ScanStats last;
@@ -82,6 +98,7 @@ struct GpuEngine {
 extern std::mutex g_api_mutex;  // the engine is not re-entrant (one stream, one scratch set)
 GpuEngine *as_engine(struct engineS *e);  // nullptr (and error set) if e is not one of ours
 void set_error(const std::string &msg);
+double now_ms();
 bool cuda_ok(cudaError_t e, const char *what);
 
 // create an engine with an empty table; nullptr if no device
@@ -97,6 +114,10 @@ bool engine_append(GpuEngine *g, const record &r);
 bool engine_upload(GpuEngine *g, const HostColumns &hc);  // replaces the table
 bool engine_add_index(GpuEngine *g, const char *name, int attributeType);
 bool engine_ensure_ids(GpuEngine *g, int64_t n);
+// resolve the event times of the most recent match phase into g->last (no-op when already done)
+void engine_resolve_timing(GpuEngine *g);
+// resolve every pending slot into the accumulators (accumulate_timing)
+void engine_resolve_all(GpuEngine *g);
 
 // match phase. On success the ids are in g->d_ids[0 .. *count) (unless count_only).
 bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, bool invert, bool count_only,

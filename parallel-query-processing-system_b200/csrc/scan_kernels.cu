@@ -785,11 +785,14 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
 bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages, int max_stages,
                ScanGeometry *geo, const char **why, bool fused) {
     if (max_stages < 1 || max_stages > 4) max_stages = 4;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    int max_smem = 0, n_sm = 0;
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    // device attributes are asked once per process (one process per GPU; this runs twice per query)
+    static int max_smem = 0, n_sm = 0;
+    if (max_smem == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
     if (max_smem <= 0) max_smem = 227 * 1024;
     if (n_sm <= 0) n_sm = 148;
 
@@ -891,9 +894,13 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
 
 template <int EW, int R>
 static cudaError_t launch_scan_r(const ScanParams &p, const ScanGeometry &geo, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(geo.smem_bytes));
-    if (e != cudaSuccess) return e;
+    static size_t allowed = 0;  // per instantiation: raise the dynamic shared memory limit only when it grows
+    if (geo.smem_bytes > allowed) {
+        const cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(geo.smem_bytes));
+        if (e != cudaSuccess) return e;
+        allowed = geo.smem_bytes;
+    }
     long long grid = p.n_tiles - p.tile_begin;  // tiles of this launch
     if (grid > geo.grid) grid = geo.grid;
     if (grid < 1) grid = 1;
@@ -955,9 +962,13 @@ cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream
 
 template <int EW, int R>
 static cudaError_t launch_fused_r(const FusedParams &fp, const ScanGeometry &geo, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(scan_fused_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(geo.smem_bytes));
-    if (e != cudaSuccess) return e;
+    static size_t allowed = 0;  // per instantiation: raise the dynamic shared memory limit only when it grows
+    if (geo.smem_bytes > allowed) {
+        const cudaError_t e = cudaFuncSetAttribute(scan_fused_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(geo.smem_bytes));
+        if (e != cudaSuccess) return e;
+        allowed = geo.smem_bytes;
+    }
     scan_fused_kernel<EW, R><<<geo.grid, 32 * (1 + EW + kFuseCompactWarps), geo.smem_bytes, stream>>>(fp);
     return cudaGetLastError();
 }

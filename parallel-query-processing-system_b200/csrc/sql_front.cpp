@@ -576,11 +576,16 @@ int qpe_sql_select_ids_to(struct engineS *engine, const char *statement, unsigne
     return qpe_gpu_select_ids_to(engine, pw.wc, dst_device, dst_capacity, global_ids, count_out, stats);
 }
 
+extern "C" void qpe_gpu_trace_put(struct engineS *engine, int slot, double ms);  // capi.cu (diagnostics)
+
 int qpe_sql_shard_select(struct engineS *engine, const char *statement, int to_host,
                          unsigned long long *counts_out, qpe_scan_stats *stats) {
+    const auto t0 = std::chrono::steady_clock::now();
     ParsedWhere pw(statement);
     if (!pw.ok) return -7;
-    return qpe_shard_select(engine, pw.wc, to_host, counts_out, stats);
+    const int rc = qpe_shard_select(engine, pw.wc, to_host, counts_out, stats);
+    qpe_gpu_trace_put(engine, 5, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    return rc;
 }
 
 int qpe_sql_select_segments(struct engineS *engine, const char *statement, int global_ids, int *used_index_out,

@@ -251,16 +251,22 @@ class ShardGroup:
         self._counts = (C.c_ulonglong * 16)()
         self._stats = pkg.ScanStats()
         self._C = C
+        self._pstats = C.byref(self._stats)
+        self._fn, self._h = lib.qpe_sql_shard_select, engine._h
+        self._last_sql, self._last_bytes = None, None
         dist.barrier(group=group)
 
-    def select(self, statement: str, to_host: bool = False):
-        """One sharded full-scan SELECT (every rank calls it).  Returns (total, per-rank counts, stats dict).
-        to_host=False: ids packed in the owner's HBM (`device_result`); True: in `host_ids` on every rank."""
-        rc = self.lib.qpe_sql_shard_select(self.engine._h, statement.encode(), 1 if to_host else 0, self._counts,
-                                           self._C.byref(self._stats))
-        self.engine._check(rc, "qpe_shard_select")
-        counts = [int(self._counts[r]) for r in range(self.world)]
-        return sum(counts), counts, self._stats
+    def select(self, statement: str, to_host: bool = False, stats: bool = True):
+        """One sharded full-scan SELECT (every rank calls it).  Returns (total, per-rank counts, ScanStats).
+        to_host=False: ids packed in the owner's HBM (`device_result`); True: in `host_ids` on every rank.
+        stats=False: no statistics (None); the event times stay unresolved (Engine.set_timing / timing_totals)."""
+        if statement is not self._last_sql:      # the same statement object again: no re-encoding
+            self._last_sql, self._last_bytes = statement, statement.encode()
+        rc = self._fn(self._h, self._last_bytes, 1 if to_host else 0, self._counts, self._pstats if stats else None)
+        if rc != 0:
+            self.engine._check(rc, "qpe_shard_select")
+        counts = self._counts[:self.world]
+        return sum(counts), counts, (self._stats if stats else None)
 
     def device_result_ptr(self) -> int:
         return self.lib.qpe_shard_device_result(self.engine._h)
