@@ -7,6 +7,7 @@
 #include <cstring>
 #include <chrono>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 
 #include "engine.cuh"
@@ -19,13 +20,72 @@ using namespace qpe;
 namespace {
 
 
-// results produced by this library keep their cells in one arena; freeResultSet recognises them
+// Results produced by this library keep everything -- data[] (row pointers), the cell pointers and the cell
+// text -- in ONE block; freeResultSet recognises them.  Large blocks are PINNED host memory (the projection's
+// device->host copies then run at PCIe speed, asynchronously) and go back to a small pool instead of being
+// released: a fresh 450 MB allocation costs ~150 ms of page faults / page locking, which is what a
+// SELECT * of 1 M rows spent most of its time on.  The pool holds at most kPoolBlocks blocks / kPoolBytes.
 struct ResultArena {
-    char *text = nullptr;
-    char **rows = nullptr;
+    char *block = nullptr;
+    size_t bytes = 0;
+    bool pinned = false;
+    char *text = nullptr;    // inside block
+    char **rows = nullptr;   // inside block
 };
 std::mutex g_result_mutex;
 std::unordered_map<const struct resultSetS *, ResultArena> g_results;
+std::vector<ResultArena> g_pool;
+size_t g_pool_bytes = 0;
+constexpr size_t kPoolBlocks = 6;
+constexpr size_t kPoolBytes = size_t(3) << 30;
+constexpr size_t kPinThreshold = size_t(1) << 20;
+
+ResultArena arena_acquire(size_t need) {
+    {
+        std::lock_guard<std::mutex> lk(g_result_mutex);
+        int best = -1;
+        for (size_t i = 0; i < g_pool.size(); ++i)
+            if (g_pool[i].bytes >= need && (best < 0 || g_pool[i].bytes < g_pool[best].bytes)) best = static_cast<int>(i);
+        if (best >= 0 && g_pool[best].bytes <= 8 * need + (size_t(64) << 20)) {
+            ResultArena a = g_pool[best];
+            g_pool.erase(g_pool.begin() + best);
+            g_pool_bytes -= a.bytes;
+            return a;
+        }
+    }
+    ResultArena a;
+    if (need >= kPinThreshold) {
+        const size_t want = (need + need / 4 + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);  // head-room for reuse
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, want, cudaHostAllocPortable) == cudaSuccess) {
+            a.block = static_cast<char *>(p);
+            a.bytes = want;
+            a.pinned = true;
+            return a;
+        }
+        cudaGetLastError();  // no pinned memory left: plain memory works too, only slower
+    }
+    a.block = static_cast<char *>(std::malloc(need ? need : 1));
+    a.bytes = need;
+    a.pinned = false;
+    return a;
+}
+
+void arena_release(ResultArena a) {
+    if (!a.block) return;
+    if (a.pinned) {
+        std::lock_guard<std::mutex> lk(g_result_mutex);
+        if (g_pool.size() < kPoolBlocks && g_pool_bytes + a.bytes <= kPoolBytes) {
+            g_pool.push_back(a);
+            g_pool_bytes += a.bytes;
+            return;
+        }
+    }
+    if (a.pinned)
+        cudaFreeHost(a.block);
+    else
+        std::free(a.block);
+}
 
 const char *const kAllColumns[NUM_COLS] = {"command_id", "raw_command", "base_command", "shell_type",
                                            "exit_code",  "timestamp",   "sudo_used",    "working_directory",
@@ -98,87 +158,116 @@ bool materialise(GpuEngine *g, const char **selectItems, int numItems, int64_t m
     res->columnNames = static_cast<char **>(std::malloc(sizeof(char *) * (numItems > 0 ? numItems : 1)));
     for (int j = 0; j < numItems; ++j) res->columnNames[j] = strdup(selectItems[j]);
 
-    // fetch each distinct known column once
-    std::vector<uint8_t> colbuf[NUM_COLS];
-    bool have[NUM_COLS] = {false};
+    // K7: every distinct known column is rendered ON THE DEVICE into fixed-width NUL-terminated slots
+    // (format.cu) and lands in its own region of one arena; a cell pointer is then pure arithmetic.
     std::vector<int> colid(numItems);
+    uint32_t slot[NUM_COLS] = {0};
+    size_t region[NUM_COLS] = {0};
+    bool have[NUM_COLS] = {false};
+    size_t text_bytes = 16;  // [0..5) = "NULL" for unknown columns (:245-247)
+    size_t row_slots = 0;
     for (int j = 0; j < numItems; ++j) {
         const int c = col_by_name(selectItems[j]);
         colid[j] = c;
         if (c >= 0 && !have[c]) {
-            if (!engine_fetch_rows(g, c, g->d_ids, m, &colbuf[c])) return false;
+            if (m > 0 && !g->table.col[c].d) {
+                set_error(std::string("column '") + kCols[c].name + "' is not resident on the device");
+                res->numRecords = 0;
+                return false;
+            }
             have[c] = true;
+            slot[c] = format_slot_width(kCols[c].type, g->table.col[c].width);
+            region[c] = text_bytes;
+            text_bytes += static_cast<size_t>(m) * slot[c];
+            row_slots += slot[c];
         }
     }
-    // size the text arena
-    size_t text_bytes = 16;
-    for (int j = 0; j < numItems; ++j) {
-        const int c = colid[j];
-        if (c < 0)
-            text_bytes += static_cast<size_t>(m) * 5;  // "NULL"
-        else if (kCols[c].type == T_U64)
-            text_bytes += static_cast<size_t>(m) * 21;
-        else if (kCols[c].type == T_I32)
-            text_bytes += static_cast<size_t>(m) * 12;
-        else if (kCols[c].type == T_BOOL)
-            text_bytes += static_cast<size_t>(m) * 6;
-        else
-            text_bytes += static_cast<size_t>(m) * (g->table.col[c].width + 1);
-    }
-    ResultArena arena;
-    arena.text = static_cast<char *>(std::malloc(text_bytes));
-    arena.rows = static_cast<char **>(std::malloc(sizeof(char *) * (static_cast<size_t>(m) * numItems + 1)));
-    res->data = static_cast<char ***>(std::malloc(sizeof(char **) * static_cast<size_t>(m)));  // malloc(0) != NULL on glibc
-    if (!arena.text || !arena.rows || (m > 0 && !res->data)) {
+    // one block: data[m] | cell pointers [m x numItems] | text.  data is never NULL, also for zero matches
+    // (printTable then prints an empty framed table, printHelper.c:38-41)
+    const size_t data_bytes = (sizeof(char **) * static_cast<size_t>(m) + 63) & ~size_t(63);
+    const size_t rows_bytes = (sizeof(char *) * (static_cast<size_t>(m) * numItems + 1) + 63) & ~size_t(63);
+    cudaSetDevice(g->device);
+    ResultArena arena = arena_acquire(data_bytes + rows_bytes + text_bytes + 64);
+    if (!arena.block) {
         std::fprintf(stderr, "Memory allocation failed\n");
         std::exit(EXIT_FAILURE);
     }
-    if (!res->data) res->data = static_cast<char ***>(std::malloc(1));
-    char *tp = arena.text;
-    for (int64_t i = 0; i < m; ++i) {
-        char **row = arena.rows + static_cast<size_t>(i) * numItems;
-        res->data[i] = row;
-        for (int j = 0; j < numItems; ++j) {
-            const int c = colid[j];
-            row[j] = tp;
-            if (c < 0) {
-                std::memcpy(tp, "NULL", 5);
-                tp += 5;
-                continue;
-            }
-            const uint32_t w = g->table.col[c].width;
-            const uint8_t *cell = colbuf[c].data() + static_cast<size_t>(i) * w;
-            switch (kCols[c].type) {
-                case T_U64: {
-                    unsigned long long v;
-                    std::memcpy(&v, cell, 8);
-                    tp += fmt_u64(v, tp) + 1;
-                    break;
-                }
-                case T_I32: {
-                    int v;
-                    std::memcpy(&v, cell, 4);
-                    tp += fmt_i32(v, tp) + 1;
-                    break;
-                }
-                case T_BOOL:
-                    if (cell[0]) {
-                        std::memcpy(tp, "true", 5);
-                        tp += 5;
-                    } else {
-                        std::memcpy(tp, "false", 6);
-                        tp += 6;
-                    }
-                    break;
-                default: {
-                    const size_t len = strnlen(reinterpret_cast<const char *>(cell), w);
-                    std::memcpy(tp, cell, len);
-                    tp[len] = '\0';
-                    tp += len + 1;
-                    break;
-                }
+    res->data = reinterpret_cast<char ***>(arena.block);
+    arena.rows = reinterpret_cast<char **>(arena.block + data_bytes + (data_bytes ? 0 : 64));
+    arena.text = arena.block + (data_bytes ? data_bytes : 64) + rows_bytes;
+    std::memcpy(arena.text, "NULL", 5);
+
+    // device side, in row chunks that keep the scratch under 1 GiB: render, then copy each column's slots
+    // to its arena region; the copies of a chunk run while the host lays out the row pointers
+    bool ok = true;
+    int64_t chunk_rows = m;
+    if (row_slots > 0 && m > 0) {
+        const size_t kScratch = size_t(1) << 30;
+        if (static_cast<size_t>(m) * row_slots > kScratch) chunk_rows = static_cast<int64_t>(kScratch / row_slots);
+        size_t need = 0;  // every column's slots start on a 256-byte boundary of the scratch
+        for (int c = 0; c < NUM_COLS; ++c)
+            if (have[c]) need += (static_cast<size_t>(chunk_rows) * slot[c] + 255) & ~size_t(255);
+        if (need > g->fmt_cap) {
+            if (g->d_fmt) cudaFree(g->d_fmt);
+            g->d_fmt = nullptr;
+            g->fmt_cap = 0;
+            ok = cuda_ok(cudaMalloc(&g->d_fmt, need + 256), "cudaMalloc projection scratch");
+            if (ok) g->fmt_cap = need;
+        }
+    }
+    auto enqueue_chunk = [&](int64_t r0, int64_t r1) {
+        size_t off = 0;
+        for (int c = 0; c < NUM_COLS && ok; ++c) {
+            if (!have[c]) continue;
+            const size_t bytes = static_cast<size_t>(r1 - r0) * slot[c];
+            ok = cuda_ok(format_launch(g->table.col[c].d, kCols[c].type, g->table.col[c].width, g->d_ids + r0, r1 - r0,
+                                       g->d_fmt + off, g->stream),
+                         "projection kernel launch") &&
+                 cuda_ok(cudaMemcpyAsync(arena.text + region[c] + static_cast<size_t>(r0) * slot[c], g->d_fmt + off, bytes,
+                                         cudaMemcpyDeviceToHost, g->stream),
+                         "download projection");
+            off += (bytes + 255) & ~size_t(255);
+            ++g->last.launches;
+        }
+    };
+    if (ok && row_slots > 0 && m > 0) enqueue_chunk(0, chunk_rows < m ? chunk_rows : m);
+
+    // row pointers (the reference's char ***data): arithmetic only, split over a few threads when large
+    auto lay_rows = [&](int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; ++i) {
+            char **row = arena.rows + static_cast<size_t>(i) * numItems;
+            res->data[i] = row;
+            for (int j = 0; j < numItems; ++j) {
+                const int c = colid[j];
+                row[j] = c < 0 ? arena.text : arena.text + region[c] + static_cast<size_t>(i) * slot[c];
             }
         }
+    };
+    const int64_t cells = m * numItems;
+    int n_thr = cells > (int64_t(1) << 20) ? 8 : 1;
+    const unsigned hw = std::thread::hardware_concurrency();
+    if (hw && static_cast<unsigned>(n_thr) > hw) n_thr = static_cast<int>(hw);
+    if (n_thr <= 1) {
+        lay_rows(0, m);
+    } else {
+        std::vector<std::thread> pool;
+        const int64_t per = (m + n_thr - 1) / n_thr;
+        for (int t = 0; t < n_thr; ++t) {
+            const int64_t a = t * per, b = (a + per < m) ? a + per : m;
+            if (a < b) pool.emplace_back(lay_rows, a, b);
+        }
+        for (auto &th : pool) th.join();
+    }
+    ok = cuda_ok(cudaStreamSynchronize(g->stream), "projection sync") && ok;
+    for (int64_t r0 = chunk_rows; ok && r0 < m; r0 += chunk_rows) {
+        enqueue_chunk(r0, r0 + chunk_rows < m ? r0 + chunk_rows : m);
+        ok = cuda_ok(cudaStreamSynchronize(g->stream), "projection sync") && ok;
+    }
+    if (!ok) {
+        arena_release(arena);
+        res->data = nullptr;
+        res->numRecords = 0;
+        return false;
     }
     res->columnTypes = static_cast<FieldType *>(std::calloc(numItems > 0 ? numItems : 1, sizeof(FieldType)));  // :524-525
     {
@@ -433,9 +522,7 @@ void freeResultSet(struct resultSetS *result) {
     }
     std::free(result->columnTypes);
     if (ours) {
-        std::free(arena.text);
-        std::free(arena.rows);
-        std::free(result->data);
+        arena_release(arena);  // data[], the cell pointers and the text are one block
     } else if (result->data) {
         // a result built by someone else, cell by cell: the reference's destructor (:881-908)
         for (int i = 0; i < result->numRecords; ++i) {

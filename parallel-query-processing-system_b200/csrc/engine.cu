@@ -35,6 +35,7 @@ const char *last_error_cstr() { return g_last_error.c_str(); }
 
 bool cuda_ok(cudaError_t e, const char *what) {
     if (e == cudaSuccess) return true;
+    cudaGetLastError();  // reported here: a non-sticky error must not resurface at the next launch check
     set_error(std::string(what) + ": " + cudaGetErrorString(e));
     std::fprintf(stderr, "libqpegpu: %s: %s\n", what, cudaGetErrorString(e));
     return false;
@@ -165,6 +166,7 @@ void engine_destroy(GpuEngine *g) {
     if (g->d_tile_desc) cudaFree(g->d_tile_desc);
     if (g->d_ids) cudaFree(g->d_ids);
     if (g->d_bitmap) cudaFree(g->d_bitmap);
+    if (g->d_fmt) cudaFree(g->d_fmt);
     if (g->d_probe_lo) cudaFree(g->d_probe_lo);
     if (g->d_probe_hi) cudaFree(g->d_probe_hi);
     if (g->d_probe_first) cudaFree(g->d_probe_first);

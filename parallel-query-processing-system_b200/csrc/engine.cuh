@@ -67,6 +67,8 @@ struct GpuEngine {
     int64_t ids_cap = 0;
     uint32_t *d_bitmap = nullptr;
     int64_t bitmap_cap_words = 0;
+    uint8_t *d_fmt = nullptr;        // K7 scratch: rendered projection slots of one row chunk (grow-only)
+    size_t fmt_cap = 0;
     // destination override for the next full-scan match (qpe_gpu_select_ids_to): ids go to out_override
     // (this GPU's or a peer's memory, out_override_cap ids at most) with id_base_override added
     uint32_t *out_override = nullptr;

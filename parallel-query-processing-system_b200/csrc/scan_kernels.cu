@@ -821,10 +821,12 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
         T = T ? T : kMaxTileRows;
         S = S ? S : 2;
     } else if (!T) {
-        // largest tile that still leaves >= 3 stages in flight; else the largest with 2; else 1
+        // largest tile that still leaves >= 2 stages in flight; else the largest with 1.  Measured (100 M rows,
+        // profiles/r1_perf_history.md): the per-tile fixed work (program dispatch, barrier waits, ballots) costs
+        // more than a third stage buys -- QS 2048x2 6.9 TB/s vs 1024x4 5.3, QD 2048x2 5.4 TB/s vs 1024x4 3.1.
         static const int kTiles[] = {4096, 2048, 1024, 512, 256};
         int best_T = 0, best_S = 0;
-        for (int want = 3; want >= 1 && !best_T; --want)
+        for (int want = 2; want >= 1 && !best_T; --want)
             for (int cand : kTiles) {
                 const size_t sb = stage_bytes_for(cand);
                 int fit = static_cast<int>(budget / (sb ? sb : 1));

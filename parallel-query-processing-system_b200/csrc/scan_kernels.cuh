@@ -99,6 +99,12 @@ int64_t filter_tiles(long long n_candidates);
 // K2: projection gather  out[k] = column[ids[k]]  (width bytes per row)
 cudaError_t gather_launch(const uint8_t *col, uint32_t width, const uint32_t *ids, int64_t n_ids,
                           uint8_t *out, cudaStream_t stream);
+
+// K7 (format.cu): projection of one column for a list of row ids, rendered as fixed-width NUL-terminated text
+// slots (numeric columns: 24 / 16 / 8 bytes; text columns: the cell itself, i.e. K2).  out holds n slots.
+uint32_t format_slot_width(int col_type, uint32_t cell_width);
+cudaError_t format_launch(const uint8_t *col, int col_type, uint32_t cell_width, const uint32_t *ids, int64_t n,
+                          uint8_t *out, cudaStream_t stream);
 // same, but ids come from a bitmap-free "keep list" and output goes to a new column (DELETE)
 // -- identical kernel; alias kept for readability at call sites.
 

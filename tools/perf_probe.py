@@ -21,18 +21,34 @@ QS = {
 tiles = [(0, 0)]
 if len(sys.argv) > 2:
     tiles = [tuple(int(x) for x in a.split("x")) for a in sys.argv[2].split(",")]
+pipe = int(sys.argv[3]) if len(sys.argv) > 3 else 0          # 0 = fused K1f, 1 = K1 then K1c
+only = sys.argv[4].split(",") if len(sys.argv) > 4 else list(QS)
+fracs = [float(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0.0001, 0.01, 0.1, 0.5]
+eng.set_pipeline(pipe)
 for tr, stg in tiles:
-    eng.set_tile(tr, stg)
+    try:
+        eng.set_tile(tr, stg)
+    except Exception as e:
+        print(f"tile {tr}x{stg}: {e}")
+        continue
     for name, q in QS.items():
-        for frac in (0.0001, 0.01, 0.1, 0.5):
+        if name not in only:
+            continue
+        for frac in fracs:
             sql = q.format(K=int(N * frac))
             best = None
             for rep in range(4):
-                cnt, dptr, st = eng.select_ids_device(sql, force_scan=True)
+                try:
+                    cnt, dptr, st = eng.select_ids_device(sql, force_scan=True)
+                except Exception as e:
+                    print(f"{name} tile {tr}x{stg}: {e}")
+                    break
                 if best is None or st["kernel_ms"] < best["kernel_ms"]:
                     best = st
+            if best is None:
+                continue
             gbs = best["algo_bytes"] / best["kernel_ms"] / 1e6
-            print(f"{name} sel={frac:<7} tile={best['tile_rows']}x{best['stages']} grid={best['grid']} "
+            print(f"pipe={pipe} {name} sel={frac:<7} tile={best['tile_rows']}x{best['stages']} grid={best['grid']} "
                   f"M={best['matches']:>10} kernel={best['kernel_ms']:.3f} ms  {gbs:8.1f} GB/s  "
                   f"{N / best['kernel_ms'] / 1e6:.2f} Grows/s total_ms={best['total_ms']:.3f}", flush=True)
 eng.close()
