@@ -2,6 +2,9 @@
 // include/executeEngine-serial.h:69-151 of the reference), include/buildEngine-gpu.h and the
 // low-level row-id interface of include/qpe_gpu.h.
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <climits>
 #include <cstdlib>
 #include <cstring>
@@ -286,6 +289,83 @@ bool engine_load_indexes(GpuEngine *g, int num_indexes, const char *indexed_attr
     return true;
 }
 
+// K8: the data file rewritten from the device columns (executeEngine-serial.c:683-706): the text is rendered on
+// the GPU in chunks of <= 4 Mi rows, copied into a pooled pinned block and written with one write() per chunk.
+// Returns false (error set) if anything fails; the caller then falls back to nothing -- there is no host path.
+bool persist_csv_device(GpuEngine *g, const char *path) {
+    cudaSetDevice(g->device);
+    const DevTable &t = g->table;
+    for (int c = 0; c < NUM_COLS; ++c)
+        if (t.n > 0 && !t.col[c].d) {
+            set_error(std::string("cannot rewrite the data file: column '") + kCols[c].name + "' is not resident");
+            return false;
+        }
+    const int fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) {
+        set_error(std::string("cannot open ") + path + " for writing");
+        return false;
+    }
+    if (t.n == 0) {
+        ::close(fd);
+        return true;
+    }
+    unsigned long long *d_offs = nullptr;
+    void *d_tmp = nullptr;
+    char *d_text = nullptr;
+    size_t tmp_bytes = 0, text_cap = 0;
+    ResultArena pin;
+    bool ok = cuda_ok(cudaMalloc(&d_offs, sizeof(unsigned long long) * (t.n + 1)), "cudaMalloc csv offsets") &&
+              cuda_ok(csv_measure(t, d_offs, nullptr, &tmp_bytes, g->stream), "csv scan sizing") &&
+              cuda_ok(cudaMalloc(&d_tmp, tmp_bytes + 16), "cudaMalloc csv scan") &&
+              cuda_ok(csv_measure(t, d_offs, d_tmp, &tmp_bytes, g->stream), "csv measure kernels");
+    const int64_t kChunkRows = int64_t(4) << 20;
+    for (int64_t r0 = 0; ok && r0 < t.n; r0 += kChunkRows) {
+        const int64_t r1 = (r0 + kChunkRows < t.n) ? r0 + kChunkRows : t.n;
+        unsigned long long edge[2] = {0, 0};
+        ok = cuda_ok(cudaMemcpyAsync(&edge[0], d_offs + r0, 8, cudaMemcpyDeviceToHost, g->stream), "csv offsets") &&
+             cuda_ok(cudaMemcpyAsync(&edge[1], d_offs + r1, 8, cudaMemcpyDeviceToHost, g->stream), "csv offsets") &&
+             cuda_ok(cudaStreamSynchronize(g->stream), "csv offsets");
+        if (!ok) break;
+        const size_t bytes = static_cast<size_t>(edge[1] - edge[0]);
+        if (bytes + 32 > text_cap) {
+            if (d_text) cudaFree(d_text);
+            d_text = nullptr;
+            text_cap = 0;
+            ok = cuda_ok(cudaMalloc(&d_text, bytes + bytes / 8 + 64), "cudaMalloc csv text");
+            if (!ok) break;
+            text_cap = bytes + bytes / 8 + 64;
+        }
+        if (pin.bytes < bytes) {
+            arena_release(pin);
+            pin = arena_acquire(bytes + bytes / 8);
+            if (!pin.block) {
+                set_error("out of host memory for the CSV text");
+                ok = false;
+                break;
+            }
+        }
+        g->last.launches += 1;
+        ok = cuda_ok(csv_write(t, d_offs, r0, r1, edge[0], d_text, g->stream), "csv write kernel") &&
+             cuda_ok(cudaMemcpyAsync(pin.block, d_text, bytes, cudaMemcpyDeviceToHost, g->stream), "download csv text") &&
+             cuda_ok(cudaStreamSynchronize(g->stream), "csv text sync");
+        for (size_t done = 0; ok && done < bytes;) {
+            const ssize_t w = ::write(fd, pin.block + done, bytes - done);
+            if (w <= 0) {
+                set_error(std::string("write failed on ") + path);
+                ok = false;
+                break;
+            }
+            done += static_cast<size_t>(w);
+        }
+    }
+    ::close(fd);
+    arena_release(pin);
+    if (d_text) cudaFree(d_text);
+    if (d_tmp) cudaFree(d_tmp);
+    if (d_offs) cudaFree(d_offs);
+    return ok;
+}
+
 // CSV line format shared by INSERT's append and DELETE's rewrite (:562-575, :687-700)
 void write_csv_row(FILE *f, const HostColumns &hc, int64_t i) {
     auto cell = [&](int c) { return hc.data[c].data() + static_cast<size_t>(i) * hc.width[c]; };
@@ -426,18 +506,8 @@ struct resultSetS *executeQueryDeleteGPU(struct engineS *engine, const char *tab
         return res;
     }
     // the reference rewrites the whole CSV after every DELETE, matched rows or not (:683-706)
-    if (g->head.datafile) {
-        HostColumns hc;
-        if (engine_download_all(g, &hc)) {
-            FILE *f = std::fopen(g->head.datafile, "w");
-            if (f) {
-                static thread_local std::vector<char> iobuf(1 << 20);
-                std::setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
-                for (int64_t i = 0; i < hc.n; ++i) write_csv_row(f, hc, i);
-                std::fclose(f);
-            }
-        }
-    }
+    if (g->head.datafile && !persist_csv_device(g, g->head.datafile))
+        std::fprintf(stderr, "libqpegpu: executeQueryDeleteGPU: %s\n", qpe_gpu_last_error());  // the reference ignores fopen failures too (:684)
     res->numRecords = static_cast<int>(deleted);
     res->queryTime = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     res->success = true;

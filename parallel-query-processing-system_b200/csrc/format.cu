@@ -12,6 +12,8 @@
 
 #include "scan_kernels.cuh"
 
+#include <cub/device/device_scan.cuh>
+
 namespace qpe {
 
 namespace {
@@ -105,6 +107,184 @@ cudaError_t format_launch(const uint8_t *col, int col_type, uint32_t cell_width,
         default:
             return gather_launch(col, cell_width, ids, n, out, stream);
     }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K8: the table rendered as CSV text on the device
+//
+// executeQueryDeleteSerial rewrites the WHOLE data file after every DELETE, one fprintf per row
+// (engine/serial/executeEngine-serial.c:683-706): "%llu,%s,%s,%s,%d,%s,%d,%s,%d,%s,%s,%d\n", no header, no
+// quoting, sudo_used as 0/1.  Here: csv_len_kernel (bytes of every row) -> exclusive scan (cub::DeviceScan, a
+// library primitive off the query path, like the index build's radix sort) -> csv_write_kernel (a CTA renders
+// its 128 rows into shared memory at their offsets and copies the contiguous text out with 16-byte stores);
+// the host then writes the file with ONE write().  Bound: HBM (all columns read twice) + PCIe + the file write.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct CsvCols {
+    const uint8_t *col[NUM_COLS];
+    uint32_t width[NUM_COLS];
+};
+
+__device__ __forceinline__ int dec_len_u64(unsigned long long v) {
+    int n = 1;
+    while (v >= 10ull) {
+        v /= 10ull;
+        ++n;
+    }
+    return n;
+}
+
+// length of the NUL-padded text cell (the cell always holds at least one NUL)
+__device__ __forceinline__ int text_len(const uint8_t *cell, uint32_t w) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(cell);
+    for (uint32_t k = 0; k < (w >> 4); ++k) {
+        const uint4 v = __ldg(q + k);
+        const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t x = words[i];
+            const uint32_t z = (x - 0x01010101u) & ~x & 0x80808080u;  // a zero byte in x
+            if (z) return static_cast<int>(k * 16 + i * 4 + ((__ffs(z) - 1) >> 3));
+        }
+    }
+    return static_cast<int>(w);
+}
+
+__device__ __forceinline__ char *put_text(char *dst, const uint8_t *cell, uint32_t w) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(cell);
+    for (uint32_t k = 0; k < (w >> 4); ++k) {
+        const uint4 v = __ldg(q + k);
+        const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const char c = static_cast<char>((words[i] >> (8 * b)) & 0xffu);
+                if (c == 0) return dst;
+                *dst++ = c;
+            }
+        }
+    }
+    return dst;
+}
+
+__device__ __forceinline__ char *put_i32(char *dst, int v) {
+    unsigned int mag = static_cast<unsigned int>(v);
+    if (v < 0) {
+        *dst++ = '-';
+        mag = 0u - mag;
+    }
+    return dst + render_u64(mag, dst);
+}
+
+__device__ __forceinline__ unsigned int row_len(const CsvCols &t, long long r) {
+    unsigned int n = 12;  // 11 commas + '\n'
+#pragma unroll
+    for (int c = 0; c < NUM_COLS; ++c) {
+        const uint8_t *cell = t.col[c] + static_cast<size_t>(r) * t.width[c];
+        if (c == C_COMMAND_ID) {
+            n += dec_len_u64(*reinterpret_cast<const unsigned long long *>(cell));
+        } else if (c == C_EXIT_CODE || c == C_USER_ID || c == C_RISK_LEVEL) {
+            const int v = *reinterpret_cast<const int *>(cell);
+            n += (v < 0 ? 1 : 0) + dec_len_u64(v < 0 ? 0u - static_cast<unsigned int>(v) : static_cast<unsigned int>(v));
+        } else if (c == C_SUDO_USED) {
+            n += 1;
+        } else {
+            n += text_len(cell, t.width[c]);
+        }
+    }
+    return n;
+}
+
+__device__ __forceinline__ void render_row(const CsvCols &t, long long r, char *dst) {
+#pragma unroll
+    for (int c = 0; c < NUM_COLS; ++c) {
+        const uint8_t *cell = t.col[c] + static_cast<size_t>(r) * t.width[c];
+        if (c == C_COMMAND_ID)
+            dst += render_u64(*reinterpret_cast<const unsigned long long *>(cell), dst);
+        else if (c == C_EXIT_CODE || c == C_USER_ID || c == C_RISK_LEVEL)
+            dst = put_i32(dst, *reinterpret_cast<const int *>(cell));
+        else if (c == C_SUDO_USED)
+            *dst++ = cell[0] ? '1' : '0';
+        else
+            dst = put_text(dst, cell, t.width[c]);
+        *dst++ = (c == NUM_COLS - 1) ? '\n' : ',';
+    }
+}
+
+constexpr int kCsvRows = 128;           // rows (= threads) per CTA
+constexpr int kCsvStage = 40 * 1024;    // shared-memory stage; a CTA whose text is longer writes straight to HBM
+
+__global__ void __launch_bounds__(kCsvRows) csv_len_kernel(const CsvCols t, long long n, unsigned long long *lens) {
+    const long long r = blockIdx.x * static_cast<long long>(kCsvRows) + threadIdx.x;
+    if (r < n) lens[r] = row_len(t, r);
+    if (r == n) lens[r] = 0;  // slot n: the scan leaves the total there
+}
+
+// rows [row_begin, n) of the table; out[0] is the byte at file offset base_off (= offs[row_begin])
+__global__ void __launch_bounds__(kCsvRows) csv_write_kernel(const CsvCols t, long long row_begin, long long n,
+                                                             const unsigned long long *__restrict__ offs,
+                                                             unsigned long long base_off, char *out_chunk) {
+    __shared__ __align__(16) char stage[kCsvStage];
+    char *out = out_chunk - base_off;  // only dereferenced at offsets >= base_off
+    const long long r0 = row_begin + blockIdx.x * static_cast<long long>(kCsvRows);
+    const long long r1 = (r0 + kCsvRows < n) ? r0 + kCsvRows : n;
+    const long long r = r0 + threadIdx.x;
+    const unsigned long long begin = offs[r0], end = offs[r1];
+    const unsigned long long bytes = end - begin;
+    const unsigned int pad = static_cast<unsigned int>(reinterpret_cast<uintptr_t>(out + begin) & 15u);
+    if (pad + bytes > kCsvStage) {  // unusually long rows: no staging
+        if (r < r1) render_row(t, r, out + offs[r]);
+        return;
+    }
+    // stage[pad + i] <-> out[begin + i]: shared and global addresses agree modulo 16
+    if (r < r1) render_row(t, r, stage + pad + (offs[r] - begin));
+    __syncthreads();
+    char *gbase = out + begin - pad;  // 16-byte aligned
+    const unsigned int lo = pad, hi = pad + static_cast<unsigned int>(bytes);
+    const unsigned int s0 = (lo + 15u) & ~15u, e0 = hi & ~15u;
+    if (s0 >= e0) {
+        for (unsigned int i = lo + threadIdx.x; i < hi; i += kCsvRows) gbase[i] = stage[i];
+        return;
+    }
+    for (unsigned int i = lo + threadIdx.x; i < s0; i += kCsvRows) gbase[i] = stage[i];
+    for (unsigned int i = s0 / 16 + threadIdx.x; i < e0 / 16; i += kCsvRows)
+        reinterpret_cast<uint4 *>(gbase)[i] = reinterpret_cast<const uint4 *>(stage)[i];
+    for (unsigned int i = e0 + threadIdx.x; i < hi; i += kCsvRows) gbase[i] = stage[i];
+}
+
+}  // namespace
+
+// Phase 1: row lengths + scan.  d_offs holds n + 1 entries; after the call d_offs[i] = byte offset of row i and
+// d_offs[n] = total bytes.  scan_tmp / scan_tmp_bytes: cub scratch (call with scan_tmp == nullptr to size it).
+cudaError_t csv_measure(const DevTable &t, unsigned long long *d_offs, void *scan_tmp, size_t *scan_tmp_bytes,
+                        cudaStream_t stream) {
+    if (!scan_tmp) return cub::DeviceScan::ExclusiveSum(nullptr, *scan_tmp_bytes, d_offs, d_offs, t.n + 1, stream);
+    CsvCols cc;
+    for (int c = 0; c < NUM_COLS; ++c) {
+        cc.col[c] = t.col[c].d;
+        cc.width[c] = t.col[c].width;
+    }
+    const long long blocks = (t.n + 1 + kCsvRows - 1) / kCsvRows;
+    csv_len_kernel<<<static_cast<unsigned int>(blocks), kCsvRows, 0, stream>>>(cc, t.n, d_offs);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cub::DeviceScan::ExclusiveSum(scan_tmp, *scan_tmp_bytes, d_offs, d_offs, t.n + 1, stream);
+}
+
+// Phase 2: the text of rows [r0, r1) into d_out, whose first byte is file offset base_off = d_offs[r0]
+cudaError_t csv_write(const DevTable &t, const unsigned long long *d_offs, long long r0, long long r1,
+                      unsigned long long base_off, char *d_out, cudaStream_t stream) {
+    if (r1 <= r0) return cudaSuccess;
+    CsvCols cc;
+    for (int c = 0; c < NUM_COLS; ++c) {
+        cc.col[c] = t.col[c].d;
+        cc.width[c] = t.col[c].width;
+    }
+    const long long blocks = (r1 - r0 + kCsvRows - 1) / kCsvRows;
+    csv_write_kernel<<<static_cast<unsigned int>(blocks), kCsvRows, 0, stream>>>(cc, r0, r1, d_offs, base_off, d_out);
     return cudaGetLastError();
 }
 

@@ -997,7 +997,16 @@ cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStre
         case 512: return launch_fused_r<kEvalWarps, 1>(fp, geo, stream);
         case 1024: return launch_fused_r<kEvalWarps, 2>(fp, geo, stream);
         case 2048: return launch_fused_r<kEvalWarps, 4>(fp, geo, stream);
-        case 4096: return launch_fused_r<kEvalWarps, 8>(fp, geo, stream);
+        case 4096: {
+            // experiment knob (QPE_EVAL_WARPS=8): 8 evaluator warps x 16 rows per lane -- the per-tile dispatch
+            // of the program is then amortised over twice the rows per warp
+            static const int ew = [] {
+                const char *e = std::getenv("QPE_EVAL_WARPS");
+                return e ? std::atoi(e) : 0;
+            }();
+            if (ew == 8) return launch_fused_r<8, 16>(fp, geo, stream);
+            return launch_fused_r<kEvalWarps, 8>(fp, geo, stream);
+        }
         default: return cudaErrorInvalidValue;
     }
 }

@@ -105,6 +105,15 @@ cudaError_t gather_launch(const uint8_t *col, uint32_t width, const uint32_t *id
 uint32_t format_slot_width(int col_type, uint32_t cell_width);
 cudaError_t format_launch(const uint8_t *col, int col_type, uint32_t cell_width, const uint32_t *ids, int64_t n,
                           uint8_t *out, cudaStream_t stream);
+
+// K8 (format.cu): the whole table as CSV text in the format of the reference's DELETE rewrite / INSERT append
+// (executeEngine-serial.c:562-575, :687-700).  csv_measure: d_offs[i] = byte offset of row i, d_offs[n] = total
+// (d_offs holds n + 1 entries; scan_tmp == nullptr sizes the scan scratch); csv_write: the text of rows [r0, r1)
+// into d_out, whose first byte is file offset base_off = d_offs[r0].
+cudaError_t csv_measure(const DevTable &t, unsigned long long *d_offs, void *scan_tmp, size_t *scan_tmp_bytes,
+                        cudaStream_t stream);
+cudaError_t csv_write(const DevTable &t, const unsigned long long *d_offs, long long r0, long long r1,
+                      unsigned long long base_off, char *d_out, cudaStream_t stream);
 // same, but ids come from a bitmap-free "keep list" and output goes to a new column (DELETE)
 // -- identical kernel; alias kept for readability at call sites.
 

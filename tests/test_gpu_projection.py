@@ -103,3 +103,46 @@ def test_projection_large_result_multi_chunk_pointers():
     finally:
         lib.freeResultSet(res)
         eng.close()
+
+
+# ---- K8: the data file rewritten from the device columns after DELETE -------------------------------------
+def _expected_csv(eng, pkg):
+    cols = {c: eng.fetch_column(c) for c in pkg.COLUMNS}
+    n = eng.num_rows
+
+    def text(c, i):
+        return bytes(cols[c][i]).split(b"\0", 1)[0]
+
+    out = []
+    for i in range(n):
+        out.append(b",".join([
+            str(int(cols["command_id"][i])).encode(), text("raw_command", i), text("base_command", i),
+            text("shell_type", i), str(int(cols["exit_code"][i])).encode(), text("timestamp", i),
+            b"1" if cols["sudo_used"][i] else b"0", text("working_directory", i), str(int(cols["user_id"][i])).encode(),
+            text("user_name", i), text("host_name", i), str(int(cols["risk_level"][i])).encode()]) + b"\n")
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("long_rows", [False, True])
+def test_delete_rewrites_csv_from_device_text(tmp_path, long_rows):
+    """executeQueryDeleteSerial rewrites the whole file with one fprintf per row (:683-706); K8 renders the same
+    bytes on the device.  long_rows: 300 rows of ~700 bytes each, so whole CTAs overflow the shared-memory
+    stage and take the direct-store path."""
+    pkg = support.load_pkg()
+    csv = str(tmp_path / "t.csv")
+    rows = nasty_rows(seed=23, n=900)
+    if long_rows:
+        rows = [f'{i + 1},"{"r" * 480} {i}",{"b" * 90},zsh,{i - 150},2026-03-01T00:00:00.000Z,true,/{"w" * 150},{i},'
+                f'user{i},host-{i},{i % 5}' for i in range(300)] + rows
+    write_csv(csv, rows)
+    eng = pkg.Engine.from_csv(csv, indexes=())
+    try:
+        n0 = eng.num_rows
+        out = eng.run("DELETE FROM Commands WHERE command_id = 4000000000000", 5)      # matches nothing
+        assert "Rows affected: 0" in out
+        assert open(csv, "rb").read() == _expected_csv(eng, pkg)
+        out = eng.run("DELETE FROM Commands WHERE (risk_level > 0) AND (sudo_used = TRUE)", 5)
+        assert eng.num_rows < n0
+        assert open(csv, "rb").read() == _expected_csv(eng, pkg)
+    finally:
+        eng.close()
