@@ -300,11 +300,14 @@ bool persist_csv_device(GpuEngine *g, const char *path) {
             set_error(std::string("cannot rewrite the data file: column '") + kCols[c].name + "' is not resident");
             return false;
         }
+    static const bool trace = std::getenv("QPE_TRACE_DML") != nullptr;
+    const double t_open0 = now_ms();
     const int fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
     if (fd < 0) {
         set_error(std::string("cannot open ") + path + " for writing");
         return false;
     }
+    double t_open = now_ms() - t_open0, t_dev = 0, t_write = 0;
     if (t.n == 0) {
         ::close(fd);
         return true;
@@ -320,6 +323,7 @@ bool persist_csv_device(GpuEngine *g, const char *path) {
               cuda_ok(csv_measure(t, d_offs, d_tmp, &tmp_bytes, g->stream), "csv measure kernels");
     const int64_t kChunkRows = int64_t(4) << 20;
     for (int64_t r0 = 0; ok && r0 < t.n; r0 += kChunkRows) {
+        const double t_c0 = now_ms();
         const int64_t r1 = (r0 + kChunkRows < t.n) ? r0 + kChunkRows : t.n;
         unsigned long long edge[2] = {0, 0};
         ok = cuda_ok(cudaMemcpyAsync(&edge[0], d_offs + r0, 8, cudaMemcpyDeviceToHost, g->stream), "csv offsets") &&
@@ -348,6 +352,8 @@ bool persist_csv_device(GpuEngine *g, const char *path) {
         ok = cuda_ok(csv_write(t, d_offs, r0, r1, edge[0], d_text, g->stream), "csv write kernel") &&
              cuda_ok(cudaMemcpyAsync(pin.block, d_text, bytes, cudaMemcpyDeviceToHost, g->stream), "download csv text") &&
              cuda_ok(cudaStreamSynchronize(g->stream), "csv text sync");
+        const double t_c1 = now_ms();
+        t_dev += t_c1 - t_c0;
         for (size_t done = 0; ok && done < bytes;) {
             const ssize_t w = ::write(fd, pin.block + done, bytes - done);
             if (w <= 0) {
@@ -357,8 +363,14 @@ bool persist_csv_device(GpuEngine *g, const char *path) {
             }
             done += static_cast<size_t>(w);
         }
+        t_write += now_ms() - t_c1;
     }
+    const double t_cl0 = now_ms();
     ::close(fd);
+    if (trace)
+        std::fprintf(stderr, "libqpegpu: csv rewrite of %lld rows: open+truncate %.2f ms, device render + copy %.2f ms, "
+                             "write() %.2f ms, close %.2f ms\n",
+                     static_cast<long long>(t.n), t_open, t_dev, t_write, now_ms() - t_cl0);
     arena_release(pin);
     if (d_text) cudaFree(d_text);
     if (d_tmp) cudaFree(d_tmp);
