@@ -61,6 +61,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe of a barrier phase (try_wait may suspend the thread for a while; this never does)
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Every spin in this file is bounded: a protocol bug (or a peer that never arrives) ends in a trapped
 // kernel and a CUDA error on the host, never in a hung GPU.  2^31 polls are minutes of waiting.
 constexpr uint32_t kSpinLimit = 0x7fffffffu;
@@ -189,18 +201,18 @@ __device__ __forceinline__ uint32_t rows_mask(F pred) {
     return m;
 }
 
-// numeric leaf: the operator is warp-uniform, so it is dispatched ONCE per tile and each case is
-// a straight run of R (load, compare, predicated OR) triples
-template <int R, typename T>
-__device__ __forceinline__ uint32_t cmp_numeric(const T *c, const T lit, const uint32_t tt) {
+// numeric leaf: the operator is warp-uniform, so it is dispatched ONCE per evaluation and each case is
+// a straight run of RB (load, compare, predicated OR) triples; ld(j) loads the value of this lane's j-th row
+template <int RB, typename T, typename Ld>
+__device__ __forceinline__ uint32_t cmp_numeric(Ld ld, const T lit, const uint32_t tt) {
     switch (tt) {
-        case 0b010: return rows_mask<R>([&](int j) { return c[j * 32] == lit; });
-        case 0b101: return rows_mask<R>([&](int j) { return c[j * 32] != lit; });
-        case 0b100: return rows_mask<R>([&](int j) { return c[j * 32] > lit; });
-        case 0b001: return rows_mask<R>([&](int j) { return c[j * 32] < lit; });
-        case 0b110: return rows_mask<R>([&](int j) { return c[j * 32] >= lit; });
-        case 0b011: return rows_mask<R>([&](int j) { return c[j * 32] <= lit; });
-        case 0b111: return (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
+        case 0b010: return rows_mask<RB>([&](int j) { return ld(j) == lit; });
+        case 0b101: return rows_mask<RB>([&](int j) { return ld(j) != lit; });
+        case 0b100: return rows_mask<RB>([&](int j) { return ld(j) > lit; });
+        case 0b001: return rows_mask<RB>([&](int j) { return ld(j) < lit; });
+        case 0b110: return rows_mask<RB>([&](int j) { return ld(j) >= lit; });
+        case 0b011: return rows_mask<RB>([&](int j) { return ld(j) <= lit; });
+        case 0b111: return (RB >= 32) ? 0xffffffffu : ((1u << RB) - 1u);
         default: return 0u;
     }
 }
@@ -209,24 +221,37 @@ __device__ __forceinline__ uint32_t diff16(const uint4 v, const uint4 l) {
     return (v.x ^ l.x) | (v.y ^ l.y) | (v.z ^ l.z) | (v.w ^ l.w);
 }
 
-// evaluate one leaf for the R rows of this lane (rows lrow, lrow+32, ...) out of a staged tile
-template <int R>
+// Evaluate one leaf for this lane's rows of NT staged tiles at once (NT = 1: rows lrow, lrow+32, ... of the
+// tile at `stage`; NT = 2: also the same rows of the tile at `stage + dB`, which become mask bits R .. 2R-1).
+// Two tiles per call halve the per-tile cost of interpreting the program (~60 % of the evaluators'
+// instructions for a 3-leaf WHERE), so the fused kernel takes two whenever the next stage has already landed.
+template <int R, int NT>
 __device__ __forceinline__ uint32_t eval_leaf_tile(const PLeaf &lf, const Program *sp, const uint8_t *stage,
-                                                   const ScanParams &p, int lrow) {
+                                                   const int dB, const ScanParams &p, int lrow) {
+    constexpr int RB = R * NT;
     const uint8_t *base = stage + p.smem_off[lf.col];
     const uint32_t tt = lf.tt;
-    constexpr uint32_t kAll = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
+    constexpr uint32_t kAll = (RB >= 32) ? 0xffffffffu : ((1u << RB) - 1u);
+    // byte address of this lane's j-th row of a column with `w`-byte cells (j is a constant after unrolling)
+    auto row_ptr = [&](const uint8_t *c0, int j, uint32_t w) -> const uint8_t * {
+        return (j < R) ? c0 + static_cast<size_t>(j) * 32u * w : c0 + dB + static_cast<size_t>(j - R) * 32u * w;
+    };
     switch (lf.type) {
-        case T_I32:
-            return cmp_numeric<R, int32_t>(reinterpret_cast<const int32_t *>(base) + lrow, lf.lit_i32, tt);
-        case T_U64:
-            return cmp_numeric<R, unsigned long long>(reinterpret_cast<const unsigned long long *>(base) + lrow,
-                                                      lf.lit_u64, tt);
+        case T_I32: {
+            const uint8_t *c = base + static_cast<size_t>(lrow) * 4u;
+            return cmp_numeric<RB, int32_t>([&](int j) { return *reinterpret_cast<const int32_t *>(row_ptr(c, j, 4)); },
+                                            lf.lit_i32, tt);
+        }
+        case T_U64: {
+            const uint8_t *c = base + static_cast<size_t>(lrow) * 8u;
+            return cmp_numeric<RB, unsigned long long>(
+                [&](int j) { return *reinterpret_cast<const unsigned long long *>(row_ptr(c, j, 8)); }, lf.lit_u64, tt);
+        }
         case T_BOOL: {
             // only = and != exist; (cell != 0) == want
             const uint8_t *c = base + lrow;
             const bool want = ((tt == 0b010u) == ((lf.lit_i32 & 1) != 0));
-            const uint32_t nz = rows_mask<R>([&](int j) { return c[j * 32] != 0; });
+            const uint32_t nz = rows_mask<RB>([&](int j) { return *row_ptr(c, j, 1) != 0; });
             return want ? nz : (~nz & kAll);
         }
         default: {  // T_STR: strcmp order == unsigned byte order over the NUL-padded cell
@@ -234,21 +259,17 @@ __device__ __forceinline__ uint32_t eval_leaf_tile(const PLeaf &lf, const Progra
             const int nch = static_cast<int>(w >> 4);
             const uint4 *lit = reinterpret_cast<const uint4 *>(sp->lit_pool + lf.lit_off);
             const uint8_t *c = base + static_cast<size_t>(lrow) * w;
-            const size_t jstride = static_cast<size_t>(32u) * w;
+            auto cell = [&](int j) { return reinterpret_cast<const uint4 *>(row_ptr(c, j, w)); };
             if (tt == 0b010u || tt == 0b101u) {
                 // equality only: OR of XORs, no byte swapping
                 uint32_t ne = 0;
                 if (nch == 1) {
                     const uint4 l0 = lit[0];
-                    ne = rows_mask<R>([&](int j) {
-                        return diff16(*reinterpret_cast<const uint4 *>(c + j * jstride), l0) != 0u;
-                    });
+                    ne = rows_mask<RB>([&](int j) { return diff16(*cell(j), l0) != 0u; });
                 } else {
                     for (int k = 0; k < nch; ++k) {
                         const uint4 lk = lit[k];
-                        ne |= rows_mask<R>([&](int j) {
-                            return diff16(reinterpret_cast<const uint4 *>(c + j * jstride)[k], lk) != 0u;
-                        });
+                        ne |= rows_mask<RB>([&](int j) { return diff16(cell(j)[k], lk) != 0u; });
                         if (__all_sync(0xffffffffu, ne == kAll)) break;  // warp-uniform early exit
                     }
                 }
@@ -261,8 +282,8 @@ __device__ __forceinline__ uint32_t eval_leaf_tile(const PLeaf &lf, const Progra
                 const uint32_t b0 = bswap32(lk.x), b1 = bswap32(lk.y), b2 = bswap32(lk.z), b3 = bswap32(lk.w);
                 uint32_t dk = 0, ltk = 0;
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const uint4 v = reinterpret_cast<const uint4 *>(c + j * jstride)[k];
+                for (int j = 0; j < RB; ++j) {
+                    const uint4 v = cell(j)[k];
                     const uint32_t a0 = bswap32(v.x), a1 = bswap32(v.y), a2 = bswap32(v.z), a3 = bswap32(v.w);
                     const bool d0 = a0 != b0, d1 = a1 != b1, d2 = a2 != b2, d3 = a3 != b3;
                     const bool l = d0 ? (a0 < b0) : d1 ? (a1 < b1) : d2 ? (a2 < b2) : (a3 < b3);
@@ -447,7 +468,7 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_tma_kernel(const __grid
 
             const uint8_t *stage = stages + static_cast<size_t>(s) * p.stage_bytes;
             uint32_t acc = run_program(sp, all_mask, [&](const PLeaf &lf) {
-                return eval_leaf_tile<R>(lf, sp, stage, p, lrow);
+                return eval_leaf_tile<R, 1>(lf, sp, stage, 0, p, lrow);
             });
             // the stage can be refilled as soon as every evaluator has read it
             __syncwarp();
@@ -548,6 +569,7 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
     constexpr int T = 32 * EW * R;   // rows per tile
     constexpr int WPT = T >> 5;      // bitmap words per tile
     constexpr uint32_t kThreads = 32 * (1 + EW + kFuseCompactWarps);
+    constexpr bool kDual = (2 * R <= 16);  // two tiles per pass of the program (mask bits 0..2R-1)
     const int CT = fp.chunk_tiles;
 
     {
@@ -620,12 +642,68 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
             uint32_t *cb = cbuf + buf * kFuseChunkWords;
             const long long t0 = chunk * CT;
             const int nt = static_cast<int>((p.n_tiles - t0 < CT) ? (p.n_tiles - t0) : CT);
-            for (int j = 0; j < nt; ++j) {
+            for (int j = 0; j < nt;) {
                 mbar_wait(&sh->full[s], sphase);
                 const long long tile = t0 + j;
                 const uint8_t *stage = stages + static_cast<size_t>(s) * p.stage_bytes;
+                int s2 = s + 1;
+                uint32_t phase2 = sphase;
+                if (s2 == S) {
+                    s2 = 0;
+                    phase2 ^= 1u;
+                }
+                // Two tiles in one pass of the program when the NEXT stage has already landed (the scan is then
+                // instruction-bound, not waiting for HBM) and a further stage stays in flight (S >= 3).
+                bool dual = false;
+                if (kDual && S >= 3 && j + 1 < nt) {
+                    uint32_t ready = 0;
+                    if (lane == 0) ready = mbar_test(&sh->full[s2], phase2) ? 1u : 0u;
+                    dual = __shfl_sync(0xffffffffu, ready, 0) != 0u;
+                }
+                if (dual) {
+                    if constexpr (kDual) {
+                        mbar_wait(&sh->full[s2], phase2);  // every lane observes the phase (returns at once)
+                        const int dB = (s2 - s) * static_cast<int>(p.stage_bytes);
+                        constexpr uint32_t all2 = (2 * R >= 32) ? 0xffffffffu : ((1u << (2 * R)) - 1u);
+                        uint32_t acc2 = run_program(sp, all2, [&](const PLeaf &lf) {
+                            return eval_leaf_tile<R, 2>(lf, sp, stage, dB, p, lrow);
+                        });
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive(&sh->empty[s]);
+                            mbar_arrive(&sh->empty[s2]);
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const long long tl = tile + h;
+                            uint32_t acc = (acc2 >> (h * R)) & all_mask;
+                            const long long row_base = tl * T + lrow;
+                            if (tl * T + T > p.n_rows)
+                                acc &= rows_mask<R>([&](int jj) { return row_base + 32ll * jj < p.n_rows; });
+                            my_count += static_cast<uint32_t>(__popc(acc));
+                            uint32_t myword = 0;
+#pragma unroll
+                            for (int jj = 0; jj < R; ++jj) {
+                                const uint32_t bal = __ballot_sync(0xffffffffu, (acc >> jj) & 1u);
+                                if (static_cast<int>(lane) == jj) myword = bal;
+                            }
+                            if (static_cast<int>(lane) < R) {
+                                cb[(j + h) * WPT + ew * R + lane] = myword;
+                                if (p.out_bitmap) p.out_bitmap[tl * WPT + ew * R + lane] = myword;
+                            }
+                        }
+                    }
+                    j += 2;
+                    s = s2 + 1;
+                    sphase = phase2;
+                    if (s == S) {
+                        s = 0;
+                        sphase ^= 1u;
+                    }
+                    continue;
+                }
                 uint32_t acc = run_program(sp, all_mask, [&](const PLeaf &lf) {
-                    return eval_leaf_tile<R>(lf, sp, stage, p, lrow);
+                    return eval_leaf_tile<R, 1>(lf, sp, stage, 0, p, lrow);
                 });
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh->empty[s]);
@@ -644,6 +722,7 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
                     cb[j * WPT + ew * R + lane] = myword;
                     if (p.out_bitmap) p.out_bitmap[tile * WPT + ew * R + lane] = myword;
                 }
+                ++j;
                 if (++s == S) {
                     s = 0;
                     sphase ^= 1u;
