@@ -66,6 +66,16 @@ long long qpe_gpu_num_rows(const struct engineS *engine);
 int qpe_gpu_select_ids(struct engineS *engine, struct whereClauseS *whereClause, unsigned int **ids_out,
                        size_t *n_out, qpe_scan_stats *stats);
 
+/* Query batch (the GPU analogue of QPEOMP's query-level parallelism, QPEOMP.c:234-335): the match phase of
+ * n_queries SELECTs, result by result identical to n_queries calls of qpe_gpu_select_ids.  Queries on the
+ * index path run one by one; full-scan queries that reference the SAME set of columns are evaluated together --
+ * up to 8 WHERE programs per pass, so those columns are read once per 8 queries.  ids_out[q] is
+ * malloc'ed (qpe_gpu_free), n_out[q] its length.  stats (optional) = sums over the passes. */
+int qpe_gpu_select_ids_batch(struct engineS *engine, struct whereClauseS *const *whereClauses, int n_queries,
+                             unsigned int **ids_out, size_t *n_out, qpe_scan_stats *stats);
+int qpe_sql_select_ids_batch(struct engineS *engine, const char *const *statements, int n_queries,
+                             unsigned int **ids_out, size_t *n_out, qpe_scan_stats *stats);
+
 /* Same match phase, result left in HBM (device pointer valid until the next call on this
  * engine).  flags: bit0 = force the full-scan path even if an index applies;
  * bit1 = count only (no ids written); bit2 = global row ids (see QPE_SCAN_GLOBAL_IDS). */

@@ -107,6 +107,7 @@ def load_library() -> C.CDLL:
         "qpe_sql_run": (None, [vp, cp, i, vp]),
         "qpe_sql_run_to_text": (vp, [vp, cp, i]),
         "qpe_sql_select_ids": (i, [vp, cp, i, C.POINTER(vp), C.POINTER(sz), pstats]),
+        "qpe_sql_select_ids_batch": (i, [vp, C.POINTER(cp), i, C.POINTER(vp), C.POINTER(sz), pstats]),
         "qpe_sql_select_ids_device": (i, [vp, cp, i, C.POINTER(ull), C.POINTER(vp), pstats]),
         "qpe_sql_select_ids_into": (i, [vp, cp, i, vp, sz, C.POINTER(sz), pstats]),
         "qpe_sql_match_mask": (i, [vp, cp, vp, sz, C.POINTER(ull), pstats]),
@@ -335,6 +336,26 @@ class Engine:
             out = np.ctypeslib.as_array(C.cast(ids, C.POINTER(C.c_uint32)), shape=(max(n.value, 1),))[:n.value].copy()
         finally:
             self._lib.qpe_gpu_free(ids)
+        return out, st.as_dict()
+
+    def select_ids_batch(self, statements: Sequence[str]) -> Tuple[List[np.ndarray], dict]:
+        """Match phase of many SELECTs; each result equals select_ids(statement).  Full-scan queries share
+        passes over the table (8 WHERE programs per pass, K9); index-path queries run one by one."""
+        n = len(statements)
+        arr = (C.c_char_p * max(n, 1))(*[s.encode() for s in statements])
+        ids = (C.c_void_p * max(n, 1))()
+        cnt = (C.c_size_t * max(n, 1))()
+        st = ScanStats()
+        rc = self._lib.qpe_sql_select_ids_batch(self._h, arr, n, ids, cnt, C.byref(st))
+        self._check(rc, "select_ids_batch")
+        out = []
+        try:
+            for q in range(n):
+                m = cnt[q]
+                out.append(np.ctypeslib.as_array(C.cast(ids[q], C.POINTER(C.c_uint32)), shape=(max(m, 1),))[:m].copy())
+        finally:
+            for q in range(n):
+                self._lib.qpe_gpu_free(ids[q])
         return out, st.as_dict()
 
     def select_ids_into(self, statement: str, out: np.ndarray, force_scan: bool = False,

@@ -653,6 +653,106 @@ int qpe_gpu_select_ids_device(struct engineS *engine, struct whereClauseS *where
     return 0;
 }
 
+/* K9: the match phase of n SELECTs.  Result by result identical to n calls of qpe_gpu_select_ids (same path
+ * rule, same order): queries the reference would send down the index path run one by one through it; all the
+ * full-scan queries that reference the same set of columns are evaluated together, up to 8 programs per pass. */
+int qpe_gpu_select_ids_batch(struct engineS *engine, struct whereClauseS *const *whereClauses, int n_queries,
+                             unsigned int **ids_out, size_t *n_out, qpe_scan_stats *stats) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    if (n_queries < 0 || (n_queries > 0 && (!whereClauses || !ids_out || !n_out))) {
+        set_error("qpe_gpu_select_ids_batch: bad arguments");
+        return -5;
+    }
+    for (int q = 0; q < n_queries; ++q) {
+        ids_out[q] = nullptr;
+        n_out[q] = 0;
+    }
+    auto fail = [&](int rc) {
+        for (int q = 0; q < n_queries; ++q) {
+            std::free(ids_out[q]);
+            ids_out[q] = nullptr;
+        }
+        return rc;
+    };
+    auto download = [&](int q, const uint32_t *d_src, uint64_t m) -> bool {
+        ids_out[q] = static_cast<unsigned int *>(std::malloc(sizeof(unsigned int) * (m ? m : 1)));
+        if (!ids_out[q]) {
+            set_error("out of host memory");
+            return false;
+        }
+        n_out[q] = static_cast<size_t>(m);
+        return m == 0 || cuda_ok(cudaMemcpyAsync(ids_out[q], d_src, m * 4, cudaMemcpyDeviceToHost, g->stream), "download ids");
+    };
+    qpe_scan_stats total{};
+    auto add_stats = [&]() {
+        qpe_scan_stats s1{};
+        fill_stats(g, &s1);
+        total.kernel_ms += s1.kernel_ms;
+        total.total_ms += s1.total_ms;
+        total.rows_scanned += s1.rows_scanned;
+        total.candidates += s1.candidates;
+        total.matches += s1.matches;
+        total.algo_bytes += s1.algo_bytes;
+        total.launches += s1.launches;
+        total.scan_ms += s1.scan_ms;
+        total.compact_ms += s1.compact_ms;
+        total.tile_rows = s1.tile_rows;
+        total.stages = s1.stages;
+        total.grid = s1.grid;
+    };
+    // Queries that reference the SAME set of columns share a pass: the staged tile is then exactly what each of
+    // them would stage alone, so the batch costs one scan's HBM traffic and no tile geometry is given up.
+    // (A union of different column sets shrinks the tile: measured slower than running the queries one by
+    // one, profiles/r1_batch_probe.json.)  Everything else takes the single-query path (K1f / index).
+    std::vector<std::pair<uint32_t, std::vector<int>>> groups;
+    auto run_single = [&](int q) -> int {
+        uint64_t m = 0;
+        if (!engine_match(g, whereClauses[q], false, false, false, false, &m)) return -2;
+        if (!download(q, g->d_ids, m) || !cuda_ok(cudaStreamSynchronize(g->stream), "download ids")) return -4;
+        if (stats) add_stats();
+        return 0;
+    };
+    for (int q = 0; q < n_queries; ++q) {
+        if (engine_uses_index(g, whereClauses[q])) {
+            const int rc = run_single(q);
+            if (rc) return fail(rc);
+            total.path = 1;
+            continue;
+        }
+        uint32_t mask = 0;
+        if (!engine_where_columns(g, whereClauses[q], &mask)) return fail(-2);
+        size_t k = 0;
+        while (k < groups.size() && groups[k].first != mask) ++k;
+        if (k == groups.size()) groups.emplace_back(mask, std::vector<int>());
+        groups[k].second.push_back(q);
+    }
+    for (const auto &grp : groups) {
+        const std::vector<int> &qs = grp.second;
+        if (qs.size() == 1 || grp.first == 0u) {  // alone, or no column referenced at all
+            for (int q : qs) {
+                const int rc = run_single(q);
+                if (rc) return fail(rc);
+            }
+            continue;
+        }
+        for (size_t b = 0; b < qs.size(); b += kMaxBatch) {
+            const int nb = static_cast<int>(qs.size() - b < static_cast<size_t>(kMaxBatch) ? qs.size() - b : kMaxBatch);
+            const struct whereClauseS *wcs[kMaxBatch];
+            for (int k = 0; k < nb; ++k) wcs[k] = whereClauses[qs[b + k]];
+            uint64_t offs[kMaxBatch + 1];
+            if (!engine_match_batch(g, wcs, nb, offs)) return fail(-2);
+            for (int k = 0; k < nb; ++k)
+                if (!download(qs[b + k], g->d_ids + offs[k], offs[k + 1] - offs[k])) return fail(-4);
+            if (!cuda_ok(cudaStreamSynchronize(g->stream), "download ids")) return fail(-4);
+            if (stats) add_stats();
+        }
+    }
+    if (stats) *stats = total;
+    return 0;
+}
+
 int qpe_gpu_select_ids(struct engineS *engine, struct whereClauseS *whereClause, unsigned int **ids_out, size_t *n_out,
                        qpe_scan_stats *stats) {
     std::lock_guard<std::mutex> lk(g_api_mutex);

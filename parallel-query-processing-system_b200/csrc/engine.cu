@@ -167,6 +167,12 @@ void engine_destroy(GpuEngine *g) {
     if (g->d_ids) cudaFree(g->d_ids);
     if (g->d_bitmap) cudaFree(g->d_bitmap);
     if (g->d_fmt) cudaFree(g->d_fmt);
+    if (g->h_bprogs) cudaFreeHost(g->h_bprogs);
+    if (g->d_bprogs) cudaFree(g->d_bprogs);
+    if (g->d_bctl) cudaFree(g->d_bctl);
+    if (g->d_bcounts) cudaFree(g->d_bcounts);
+    if (g->h_bcounts) cudaFreeHost(g->h_bcounts);
+    if (g->d_bbitmaps) cudaFree(g->d_bbitmaps);
     if (g->d_probe_lo) cudaFree(g->d_probe_lo);
     if (g->d_probe_hi) cudaFree(g->d_probe_hi);
     if (g->d_probe_first) cudaFree(g->d_probe_first);
@@ -775,6 +781,152 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     g->last = st;
     g->last_bm_count = hc->out_count;
     if (count) *count = hc->out_count;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// K9: query batch (the reference's query-level parallelism, QPEOMP.c:234-335)
+// ------------------------------------------------------------------------------------------
+bool engine_uses_index(GpuEngine *g, const struct whereClauseS *wc) {
+    SegmentPlan segs[kMaxSegments];
+    bool too_many = false;
+    return plan_segments(g, wc, segs, kMaxSegments, &too_many) > 0 || too_many;
+}
+
+bool engine_where_columns(GpuEngine *g, const struct whereClauseS *wc, uint32_t *mask) {
+    uint32_t widths[NUM_COLS];
+    for (int c = 0; c < NUM_COLS; ++c) widths[c] = g->table.col[c].width;
+    static thread_local Program tmp;
+    const std::string err = compile_where(wc, widths, &tmp, false);
+    if (!err.empty()) {
+        set_error(err);
+        return false;
+    }
+    *mask = tmp.col_mask;
+    return true;
+}
+
+bool engine_match_batch(GpuEngine *g, const struct whereClauseS *const *wcs, int nq, uint64_t *offsets) {
+    cudaSetDevice(g->device);
+    if (nq < 1 || nq > kMaxBatch) {
+        set_error("query batch: between 1 and 8 queries per pass");
+        return false;
+    }
+    const double t_begin = now_ms();
+    const DevTable &t = g->table;
+    g->last_bm_words = 0;
+    if (!g->h_bprogs) {
+        bool ok = cuda_ok(cudaHostAlloc(&g->h_bprogs, sizeof(Program) * kMaxBatch, cudaHostAllocDefault), "cudaHostAlloc batch") &&
+                  cuda_ok(cudaMalloc(&g->d_bprogs, sizeof(Program) * kMaxBatch), "cudaMalloc batch") &&
+                  cuda_ok(cudaMalloc(&g->d_bctl, sizeof(QueryCtl) * kMaxBatch), "cudaMalloc batch") &&
+                  cuda_ok(cudaMalloc(&g->d_bcounts, sizeof(unsigned long long) * kMaxBatch), "cudaMalloc batch") &&
+                  cuda_ok(cudaHostAlloc(&g->h_bcounts, sizeof(unsigned long long) * kMaxBatch, cudaHostAllocDefault),
+                          "cudaHostAlloc batch");
+        if (!ok) return false;
+    }
+    uint32_t widths[NUM_COLS];
+    for (int c = 0; c < NUM_COLS; ++c) widths[c] = t.col[c].width;
+    Program uni{};  // only its column mask is used: the union of what the queries reference
+    for (int q = 0; q < nq; ++q) {
+        const std::string err = compile_where(wcs[q], widths, &g->h_bprogs[q], false);
+        if (!err.empty()) {
+            set_error(err);
+            return false;
+        }
+        uni.col_mask |= g->h_bprogs[q].col_mask;
+    }
+    int64_t bytes_per_row = 0;
+    for (int c = 0; c < NUM_COLS; ++c)
+        if (uni.col_mask & (1u << c)) {
+            if (!t.resident(c)) {
+                set_error(std::string("WHERE references column '") + kCols[c].name + "' which is not resident on the device");
+                return false;
+            }
+            bytes_per_row += t.col[c].width;
+        }
+    ScanGeometry geo{};
+    const char *why = nullptr;
+    if (!scan_plan(t, uni, g->force_tile_rows, g->force_stages, 4, &geo, &why, false, batch_smem_bytes(nq))) {
+        set_error(std::string("query batch cannot be staged: ") + (why ? why : "row too wide"));
+        return false;
+    }
+    const int64_t bm_words = geo.n_tiles * (geo.tile_rows / 32);
+    const int64_t n_chunks = compact_chunks(bm_words);
+    const int64_t bm_stride = (bm_words + 63) & ~int64_t(63);
+    if (bm_stride * nq > g->bbitmap_cap_words || !g->d_bbitmaps) {
+        if (g->d_bbitmaps) cudaFree(g->d_bbitmaps);
+        g->d_bbitmaps = nullptr;
+        g->bbitmap_cap_words = 0;
+        if (!cuda_ok(cudaMalloc(&g->d_bbitmaps, static_cast<size_t>(bm_stride * kMaxBatch + 1024) * 4), "cudaMalloc batch bitmaps"))
+            return false;
+        g->bbitmap_cap_words = bm_stride * kMaxBatch;
+    }
+    if (!ensure_desc(g, n_chunks)) return false;
+    {
+        GpuEngine::TimingSlot *slot = &g->ring[g->ring_head];
+        g->ring_head = (g->ring_head + 1) % GpuEngine::kTimingRing;
+        if (slot->pending && g->accumulate_timing) resolve_slot(g, slot, nullptr);
+        slot->pending = false;
+        if (g->cur_slot && g->cur_slot->pending && !g->accumulate_timing) g->cur_slot->pending = false;
+        g->cur_slot = slot;
+        g->ev0 = slot->ev[0];
+        g->ev_mid = slot->ev[1];
+        g->ev1 = slot->ev[2];
+        g->ev_post = slot->ev[3];
+    }
+    uint32_t *bitmaps[kMaxBatch] = {nullptr};
+    for (int q = 0; q < nq; ++q) bitmaps[q] = g->d_bbitmaps + static_cast<size_t>(q) * bm_stride;
+    ScanLaunch L{};
+    L.table = &t;
+    L.d_ctl = g->d_ctl;
+    L.h_prog = &uni;
+    bool ok = cuda_ok(cudaMemcpyAsync(g->d_bprogs, g->h_bprogs, sizeof(Program) * nq, cudaMemcpyHostToDevice, g->stream),
+                      "upload batch programs") &&
+              cuda_ok(cudaMemsetAsync(g->d_bcounts, 0, sizeof(unsigned long long) * kMaxBatch, g->stream), "reset batch counts") &&
+              cuda_ok(cudaMemsetAsync(g->d_bctl, 0, sizeof(QueryCtl) * kMaxBatch, g->stream), "reset batch control");
+    if (!ok) return false;
+    cudaEventRecord(g->ev0, g->stream);
+    if (t.n > 0 && !cuda_ok(batch_launch(L, geo, nq, g->d_bprogs, bitmaps, g->d_bcounts, g->stream), "batch scan kernel launch"))
+        return false;
+    cudaEventRecord(g->ev_mid, g->stream);
+    if (!cuda_ok(cudaMemcpyAsync(g->h_bcounts, g->d_bcounts, sizeof(unsigned long long) * nq, cudaMemcpyDeviceToHost, g->stream),
+                 "download batch counts") ||
+        !cuda_ok(cudaStreamSynchronize(g->stream), "batch scan sync"))
+        return false;
+    uint64_t total = 0;
+    for (int q = 0; q < nq; ++q) {
+        offsets[q] = total;
+        total += g->h_bcounts[q];
+    }
+    offsets[nq] = total;
+    if (!engine_ensure_ids(g, static_cast<int64_t>(total))) return false;
+    int launches = t.n > 0 ? 1 : 0;
+    for (int q = 0; q < nq; ++q) {
+        const uint64_t m = g->h_bcounts[q];
+        if (m == 0 || t.n == 0) continue;
+        if (!cuda_ok(compact_launch(bitmaps[q], bm_words, &g->d_bctl[q], g->d_tile_desc, next_epoch(g), g->d_ids + offsets[q],
+                                    0u, m, g->stream),
+                     "compaction kernel launch"))
+            return false;
+        ++launches;
+    }
+    cudaEventRecord(g->ev1, g->stream);
+    if (!cuda_ok(cudaStreamSynchronize(g->stream), "batch compaction sync")) return false;
+    ScanStats st;
+    st.path = 0;
+    st.rows_scanned = t.n;
+    st.matches = static_cast<int64_t>(total);
+    st.algo_bytes = t.n * bytes_per_row + 4 * static_cast<int64_t>(total);
+    st.launches = launches;
+    st.tile_rows = geo.tile_rows;
+    st.stages = geo.stages;
+    st.grid = geo.grid;
+    st.total_ms = now_ms() - t_begin;
+    g->last = st;
+    g->cur_slot->pending = true;
+    g->cur_slot->staged = true;
+    g->cur_slot->two_kernels = true;
+    g->cur_slot->has_post = false;
     return true;
 }
 

@@ -67,6 +67,13 @@ struct GpuEngine {
     int64_t ids_cap = 0;
     uint32_t *d_bitmap = nullptr;
     int64_t bitmap_cap_words = 0;
+    // K9 query batch: programs (pinned host + device), per-query control blocks (K1c chunk counters), counts,
+    // and one bitmap per query in a single allocation
+    Program *h_bprogs = nullptr, *d_bprogs = nullptr;
+    QueryCtl *d_bctl = nullptr;
+    unsigned long long *d_bcounts = nullptr, *h_bcounts = nullptr;
+    uint32_t *d_bbitmaps = nullptr;
+    int64_t bbitmap_cap_words = 0;
     uint8_t *d_fmt = nullptr;        // K7 scratch: rendered projection slots of one row chunk (grow-only)
     size_t fmt_cap = 0;
     // destination override for the next full-scan match (qpe_gpu_select_ids_to): ids go to out_override
@@ -124,6 +131,15 @@ void engine_resolve_all(GpuEngine *g);
 // match phase. On success the ids are in g->d_ids[0 .. *count) (unless count_only).
 bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, bool invert, bool count_only,
                   bool want_bitmap, uint64_t *count);
+
+// K9: the match phase of up to kMaxBatch full-scan queries in ONE pass over the columns.  On success the ids of
+// query q are g->d_ids[offsets[q] .. offsets[q + 1]) in table order.  Every query must be a full-scan query
+// (engine_uses_index(...) == false); returns false with an error if the union of columns cannot be staged.
+bool engine_match_batch(GpuEngine *g, const struct whereClauseS *const *wcs, int nq, uint64_t *offsets);
+// true when the reference's path rule sends this WHERE down the index path (a top-level condition on a u64/int index)
+bool engine_uses_index(GpuEngine *g, const struct whereClauseS *wc);
+// bit c set = the WHERE references schema column c (0 and an error if it does not compile)
+bool engine_where_columns(GpuEngine *g, const struct whereClauseS *wc, uint32_t *mask);
 
 // K1c alone: compact the bitmap left by the last count-only full-scan match into `dst` (device
 // memory of this GPU or a peer mapping), adding id_base to every id

@@ -502,6 +502,123 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_tma_kernel(const __grid
 
 
 // ------------------------------------------------------------------------------------------
+// K9: query batch -- up to kMaxBatch WHERE programs over ONE pass of the columns
+//
+// The GPU analogue of QPEOMP's query-level parallelism (QPEOMP.c:234-335: one thread per query over one
+// engine): the union of the columns the queries reference is staged once per tile, the evaluators run every
+// program on the staged tile and leave one match bitmap + count per query; K1c then compacts each bitmap.
+// HBM traffic is that of ONE scan, so a batch is bound by the evaluators' instruction rate instead.
+// ------------------------------------------------------------------------------------------
+struct BatchParams {
+    ScanParams s;
+    int32_t n_prog;
+    int32_t pad;
+    const Program *progs;                 // device, n_prog programs
+    uint32_t *bitmap[kMaxBatch];          // device, one per query
+    unsigned long long *counts;           // device, n_prog match counts (zeroed by the caller)
+};
+
+template <int EW, int R>
+__global__ void __launch_bounds__(32 * (1 + EW), 1) scan_batch_kernel(const __grid_constant__ BatchParams bp) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const ScanParams &p = bp.s;
+    ScanSmemHeader *sh = reinterpret_cast<ScanSmemHeader *>(smem_raw);  // its own prog slot is unused here
+    __shared__ unsigned long long s_count[kMaxBatch];
+    Program *progs = reinterpret_cast<Program *>(smem_raw + ((sizeof(ScanSmemHeader) + 127) & ~size_t(127)));
+    const int Q = bp.n_prog;
+    uint8_t *stages = reinterpret_cast<uint8_t *>(progs) + ((static_cast<size_t>(Q) * sizeof(Program) + 127) & ~size_t(127));
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5;
+    const uint32_t lane = tid & 31u;
+    const int S = p.n_stages;
+    constexpr int T = 32 * EW * R;
+    constexpr int WPT = T >> 5;
+    constexpr uint32_t kThreads = 32 * (1 + EW);
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(bp.progs);
+        uint4 *dst = reinterpret_cast<uint4 *>(progs);
+        for (uint32_t i = tid; i < static_cast<uint32_t>(Q) * (sizeof(Program) / 16); i += kThreads) dst[i] = src[i];
+    }
+    if (tid < kMaxBatch) s_count[tid] = 0;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&sh->full[s], 1);
+            mbar_init(&sh->empty[s], EW);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            for (long long k = 0;; ++k) {
+                mbar_wait(&sh->empty[s], phase ^ 1u);
+                const long long tile = static_cast<long long>(blockIdx.x) + k * gridDim.x;
+                if (tile >= p.n_tiles) {
+                    sh->tile_of_stage[s] = -1;
+                    mbar_arrive(&sh->full[s]);
+                    break;
+                }
+                sh->tile_of_stage[s] = tile;
+                mbar_arrive_expect_tx(&sh->full[s], p.stage_bytes);
+                uint8_t *dst = stages + static_cast<size_t>(s) * p.stage_bytes;
+                for (int r = 0; r < p.n_ref; ++r) {
+                    const int c = p.ref_col[r];
+                    const uint32_t w = p.width[c];
+                    tma_bulk_g2s(dst + p.smem_off[c], p.col[c] + static_cast<size_t>(tile) * T * w,
+                                 static_cast<uint32_t>(T) * w, &sh->full[s]);
+                }
+                if (++s == S) {
+                    s = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        const int ew = static_cast<int>(warp) - 1;
+        constexpr uint32_t all_mask = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
+        const int lrow = ew * (32 * R) + static_cast<int>(lane);
+        int s = 0;
+        uint32_t sphase = 0;
+        for (;;) {
+            mbar_wait(&sh->full[s], sphase);
+            const long long tile = sh->tile_of_stage[s];
+            if (tile < 0) break;
+            const uint8_t *stage = stages + static_cast<size_t>(s) * p.stage_bytes;
+            const long long row_base = tile * T + lrow;
+            uint32_t tail = all_mask;
+            if (tile * T + T > p.n_rows) tail = rows_mask<R>([&](int j) { return row_base + 32ll * j < p.n_rows; });
+            for (int q = 0; q < Q; ++q) {
+                const Program *sp = progs + q;
+                const uint32_t acc = tail & run_program(sp, all_mask, [&](const PLeaf &lf) {
+                                         return eval_leaf_tile<R, 1>(lf, sp, stage, 0, p, lrow);
+                                     });
+                const uint32_t warp_cnt = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(__popc(acc)));
+                if (lane == 0 && warp_cnt) atomicAdd(&s_count[q], static_cast<unsigned long long>(warp_cnt));
+                uint32_t myword = 0;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const uint32_t bal = __ballot_sync(0xffffffffu, (acc >> j) & 1u);
+                    if (static_cast<int>(lane) == j) myword = bal;
+                }
+                if (static_cast<int>(lane) < R) bp.bitmap[q][tile * WPT + ew * R + lane] = myword;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh->empty[s]);  // every program has read the stage
+            if (++s == S) {
+                s = 0;
+                sphase ^= 1u;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < static_cast<uint32_t>(Q) && s_count[tid]) atomicAdd(&bp.counts[tid], s_count[tid]);
+}
+
+// ------------------------------------------------------------------------------------------
 // K1f: fused scan + ordered compaction (one launch, ids leave the SM while the scan is running)
 //
 // Same producer / evaluator roles as K1, plus kFuseCompactWarps COMPACTION warps per CTA.  Work is
@@ -862,7 +979,7 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
 }
 
 bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages, int max_stages,
-               ScanGeometry *geo, const char **why, bool fused) {
+               ScanGeometry *geo, const char **why, bool fused, size_t extra_reserve) {
     if (max_stages < 1 || max_stages > 4) max_stages = 4;
     // device attributes are asked once per process (one process per GPU; this runs twice per query)
     static int max_smem = 0, n_sm = 0;
@@ -885,7 +1002,7 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
             bpr += t.col[c].width;
         }
     const size_t header = ((fused ? sizeof(FusedSmemHeader) : sizeof(ScanSmemHeader)) + 127) & ~size_t(127);
-    const size_t budget = static_cast<size_t>(max_smem) - header - 256 - (fused ? kFuseReserveBytes : 0);
+    const size_t budget = static_cast<size_t>(max_smem) - header - 256 - (fused ? kFuseReserveBytes : 0) - extra_reserve;
 
     auto stage_bytes_for = [&](int T) {
         size_t sb = 0;
@@ -940,7 +1057,7 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
     geo->stages = S;
     geo->n_tiles = (t.n + T - 1) / T;
     geo->bytes_per_row = bpr;
-    geo->smem_bytes = header + stage_bytes * S + 128 + (fused ? kFuseReserveBytes : 0);
+    geo->smem_bytes = header + stage_bytes * S + 128 + (fused ? kFuseReserveBytes : 0) + extra_reserve;
     int64_t grid = geo->n_tiles < n_sm ? geo->n_tiles : n_sm;
     if (grid < 1) grid = 1;
     geo->grid = static_cast<int>(grid);
@@ -1037,6 +1154,44 @@ cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream
         case 1024: return launch_scan_r<kEvalWarps, 2>(p, geo, stream);
         case 2048: return launch_scan_r<kEvalWarps, 4>(p, geo, stream);
         case 4096: return launch_scan_r<kEvalWarps, 8>(p, geo, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int EW, int R>
+static cudaError_t launch_batch_r(const BatchParams &bp, const ScanGeometry &geo, cudaStream_t stream) {
+    static size_t allowed = 0;
+    if (geo.smem_bytes > allowed) {
+        const cudaError_t e = cudaFuncSetAttribute(scan_batch_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(geo.smem_bytes));
+        if (e != cudaSuccess) return e;
+        allowed = geo.smem_bytes;
+    }
+    scan_batch_kernel<EW, R><<<geo.grid, 32 * (1 + EW), geo.smem_bytes, stream>>>(bp);
+    return cudaGetLastError();
+}
+
+// geo comes from scan_plan(..., extra_reserve = batch_smem_bytes(n_prog)) over the UNION of the programs' columns
+size_t batch_smem_bytes(int n_prog) { return ((static_cast<size_t>(n_prog) * sizeof(Program) + 127) & ~size_t(127)); }
+
+cudaError_t batch_launch(const ScanLaunch &L, const ScanGeometry &geo, int n_prog, const Program *d_progs,
+                         uint32_t *const *d_bitmaps, unsigned long long *d_counts, cudaStream_t stream) {
+    if (n_prog < 1 || n_prog > kMaxBatch) return cudaErrorInvalidValue;
+    BatchParams bp{};
+    const cudaError_t e = fill_scan_params(L, geo, bp.s);
+    if (e != cudaSuccess) return e;
+    bp.s.dynamic_tiles = 0;
+    bp.n_prog = n_prog;
+    bp.progs = d_progs;
+    for (int q = 0; q < n_prog; ++q) bp.bitmap[q] = d_bitmaps[q];
+    bp.counts = d_counts;
+    if (geo.n_tiles == 0) return cudaSuccess;
+    switch (geo.tile_rows) {
+        case 256: return launch_batch_r<kEvalWarpsWide, 1>(bp, geo, stream);
+        case 512: return launch_batch_r<kEvalWarps, 1>(bp, geo, stream);
+        case 1024: return launch_batch_r<kEvalWarps, 2>(bp, geo, stream);
+        case 2048: return launch_batch_r<kEvalWarps, 4>(bp, geo, stream);
+        case 4096: return launch_batch_r<kEvalWarps, 8>(bp, geo, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -52,7 +52,13 @@ struct ScanGeometry {
 // fused: plan for K1f (larger header, kFuseReserveBytes of shared memory set aside; geo->chunk_tiles and
 // geo->n_chunks are filled in).
 bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages, int max_stages,
-               ScanGeometry *geo, const char **why, bool fused = false);
+               ScanGeometry *geo, const char **why, bool fused = false, size_t extra_reserve = 0);
+
+// K9: up to kMaxBatch programs over one pass of the union of their columns -> one bitmap + count per query
+constexpr int kMaxBatch = 8;
+size_t batch_smem_bytes(int n_prog);
+cudaError_t batch_launch(const ScanLaunch &L, const ScanGeometry &geo, int n_prog, const Program *d_progs,
+                         uint32_t *const *d_bitmaps, unsigned long long *d_counts, cudaStream_t stream);
 
 // K1f: scan + ordered compaction in one launch.  desc needs geo.n_chunks descriptors; progress (may be
 // null) points to mapped pinned host memory with one word per table segment of seg_chunks chunks.

@@ -576,6 +576,19 @@ int qpe_sql_select_ids_to(struct engineS *engine, const char *statement, unsigne
     return qpe_gpu_select_ids_to(engine, pw.wc, dst_device, dst_capacity, global_ids, count_out, stats);
 }
 
+int qpe_sql_select_ids_batch(struct engineS *engine, const char *const *statements, int n_queries,
+                             unsigned int **ids_out, size_t *n_out, qpe_scan_stats *stats) {
+    if (n_queries < 0 || (n_queries > 0 && !statements)) return -5;
+    std::vector<std::unique_ptr<ParsedWhere>> parsed;
+    std::vector<struct whereClauseS *> wcs;
+    for (int q = 0; q < n_queries; ++q) {
+        parsed.emplace_back(new ParsedWhere(statements[q]));
+        if (!parsed.back()->ok) return -7;
+        wcs.push_back(parsed.back()->wc);
+    }
+    return qpe_gpu_select_ids_batch(engine, wcs.data(), n_queries, ids_out, n_out, stats);
+}
+
 extern "C" void qpe_gpu_trace_put(struct engineS *engine, int slot, double ms);  // capi.cu (diagnostics)
 
 int qpe_sql_shard_select(struct engineS *engine, const char *statement, int to_host,
