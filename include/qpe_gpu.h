@@ -164,6 +164,13 @@ int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, i
                      unsigned long long *counts_out, qpe_scan_stats *stats);
 int qpe_sql_shard_select(struct engineS *engine, const char *statement, int to_host,
                          unsigned long long *counts_out, qpe_scan_stats *stats);
+/* DELETE on the sharded table: every rank deletes its shard's matches, the new shard sizes are all-gathered
+ * through the comm blocks and the shards are renumbered so that global row ids stay positions in the whole
+ * table (engine/mpi/executeEngine-mpi.c:703-770).  Outputs: rows deleted / rows left, over all shards. */
+int qpe_shard_delete(struct engineS *engine, struct whereClauseS *whereClause, unsigned long long *deleted_total_out,
+                     unsigned long long *rows_total_out);
+int qpe_sql_shard_delete(struct engineS *engine, const char *statement, unsigned long long *deleted_total_out,
+                         unsigned long long *rows_total_out);
 
 /* cudaMemcpy device -> host for pointers handed out by the *_device calls. 0 on success. */
 int qpe_gpu_copy_from_device(void *dst_host, const void *src_device, size_t bytes);

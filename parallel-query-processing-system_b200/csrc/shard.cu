@@ -155,6 +155,19 @@ __global__ void __launch_bounds__(256) post_kernel(const QueryCtl *ctl, PeerPtrs
     }
 }
 
+// A plain all-gather of one 32-bit value per rank through the comm blocks (same slots, same epoch protocol as
+// the post-scan kernel): thread r stores (epoch, value) into rank r's block, then waits for rank r's value.
+__global__ void exchange_kernel(PeerPtrs peers, int rank, int world, uint32_t epoch, unsigned long long value,
+                                unsigned long long *host_values) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    __threadfence_system();
+    st_release_sys(&peers.comm[r]->count[epoch & 1u][rank],
+                   (static_cast<unsigned long long>(epoch) << 32) | (value & 0xffffffffull));
+    host_values[r] = (r == rank) ? (value & 0xffffffffull)
+                                 : (wait_slot(&peers.comm[rank]->count[epoch & 1u][r], epoch) & 0xffffffffull);
+}
+
 static ShardState *shard_of(GpuEngine *g) { return static_cast<ShardState *>(g->shard); }
 
 void shard_destroy(GpuEngine *g) {
@@ -418,6 +431,50 @@ int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, i
     if (rc == -5) set_error("a rank's ids did not fit the result buffer (nothing was written past it)");
     if (stats) qpe_gpu_last_stats(engine, stats);
     return rc;
+}
+
+/* DELETE on a sharded table (the MPI engine's executeQueryDeleteMPI, engine/mpi/executeEngine-mpi.c:703-770:
+ * local match flags, MPI_Allreduce of the count, renumbering): every rank deletes the matching rows of ITS shard
+ * (K1 with the inverted program + stable column compaction, as executeQueryDeleteGPU), then the new shard sizes
+ * and the deleted counts are all-gathered through the comm blocks and every shard's first global row becomes
+ * the sum of the lower shards' new sizes -- global row ids stay positions in the whole table, in table order.
+ * Every rank calls it with the same statement.  No data file is touched (a sharded table has none). */
+int qpe_shard_delete(struct engineS *engine, struct whereClauseS *whereClause, unsigned long long *deleted_total_out,
+                     unsigned long long *rows_total_out) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    if (!s) {
+        set_error("qpe_shard_delete: call qpe_shard_init / qpe_shard_connect first");
+        return -1;
+    }
+    cudaSetDevice(g->device);
+    int64_t deleted = 0;
+    if (!engine_delete(g, whereClause, &deleted)) return -2;
+    PeerPtrs peers{};
+    for (int r = 0; r < s->world; ++r) peers.comm[r] = s->comm[r];
+    unsigned long long rows_before = 0, rows_total = 0, deleted_total = 0;
+    const unsigned long long mine[2] = {static_cast<unsigned long long>(g->table.n), static_cast<unsigned long long>(deleted)};
+    for (int pass = 0; pass < 2; ++pass) {
+        if (++s->epoch == 0) s->epoch = 1;
+        exchange_kernel<<<1, 32, 0, g->stream>>>(peers, s->rank, s->world, s->epoch, mine[pass], s->d_counts);
+        if (!cuda_ok(cudaGetLastError(), "shard exchange kernel launch") ||
+            !cuda_ok(cudaStreamSynchronize(g->stream), "shard exchange"))
+            return -4;
+        for (int r = 0; r < s->world; ++r) {
+            const unsigned long long v = s->h_counts[r];
+            if (pass == 0) {
+                rows_total += v;
+                if (r < s->rank) rows_before += v;
+            } else {
+                deleted_total += v;
+            }
+        }
+    }
+    g->table.row_base = rows_before;
+    if (deleted_total_out) *deleted_total_out = deleted_total;
+    if (rows_total_out) *rows_total_out = rows_total;
+    return 0;
 }
 
 }  // extern "C"

@@ -576,6 +576,13 @@ int qpe_sql_select_ids_to(struct engineS *engine, const char *statement, unsigne
     return qpe_gpu_select_ids_to(engine, pw.wc, dst_device, dst_capacity, global_ids, count_out, stats);
 }
 
+int qpe_sql_shard_delete(struct engineS *engine, const char *statement, unsigned long long *deleted_total_out,
+                         unsigned long long *rows_total_out) {
+    ParsedWhere pw(statement);
+    if (!pw.ok || pw.sql.command != CMD_DELETE_) return -7;
+    return qpe_shard_delete(engine, pw.wc, deleted_total_out, rows_total_out);
+}
+
 int qpe_sql_select_ids_batch(struct engineS *engine, const char *const *statements, int n_queries,
                              unsigned int **ids_out, size_t *n_out, qpe_scan_stats *stats) {
     if (n_queries < 0 || (n_queries > 0 && !statements)) return -5;

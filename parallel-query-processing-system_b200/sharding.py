@@ -268,6 +268,15 @@ class ShardGroup:
         counts = self._counts[:self.world]
         return sum(counts), counts, (self._stats if stats else None)
 
+    def delete(self, statement: str):
+        """DELETE on the sharded table (every rank calls it): (rows deleted, rows left) over all shards.  The
+        shards are renumbered, so later global row ids are positions in the table after the delete."""
+        C = self._C
+        deleted, left = C.c_ulonglong(), C.c_ulonglong()
+        rc = self.lib.qpe_sql_shard_delete(self.engine._h, statement.encode(), C.byref(deleted), C.byref(left))
+        self.engine._check(rc, "qpe_shard_delete")
+        return int(deleted.value), int(left.value)
+
     def device_result_ptr(self) -> int:
         return self.lib.qpe_shard_device_result(self.engine._h)
 

@@ -24,6 +24,7 @@ QUERIES = ["SELECT command_id FROM Commands WHERE (command_id < 1700000) AND (su
            "SELECT command_id FROM Commands WHERE (command_id < 5)",            # only the first shard matches
            "SELECT command_id FROM Commands WHERE (sudo_used = TRUE) OR (risk_level < 2)"]
 COLS = ["command_id", "sudo_used", "risk_level"]
+DELETE_SQL = "DELETE FROM Commands WHERE (risk_level = 2) OR (command_id < 1000)"
 
 
 def _free_port():
@@ -55,10 +56,18 @@ def _worker(rank, world, port, ret):
             total_h, counts_h, _ = grp.select(q, to_host=True)
             if rank == 0:
                 out.append((total, counts, dev_ids, total_h, counts_h, grp.host_ids[:total_h].copy()))
+    # sharded DELETE (local compaction + renumbering through the comm blocks), then the same queries again:
+    # global row ids must be positions in the table AFTER the delete
+    deleted, left = grp.delete(DELETE_SQL)
+    after = []
+    for q in QUERIES:
+        total, counts, _ = grp.select(q, to_host=False)
+        ids = grp.device_result(total).copy() if rank == 0 else None
+        after.append((total, ids))
     grp.close()
     eng.close()
     if rank == 0:
-        ret.put(out)
+        ret.put((out, deleted, left, after))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -72,7 +81,7 @@ def test_native_shard_select_equals_single_engine(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
     for p in procs:
         p.start()
-    results = ret.get(timeout=600)
+    results, deleted, left, after = ret.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -84,4 +93,10 @@ def test_native_shard_select_equals_single_engine(world):
         assert len(counts) == world and sum(counts) == total and counts == counts_h
         assert np.array_equal(dev_ids, want), q
         assert np.array_equal(host_ids, want), q
+    # the same DELETE on the whole table, then the same queries
+    out = whole.run(DELETE_SQL, 5)
+    assert f"Rows affected: {deleted}" in out and whole.num_rows == left == TOTAL - deleted
+    for q, (total, ids) in zip(QUERIES, after):
+        want, _ = whole.select_ids(q, force_scan=True)
+        assert total == len(want) and np.array_equal(ids, want), "after DELETE: " + q
     whole.close()
