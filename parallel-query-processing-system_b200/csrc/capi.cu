@@ -74,6 +74,20 @@ ResultArena arena_acquire(size_t need) {
     return a;
 }
 
+void arena_pool_clear() {
+    std::vector<ResultArena> blocks;
+    {
+        std::lock_guard<std::mutex> lk(g_result_mutex);
+        blocks.swap(g_pool);
+        g_pool_bytes = 0;
+    }
+    for (ResultArena &a : blocks)
+        if (a.pinned)
+            cudaFreeHost(a.block);
+        else
+            std::free(a.block);
+}
+
 void arena_release(ResultArena a) {
     if (!a.block) return;
     if (a.pinned) {
@@ -469,6 +483,7 @@ void destroyEngineGPU(struct engineS *engine) {
         return;
     }
     engine_destroy(g);
+    if (engine_live_count() == 0) arena_pool_clear();  // the last engine is gone: give the pinned result blocks back
 }
 
 struct resultSetS *executeQuerySelectGPU(struct engineS *engine, const char **selectItems, int numSelectItems,

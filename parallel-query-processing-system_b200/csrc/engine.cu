@@ -14,6 +14,8 @@
 
 #include "engine.cuh"
 
+#include <atomic>
+
 #include <climits>
 #include <cstdlib>
 #include <cstring>
@@ -23,6 +25,8 @@
 namespace qpe {
 
 std::mutex g_api_mutex;
+static std::atomic<int> g_live_engines{0};
+int engine_live_count() { return g_live_engines.load(); }
 
 
 // ------------------------------------------------------------------------------------------
@@ -88,6 +92,7 @@ GpuEngine *engine_create(const char *tableName, const char *datafile, int index_
         return nullptr;
     }
     GpuEngine *g = new GpuEngine();
+    ++g_live_engines;
     g->device = pick_device();
     if (!cuda_ok(cudaSetDevice(g->device), "cudaSetDevice")) {
         delete g;
@@ -194,6 +199,7 @@ void engine_destroy(GpuEngine *g) {
     std::free(g->head.datafile);
     g->magic = 0;
     delete g;
+    --g_live_engines;
 }
 
 // rows to allocate for a table of n rows: head-room for INSERTs plus one full tile of slack so

@@ -113,6 +113,7 @@ bool cuda_ok(cudaError_t e, const char *what);
 // create an engine with an empty table; nullptr if no device
 GpuEngine *engine_create(const char *tableName, const char *datafile, int index_slots);
 void engine_destroy(GpuEngine *g);
+int engine_live_count();  // engines alive in this process
 void shard_destroy(GpuEngine *g);  // shard.cu: releases the peer mappings / shared host buffer, if any
 int device_count();
 const char *last_error_cstr();

@@ -168,44 +168,66 @@ struct ProbeParams {
     uint32_t *count;  // Q
 };
 
+// Latency-bound by construction: a descent is n_levels + 1 DEPENDENT node reads (~0.6 us each once the lower
+// levels miss L1), so throughput = (descents in flight) / latency.  Each half-warp therefore owns kProbeU
+// queries per iteration and walks the lower-bound and the upper-bound descent of all of them together:
+// 2 * kProbeU independent loads in flight per lane, 4 * kProbeU descents per warp (the first version had one
+// query per warp, lanes 0-15 on the lower bound and 16-31 on the upper: 2.2 G probes/s over 100 M keys).
+constexpr int kProbeU = 2;
+
 template <typename K>
 __global__ void __launch_bounds__(256) probe_kernel(const __grid_constant__ ProbeParams p) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t sub = lane & 15u;
-    const bool upper = lane >= 16u;  // second half-warp searches the upper bound
-    const uint32_t half_mask = upper ? 0xffff0000u : 0x0000ffffu;
+    const uint32_t half = lane >> 4;  // which of the warp's two query slots this lane serves
     const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
     const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     const K *lo = static_cast<const K *>(p.lo);
     const K *hi = static_cast<const K *>(p.hi);
-    for (long long qi = warp_global; qi < p.q; qi += n_warps) {
-        const K key = upper ? hi[qi] : lo[qi];
-        long long group = 0;  // node index within the current level
-        for (int l = 0; l <= p.n_levels; ++l) {
+    constexpr int kPerWarp = 2 * kProbeU;
+    for (long long q0 = warp_global * kPerWarp; q0 < p.q; q0 += n_warps * kPerWarp) {
+        long long qi[kProbeU];
+        K key_lo[kProbeU], key_hi[kProbeU];
+        long long g_lo[kProbeU], g_hi[kProbeU];  // node index within the current level, per descent
+#pragma unroll
+        for (int u = 0; u < kProbeU; ++u) {
+            qi[u] = q0 + 2 * u + half;
+            const bool live = qi[u] < p.q;
+            key_lo[u] = live ? lo[qi[u]] : K(0);
+            key_hi[u] = live ? hi[qi[u]] : K(0);
+            g_lo[u] = 0;
+            g_hi[u] = 0;
+        }
+        for (int l = 0; l <= p.n_levels; ++l) {  // warp-uniform trip count: every lane takes part in the ballots
             const bool leaf = (l == p.n_levels);
             const K *arr = static_cast<const K *>(leaf ? p.keys : p.level[l]);
             const long long cnt = leaf ? p.n : p.level_cnt[l];
-            const long long base = group * kFanout;
-            const long long idx = base + sub;
-            bool less = false;
-            if (idx < cnt) {
-                const K v = __ldg(arr + idx);
-                less = upper ? (v <= key) : (v < key);
+            bool less_lo[kProbeU], less_hi[kProbeU];
+#pragma unroll
+            for (int u = 0; u < kProbeU; ++u) {  // all loads first: 2 * kProbeU independent reads in flight
+                const long long i_lo = g_lo[u] * kFanout + sub, i_hi = g_hi[u] * kFanout + sub;
+                const K v_lo = i_lo < cnt ? __ldg(arr + i_lo) : K(0);
+                const K v_hi = i_hi < cnt ? __ldg(arr + i_hi) : K(0);
+                less_lo[u] = i_lo < cnt && v_lo < key_lo[u];
+                less_hi[u] = i_hi < cnt && v_hi <= key_hi[u];
             }
-            const uint32_t bal = __ballot_sync(0xffffffffu, less) & half_mask;
-            const int rank = __popc(bal);  // entries of this node ordered before the key
-            if (leaf) {
-                group = base + rank;  // final position
-            } else {
-                // descend into the last group whose first key is ordered before the key
-                group = base + (rank > 0 ? rank - 1 : 0);
+#pragma unroll
+            for (int u = 0; u < kProbeU; ++u) {
+                const uint32_t b_lo = (__ballot_sync(0xffffffffu, less_lo[u]) >> (16u * half)) & 0xffffu;
+                const uint32_t b_hi = (__ballot_sync(0xffffffffu, less_hi[u]) >> (16u * half)) & 0xffffu;
+                const int r_lo = __popc(b_lo), r_hi = __popc(b_hi);  // entries of the node ordered before the key
+                // leaf: final position; above: descend into the last group whose first key is ordered before the key
+                g_lo[u] = g_lo[u] * kFanout + (leaf ? r_lo : (r_lo > 0 ? r_lo - 1 : 0));
+                g_hi[u] = g_hi[u] * kFanout + (leaf ? r_hi : (r_hi > 0 ? r_hi - 1 : 0));
             }
         }
-        const long long pos_lo = __shfl_sync(0xffffffffu, group, 0);
-        const long long pos_hi = __shfl_sync(0xffffffffu, group, 16);
-        if (lane == 0) {
-            p.first[qi] = static_cast<uint32_t>(pos_lo);
-            p.count[qi] = pos_hi > pos_lo ? static_cast<uint32_t>(pos_hi - pos_lo) : 0u;
+        if (sub == 0) {
+#pragma unroll
+            for (int u = 0; u < kProbeU; ++u)
+                if (qi[u] < p.q) {
+                    p.first[qi[u]] = static_cast<uint32_t>(g_lo[u]);
+                    p.count[qi[u]] = g_hi[u] > g_lo[u] ? static_cast<uint32_t>(g_hi[u] - g_lo[u]) : 0u;
+                }
         }
     }
 }
@@ -227,9 +249,22 @@ cudaError_t index_probe(const DevIndex &ix, const void *d_lo, const void *d_hi, 
     p.first = d_first;
     p.count = d_count;
     const int threads = 256;
-    long long warps = q;
+    long long warps = (q + 2 * kProbeU - 1) / (2 * kProbeU);
     long long blocks = (warps * 32 + threads - 1) / threads;
-    if (blocks > 148ll * 8) blocks = 148ll * 8;
+    // one resident wave: SM count x the occupancy of this instantiation (asked once)
+    static int wave_u64 = 0, wave_i32 = 0;
+    int &wave = ix.type == T_U64 ? wave_u64 : wave_i32;
+    if (wave == 0) {
+        int dev = 0, n_sm = 148, per_sm = 4;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (ix.type == T_U64)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_kernel<unsigned long long>, threads, 0);
+        else
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_kernel<int>, threads, 0);
+        wave = n_sm * (per_sm > 0 ? per_sm : 1);
+    }
+    if (blocks > wave) blocks = wave;
     if (ix.type == T_U64)
         probe_kernel<unsigned long long><<<static_cast<int>(blocks), threads, 0, stream>>>(p);
     else

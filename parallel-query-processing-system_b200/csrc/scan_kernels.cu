@@ -82,6 +82,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         if (++spins == kSpinLimit) __trap();
     }
 }
+// The same wait for a thread that expects to wait LONG (the TMA producer waits ~1 us per tile for a stage to be
+// released): sleep between polls.  A tight poll loop is 6 instructions per poll; ncu showed the single producer
+// lane issuing 12 % of the whole kernel's instructions that way, on a scheduler it shares with four evaluator warps.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, uint32_t sleep_ns) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(sleep_ns);
+        if (++spins == kSpinLimit) __trap();
+    }
+}
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -426,7 +436,7 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_tma_kernel(const __grid
             int s = 0;
             uint32_t phase = 0;
             for (long long k = 0;; ++k) {
-                mbar_wait(&sh->empty[s], phase ^ 1u);
+                mbar_wait_relaxed(&sh->empty[s], phase ^ 1u, 128);
                 // static round-robin keeps the claim off the critical path (a global atomic costs a
                 // full round trip per tile); every CTA is resident (grid <= SM count) and walks its
                 // tiles in increasing order, so the look-back chain always makes progress.
@@ -555,7 +565,7 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_batch_kernel(const __gr
             int s = 0;
             uint32_t phase = 0;
             for (long long k = 0;; ++k) {
-                mbar_wait(&sh->empty[s], phase ^ 1u);
+                mbar_wait_relaxed(&sh->empty[s], phase ^ 1u, 128);
                 const long long tile = static_cast<long long>(blockIdx.x) + k * gridDim.x;
                 if (tile >= p.n_tiles) {
                     sh->tile_of_stage[s] = -1;
@@ -719,7 +729,7 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
                 const long long t0 = chunk * CT;
                 const int nt = done ? 1 : static_cast<int>((p.n_tiles - t0 < CT) ? (p.n_tiles - t0) : CT);
                 for (int j = 0; j < nt; ++j) {
-                    mbar_wait(&sh->empty[s], phase ^ 1u);
+                    mbar_wait_relaxed(&sh->empty[s], phase ^ 1u, 128);
                     if (done) {
                         sh->tile_of_stage[s] = -1;
                         mbar_arrive(&sh->full[s]);
@@ -863,7 +873,7 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
             const long long t0 = chunk * CT;
             const int nt = static_cast<int>((p.n_tiles - t0 < CT) ? (p.n_tiles - t0) : CT);
             const uint32_t nw = static_cast<uint32_t>(nt) * WPT;
-            mbar_wait(&sh->cb_full[buf], (k >> 1) & 1u);
+            mbar_wait_relaxed(&sh->cb_full[buf], (k >> 1) & 1u, 256);
             const uint32_t *cb = cbuf + buf * kFuseChunkWords;
             // 1. words -> registers, popc, warp-inclusive scan per round
             uint32_t word[kFuseRounds], off[kFuseRounds];
@@ -978,17 +988,27 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
     if (tid == 0 && sh->cta_count) atomicAdd(&p.ctl->out_count, sh->cta_count);
 }
 
+// function attributes are per device: cache what was set per (instantiation, device)
+constexpr int kMaxDevices = 64;
+static int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages, int max_stages,
                ScanGeometry *geo, const char **why, bool fused, size_t extra_reserve) {
     if (max_stages < 1 || max_stages > 4) max_stages = 4;
     // device attributes are asked once per process (one process per GPU; this runs twice per query)
-    static int max_smem = 0, n_sm = 0;
-    if (max_smem == 0) {
+    static int max_smem_by_device[kMaxDevices] = {0}, n_sm_by_device[kMaxDevices] = {0};
+    const int slot = current_device_slot();
+    if (max_smem_by_device[slot] == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&max_smem_by_device[slot], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&n_sm_by_device[slot], cudaDevAttrMultiProcessorCount, dev);
     }
+    int max_smem = max_smem_by_device[slot], n_sm = n_sm_by_device[slot];
     if (max_smem <= 0) max_smem = 227 * 1024;
     if (n_sm <= 0) n_sm = 148;
 
@@ -1092,7 +1112,9 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
 
 template <int EW, int R>
 static cudaError_t launch_scan_r(const ScanParams &p, const ScanGeometry &geo, cudaStream_t stream) {
-    static size_t allowed = 0;  // per instantiation: raise the dynamic shared memory limit only when it grows
+    // per instantiation and device: raise the dynamic shared memory limit only when it grows
+    static size_t allowed_by_device[kMaxDevices] = {0};
+    size_t &allowed = allowed_by_device[current_device_slot()];
     if (geo.smem_bytes > allowed) {
         const cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(geo.smem_bytes));
@@ -1160,7 +1182,8 @@ cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream
 
 template <int EW, int R>
 static cudaError_t launch_batch_r(const BatchParams &bp, const ScanGeometry &geo, cudaStream_t stream) {
-    static size_t allowed = 0;
+    static size_t allowed_by_device[kMaxDevices] = {0};
+    size_t &allowed = allowed_by_device[current_device_slot()];
     if (geo.smem_bytes > allowed) {
         const cudaError_t e = cudaFuncSetAttribute(scan_batch_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(geo.smem_bytes));
@@ -1198,7 +1221,9 @@ cudaError_t batch_launch(const ScanLaunch &L, const ScanGeometry &geo, int n_pro
 
 template <int EW, int R>
 static cudaError_t launch_fused_r(const FusedParams &fp, const ScanGeometry &geo, cudaStream_t stream) {
-    static size_t allowed = 0;  // per instantiation: raise the dynamic shared memory limit only when it grows
+    // per instantiation and device: raise the dynamic shared memory limit only when it grows
+    static size_t allowed_by_device[kMaxDevices] = {0};
+    size_t &allowed = allowed_by_device[current_device_slot()];
     if (geo.smem_bytes > allowed) {
         const cudaError_t e = cudaFuncSetAttribute(scan_fused_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(geo.smem_bytes));
