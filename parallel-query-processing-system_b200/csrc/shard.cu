@@ -42,6 +42,7 @@ constexpr int kMaxRanks = 16;
 
 struct ShardComm {                      // device memory of one rank, mapped by all the others
     unsigned long long count[2][kMaxRanks];  // [epoch parity][source rank] = epoch << 32 | match count
+    unsigned long long packed[2];            // [epoch parity] = epoch whose dense result the owner has packed
 };
 
 struct ShardHostHeader {                // start of the shared host buffer
@@ -59,6 +60,7 @@ struct ShardState {
     uint32_t *seg_base = nullptr;
     uint64_t seg_cap = 0;
     uint32_t last_parity = 0;           // parity of the most recent device-result query
+    int multipath = -1;                 // host result over every rank's PCIe link: -1 = auto (world >= 4), 0, 1
     // host result
     void *host_map = nullptr;           // shared mapping: ShardHostHeader, then the ids
     size_t host_bytes = 0;
@@ -166,6 +168,23 @@ __global__ void exchange_kernel(PeerPtrs peers, int rank, int world, uint32_t ep
                    (static_cast<unsigned long long>(epoch) << 32) | (value & 0xffffffffull));
     host_values[r] = (r == rank) ? (value & 0xffffffffull)
                                  : (wait_slot(&peers.comm[rank]->count[epoch & 1u][r], epoch) & 0xffffffffull);
+}
+
+// owner, after its pack: tell every rank that the dense result of this epoch is complete
+__global__ void packed_flag_kernel(PeerPtrs peers, int world, uint32_t epoch) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    __threadfence_system();
+    st_release_sys(&peers.comm[r]->packed[epoch & 1u], static_cast<unsigned long long>(epoch));
+}
+// every other rank: wait for it (bounded) before reading the owner's memory
+__global__ void packed_wait_kernel(const ShardComm *mine, uint32_t epoch) {
+    if (threadIdx.x != 0) return;
+    uint32_t spins = 0;
+    while (ld_acquire_sys(&mine->packed[epoch & 1u]) != static_cast<unsigned long long>(epoch)) {
+        __nanosleep(200);
+        if (++spins == 100000000u) __trap();
+    }
 }
 
 static ShardState *shard_of(GpuEngine *g) { return static_cast<ShardState *>(g->shard); }
@@ -314,6 +333,20 @@ unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *nam
     return reinterpret_cast<unsigned int *>(static_cast<uint8_t *>(p) + sizeof(ShardHostHeader));
 }
 
+/* Host result path: -1 = automatic (every rank's PCIe link from 4 ranks up), 0 = the first shard streams during its
+ * scan and the others copy afterwards, 1 = always over every link.  Every rank must choose the same. */
+int qpe_shard_set_multipath(struct engineS *engine, int mode) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    if (!s || mode < -1 || mode > 1) {
+        set_error("qpe_shard_set_multipath: call qpe_shard_init first; mode is -1, 0 or 1");
+        return -1;
+    }
+    s->multipath = mode;
+    return 0;
+}
+
 const unsigned int *qpe_shard_device_result(struct engineS *engine) {
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
@@ -353,15 +386,29 @@ int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, i
     PeerPtrs peers{};
     for (int r = 0; r < s->world; ++r) peers.comm[r] = s->comm[r];
 
-    // the kernel that follows the scan on the engine's stream, before its single synchronisation
-    uint32_t *set = to_host ? nullptr : s->seg_base + (epoch & 1u) * set_ids(s->world, s->seg_cap);
-    const int pack = (!to_host && s->rank == s->owner && s->world > 1) ? 1 : 0;
+    // Host result over EVERY rank's PCIe link ("multipath"): the ids first land in the owner's HBM exactly as for
+    // a device result, then each rank copies 1/world of the packed list (read over NVLink from the owner) to the
+    // shared host buffer over its own link.  It pays when one link's copy of the whole result outlasts a shard's
+    // scan: 38 MB take 0.85 ms over one link, a 125 M-row shard scans in 0.3 ms.  Otherwise (few ranks) the first
+    // shard streams its ids out during the scan and the others copy theirs afterwards.
+    const bool multi = to_host && s->world > 1 && s->seg_base != nullptr &&
+                       (s->multipath == 1 || (s->multipath < 0 && s->world >= 4));
+    const bool to_segments = !to_host || multi;
+    // the kernels that follow the scan on the engine's stream, before its single synchronisation
+    uint32_t *set = to_segments ? s->seg_base + (epoch & 1u) * set_ids(s->world, s->seg_cap) : nullptr;
+    const int pack = (to_segments && s->rank == s->owner && s->world > 1) ? 1 : 0;
     g->post_match = [&]() -> bool {
         post_kernel<<<pack ? 148 * 8 : 1, 256, 0, g->stream>>>(g->d_ctl, peers, s->rank, s->world, epoch, s->d_counts,
                                                                pack, set, s->seg_cap);
+        if (multi) {
+            if (s->rank == s->owner)
+                packed_flag_kernel<<<1, 32, 0, g->stream>>>(peers, s->world, epoch);
+            else
+                packed_wait_kernel<<<1, 32, 0, g->stream>>>(s->comm[s->rank], epoch);
+        }
         return cuda_ok(cudaGetLastError(), "shard post-scan kernel launch");
     };
-    if (!to_host) {
+    if (to_segments) {
         // the first shard's offset in the result is always 0: its scan writes the dense result in place
         g->out_override = s->rank == 0 ? set : set + (static_cast<size_t>(s->world) + (s->rank - 1)) * s->seg_cap;
         g->out_override_cap = s->seg_cap;
@@ -369,7 +416,7 @@ int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, i
     }
     uint32_t *host_ids =
         to_host ? reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(s->host_map) + sizeof(ShardHostHeader)) : nullptr;
-    if (to_host && s->rank == 0) {
+    if (to_host && !multi && s->rank == 0) {
         // the first shard's offset is always 0: its ids are copied out segment by segment DURING the scan
         g->host_out = host_ids;
         g->host_out_cap = s->host_cap;
@@ -394,19 +441,30 @@ int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, i
         set_error("qpe_shard_select: this WHERE cannot be staged by the scan kernel (too wide for shared memory)");
         return -6;
     }
-    g->last.launches += 1;
+    g->last.launches += multi ? 2 : 1;
 
     int rc = 0;
-    unsigned long long before = 0;
+    unsigned long long before = 0, total = 0;
     for (int r = 0; r < s->world; ++r) {
         const unsigned long long c = s->h_counts[r];
         if (counts_out) counts_out[r] = c;
         if (r < s->rank) before += c;
-        if (!to_host && c > s->seg_cap) rc = -5;
+        total += c;
+        if (to_segments && c > s->seg_cap) rc = -5;
     }
     if (to_host) {
         ShardHostHeader *hh = static_cast<ShardHostHeader *>(s->host_map);
-        if (before + m > s->host_cap) {
+        if (multi) {
+            // this rank's 1/world of the packed result: owner's HBM -> (NVLink) -> this GPU -> (its PCIe) -> host
+            const unsigned long long lo = total * s->rank / s->world, hi = total * (s->rank + 1) / s->world;
+            if (total > s->host_cap) rc = -5;
+            if (rc == 0 && hi > lo) {
+                if (!cuda_ok(cudaMemcpyAsync(host_ids + lo, set + lo, (hi - lo) * 4, cudaMemcpyDeviceToHost, g->stream),
+                             "download ids") ||
+                    !cuda_ok(cudaStreamSynchronize(g->stream), "download ids"))
+                    return -4;
+            }
+        } else if (before + m > s->host_cap) {
             rc = -5;
         } else if (m && !delivered) {
             if (!cuda_ok(cudaMemcpyAsync(host_ids + before, g->d_ids, m * 4, cudaMemcpyDeviceToHost, g->stream),

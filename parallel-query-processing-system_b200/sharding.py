@@ -268,6 +268,10 @@ class ShardGroup:
         counts = self._counts[:self.world]
         return sum(counts), counts, (self._stats if stats else None)
 
+    def set_multipath(self, mode: int):
+        """host result over every rank's PCIe link: -1 auto (from 4 ranks up), 0 off, 1 on; same on every rank"""
+        self.engine._check(self.lib.qpe_shard_set_multipath(self.engine._h, mode), "qpe_shard_set_multipath")
+
     def delete(self, statement: str):
         """DELETE on the sharded table (every rank calls it): (rows deleted, rows left) over all shards.  The
         shards are renumbered, so later global row ids are positions in the table after the delete."""
