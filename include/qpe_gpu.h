@@ -161,7 +161,7 @@ unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *nam
 const unsigned int *qpe_shard_device_result(struct engineS *engine);
 /* Host result path: 1 = every rank copies 1/world of the packed result (read from the owner over NVLink) to the
  * host over its OWN PCIe link; 0 = the first shard streams its ids out during its scan, the others copy theirs
- * afterwards; -1 (default) = 1 from four ranks up.  Every rank must choose the same. */
+ * afterwards; -1 (default) = 1 from eight ranks up.  Every rank must choose the same. */
 int qpe_shard_set_multipath(struct engineS *engine, int mode);
 void qpe_shard_close(struct engineS *engine);
 int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, int to_host,

@@ -60,7 +60,7 @@ struct ShardState {
     uint32_t *seg_base = nullptr;
     uint64_t seg_cap = 0;
     uint32_t last_parity = 0;           // parity of the most recent device-result query
-    int multipath = -1;                 // host result over every rank's PCIe link: -1 = auto (world >= 4), 0, 1
+    int multipath = -1;                 // host result over every rank's PCIe link: -1 = auto (world >= 8), 0, 1
     // host result
     void *host_map = nullptr;           // shared mapping: ShardHostHeader, then the ids
     size_t host_bytes = 0;
@@ -185,6 +185,24 @@ __global__ void packed_wait_kernel(const ShardComm *mine, uint32_t epoch) {
         __nanosleep(200);
         if (++spins == 100000000u) __trap();
     }
+}
+
+// this rank's slice of the packed result: owner's HBM -> (NVLink) -> local HBM, 4 independent loads in flight per
+// thread; the copy engine then takes it to the host over this GPU's own PCIe link.  (A cudaMemcpy straight from the
+// peer mapping to the host measured 12 GB/s per rank.)
+__global__ void __launch_bounds__(256) pull_slice_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
+                                                         unsigned long long n) {
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const uint32_t a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride),
+                       d = __ldcs(src + i + 3 * stride);
+        dst[i] = a;
+        dst[i + stride] = b;
+        dst[i + 2 * stride] = c;
+        dst[i + 3 * stride] = d;
+    }
+    for (; i < n; i += stride) dst[i] = src[i];
 }
 
 static ShardState *shard_of(GpuEngine *g) { return static_cast<ShardState *>(g->shard); }
@@ -333,7 +351,7 @@ unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *nam
     return reinterpret_cast<unsigned int *>(static_cast<uint8_t *>(p) + sizeof(ShardHostHeader));
 }
 
-/* Host result path: -1 = automatic (every rank's PCIe link from 4 ranks up), 0 = the first shard streams during its
+/* Host result path: -1 = automatic (every rank's PCIe link from 8 ranks up), 0 = the first shard streams during its
  * scan and the others copy afterwards, 1 = always over every link.  Every rank must choose the same. */
 int qpe_shard_set_multipath(struct engineS *engine, int mode) {
     std::lock_guard<std::mutex> lk(g_api_mutex);
@@ -388,11 +406,13 @@ int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, i
 
     // Host result over EVERY rank's PCIe link ("multipath"): the ids first land in the owner's HBM exactly as for
     // a device result, then each rank copies 1/world of the packed list (read over NVLink from the owner) to the
-    // shared host buffer over its own link.  It pays when one link's copy of the whole result outlasts a shard's
-    // scan: 38 MB take 0.85 ms over one link, a 125 M-row shard scans in 0.3 ms.  Otherwise (few ranks) the first
-    // shard streams its ids out during the scan and the others copy theirs afterwards.
+    // shared host buffer over its own link.  It pays when one link's copy of the whole result far outlasts a shard's
+    // scan.  Measured (1 B rows, 9.45 M ids = 38 MB, all from the first shard): 8 ranks 0.845 -> 0.748 ms per query;
+    // 4 ranks 0.849 -> 1.07 ms (the small per-rank copies reach only ~13-20 GB/s each, and the first shard's
+    // streaming copy hides most of itself under a 0.56 ms scan), hence automatic from 8 ranks up.  Otherwise the
+    // first shard streams its ids out during the scan and the others copy theirs afterwards.
     const bool multi = to_host && s->world > 1 && s->seg_base != nullptr &&
-                       (s->multipath == 1 || (s->multipath < 0 && s->world >= 4));
+                       (s->multipath == 1 || (s->multipath < 0 && s->world >= 8));
     const bool to_segments = !to_host || multi;
     // the kernels that follow the scan on the engine's stream, before its single synchronisation
     uint32_t *set = to_segments ? s->seg_base + (epoch & 1u) * set_ids(s->world, s->seg_cap) : nullptr;
@@ -459,7 +479,15 @@ int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, i
             const unsigned long long lo = total * s->rank / s->world, hi = total * (s->rank + 1) / s->world;
             if (total > s->host_cap) rc = -5;
             if (rc == 0 && hi > lo) {
-                if (!cuda_ok(cudaMemcpyAsync(host_ids + lo, set + lo, (hi - lo) * 4, cudaMemcpyDeviceToHost, g->stream),
+                const uint32_t *src = set + lo;
+                if (s->rank != s->owner) {
+                    if (!engine_ensure_ids(g, static_cast<int64_t>(hi - lo))) return -4;
+                    pull_slice_kernel<<<148 * 4, 256, 0, g->stream>>>(set + lo, g->d_ids, hi - lo);
+                    if (!cuda_ok(cudaGetLastError(), "shard slice kernel launch")) return -4;
+                    g->last.launches += 1;
+                    src = g->d_ids;
+                }
+                if (!cuda_ok(cudaMemcpyAsync(host_ids + lo, src, (hi - lo) * 4, cudaMemcpyDeviceToHost, g->stream),
                              "download ids") ||
                     !cuda_ok(cudaStreamSynchronize(g->stream), "download ids"))
                     return -4;

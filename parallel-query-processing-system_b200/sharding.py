@@ -269,7 +269,7 @@ class ShardGroup:
         return sum(counts), counts, (self._stats if stats else None)
 
     def set_multipath(self, mode: int):
-        """host result over every rank's PCIe link: -1 auto (from 4 ranks up), 0 off, 1 on; same on every rank"""
+        """host result over every rank's PCIe link: -1 auto (from 8 ranks up), 0 off, 1 on; same on every rank"""
         self.engine._check(self.lib.qpe_shard_set_multipath(self.engine._h, mode), "qpe_shard_set_multipath")
 
     def delete(self, statement: str):

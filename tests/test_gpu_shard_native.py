@@ -47,7 +47,7 @@ def _worker(rank, world, port, ret):
     eng = pkg.Engine.from_synth(TOTAL, n_rows=n, row_base=start, columns=COLS)
     grp = sharding.ShardGroup(pkg, eng, segment_capacity=n + 1, host_capacity=TOTAL)
     # both host-result paths: the first shard streaming during its scan (2 ranks) and every rank copying its
-    # 1/world of the packed result out of the owner's memory (3 ranks; automatic only from 4 ranks up)
+    # 1/world of the packed result out of the owner's memory (3 ranks; automatic only from 8 ranks up)
     grp.set_multipath(1 if world == 3 else 0)
     out = []
     # every query twice in a row (device result then host result), then the whole list again: epochs and
