@@ -312,6 +312,37 @@ __device__ __forceinline__ uint32_t eval_leaf_tile(const PLeaf &lf, const Progra
     }
 }
 
+// Transpose this warp's R-bit row masks into R bitmap words (word j = rows [32 j, 32 j + 32) of the warp's slice
+// of a tile) and store them with ONE lane: every ballot result is warp-uniform, so lane 0 holds all R words and
+// writes them as 16-byte vectors (dst is R*4-byte aligned).  The earlier form -- lane j keeps word j, R lanes store
+// one word each -- spent 8 compares + selects per tile on picking the word.
+template <int R>
+__device__ __forceinline__ void store_mask_words(uint32_t acc, uint32_t lane, uint32_t *dst, uint32_t *dst2) {
+    uint32_t w[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) w[j] = __ballot_sync(0xffffffffu, (acc & (1u << j)) != 0u);
+    if (lane == 0) {
+        if constexpr (R % 4 == 0) {
+#pragma unroll
+            for (int j = 0; j < R; j += 4) {
+                const uint4 v = make_uint4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+                *reinterpret_cast<uint4 *>(dst + j) = v;
+                if (dst2) *reinterpret_cast<uint4 *>(dst2 + j) = v;
+            }
+        } else if constexpr (R == 2) {
+            const uint2 v = make_uint2(w[0], w[1]);
+            *reinterpret_cast<uint2 *>(dst) = v;
+            if (dst2) *reinterpret_cast<uint2 *>(dst2) = v;
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                dst[j] = w[j];
+                if (dst2) dst2[j] = w[j];
+            }
+        }
+    }
+}
+
 // run the compiled WHERE program; returns the R-bit match mask of this lane's rows
 template <typename LeafFn>
 __device__ __forceinline__ uint32_t run_program(const Program *sp, uint32_t all_mask, LeafFn leaf_fn) {
@@ -488,16 +519,7 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_tma_kernel(const __grid
             if (tile * T + T > p.n_rows)                 // last (partial) tile: drop the padding rows
                 acc &= rows_mask<R>([&](int j) { return row_base + 32ll * j < p.n_rows; });
             my_count += static_cast<uint32_t>(__popc(acc));
-            if (p.out_bitmap) {
-                // transpose: lane j ends up with the word of rows [32 j, 32 j + 32) of this warp's slice
-                uint32_t myword = 0;
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const uint32_t bal = __ballot_sync(0xffffffffu, (acc >> j) & 1u);
-                    if (static_cast<int>(lane) == j) myword = bal;
-                }
-                if (static_cast<int>(lane) < R) p.out_bitmap[tile * WPT + ew * R + lane] = myword;
-            }
+            if (p.out_bitmap) store_mask_words<R>(acc, lane, p.out_bitmap + tile * WPT + ew * R, nullptr);
             if (++s == S) {
                 s = 0;
                 sphase ^= 1u;
@@ -608,13 +630,7 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_batch_kernel(const __gr
                                      });
                 const uint32_t warp_cnt = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(__popc(acc)));
                 if (lane == 0 && warp_cnt) atomicAdd(&s_count[q], static_cast<unsigned long long>(warp_cnt));
-                uint32_t myword = 0;
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const uint32_t bal = __ballot_sync(0xffffffffu, (acc >> j) & 1u);
-                    if (static_cast<int>(lane) == j) myword = bal;
-                }
-                if (static_cast<int>(lane) < R) bp.bitmap[q][tile * WPT + ew * R + lane] = myword;
+                store_mask_words<R>(acc, lane, bp.bitmap[q] + tile * WPT + ew * R, nullptr);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh->empty[s]);  // every program has read the stage
@@ -808,16 +824,8 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
                             if (tl * T + T > p.n_rows)
                                 acc &= rows_mask<R>([&](int jj) { return row_base + 32ll * jj < p.n_rows; });
                             my_count += static_cast<uint32_t>(__popc(acc));
-                            uint32_t myword = 0;
-#pragma unroll
-                            for (int jj = 0; jj < R; ++jj) {
-                                const uint32_t bal = __ballot_sync(0xffffffffu, (acc >> jj) & 1u);
-                                if (static_cast<int>(lane) == jj) myword = bal;
-                            }
-                            if (static_cast<int>(lane) < R) {
-                                cb[(j + h) * WPT + ew * R + lane] = myword;
-                                if (p.out_bitmap) p.out_bitmap[tl * WPT + ew * R + lane] = myword;
-                            }
+                            store_mask_words<R>(acc, lane, cb + (j + h) * WPT + ew * R,
+                                                p.out_bitmap ? p.out_bitmap + tl * WPT + ew * R : nullptr);
                         }
                     }
                     j += 2;
@@ -839,16 +847,8 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
                 if (tile * T + T > p.n_rows)
                     acc &= rows_mask<R>([&](int jj) { return row_base + 32ll * jj < p.n_rows; });
                 my_count += static_cast<uint32_t>(__popc(acc));
-                uint32_t myword = 0;
-#pragma unroll
-                for (int jj = 0; jj < R; ++jj) {
-                    const uint32_t bal = __ballot_sync(0xffffffffu, (acc >> jj) & 1u);
-                    if (static_cast<int>(lane) == jj) myword = bal;
-                }
-                if (static_cast<int>(lane) < R) {
-                    cb[j * WPT + ew * R + lane] = myword;
-                    if (p.out_bitmap) p.out_bitmap[tile * WPT + ew * R + lane] = myword;
-                }
+                store_mask_words<R>(acc, lane, cb + j * WPT + ew * R,
+                                    p.out_bitmap ? p.out_bitmap + tile * WPT + ew * R : nullptr);
                 ++j;
                 if (++s == S) {
                     s = 0;
