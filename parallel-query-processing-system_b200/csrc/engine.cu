@@ -494,8 +494,11 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     for (int c = 0; c < NUM_COLS; ++c)
         if (hc->prog.col_mask & (1u << c)) bytes_per_row += t.col[c].width;
 
-    if (!cuda_ok(cudaMemcpyAsync(g->d_ctl, hc, sizeof(QueryCtl), cudaMemcpyHostToDevice, g->stream), "upload query"))
-        return false;
+    // the compiled query goes up right before the first kernel of whichever path runs (all host-side planning
+    // first: the device then never idles between this copy and the launch that waits for it)
+    auto upload_query = [&]() {
+        return cuda_ok(cudaMemcpyAsync(g->d_ctl, hc, sizeof(QueryCtl), cudaMemcpyHostToDevice, g->stream), "upload query");
+    };
 
     if (n_seg == 0) {
         // ===== full-scan path: linearSearchRecords over the table (:464-467) =====
@@ -538,6 +541,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
                     n_prog = static_cast<int>((fg.n_chunks + F.seg_chunks - 1) / F.seg_chunks);
                     F.progress = g->d_progress;
                 }
+                if (!upload_query()) return false;
                 cudaEventRecord(g->ev0, g->stream);
                 if (!cuda_ok(fused_launch(F, fg, g->stream), "fused scan kernel launch")) return false;
                 cudaEventRecord(g->ev_mid, g->stream);
@@ -622,6 +626,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
             const unsigned long long cap =
                 g->out_override ? g->out_override_cap : static_cast<unsigned long long>(g->ids_cap);
             const uint32_t id_base = (g->out_override || g->id_base_always) ? g->id_base_override : 0u;
+            if (!upload_query()) return false;
             cudaEventRecord(g->ev0, g->stream);
             if (P == 1) {
                 if (!cuda_ok(scan_launch(L, geo, g->stream), "scan kernel launch")) return false;
@@ -680,6 +685,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
             cs.vstart[1] = t.n;
             if (!ensure_desc(g, filter_tiles(t.n))) return false;
             if (!count_only && !engine_ensure_ids(g, t.n)) return false;
+            if (!upload_query()) return false;
             cudaEventRecord(g->ev0, g->stream);
             if (!cuda_ok(filter_launch(t, g->d_ctl, cs, g->d_tile_desc, next_epoch(g), count_only ? nullptr : g->d_ids,
                                        g->stream),
@@ -698,6 +704,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
         int launches = 0;
         for (int s = 0; s < n_seg; ++s)
             if (!ensure_index(g, &g->idx[segs[s].index_slot], &launches)) return false;
+        if (!upload_query()) return false;
         cudaEventRecord(g->ev0, g->stream);
         for (int s = 0; s < n_seg; ++s) {
             if (segs[s].is_u64) {
