@@ -517,7 +517,22 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
         if (staged && !count_only && !want_bitmap && t.n > 0 && g->pipe_segments == 0) {
             ScanGeometry fg{};
             const char *fwhy = nullptr;
-            if (scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, 4, &fg, &fwhy, true)) {
+            static const int pinned_cw = [] {
+                const char *e = std::getenv("QPE_FUSE_CW");
+                const int v = e ? std::atoi(e) : 0;
+                return (v == 4 || v == 8) ? v : 0;
+            }();
+            const int want_cw = pinned_cw ? pinned_cw : g->fuse_cw;
+            bool planned = scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, 4, &fg, &fwhy, 4);
+            if (planned && want_cw == 8) {
+                // eight compaction warps need 16 KB more shared memory: only when that costs no tile rows or stages
+                ScanGeometry g8{};
+                const char *why8 = nullptr;
+                if (scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, 4, &g8, &why8, 8) &&
+                    g8.tile_rows == fg.tile_rows && g8.stages == fg.stages)
+                    fg = g8;
+            }
+            if (planned) {
                 if (!ensure_desc(g, fg.n_chunks)) return false;
                 if (!g->out_override && !engine_ensure_ids(g, t.n)) return false;
                 FusedLaunch F{};
@@ -787,6 +802,8 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     g->cur_slot->two_kernels = st.launches > 1;
     g->cur_slot->has_post = static_cast<bool>(g->post_match);
     st.matches = static_cast<int64_t>(hc->out_count);
+    if (st.path == 0 && st.rows_scanned > 0)  // next full scan: 8 compaction warps if this one matched > 4 % of its rows
+        g->fuse_cw = (st.matches * 25 > st.rows_scanned) ? 8 : 4;
     st.algo_bytes = st.rows_scanned * bytes_per_row + (count_only ? 0 : 4 * st.matches) +
                     (st.path == 1 ? 4 * st.candidates : 0);
     st.total_ms = now_ms() - t_begin;

@@ -661,12 +661,13 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_batch_kernel(const __gr
 // Optional progress words in pinned host memory tell the host when a table segment's ids are
 // complete in HBM, so it can start the device->host copy of that segment during the scan.
 // ------------------------------------------------------------------------------------------
-constexpr int kFuseCompactWarps = 4;
-constexpr int kFuseCompactThreads = 32 * kFuseCompactWarps;          // 128
+// CW = compaction warps per CTA, 4 or 8.  Four are plenty while few rows match (and measured 3.5 % faster there:
+// 2.07 vs 2.15 ms on 1 B rows at 1 %); from ~10 % selectivity the evaluators wait for the compaction warps
+// (ncu: 18.6 % of all samples in their wait for a free chunk buffer at 50 %), and eight cut 2.79 ms to 2.39 ms.
+// The engine picks per query from the selectivity the previous full scan saw (engine.cu).
 constexpr int kFuseChunkWords = kFuseMaxChunkRows / 32;              // 2048 words
-constexpr int kFuseRounds = kFuseChunkWords / kFuseCompactThreads;   // 16 words per compaction thread
-constexpr int kFuseStageIds = 32 * kFuseCompactThreads;              // 4096: a round never holds more ids
-static_assert(kFuseReserveBytes == 2 * kFuseChunkWords * 4 + kFuseStageIds * 4, "smem reserve");
+static_assert(fuse_reserve_bytes(4) == 2 * kFuseChunkWords * 4 + 32 * 32 * 4 * 4, "smem reserve");
+static_assert(fuse_reserve_bytes(8) == 2 * kFuseChunkWords * 4 + 32 * 32 * 8 * 4, "smem reserve");
 
 struct FusedParams {
     ScanParams s;
@@ -682,7 +683,7 @@ struct FusedParams {
     unsigned long long *progress;   // mapped pinned host memory: [seg] = epoch << 32 | ids complete through seg
 };
 
-struct FusedSmemHeader {
+struct FusedSmemHeader {   // sized for the 4-warp variant (16 rounds x 4 warps); the 8-warp one needs 8 x 8
     Program prog;
     alignas(8) uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
@@ -690,14 +691,19 @@ struct FusedSmemHeader {
     uint64_t cb_empty[2];
     long long tile_of_stage[kMaxStages];
     unsigned long long cta_count;
-    uint32_t warp_tot[kFuseRounds][kFuseCompactWarps];
-    uint32_t round_base[kFuseRounds + 1];
+    uint32_t warp_tot[64];          // [round][compaction warp]
+    uint32_t round_base[16 + 1];
     uint32_t excl;
 };
 
-template <int EW, int R>
-__global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
+template <int EW, int R, int CW>
+__global__ void __launch_bounds__(32 * (1 + EW + CW), 1)
     scan_fused_kernel(const __grid_constant__ FusedParams fp) {
+    constexpr int kFuseCompactWarps = CW;
+    constexpr int kFuseCompactThreads = 32 * CW;                           // 128 | 256
+    constexpr int kFuseRounds = kFuseChunkWords / kFuseCompactThreads;     // 16 | 8 words per compaction thread
+    constexpr int kFuseStageIds = 32 * kFuseCompactThreads;                // a round never holds more ids
+    static_assert(kFuseRounds * CW <= 64 && kFuseRounds <= 16, "FusedSmemHeader scratch");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const ScanParams &p = fp.s;
     FusedSmemHeader *sh = reinterpret_cast<FusedSmemHeader *>(smem_raw);
@@ -873,7 +879,10 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
             const long long t0 = chunk * CT;
             const int nt = static_cast<int>((p.n_tiles - t0 < CT) ? (p.n_tiles - t0) : CT);
             const uint32_t nw = static_cast<uint32_t>(nt) * WPT;
-            mbar_wait_relaxed(&sh->cb_full[buf], (k >> 1) & 1u, 256);
+            // one compaction warp polls the chunk barrier (sleeping between polls), the others block in a
+            // hardware barrier: eight warps polling cost 3 % of the whole kernel at low selectivity
+            if (cw == 0) mbar_wait_relaxed(&sh->cb_full[buf], (k >> 1) & 1u, 512);
+            named_bar_sync(1, kFuseCompactThreads);
             const uint32_t *cb = cbuf + buf * kFuseChunkWords;
             // 1. words -> registers, popc, warp-inclusive scan per round
             uint32_t word[kFuseRounds], off[kFuseRounds];
@@ -889,7 +898,7 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
                     if (lane >= static_cast<uint32_t>(d)) inc += t;
                 }
                 off[r] = inc - pc;
-                if (lane == 31) sh->warp_tot[r][cw] = inc;
+                if (lane == 31) sh->warp_tot[r * kFuseCompactWarps + cw] = inc;
             }
             named_bar_sync(1, kFuseCompactThreads);
             if (ct == 0) mbar_arrive(&sh->cb_empty[buf]);  // the evaluators may refill this buffer
@@ -898,7 +907,7 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
                 uint32_t rt = 0;
                 if (lane < kFuseRounds) {
 #pragma unroll
-                    for (int w = 0; w < kFuseCompactWarps; ++w) rt += sh->warp_tot[lane][w];
+                    for (int w = 0; w < kFuseCompactWarps; ++w) rt += sh->warp_tot[lane * kFuseCompactWarps + w];
                 }
                 uint32_t inc = rt;
 #pragma unroll
@@ -931,7 +940,7 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
                         uint32_t w = word[r];
                         if (w) {
                             uint32_t o = sh->round_base[r] + off[r];
-                            for (uint32_t q = 0; q < cw; ++q) o += sh->warp_tot[r][q];
+                            for (uint32_t q = 0; q < cw; ++q) o += sh->warp_tot[r * kFuseCompactWarps + q];
                             const uint32_t row0 = row_chunk + (r * kFuseCompactThreads + ct) * 32u;
                             while (w) {
                                 const int b = __ffs(w) - 1;
@@ -953,7 +962,7 @@ __global__ void __launch_bounds__(32 * (1 + EW + kFuseCompactWarps), 1)
                         if (cnt == 0) continue;  // uniform over the compaction warps
                         uint32_t w = word[r];
                         uint32_t o = off[r];
-                        for (uint32_t q = 0; q < cw; ++q) o += sh->warp_tot[r][q];
+                        for (uint32_t q = 0; q < cw; ++q) o += sh->warp_tot[r * kFuseCompactWarps + q];
                         const uint32_t row0 = row_chunk + (r * kFuseCompactThreads + ct) * 32u;
                         while (w) {
                             const int b = __ffs(w) - 1;
@@ -997,7 +1006,13 @@ static int current_device_slot() {
 }
 
 bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages, int max_stages,
-               ScanGeometry *geo, const char **why, bool fused, size_t extra_reserve) {
+               ScanGeometry *geo, const char **why, int fused_cw, size_t extra_reserve) {
+    const bool fused = fused_cw != 0;
+    if (fused && fused_cw != 4 && fused_cw != 8) {
+        if (why) *why = "K1f runs with 4 or 8 compaction warps";
+        return false;
+    }
+    const size_t fuse_reserve = fused ? fuse_reserve_bytes(fused_cw) : 0;
     if (max_stages < 1 || max_stages > 4) max_stages = 4;
     // device attributes are asked once per process (one process per GPU; this runs twice per query)
     static int max_smem_by_device[kMaxDevices] = {0}, n_sm_by_device[kMaxDevices] = {0};
@@ -1022,7 +1037,7 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
             bpr += t.col[c].width;
         }
     const size_t header = ((fused ? sizeof(FusedSmemHeader) : sizeof(ScanSmemHeader)) + 127) & ~size_t(127);
-    const size_t budget = static_cast<size_t>(max_smem) - header - 256 - (fused ? kFuseReserveBytes : 0) - extra_reserve;
+    const size_t budget = static_cast<size_t>(max_smem) - header - 256 - fuse_reserve - extra_reserve;
 
     auto stage_bytes_for = [&](int T) {
         size_t sb = 0;
@@ -1077,7 +1092,8 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
     geo->stages = S;
     geo->n_tiles = (t.n + T - 1) / T;
     geo->bytes_per_row = bpr;
-    geo->smem_bytes = header + stage_bytes * S + 128 + (fused ? kFuseReserveBytes : 0) + extra_reserve;
+    geo->smem_bytes = header + stage_bytes * S + 128 + fuse_reserve + extra_reserve;
+    geo->compact_warps = fused_cw;
     int64_t grid = geo->n_tiles < n_sm ? geo->n_tiles : n_sm;
     if (grid < 1) grid = 1;
     geo->grid = static_cast<int>(grid);
@@ -1219,26 +1235,31 @@ cudaError_t batch_launch(const ScanLaunch &L, const ScanGeometry &geo, int n_pro
     }
 }
 
-template <int EW, int R>
+template <int EW, int R, int CW>
 static cudaError_t launch_fused_r(const FusedParams &fp, const ScanGeometry &geo, cudaStream_t stream) {
-    // per instantiation and device: raise the dynamic shared memory limit only when it grows
     static size_t allowed_by_device[kMaxDevices] = {0};
     size_t &allowed = allowed_by_device[current_device_slot()];
     if (geo.smem_bytes > allowed) {
-        const cudaError_t e = cudaFuncSetAttribute(scan_fused_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        const cudaError_t e = cudaFuncSetAttribute(scan_fused_kernel<EW, R, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(geo.smem_bytes));
         if (e != cudaSuccess) return e;
         allowed = geo.smem_bytes;
     }
-    scan_fused_kernel<EW, R><<<geo.grid, 32 * (1 + EW + kFuseCompactWarps), geo.smem_bytes, stream>>>(fp);
+    scan_fused_kernel<EW, R, CW><<<geo.grid, 32 * (1 + EW + CW), geo.smem_bytes, stream>>>(fp);
     return cudaGetLastError();
+}
+
+template <int EW, int R>
+static cudaError_t launch_fused_cw(const FusedParams &fp, const ScanGeometry &geo, cudaStream_t stream) {
+    return geo.compact_warps == 8 ? launch_fused_r<EW, R, 8>(fp, geo, stream) : launch_fused_r<EW, R, 4>(fp, geo, stream);
 }
 
 cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStream_t stream) {
     FusedParams fp{};
     const cudaError_t e = fill_scan_params(L.scan, geo, fp.s);
     if (e != cudaSuccess) return e;
-    if (geo.chunk_tiles < 1 || static_cast<long long>(geo.chunk_tiles) * geo.tile_rows > kFuseMaxChunkRows)
+    if (geo.chunk_tiles < 1 || static_cast<long long>(geo.chunk_tiles) * geo.tile_rows > kFuseMaxChunkRows ||
+        (geo.compact_warps != 4 && geo.compact_warps != 8))
         return cudaErrorInvalidValue;
     fp.s.dynamic_tiles = 0;
     fp.chunk_tiles = geo.chunk_tiles;
@@ -1252,20 +1273,11 @@ cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStre
     fp.progress = L.progress;
     if (fp.n_chunks == 0) return cudaSuccess;
     switch (geo.tile_rows) {
-        case 256: return launch_fused_r<kEvalWarpsWide, 1>(fp, geo, stream);
-        case 512: return launch_fused_r<kEvalWarps, 1>(fp, geo, stream);
-        case 1024: return launch_fused_r<kEvalWarps, 2>(fp, geo, stream);
-        case 2048: return launch_fused_r<kEvalWarps, 4>(fp, geo, stream);
-        case 4096: {
-            // experiment knob (QPE_EVAL_WARPS=8): 8 evaluator warps x 16 rows per lane -- the per-tile dispatch
-            // of the program is then amortised over twice the rows per warp
-            static const int ew = [] {
-                const char *e = std::getenv("QPE_EVAL_WARPS");
-                return e ? std::atoi(e) : 0;
-            }();
-            if (ew == 8) return launch_fused_r<8, 16>(fp, geo, stream);
-            return launch_fused_r<kEvalWarps, 8>(fp, geo, stream);
-        }
+        case 256: return launch_fused_cw<kEvalWarpsWide, 1>(fp, geo, stream);
+        case 512: return launch_fused_cw<kEvalWarps, 1>(fp, geo, stream);
+        case 1024: return launch_fused_cw<kEvalWarps, 2>(fp, geo, stream);
+        case 2048: return launch_fused_cw<kEvalWarps, 4>(fp, geo, stream);
+        case 4096: return launch_fused_cw<kEvalWarps, 8>(fp, geo, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -21,7 +21,10 @@ struct QueryCtl {
 // K1f (fused scan + compaction): chunk = consecutive tiles, at most this many rows; the kernel keeps
 // two chunk bitmaps and one id stage in shared memory beside the TMA stages
 constexpr int kFuseMaxChunkRows = 65536;
-constexpr int kFuseReserveBytes = 2 * (kFuseMaxChunkRows / 32) * 4 + 4096 * 4;
+// shared memory K1f sets aside beside the TMA stages: two chunk bitmaps + the id stage of its compaction warps
+constexpr size_t fuse_reserve_bytes(int compact_warps) {
+    return 2 * (kFuseMaxChunkRows / 32) * 4 + static_cast<size_t>(32 * 32 * compact_warps) * 4;
+}
 
 struct ScanLaunch {
     const DevTable *table;
@@ -43,16 +46,18 @@ struct ScanGeometry {
     int64_t bytes_per_row;
     int chunk_tiles;      // K1f only
     int64_t n_chunks;     // K1f only
+    int compact_warps;    // K1f only: 4 or 8
 };
 
 // K1: TMA-staged predicate evaluation over the whole table -> match bitmap + count (ctl->out_count).
 // Returns false (and sets *why) if the query cannot be staged (row too wide for shared memory):
 // the caller then uses the gather path below with an identity candidate list.
 // max_stages (1..4) caps the pipeline depth: 3 leaves room for a K1c CTA beside K1's on every SM.
-// fused: plan for K1f (larger header, kFuseReserveBytes of shared memory set aside; geo->chunk_tiles and
+// fused_cw != 0: plan for K1f (larger header, fuse_reserve_bytes(cw) of shared memory set aside; geo->chunk_tiles and
 // geo->n_chunks are filled in).
+// fused_cw: 0 = plan for K1 / K9, 4 or 8 = plan for K1f with that many compaction warps
 bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int force_stages, int max_stages,
-               ScanGeometry *geo, const char **why, bool fused = false, size_t extra_reserve = 0);
+               ScanGeometry *geo, const char **why, int fused_cw = 0, size_t extra_reserve = 0);
 
 // K9: up to kMaxBatch programs over one pass of the union of their columns -> one bitmap + count per query
 constexpr int kMaxBatch = 8;
