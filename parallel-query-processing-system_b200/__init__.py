@@ -24,7 +24,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqpegpu.so")
+LIB_PATH = os.environ.get("QPE_LIB_PATH") or os.path.join(_HERE, "libqpegpu.so")  # override: A/B of two builds
 
 COLUMNS = ("command_id", "raw_command", "base_command", "shell_type", "exit_code", "timestamp", "sudo_used",
            "working_directory", "user_id", "user_name", "host_name", "risk_level")
