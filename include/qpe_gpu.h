@@ -59,6 +59,8 @@ struct engineS *qpe_gpu_engine_synth(unsigned long long total_rows, unsigned lon
                                      const char *indexed_attributes[], const int attribute_types[]);
 
 long long qpe_gpu_num_rows(const struct engineS *engine);
+/* Global row id of this engine's row 0 (non-zero for a shard of a row-range sharded table). */
+unsigned long long qpe_gpu_row_base(const struct engineS *engine);
 
 /* Match phase of SELECT with the reference's path rule (index path iff a top-level condition
  * names a u64/int index; else full scan).  *ids_out receives the matching row ids in the
@@ -213,6 +215,9 @@ int qpe_gpu_probe_batch(struct engineS *engine, const char *attribute, const KEY
 /* Row ids of index entries [first, first + count) of `attribute`'s index. */
 int qpe_gpu_index_slice(struct engineS *engine, const char *attribute, unsigned int first, unsigned int count,
                         unsigned int *row_ids_out);
+/* Keys of the same index entries (u64 keys as long long bits, int keys sign-extended). */
+int qpe_gpu_index_slice_keys(struct engineS *engine, const char *attribute, unsigned int first, unsigned int count,
+                             long long *keys_out);
 
 /* Copy n_rows values of a column to the host in device layout (u64 / int32 / u8 / fixed-width
  * NUL-padded text); *width_out = bytes per row.  out must hold n_rows * width bytes; pass

@@ -92,8 +92,10 @@ def load_library() -> C.CDLL:
         "qpe_gpu_engine_synth": (vp, [ull, ull, ull, ull, C.c_uint, i, C.POINTER(cp), C.POINTER(i)]),
         "qpe_gpu_engine_from_records": (vp, [vp, ll, i, C.POINTER(cp), C.POINTER(i), cp, cp]),
         "qpe_gpu_num_rows": (ll, [vp]),
+        "qpe_gpu_row_base": (ull, [vp]),
         "qpe_gpu_probe_batch": (i, [vp, cp, C.POINTER(KeyT), C.POINTER(KeyT), sz, vp, vp, pstats]),
         "qpe_gpu_index_slice": (i, [vp, cp, C.c_uint, C.c_uint, vp]),
+        "qpe_gpu_index_slice_keys": (i, [vp, cp, C.c_uint, C.c_uint, vp]),
         "qpe_gpu_fetch_column": (i, [vp, cp, ll, ll, vp, C.POINTER(C.c_uint)]),
         "qpe_gpu_set_tile": (i, [vp, i, i]),
         "qpe_gpu_set_pipeline": (i, [vp, i]),
@@ -485,6 +487,13 @@ class Engine:
         out = np.zeros(max(count, 1), dtype=np.uint32)
         self._check(self._lib.qpe_gpu_index_slice(self._h, attribute.encode(), first, count, out.ctypes.data),
                     "index_slice")
+        return out[:count]
+
+    def index_slice_keys(self, attribute: str, first: int, count: int) -> np.ndarray:
+        """keys of index entries [first, first + count) (int64; u64 keys as bits)"""
+        out = np.zeros(max(count, 1), dtype=np.int64)
+        self._check(self._lib.qpe_gpu_index_slice_keys(self._h, attribute.encode(), first, count, out.ctypes.data),
+                    "index_slice_keys")
         return out[:count]
 
     # ---- column access --------------------------------------------------------------------

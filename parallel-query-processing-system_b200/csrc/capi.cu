@@ -636,6 +636,11 @@ void freeResultSet(struct resultSetS *result) {
 // ------------------------------------------------------------------------------------------
 // include/qpe_gpu.h : row-id interface
 // ------------------------------------------------------------------------------------------
+unsigned long long qpe_gpu_row_base(const struct engineS *engine) {
+    GpuEngine *g = as_engine(const_cast<struct engineS *>(engine));
+    return g ? g->table.row_base : 0ull;
+}
+
 long long qpe_gpu_num_rows(const struct engineS *engine) {
     GpuEngine *g = as_engine(const_cast<struct engineS *>(engine));
     return g ? g->table.n : -1;
@@ -959,6 +964,36 @@ int qpe_gpu_index_slice(struct engineS *engine, const char *attribute, unsigned 
     if (count && !cuda_ok(cudaMemcpy(row_ids_out, ix.perm + first, static_cast<size_t>(count) * 4, cudaMemcpyDeviceToHost),
                           "download slice"))
         return -4;
+    return 0;
+}
+
+int qpe_gpu_index_slice_keys(struct engineS *engine, const char *attribute, unsigned int first, unsigned int count,
+                             long long *keys_out) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g) return -1;
+    cudaSetDevice(g->device);
+    const int slot = isAttributeIndexed(engine, attribute);
+    if (slot < 0 || !g->idx[slot].usable) {
+        set_error("attribute has no probe-able (u64 / int) index");
+        return -6;
+    }
+    DevIndex &ix = g->idx[slot];
+    int launches = 0;
+    if (ix.dirty && !cuda_ok(index_build(&ix, g->table, g->stream, &launches), "index rebuild")) return -2;
+    if (static_cast<long long>(first) + count > ix.n) {
+        set_error("index slice out of range");
+        return -5;
+    }
+    if (count == 0) return 0;
+    if (ix.type == T_U64)
+        return cuda_ok(cudaMemcpy(keys_out, static_cast<const unsigned long long *>(ix.keys) + first,
+                                  static_cast<size_t>(count) * 8, cudaMemcpyDeviceToHost), "download keys") ? 0 : -4;
+    std::vector<int> tmp(count);
+    if (!cuda_ok(cudaMemcpy(tmp.data(), static_cast<const int *>(ix.keys) + first, static_cast<size_t>(count) * 4,
+                            cudaMemcpyDeviceToHost), "download keys"))
+        return -4;
+    for (unsigned int i = 0; i < count; ++i) keys_out[i] = tmp[i];
     return 0;
 }
 

@@ -128,6 +128,52 @@ def sharded_select(engine, statement: str, device="cpu", dst: int = 0, group=Non
     return out[:total].cpu().numpy().astype(np.uint32)
 
 
+def sharded_probe(engine, attribute: str, lo, hi, device="cpu", rows: bool = False, dst: int = 0, group=None):
+    """Batched findRange on a row-range sharded table: the query batch is replicated, every rank
+    probes the index of ITS shard (K3), the per-query counts are summed over the ranks, and -- with rows=True --
+    the answers are concatenated per query from the HIGHEST rank to the lowest and sorted stably by key, which
+    is (key ASC, global position DESC): the leaf-chain order of one B+ tree over the whole table
+    (engine/bplus.c:282-314).
+    Returns (total counts per query on every rank, list of global-row-id arrays on rank `dst` / None)."""
+    import numpy as np
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    first, count, _ = engine.probe_batch(attribute, lo, hi)
+    device = torch.device(device)
+    total = torch.from_numpy(count.astype(np.int64)).to(device)
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    total = total.cpu().numpy()
+    if not rows:
+        return total, None
+    # this shard's answers, flattened query by query, with global row ids
+    base = int(engine._lib.qpe_gpu_row_base(engine._h))
+    local = [engine.index_slice(attribute, int(f), int(c)).astype(np.int64) + base for f, c in zip(first, count)]
+    flat = np.concatenate(local) if local else np.zeros(0, dtype=np.int64)
+    keys = [engine.index_slice_keys(attribute, int(f), int(c)) for f, c in zip(first, count)]
+    flat_keys = np.concatenate(keys) if keys else np.zeros(0, dtype=np.int64)
+    if attribute == "command_id":   # u64 keys travel as bits: order them as unsigned
+        flat_keys = (flat_keys.view(np.uint64) ^ np.uint64(1 << 63)).view(np.int64)
+    _, flat_counts, all_flat = ordered_gather(torch.from_numpy(flat).to(device), None, dst, group)
+    _, _, all_keys = ordered_gather(torch.from_numpy(flat_keys).to(device), None, dst, group)
+    _, _, all_cnt = ordered_gather(torch.from_numpy(count.astype(np.int64)).to(device), None, dst, group)
+    if rank != dst:
+        return total, None
+    q = len(count)
+    all_flat = all_flat.cpu().numpy()
+    all_keys = all_keys.cpu().numpy()
+    per_rank_cnt = all_cnt.cpu().numpy()[:q * world].reshape(world, q)
+    starts = np.zeros(world, dtype=np.int64)
+    starts[1:] = np.cumsum(flat_counts)[:-1]
+    offs = [np.concatenate(([0], np.cumsum(per_rank_cnt[r]))) for r in range(world)]
+    out = []
+    for k in range(q):
+        sl = [slice(starts[r] + offs[r][k], starts[r] + offs[r][k + 1]) for r in range(world - 1, -1, -1)]
+        ids_k = np.concatenate([all_flat[x] for x in sl])
+        keys_k = np.concatenate([all_keys[x] for x in sl])
+        out.append(ids_k[np.argsort(keys_k, kind="stable")].astype(np.uint32))
+    return total, out
+
+
 class PeerGather:
     """Ordered gather of a sharded full scan WITHOUT a transfer step of its own: rank `dst` owns the
     result buffer, every other rank maps it through CUDA IPC, and each rank's compaction kernel

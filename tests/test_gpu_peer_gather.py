@@ -92,6 +92,8 @@ SHARDED_QUERIES = [
     'SELECT command_id FROM Commands WHERE (risk_level > 3) AND (shell_type = "zsh")',   # groups only: scan path
     'SELECT command_id FROM Commands WHERE user_id = 999999',
 ]
+PROBES = [("user_id", [1001, 2450, 999999, 1500], [1001, 2452, 999999, 1499]),
+          ("command_id", [0, 500000, 999990, 2000000], [9, 500000, 1000010, 2000005])]
 SH_TOTAL = 1_000_003
 SH_COLS = ["command_id", "sudo_used", "risk_level", "exit_code", "user_id", "shell_type"]
 SH_IDX = (("command_id", 0), ("user_id", 1), ("risk_level", 1), ("exit_code", 1), ("sudo_used", 3))
@@ -112,6 +114,11 @@ def _sharded_worker(rank, world, port, ret):
         ids = sharding.sharded_select(eng, q)
         if rank == 0:
             out.append(ids)
+    # batched findRange over the sharded indexes: counts on every rank, row ids on rank 0
+    for attr, lo, hi in PROBES:
+        total, rows = sharding.sharded_probe(eng, attr, np.asarray(lo), np.asarray(hi), rows=True)
+        if rank == 0:
+            out.append((total, rows))
     eng.close()
     if rank == 0:
         ret.put(out)
@@ -136,4 +143,10 @@ def test_sharded_select_equals_single_engine(world):
     for q, ids in zip(SHARDED_QUERIES, results):
         want, _ = whole.select_ids(q)
         assert np.array_equal(ids, want), q
+    for (attr, lo, hi), (total, rows) in zip(PROBES, results[len(SHARDED_QUERIES):]):
+        dt = np.uint64 if attr == "command_id" else np.int32
+        first, count, _ = whole.probe_batch(attr, np.asarray(lo, dtype=dt), np.asarray(hi, dtype=dt))
+        assert np.array_equal(total, count.astype(np.int64)), attr
+        for k in range(len(lo)):
+            assert np.array_equal(rows[k], whole.index_slice(attr, int(first[k]), int(count[k]))), (attr, k)
     whole.close()
