@@ -213,6 +213,43 @@ def test_properties_at_100m_rows(pkg):
     eng.close()
 
 
+def test_properties_at_1b_rows(pkg):
+    """BASELINE configs[4] at its full size (1 B rows, the bench's table): size-independent properties plus
+    1 M-row windows checked bit-exactly against the oracle; the dense query runs twice so that the second scan
+    uses the 8-compaction-warp kernel (chosen from the first scan's selectivity)."""
+    n = 1_000_000_000
+    cols = ["command_id", "sudo_used", "risk_level"]
+    eng = pkg.Engine.from_synth(n, columns=cols)
+    try:
+        k = n // 100
+        w = f"(command_id < {k}) AND (sudo_used = FALSE OR risk_level > 3)"     # the bench's QN at 1 %
+        ids, st = eng.select_ids(f"SELECT command_id FROM Commands WHERE {w}", force_scan=True)
+        cnt, _, _ = eng.select_ids_device(f"SELECT command_id FROM Commands WHERE {w}", force_scan=True, count_only=True)
+        assert cnt == len(ids) and st["path"] == 0 and st["launches"] == 1
+        assert np.all(np.diff(ids.astype(np.int64)) > 0) and ids[-1] < k
+        for a in (0, k - 1_000_000):
+            win = {c: eng.fetch_column(c, a, 1_000_000) for c in cols}
+            want = Oracle.from_columns(win).scan(w).astype(np.int64) + a
+            got = ids[(ids >= a) & (ids < a + 1_000_000)]
+            assert np.array_equal(got.astype(np.int64), want), a
+        # complement counts over the whole table
+        ca, _, _ = eng.select_ids_device("SELECT c FROM t WHERE (risk_level > 2)", force_scan=True, count_only=True)
+        cb, _, _ = eng.select_ids_device("SELECT c FROM t WHERE (risk_level <= 2)", force_scan=True, count_only=True)
+        assert ca + cb == n
+        # a dense result (600 M consecutive ids): count in closed form, ids an arithmetic sequence at both ends and
+        # across a chunk boundary in the middle
+        lo = 400_000_000
+        dense = f"SELECT command_id FROM Commands WHERE (command_id >= {lo})"
+        for rep in range(2):
+            cnt, dptr, st = eng.select_ids_device(dense, force_scan=True)
+            assert cnt == n - lo
+            for off in (0, 300_000_000 - 12_345, cnt - 1_000_000):
+                got = eng.copy_from_device(dptr + 4 * off, 1_000_000)
+                assert np.array_equal(got.astype(np.int64), np.arange(lo + off, lo + off + 1_000_000)), (rep, off)
+    finally:
+        eng.close()
+
+
 def test_insert_delete_on_synthetic_table_vs_oracle(pkg, tmp_path):
     """DELETE mask + stable compaction + index rebuild, then INSERT, checked against the oracle"""
     n = 300_000
