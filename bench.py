@@ -460,7 +460,8 @@ def run_ours(args):
             "scan_gbs": (total * bpr + 4 * n_matches) / step_s / 1e9,
             "clocks": clocks,
             "e2e": {"value": total / e2e_s, "unit": "rows/s", "ms_per_step": e2e_s * 1e3,
-                    "h2d_bytes_per_step": 3664 * world, "d2h_bytes_per_step": int(4 * n_matches + 8 * world)},
+                    "h2d_bytes_per_step": int(pkg.load_library().qpe_gpu_query_upload_bytes()) * world,
+                    "d2h_bytes_per_step": int(4 * n_matches + 8 * world)},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "kernel": "scan_fused_kernel (K1f)" if fused else "scan_tma_kernel (K1)",
                          "achieved": achieved, "peak": peak,

@@ -100,6 +100,7 @@ def load_library() -> C.CDLL:
         "qpe_gpu_set_tile": (i, [vp, i, i]),
         "qpe_gpu_set_pipeline": (i, [vp, i]),
         "qpe_gpu_stream": (vp, [vp]),
+        "qpe_gpu_query_upload_bytes": (C.c_uint, []),
         "qpe_gpu_last_trace": (i, [vp, C.POINTER(C.c_double)]),
         "qpe_gpu_set_timing": (i, [vp, i]),
         "qpe_gpu_timing_totals": (i, [vp, C.POINTER(C.c_double), C.POINTER(ll)]),

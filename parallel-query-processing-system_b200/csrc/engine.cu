@@ -118,11 +118,11 @@ GpuEngine *engine_create(const char *tableName, const char *datafile, int index_
     for (int i = 0; ok && i < kMaxPipeSegments; ++i)
         ok = cuda_ok(cudaEventCreateWithFlags(&g->ev_seg[i], cudaEventDisableTiming), "cudaEventCreate");
     if (const char *e = std::getenv("QPE_PIPE_SEGMENTS")) g->pipe_segments = std::atoi(e);
-    ok = ok && cuda_ok(cudaHostAlloc(&g->h_progress, sizeof(unsigned long long) * kMaxProgressSegments,
+    ok = ok && cuda_ok(cudaHostAlloc(&g->h_progress, sizeof(unsigned long long) * (kMaxProgressSegments + 1),
                                      cudaHostAllocMapped),
                        "cudaHostAlloc progress");
     if (ok) {
-        std::memset(g->h_progress, 0, sizeof(unsigned long long) * kMaxProgressSegments);
+        std::memset(g->h_progress, 0, sizeof(unsigned long long) * (kMaxProgressSegments + 1));
         ok = cuda_ok(cudaHostGetDevicePointer(&g->d_progress, g->h_progress, 0), "cudaHostGetDevicePointer");
     }
     for (int i = 0; i < GpuEngine::kTimingRing && ok; ++i)
@@ -445,6 +445,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     const DevTable &t = g->table;
     g->last_bm_words = 0;
     bool post_done = false;
+    const unsigned long long *count_src = g->count_mapped;  // where the match count arrives without a download (or null)
     {
         GpuEngine::TimingSlot *slot = &g->ring[g->ring_head];
         g->ring_head = (g->ring_head + 1) % GpuEngine::kTimingRing;
@@ -475,6 +476,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     hc->tile_counter = 0;
     hc->chunk_counter = 0;
     hc->out_count = 0;
+    hc->ctas_done = 0;
     std::memset(hc->seg_stored, 0, sizeof(hc->seg_stored));
     g->host_out_done = false;
 
@@ -557,6 +559,11 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
                     F.progress = g->d_progress;
                 }
                 if (!upload_query()) return false;
+                // a plain (unsharded) scan: the kernel's last CTA writes the count into mapped host memory
+                if (!g->count_mapped) {
+                    F.host_count = g->d_progress + kMaxProgressSegments;
+                    count_src = g->h_progress + kMaxProgressSegments;
+                }
                 cudaEventRecord(g->ev0, g->stream);
                 if (!cuda_ok(fused_launch(F, fg, g->stream), "fused scan kernel launch")) return false;
                 cudaEventRecord(g->ev_mid, g->stream);
@@ -784,13 +791,13 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
         if (!g->post_match()) return false;
         cudaEventRecord(g->ev_post, g->stream);
     }
-    if (!g->count_mapped && !cuda_ok(cudaMemcpyAsync(&hc->out_count, &g->d_ctl->out_count, sizeof(unsigned long long),
-                                                     cudaMemcpyDeviceToHost, g->stream),
-                                     "download count"))
+    if (!count_src && !cuda_ok(cudaMemcpyAsync(&hc->out_count, &g->d_ctl->out_count, sizeof(unsigned long long),
+                                               cudaMemcpyDeviceToHost, g->stream),
+                               "download count"))
         return false;
     const double t_enq = now_ms();
     if (!cuda_ok(cudaStreamSynchronize(g->stream), "match sync")) return false;
-    if (g->count_mapped) hc->out_count = *static_cast<const volatile unsigned long long *>(g->count_mapped);
+    if (count_src) hc->out_count = *static_cast<const volatile unsigned long long *>(count_src);
     const double t_sync = now_ms();
     g->trace[0] = t_compiled - t_begin;
     g->trace[1] = t_enq - t_compiled;

@@ -681,6 +681,7 @@ struct FusedParams {
     unsigned long long out_cap;
     long long seg_chunks;           // progress: chunks per table segment (0 = no progress words)
     unsigned long long *progress;   // mapped pinned host memory: [seg] = epoch << 32 | ids complete through seg
+    unsigned long long *host_count; // mapped pinned host memory: the match count, written by the last CTA (or null)
 };
 
 struct FusedSmemHeader {   // sized for the 4-warp variant (16 rounds x 4 warps); the 8-warp one needs 8 x 8
@@ -992,7 +993,18 @@ __global__ void __launch_bounds__(32 * (1 + EW + CW), 1)
         }
     }
     __syncthreads();
-    if (tid == 0 && sh->cta_count) atomicAdd(&p.ctl->out_count, sh->cta_count);
+    if (tid == 0) {
+        if (sh->cta_count) atomicAdd(&p.ctl->out_count, sh->cta_count);
+        if (fp.host_count) {
+            // the last CTA to get here hands the total to the host through mapped memory: no count download
+            __threadfence();
+            if (atomicAdd(&p.ctl->ctas_done, 1u) == gridDim.x - 1u) {
+                __threadfence();
+                *reinterpret_cast<volatile unsigned long long *>(fp.host_count) = atomicAdd(&p.ctl->out_count, 0ull);
+                __threadfence_system();
+            }
+        }
+    }
 }
 
 // function attributes are per device: cache what was set per (instantiation, device)
@@ -1270,6 +1282,7 @@ cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStre
     fp.out_cap = L.out_cap;
     fp.seg_chunks = L.progress ? L.seg_chunks : 0;
     fp.progress = L.progress;
+    fp.host_count = L.host_count;
     if (fp.n_chunks == 0) return cudaSuccess;
     switch (geo.tile_rows) {
         case 256: return launch_fused_cw<kEvalWarpsWide, 1>(fp, geo, stream);

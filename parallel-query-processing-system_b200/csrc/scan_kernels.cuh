@@ -16,6 +16,8 @@ struct QueryCtl {
     unsigned int chunk_counter;     // ordered chunk claim (K1c)
     unsigned long long out_count;   // total matches (written by the kernel)
     unsigned int seg_stored[kMaxProgressSegments];  // K1f: chunks of table segment s whose ids are stored
+    unsigned int ctas_done;         // K1f: CTAs that have added their count (the last one hands the total to the host)
+    unsigned int pad_;
 };
 
 // K1f (fused scan + compaction): chunk = consecutive tiles, at most this many rows; the kernel keeps
@@ -76,6 +78,7 @@ struct FusedLaunch {
     unsigned long long out_cap;
     long long seg_chunks;
     unsigned long long *progress;
+    unsigned long long *host_count;  // mapped pinned host word (device alias) that receives the match count, or null
 };
 cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStream_t stream);
 cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream_t stream);

