@@ -225,7 +225,8 @@ int qpe_gpu_index_slice_keys(struct engineS *engine, const char *attribute, unsi
 int qpe_gpu_fetch_column(struct engineS *engine, const char *attribute, long long first_row, long long n_rows,
                          void *out, unsigned int *width_out);
 
-/* Bytes copied host -> device per query: the compiled WHERE program + the kernels' control words. */
+/* Bytes that go host -> device per full-scan query: the scan kernel's parameter block, which carries the
+ * compiled WHERE program (no separate upload). */
 unsigned int qpe_gpu_query_upload_bytes(void);
 
 /* The CUDA stream (cudaStream_t) every kernel of this engine is launched on, so a caller can bracket

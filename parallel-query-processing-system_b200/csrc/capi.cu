@@ -1269,7 +1269,7 @@ int qpe_gpu_write_csv(struct engineS *engine, const char *path) {
     return 0;
 }
 
-unsigned int qpe_gpu_query_upload_bytes(void) { return static_cast<unsigned int>(sizeof(QueryCtl)); }
+unsigned int qpe_gpu_query_upload_bytes(void) { return static_cast<unsigned int>(fused_param_bytes()); }
 
 void *qpe_gpu_stream(struct engineS *engine) {
     GpuEngine *g = as_engine(engine);

@@ -134,6 +134,8 @@ GpuEngine *engine_create(const char *tableName, const char *datafile, int index_
         g->ev_post = g->ring[0].ev[3];
     }
     ok = ok && cuda_ok(cudaMalloc(&g->d_ctl, sizeof(QueryCtl)), "cudaMalloc ctl");
+    ok = ok && cuda_ok(cudaMalloc(&g->d_fctl, sizeof(FusedCtl)), "cudaMalloc ctl") &&
+         cuda_ok(cudaMemset(g->d_fctl, 0, sizeof(FusedCtl)), "cudaMemset ctl");
     ok = ok && cuda_ok(cudaMallocHost(&g->h_ctl, sizeof(QueryCtl)), "cudaMallocHost ctl");
     ok = ok && cuda_ok(cudaMalloc(&g->d_probe_lo, sizeof(unsigned long long) * kMaxSegments), "cudaMalloc probe");
     ok = ok && cuda_ok(cudaMalloc(&g->d_probe_hi, sizeof(unsigned long long) * kMaxSegments), "cudaMalloc probe");
@@ -166,6 +168,7 @@ void engine_destroy(GpuEngine *g) {
     free_table(&g->table);
     for (auto &ix : g->idx) index_free(&ix);
     if (g->d_ctl) cudaFree(g->d_ctl);
+    if (g->d_fctl) cudaFree(g->d_fctl);
     if (g->h_ctl) cudaFreeHost(g->h_ctl);
     if (g->h_progress) cudaFreeHost(g->h_progress);
     if (g->d_tile_desc) cudaFree(g->d_tile_desc);
@@ -446,6 +449,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     g->last_bm_words = 0;
     bool post_done = false;
     const unsigned long long *count_src = g->count_mapped;  // where the match count arrives without a download (or null)
+    g->count_dev = &g->d_ctl->out_count;                    // (K1f: its own control block, set below)
     {
         GpuEngine::TimingSlot *slot = &g->ring[g->ring_head];
         g->ring_head = (g->ring_head + 1) % GpuEngine::kTimingRing;
@@ -476,7 +480,6 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     hc->tile_counter = 0;
     hc->chunk_counter = 0;
     hc->out_count = 0;
-    hc->ctas_done = 0;
     std::memset(hc->seg_stored, 0, sizeof(hc->seg_stored));
     g->host_out_done = false;
 
@@ -558,7 +561,9 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
                     n_prog = static_cast<int>((fg.n_chunks + F.seg_chunks - 1) / F.seg_chunks);
                     F.progress = g->d_progress;
                 }
-                if (!upload_query()) return false;
+                // no upload: K1f takes the program as a kernel parameter and resets its own control words
+                F.d_fctl = g->d_fctl;
+                g->count_dev = &g->d_fctl->final_count;
                 // a plain (unsharded) scan: the kernel's last CTA writes the count into mapped host memory
                 if (!g->count_mapped) {
                     F.host_count = g->d_progress + kMaxProgressSegments;
@@ -791,7 +796,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
         if (!g->post_match()) return false;
         cudaEventRecord(g->ev_post, g->stream);
     }
-    if (!count_src && !cuda_ok(cudaMemcpyAsync(&hc->out_count, &g->d_ctl->out_count, sizeof(unsigned long long),
+    if (!count_src && !cuda_ok(cudaMemcpyAsync(&hc->out_count, g->count_dev, sizeof(unsigned long long),
                                                cudaMemcpyDeviceToHost, g->stream),
                                "download count"))
         return false;

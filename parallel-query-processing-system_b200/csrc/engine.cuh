@@ -58,6 +58,8 @@ struct GpuEngine {
     int idx_slots = 0;          // capacity of the head's index arrays
 
     // per-query scratch
+    FusedCtl *d_fctl = nullptr;  // K1f's self-resetting control words
+    const unsigned long long *count_dev = nullptr;  // device word holding the match count of the scan just enqueued
     QueryCtl *d_ctl = nullptr;
     QueryCtl *h_ctl = nullptr;  // pinned
     unsigned long long *d_tile_desc = nullptr;

@@ -682,6 +682,8 @@ struct FusedParams {
     long long seg_chunks;           // progress: chunks per table segment (0 = no progress words)
     unsigned long long *progress;   // mapped pinned host memory: [seg] = epoch << 32 | ids complete through seg
     unsigned long long *host_count; // mapped pinned host memory: the match count, written by the last CTA (or null)
+    FusedCtl *fctl;                 // this kernel's own control words (self-resetting)
+    Program prog;                   // the compiled WHERE, by value: no upload precedes the launch
 };
 
 struct FusedSmemHeader {   // sized for the 4-warp variant (16 rounds x 4 warps); the 8-warp one needs 8 x 8
@@ -723,7 +725,7 @@ __global__ void __launch_bounds__(32 * (1 + EW + CW), 1)
     const int CT = fp.chunk_tiles;
 
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(&p.ctl->prog);
+        const uint4 *src = reinterpret_cast<const uint4 *>(&fp.prog);  // kernel parameter space
         uint4 *dst = reinterpret_cast<uint4 *>(&sh->prog);
         for (uint32_t i = tid; i < sizeof(Program) / 16; i += kThreads) dst[i] = src[i];
     }
@@ -981,7 +983,7 @@ __global__ void __launch_bounds__(32 * (1 + EW + CW), 1)
                 const long long seg = chunk / fp.seg_chunks;
                 const long long first = seg * fp.seg_chunks;
                 const long long last = (first + fp.seg_chunks < fp.n_chunks ? first + fp.seg_chunks : fp.n_chunks) - 1;
-                const unsigned int stored = atomicAdd(&p.ctl->seg_stored[seg], 1u) + 1u;
+                const unsigned int stored = atomicAdd(&fp.fctl->seg_stored[seg], 1u) + 1u;
                 if (stored == static_cast<unsigned int>(last - first + 1)) {
                     __threadfence();
                     const unsigned long long d = ld_desc(fp.desc + last);  // PREFIX: that chunk has finished
@@ -994,18 +996,26 @@ __global__ void __launch_bounds__(32 * (1 + EW + CW), 1)
     }
     __syncthreads();
     if (tid == 0) {
-        if (sh->cta_count) atomicAdd(&p.ctl->out_count, sh->cta_count);
-        if (fp.host_count) {
-            // the last CTA to get here hands the total to the host through mapped memory: no count download
+        FusedCtl *fc = fp.fctl;
+        if (sh->cta_count) atomicAdd(&fc->out_count, sh->cta_count);
+        // The last CTA to get here hands the total over (device word for the sharded post-scan kernel, mapped host
+        // word for a plain scan: no count download) and leaves the control words zeroed for the next query.
+        __threadfence();
+        if (atomicAdd(&fc->ctas_done, 1u) == gridDim.x - 1u) {
             __threadfence();
-            if (atomicAdd(&p.ctl->ctas_done, 1u) == gridDim.x - 1u) {
-                __threadfence();
-                *reinterpret_cast<volatile unsigned long long *>(fp.host_count) = atomicAdd(&p.ctl->out_count, 0ull);
+            const unsigned long long total = atomicExch(&fc->out_count, 0ull);
+            fc->final_count = total;
+            fc->ctas_done = 0u;
+            for (int i = 0; i < kMaxProgressSegments; ++i) fc->seg_stored[i] = 0u;
+            if (fp.host_count) {
+                *reinterpret_cast<volatile unsigned long long *>(fp.host_count) = total;
                 __threadfence_system();
             }
         }
     }
 }
+
+size_t fused_param_bytes() { return sizeof(FusedParams); }
 
 // function attributes are per device: cache what was set per (instantiation, device)
 constexpr int kMaxDevices = 64;
@@ -1283,6 +1293,9 @@ cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStre
     fp.seg_chunks = L.progress ? L.seg_chunks : 0;
     fp.progress = L.progress;
     fp.host_count = L.host_count;
+    fp.fctl = L.d_fctl;
+    fp.prog = *L.scan.h_prog;
+    if (!fp.fctl) return cudaErrorInvalidValue;
     if (fp.n_chunks == 0) return cudaSuccess;
     switch (geo.tile_rows) {
         case 256: return launch_fused_cw<kEvalWarpsWide, 1>(fp, geo, stream);

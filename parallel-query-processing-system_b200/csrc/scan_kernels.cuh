@@ -15,9 +15,18 @@ struct QueryCtl {
     unsigned int tile_counter;      // dynamic tile claim (K1, K1g)
     unsigned int chunk_counter;     // ordered chunk claim (K1c)
     unsigned long long out_count;   // total matches (written by the kernel)
-    unsigned int seg_stored[kMaxProgressSegments];  // K1f: chunks of table segment s whose ids are stored
-    unsigned int ctas_done;         // K1f: CTAs that have added their count (the last one hands the total to the host)
+    unsigned int seg_stored[kMaxProgressSegments];  // (unused since K1f has its own control block)
+};
+
+// K1f keeps its few control words in a block of its own that it RESETS ITSELF (the last CTA to finish hands the
+// count over and zeroes the rest), and takes the compiled program as a kernel parameter: a fused scan needs no
+// host->device copy before its launch, so nothing sits between two queries' kernels but the launch itself.
+struct FusedCtl {
+    unsigned long long out_count;    // running sum of the CTAs' counts; zero between queries
+    unsigned long long final_count;  // the last query's match count (read by the sharded post-scan kernel)
+    unsigned int ctas_done;          // zero between queries
     unsigned int pad_;
+    unsigned int seg_stored[kMaxProgressSegments];  // chunks of table segment s whose ids are stored; zero between queries
 };
 
 // K1f (fused scan + compaction): chunk = consecutive tiles, at most this many rows; the kernel keeps
@@ -79,7 +88,9 @@ struct FusedLaunch {
     long long seg_chunks;
     unsigned long long *progress;
     unsigned long long *host_count;  // mapped pinned host word (device alias) that receives the match count, or null
+    FusedCtl *d_fctl;                // device, zeroed once at engine creation
 };
+size_t fused_param_bytes();          // bytes of K1f's kernel parameter block (carries the compiled program)
 cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStream_t stream);
 cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream_t stream);
 

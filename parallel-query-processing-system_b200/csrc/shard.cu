@@ -108,11 +108,11 @@ __host__ __device__ inline unsigned long long set_ids(int world, unsigned long l
 //      CTA 0 also hands them to the host through mapped pinned memory;
 //   3. pack != 0 (owner, device result): the segments of ranks 1.. are moved to their offsets in the dense
 //      result, 4 independent loads in flight per thread (the move is latency-bound otherwise).
-__global__ void __launch_bounds__(256) post_kernel(const QueryCtl *ctl, PeerPtrs peers, int rank, int world,
+__global__ void __launch_bounds__(256) post_kernel(const unsigned long long *count, PeerPtrs peers, int rank, int world,
                                                    uint32_t epoch, unsigned long long *host_counts, int pack,
                                                    uint32_t *set, unsigned long long seg_cap) {
     __shared__ unsigned long long s_off[kMaxRanks + 1];
-    const unsigned long long my = *reinterpret_cast<const volatile unsigned long long *>(&ctl->out_count);
+    const unsigned long long my = *reinterpret_cast<const volatile unsigned long long *>(count);
     if (blockIdx.x == 0 && threadIdx.x < world) {
         __threadfence_system();  // this rank's id stores (peer memory included) are visible before the count is
         st_release_sys(&peers.comm[threadIdx.x]->count[epoch & 1u][rank],
@@ -418,7 +418,7 @@ int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, i
     uint32_t *set = to_segments ? s->seg_base + (epoch & 1u) * set_ids(s->world, s->seg_cap) : nullptr;
     const int pack = (to_segments && s->rank == s->owner && s->world > 1) ? 1 : 0;
     g->post_match = [&]() -> bool {
-        post_kernel<<<pack ? 148 * 8 : 1, 256, 0, g->stream>>>(g->d_ctl, peers, s->rank, s->world, epoch, s->d_counts,
+        post_kernel<<<pack ? 148 * 8 : 1, 256, 0, g->stream>>>(g->count_dev, peers, s->rank, s->world, epoch, s->d_counts,
                                                                pack, set, s->seg_cap);
         if (multi) {
             if (s->rank == s->owner)
