@@ -124,25 +124,6 @@ struct resultSetS *new_result() {
     return r;
 }
 
-inline size_t fmt_u64(unsigned long long v, char *out) {  // "%llu"
-    char tmp[24];
-    size_t n = 0;
-    do {
-        tmp[n++] = static_cast<char>('0' + v % 10);
-        v /= 10;
-    } while (v);
-    for (size_t i = 0; i < n; ++i) out[i] = tmp[n - 1 - i];
-    out[n] = '\0';
-    return n;
-}
-inline size_t fmt_i32(int v, char *out) {  // "%d"
-    if (v < 0) {
-        out[0] = '-';
-        return 1 + fmt_u64(static_cast<unsigned long long>(-(static_cast<long long>(v))), out + 1);
-    }
-    return fmt_u64(static_cast<unsigned long long>(v), out);
-}
-
 void fill_stats(GpuEngine *g, qpe_scan_stats *s) {
     if (!s) return;
     engine_resolve_timing(g);
@@ -390,27 +371,6 @@ bool persist_csv_device(GpuEngine *g, const char *path) {
     if (d_tmp) cudaFree(d_tmp);
     if (d_offs) cudaFree(d_offs);
     return ok;
-}
-
-// CSV line format shared by INSERT's append and DELETE's rewrite (:562-575, :687-700)
-void write_csv_row(FILE *f, const HostColumns &hc, int64_t i) {
-    auto cell = [&](int c) { return hc.data[c].data() + static_cast<size_t>(i) * hc.width[c]; };
-    auto str = [&](int c, char *buf) {
-        const size_t len = strnlen(reinterpret_cast<const char *>(cell(c)), hc.width[c]);
-        std::memcpy(buf, cell(c), len);
-        buf[len] = '\0';
-        return buf;
-    };
-    unsigned long long id;
-    int exit_code, user_id, risk;
-    std::memcpy(&id, cell(C_COMMAND_ID), 8);
-    std::memcpy(&exit_code, cell(C_EXIT_CODE), 4);
-    std::memcpy(&user_id, cell(C_USER_ID), 4);
-    std::memcpy(&risk, cell(C_RISK_LEVEL), 4);
-    char b1[528], b2[128], b3[48], b4[48], b5[224], b6[80], b7[128];
-    std::fprintf(f, "%llu,%s,%s,%s,%d,%s,%d,%s,%d,%s,%s,%d\n", id, str(C_RAW_COMMAND, b1), str(C_BASE_COMMAND, b2),
-                 str(C_SHELL_TYPE, b3), exit_code, str(C_TIMESTAMP, b4), cell(C_SUDO_USED)[0] ? 1 : 0,
-                 str(C_WORKING_DIRECTORY, b5), user_id, str(C_USER_NAME, b6), str(C_HOST_NAME, b7), risk);
 }
 
 }  // namespace
