@@ -102,7 +102,7 @@ struct GpuEngine {
     // match phase after the synchronisation, [5] whole C-ABI call of a sharded SELECT (parse included)
     double trace[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev_post = nullptr;
-    // K1f compaction warps for the next full scan: 4, or 8 once a scan matched more than ~4 % of its rows
+    // K1f compaction warps for the next full scan: 4, or 8 once a scan matched more than 1/8 of its rows
     // (the evaluators then wait for the compaction warps); QPE_FUSE_CW=4|8 pins it
     int fuse_cw = 4;
     int force_tile_rows = 0, force_stages = 0;
