@@ -440,6 +440,8 @@ void engine_resolve_all(GpuEngine *g) {
 // ------------------------------------------------------------------------------------------
 // match phase
 // ------------------------------------------------------------------------------------------
+constexpr int kFusedMaxStages = 8;
+
 bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, bool invert, bool count_only,
                   bool want_bitmap, uint64_t *count) {
     cudaSetDevice(g->device);
@@ -528,12 +530,14 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
                 return (v == 4 || v == 8) ? v : 0;
             }();
             const int want_cw = pinned_cw ? pinned_cw : g->fuse_cw;
-            bool planned = scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, 4, &fg, &fwhy, 4);
+            // up to 8 stages: a narrow WHERE (1-8 B/row) is bound by ROWS in flight per SM (stages x tile rows over the
+            // ~3 us a stage takes to be refilled and consumed), not by bytes
+            bool planned = scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, kFusedMaxStages, &fg, &fwhy, 4);
             if (planned && want_cw == 8) {
                 // eight compaction warps need 16 KB more shared memory: only when that costs no tile rows or stages
                 ScanGeometry g8{};
                 const char *why8 = nullptr;
-                if (scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, 4, &g8, &why8, 8) &&
+                if (scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, kFusedMaxStages, &g8, &why8, 8) &&
                     g8.tile_rows == fg.tile_rows && g8.stages == fg.stages)
                     fg = g8;
             }

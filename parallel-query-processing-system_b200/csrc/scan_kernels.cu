@@ -1033,7 +1033,7 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
         return false;
     }
     const size_t fuse_reserve = fused ? fuse_reserve_bytes(fused_cw) : 0;
-    if (max_stages < 1 || max_stages > 4) max_stages = 4;
+    if (max_stages < 1 || max_stages > kMaxStages) max_stages = kMaxStages;
     // device attributes are asked once per process (one process per GPU; this runs twice per query)
     static int max_smem_by_device[kMaxDevices] = {0}, n_sm_by_device[kMaxDevices] = {0};
     const int slot = current_device_slot();
