@@ -105,11 +105,12 @@ struct PLeaf {
     uint8_t col;    // ColId
     uint8_t type;   // ColType
     uint8_t tt;     // 3-bit truth table over {lt, eq, gt}: bit0 = result when field<lit, bit1 ==, bit2 >
-    uint8_t pad;
+    uint8_t nch;    // text column: cell width / 16.  0 on the host; patched into the kernel's shared-memory copy
     uint32_t lit_off;  // string literal: byte offset into lit_pool (16-byte aligned), length = column width
     uint64_t lit_u64;  // T_U64 literal
     int32_t lit_i32;   // T_I32 literal; T_BOOL literal in bit 0
-    uint32_t pad2;
+    uint32_t smem_off; // byte offset of the column inside a staged tile.  0 on the host; patched like nch, so that a
+                       // leaf is evaluated from ONE shared-memory record (no dependent parameter look-ups)
 };
 
 struct PInstr {

@@ -231,6 +231,16 @@ __device__ __forceinline__ uint32_t diff16(const uint4 v, const uint4 l) {
     return (v.x ^ l.x) | (v.y ^ l.y) | (v.z ^ l.z) | (v.w ^ l.w);
 }
 
+// After the program has been copied into shared memory: give every leaf its column's stage offset and width, so
+// that evaluating a leaf needs nothing but the leaf record (call between two CTA-wide barriers).
+__device__ __forceinline__ void patch_leaves(Program *sp, const ScanParams &p, uint32_t tid, uint32_t n_threads) {
+    for (uint32_t k = tid; k < static_cast<uint32_t>(sp->n_leaves); k += n_threads) {
+        const int c = sp->leaf[k].col;
+        sp->leaf[k].smem_off = p.smem_off[c];
+        sp->leaf[k].nch = static_cast<uint8_t>(p.width[c] >> 4);
+    }
+}
+
 // Evaluate one leaf for this lane's rows of NT staged tiles at once (NT = 1: rows lrow, lrow+32, ... of the
 // tile at `stage`; NT = 2: also the same rows of the tile at `stage + dB`, which become mask bits R .. 2R-1).
 // Two tiles per call halve the per-tile cost of interpreting the program (~60 % of the evaluators'
@@ -239,7 +249,7 @@ template <int R, int NT>
 __device__ __forceinline__ uint32_t eval_leaf_tile(const PLeaf &lf, const Program *sp, const uint8_t *stage,
                                                    const int dB, const ScanParams &p, int lrow) {
     constexpr int RB = R * NT;
-    const uint8_t *base = stage + p.smem_off[lf.col];
+    const uint8_t *base = stage + lf.smem_off;  // patched by patch_leaves
     const uint32_t tt = lf.tt;
     constexpr uint32_t kAll = (RB >= 32) ? 0xffffffffu : ((1u << RB) - 1u);
     // byte address of this lane's j-th row of a column with `w`-byte cells (j is a constant after unrolling)
@@ -265,8 +275,8 @@ __device__ __forceinline__ uint32_t eval_leaf_tile(const PLeaf &lf, const Progra
             return want ? nz : (~nz & kAll);
         }
         default: {  // T_STR: strcmp order == unsigned byte order over the NUL-padded cell
-            const uint32_t w = p.width[lf.col];
-            const int nch = static_cast<int>(w >> 4);
+            const int nch = lf.nch;
+            const uint32_t w = static_cast<uint32_t>(nch) << 4;
             const uint4 *lit = reinterpret_cast<const uint4 *>(sp->lit_pool + lf.lit_off);
             const uint8_t *c = base + static_cast<size_t>(lrow) * w;
             auto cell = [&](int j) { return reinterpret_cast<const uint4 *>(row_ptr(c, j, w)); };
@@ -459,6 +469,8 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_tma_kernel(const __grid
         fence_mbar_init();
     }
     __syncthreads();
+    patch_leaves(&sh->prog, p, tid, kThreads);
+    __syncthreads();
     const Program *sp = &sh->prog;
 
     if (warp == 0) {
@@ -580,6 +592,8 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_batch_kernel(const __gr
         }
         fence_mbar_init();
     }
+    __syncthreads();
+    for (int q = 0; q < Q; ++q) patch_leaves(progs + q, p, tid, kThreads);
     __syncthreads();
 
     if (warp == 0) {
@@ -741,6 +755,8 @@ __global__ void __launch_bounds__(32 * (1 + EW + CW), 1)
         sh->cta_count = 0;
         fence_mbar_init();
     }
+    __syncthreads();
+    patch_leaves(&sh->prog, p, tid, kThreads);
     __syncthreads();
     const Program *sp = &sh->prog;
 
