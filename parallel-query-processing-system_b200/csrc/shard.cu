@@ -276,6 +276,10 @@ int qpe_shard_connect(struct engineS *engine, const unsigned char *all_handles) 
     cudaSetDevice(g->device);
     for (int r = 0; r < s->world; ++r) {
         if (r == s->rank) continue;
+        if (s->comm[r]) {  // connected before: drop the old mapping
+            cudaIpcCloseMemHandle(s->comm[r]);
+            s->comm[r] = nullptr;
+        }
         cudaIpcMemHandle_t h;
         std::memcpy(&h, all_handles + 64 * r, 64);
         void *p = nullptr;
@@ -321,6 +325,16 @@ unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *nam
         return nullptr;
     }
     cudaSetDevice(g->device);
+    if (s->host_map) {  // opened before: release the old buffer first
+        cudaStreamSynchronize(g->stream);
+        cudaHostUnregister(s->host_map);
+        munmap(s->host_map, s->host_bytes);
+        if (s->host_creator) shm_unlink(s->host_name);
+        s->host_map = nullptr;
+        s->host_bytes = 0;
+        s->host_cap = 0;
+        s->host_creator = false;
+    }
     const size_t bytes = sizeof(ShardHostHeader) + sizeof(uint32_t) * (capacity + 16);
     const int fd = shm_open(name, create ? (O_CREAT | O_RDWR | O_TRUNC) : O_RDWR, 0600);
     if (fd < 0) {
