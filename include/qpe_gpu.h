@@ -160,6 +160,8 @@ int qpe_shard_set_device_result(struct engineS *engine, int owner_rank, unsigned
                                 unsigned long long segment_capacity);
 unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *name, unsigned long long capacity,
                                          int create);
+/* creator, after every rank has opened the buffer: drop its /dev/shm name (mappings stay valid) */
+int qpe_shard_unlink_host_result(struct engineS *engine);
 const unsigned int *qpe_shard_device_result(struct engineS *engine);
 /* Host result path: 1 = every rank copies 1/world of the packed result (read from the owner over NVLink) to the
  * host over its OWN PCIe link; 0 = the first shard streams its ids out during its scan, the others copy theirs

@@ -133,6 +133,7 @@ def load_library() -> C.CDLL:
         "qpe_shard_open_host_result": (vp, [vp, cp, ull, i]),
         "qpe_shard_device_result": (vp, [vp]),
         "qpe_shard_close": (None, [vp]),
+        "qpe_shard_unlink_host_result": (i, [vp]),
         "qpe_shard_set_multipath": (i, [vp, i]),
         "qpe_sql_shard_select": (i, [vp, cp, i, C.POINTER(ull), pstats]),
         "qpe_sql_shard_delete": (i, [vp, cp, C.POINTER(ull), C.POINTER(ull)]),

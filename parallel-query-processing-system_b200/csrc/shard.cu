@@ -379,6 +379,20 @@ int qpe_shard_set_multipath(struct engineS *engine, int mode) {
     return 0;
 }
 
+/* Creator only, once every rank has opened the shared host buffer: remove its name from /dev/shm (the mappings
+ * stay valid), so that nothing is left behind if a process dies. */
+int qpe_shard_unlink_host_result(struct engineS *engine) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    if (!s) return -1;
+    if (s->host_map && s->host_creator) {
+        shm_unlink(s->host_name);
+        s->host_creator = false;
+    }
+    return 0;
+}
+
 const unsigned int *qpe_shard_device_result(struct engineS *engine) {
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;

@@ -301,6 +301,8 @@ class ShardGroup:
         self._fn, self._h = lib.qpe_sql_shard_select, engine._h
         self._last_sql, self._last_bytes = None, None
         dist.barrier(group=group)
+        if self.host_cap > 0 and self.rank == owner:
+            lib.qpe_shard_unlink_host_result(h)   # every rank has it mapped: no name left in /dev/shm
 
     def select(self, statement: str, to_host: bool = False, stats: bool = True):
         """One sharded full-scan SELECT (every rank calls it).  Returns (total, per-rank counts, ScanStats).
