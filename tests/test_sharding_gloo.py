@@ -147,3 +147,84 @@ def test_index_path_merge_across_shards(world):
         want, used = o.select_ids(where)
         assert used
         assert got == want.tolist(), where
+
+
+# ---- sharded B+ probe batches: host-side merge, with a numpy stand-in for the per-shard GPU index ---------
+class _StubLib:
+    def __init__(self, base):
+        self._base = base
+
+    def qpe_gpu_row_base(self, _h):
+        return self._base
+
+
+class _StubShardEngine:
+    """What sharding.sharded_probe needs from an engine, over one shard's keys: the flattened index of
+    csrc/index.cu restated in numpy ((key ASC, LOCAL position DESC) order, lower/upper bound probes)."""
+
+    def __init__(self, keys, base):
+        pos = np.arange(len(keys))
+        order = np.lexsort((-pos, keys))
+        self.keys = np.asarray(keys, dtype=np.int64)[order]
+        self.perm = pos[order].astype(np.uint32)
+        self._lib = _StubLib(base)
+        self._h = None
+
+    def probe_batch(self, attribute, lo, hi):
+        first = np.searchsorted(self.keys, np.asarray(lo, dtype=np.int64), side="left")
+        last = np.searchsorted(self.keys, np.asarray(hi, dtype=np.int64), side="right")
+        return first.astype(np.uint32), np.maximum(last - first, 0).astype(np.uint32), {}
+
+    def index_slice(self, attribute, first, count):
+        return self.perm[first:first + count]
+
+    def index_slice_keys(self, attribute, first, count):
+        return self.keys[first:first + count]
+
+
+PROBE_SETS = [("user_id", [1001, 1002, 999999, 1010], [1001, 1005, 999999, 1009]),
+              ("risk_level", [0, 3, 5, 9], [1, 3, 5, 9]),
+              ("command_id", [0, 700, 1995, 5000], [9, 700, 2100, 6000])]
+
+
+def _probe_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    support.load_pkg()
+    from importlib import import_module
+    sharding = import_module("pqps_b200.sharding")
+    o = Oracle.from_csv(CSV_2K)
+    start, n = sharding.shard_range(o.num_rows, world, rank)
+    out = []
+    for attr, lo, hi in PROBE_SETS:
+        keys = np.array([int(o.cell(p, attr)) for p in range(start, start + n)], dtype=np.int64)
+        eng = _StubShardEngine(keys, start)
+        total, rows = sharding.sharded_probe(eng, attr, np.asarray(lo), np.asarray(hi), rows=True)
+        if rank == 0:
+            out.append((total.tolist(), [r.tolist() for r in rows]))
+    if rank == 0:
+        ret.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_probe_merge_equals_one_tree(world):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_probe_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = ret.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = Oracle.from_csv(CSV_2K)
+    for (attr, lo, hi), (total, rows) in zip(PROBE_SETS, results):
+        perm = o.index_order(attr)                                   # one B+ tree over the whole table: leaf-chain order
+        keys = np.array([int(o.cell(int(p), attr)) for p in perm], dtype=np.int64)
+        for k in range(len(lo)):
+            want = perm[(keys >= lo[k]) & (keys <= hi[k])].tolist()  # findRange(lo, hi), bplus.c:282-314
+            assert total[k] == len(want) and rows[k] == want, (attr, k)
