@@ -261,6 +261,10 @@ int qpe_sql_match_mask(struct engineS *engine, const char *statement, unsigned i
 /* Full SELECT through executeQuerySelectGPU; NULL if `statement` is not a SELECT.  Release with
  * freeResultSet (executeEngine-gpu.h). */
 struct resultSetS *qpe_sql_select(struct engineS *engine, const char *statement);
+/* The predicate program the engine compiles from `statement`'s WHERE (struct Program of csrc/qpe_internal.h, raw
+ * bytes) for the given cell widths of the 12 schema columns.  Needs no device: the CPU tests interpret it row by row
+ * against the oracle.  Returns the bytes written, or -7 (parse), -2 (compile), -5 (cap too small). */
+long long qpe_sql_compile_program(const char *statement, const unsigned int widths[12], void *out, size_t cap);
 /* The whereClauseS list the front end builds for `statement`, rendered as text (malloc'ed). */
 char *qpe_sql_where_to_text(const char *statement);
 

@@ -139,6 +139,7 @@ def load_library() -> C.CDLL:
         "qpe_sql_shard_delete": (i, [vp, cp, C.POINTER(ull), C.POINTER(ull)]),
         "qpe_sql_select": (C.POINTER(ResultSet), [vp, cp]),
         "qpe_sql_where_to_text": (vp, [cp]),
+        "qpe_sql_compile_program": (ll, [cp, C.POINTER(C.c_uint), vp, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -648,6 +648,22 @@ struct resultSetS *qpe_sql_select(struct engineS *engine, const char *statement)
                                  pw.sql.table.c_str(), pw.wc);
 }
 
+// parity aid (no device needed): the predicate program compile_where builds for a statement's WHERE, as raw bytes
+// (struct Program of csrc/qpe_internal.h), for the column widths given.  Returns the number of bytes written,
+// -7 if the statement does not parse, -2 if it does not compile, -5 if `cap` is too small.
+long long qpe_sql_compile_program(const char *statement, const unsigned int widths[12], void *out, size_t cap) {
+    ParsedWhere pw(statement ? statement : "");
+    if (!pw.ok) return -7;
+    if (cap < sizeof(qpe::Program)) return -5;
+    uint32_t w[qpe::NUM_COLS];
+    for (int c = 0; c < qpe::NUM_COLS; ++c) w[c] = widths[c];
+    qpe::Program prog;
+    const std::string err = qpe::compile_where(pw.wc, w, &prog, false);
+    if (!err.empty()) return -2;
+    std::memcpy(out, &prog, sizeof(prog));
+    return static_cast<long long>(sizeof(prog));
+}
+
 // debugging / parity aid: the whereClauseS list of a statement rendered as text, e.g.
 //   "sudo_used = TRUE OR ( risk_level = 5 AND shell_type = bash )"
 char *qpe_sql_where_to_text(const char *statement) {
