@@ -171,11 +171,9 @@ __device__ __forceinline__ uint32_t str_cmp3(RowPtr row, const uint4 *lit, int n
 constexpr int kEvalWarps = 16;                   // evaluator warps per CTA (4 per scheduler: latency hiding)
 constexpr int kEvalWarpsWide = 8;                // variant for very wide rows (256-row tiles)
 constexpr int kMaxStages = 8;
-constexpr int kScanThreads = 32 * (1 + kEvalWarps);
 constexpr int kRowsPerGroup = 32 * kEvalWarps;   // rows one "row group" covers: a tile is R groups
 constexpr int kMaxR = 8;                         // rows per lane per tile: 1, 2, 4 or 8
 constexpr int kMaxTileRows = kRowsPerGroup * kMaxR;  // 4096 (<= kRowPad: a full tile is always inside the allocation)
-constexpr int kMinTileRows = 32 * kEvalWarpsWide;    // 256
 
 struct ScanParams {
     const uint8_t *col[NUM_COLS];
