@@ -82,3 +82,26 @@ def test_csv_loader_matches_oracle_loader(pkg):
         a = C.string_at(rows[i], 1040)
         b = C.string_at(orows + i * 1040, 1040)
         assert a == b, i
+
+
+def test_csv_loader_matches_oracle_loader_on_nasty_text(pkg, tmp_path):
+    """the same comparison on deliberately nasty CSV text (quotes, "" escapes, text after a closing quote, absent
+    fields, blank lines, overflowing numbers, over-long fields; the rows of tests/test_gpu_ingest.py) and on
+    both line endings -- the host loader is the exact path the device parser (K6) falls back to"""
+    if not support.Oracle.available():
+        pytest.skip("oracle not built")
+    from test_gpu_ingest import nasty_rows, write_csv
+    lib = pkg.load_library()
+    lib.getAllRecordsFromFileGPU.restype = C.POINTER(C.c_void_p)
+    lib.getAllRecordsFromFileGPU.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    olib = support.Oracle.lib()
+    for seed, eol, final_newline in ((7, "\r\n", True), (8, "\n", True), (9, "\n", False)):
+        path = str(tmp_path / f"nasty_{seed}.csv")
+        write_csv(path, nasty_rows(seed=seed, n=600), eol=eol, final_newline=final_newline)
+        n = C.c_int()
+        rows = lib.getAllRecordsFromFileGPU(path.encode(), C.byref(n))
+        on = C.c_longlong()
+        orows = olib.oracle_load_csv(path.encode(), C.byref(on))
+        assert n.value == on.value > 500
+        for i in range(n.value):
+            assert C.string_at(rows[i], 1040) == C.string_at(orows + i * 1040, 1040), (seed, i)
