@@ -21,6 +21,11 @@
 //       is DELETE's match mask.  (A first version ran the look-back per 4 Ki-row tile inside K1:
 //       at HBM speed that is >100 descriptors/us, more than a 32-wide look-back window can
 //       follow at L2 latency, and the chain fell behind; see DESIGN.md.)
+// K1f scan_fused_kernel    THE SELECT KERNEL: K1's producer / evaluators plus 4 (or 8) compaction warps per CTA that turn
+//       each finished <= 64 Ki-row chunk of the bitmap -- kept in shared memory, never written to HBM -- into
+//       row ids with the same decoupled look-back, beside the scan.  One launch per query; the program comes as a
+//       kernel parameter and the last CTA hands the count over and resets the control words (banner further down).
+// K9  scan_batch_kernel    up to 8 WHERE programs over one pass of the same columns (query batch).
 // K1g filter_kernel        same program on a gathered candidate list (index path), ordered
 //                          single-pass compaction with decoupled look-back per 1 Ki candidates.
 // K2  gather_kernel        projection / column compaction gather.

@@ -17,9 +17,14 @@
 //                   block), then moves the segments of ranks 1.. behind rank 0's ids -- rank 0's
 //                   offset is always 0, so ITS scan stores straight into the dense result and is never
 //                   moved -- giving one dense id list in partition order, which is table order;
-//   host result     each rank learns the counts of the lower ranks the same way and copies its ids
-//                   over ITS OWN PCIe link to its exact offset in a host buffer shared by all ranks
-//                   (POSIX shared memory, registered with CUDA in every process).
+//   host result     a host buffer shared by all ranks (POSIX shared memory, registered with CUDA in every
+//                   process).  Up to 7 ranks: the first shard streams its ids out during its scan (its
+//                   offset is 0), every other rank learns the counts of the lower ranks the same way and
+//                   copies its ids to its exact offset over ITS OWN PCIe link.  From 8 ranks ("multipath"):
+//                   the ids land in the owner's HBM as for a device result and every rank pulls 1/world of
+//                   the packed list over NVLink and copies that out over its own link.
+//   DELETE          qpe_shard_delete: local mask + stable compaction per shard, the new shard sizes
+//                   all-gathered through the same comm blocks, shards renumbered.
 //
 // Slots are double buffered by epoch parity: no rank finishes query e before every rank has
 // published its count of e, so a rank is never more than one query ahead of another.
