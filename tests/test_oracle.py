@@ -142,3 +142,33 @@ def test_oracle_vs_compiled_reference_live(oracle_2k, tmp_path):
         ids, _ = oracle_2k.select_ids(w)
         assert oracle_2k.rows(ids, cols) == rows, w
     r.close()
+
+
+# ---- (4) the same differential at BASELINE configs[0]'s size: 50 000 rows from the reference's OWN generator ----
+@pytest.mark.skipif(not (Ref.available() and os.path.exists("/root/reference/data-generation/generate_commands.py")),
+                    reason="needs the reference tree and oracle/_ref (authoring container only)")
+def test_oracle_vs_compiled_reference_50k(tmp_path):
+    """commands_50k.csv is a git-LFS pointer in the reference, so the file is regenerated with the reference's
+    unmodified generator (seeded, tools/gen_reference_csv.py); the compiled QPESeq engine and the oracle must
+    then agree on every probe WHERE: same rows, same order (index path included), same cell text."""
+    import subprocess
+    import sys
+    csv = str(tmp_path / "commands_50k.csv")
+    gen = os.path.join(support.ROOT, "tools", "gen_reference_csv.py")
+    subprocess.run([sys.executable, gen, "50000", csv], check=True, capture_output=True, timeout=600)
+    o = Oracle.from_csv(csv)
+    (tmp_path / "ref").mkdir()
+    r = Ref(support.scratch_copy(csv, tmp_path / "ref"))
+    try:
+        assert o.num_rows == r.num_rows == 50000
+        cols = ["command_id", "user_name", "sudo_used", "exit_code"]
+        for w in PROBE_WHERES:
+            _, rows = r.select(f"SELECT {', '.join(cols)} FROM Commands WHERE {w}")
+            ids, _ = o.select_ids(w)
+            assert len(ids) == len(rows), w
+            assert [int(x[0]) for x in rows] == [int(o.cell(int(i), "command_id")) for i in ids], w   # same rows, same order
+            step = max(1, len(ids) // 500)                                                            # cell text on a sample
+            assert o.rows(ids[::step], cols) == rows[::step], w
+    finally:
+        r.close()
+        o.close()
