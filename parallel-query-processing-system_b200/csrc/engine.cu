@@ -440,7 +440,7 @@ void engine_resolve_all(GpuEngine *g) {
 // ------------------------------------------------------------------------------------------
 // match phase
 // ------------------------------------------------------------------------------------------
-constexpr int kFusedMaxStages = 8;
+constexpr int kFusedMaxStages = 16;
 
 bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, bool invert, bool count_only,
                   bool want_bitmap, uint64_t *count) {
@@ -513,7 +513,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
         st.rows_scanned = t.n;
         ScanGeometry geo{};
         const char *why = nullptr;
-        bool staged = scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, 4, &geo, &why);
+        bool staged = scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, kFusedMaxStages, &geo, &why);
         // Pipelined scan: the table is cut into P segments of whole 64 Ki-row chunks; K1 of segment
         // i+1 (stream, high priority) runs while K1c of segment i (stream2, low priority) compacts
         // and stores its ids -- possibly straight into pinned host memory or a peer GPU -- so the
@@ -894,7 +894,7 @@ bool engine_match_batch(GpuEngine *g, const struct whereClauseS *const *wcs, int
         }
     ScanGeometry geo{};
     const char *why = nullptr;
-    if (!scan_plan(t, uni, g->force_tile_rows, g->force_stages, 4, &geo, &why, false, batch_smem_bytes(nq))) {
+    if (!scan_plan(t, uni, g->force_tile_rows, g->force_stages, kFusedMaxStages, &geo, &why, 0, batch_smem_bytes(nq))) {
         set_error(std::string("query batch cannot be staged: ") + (why ? why : "row too wide"));
         return false;
     }

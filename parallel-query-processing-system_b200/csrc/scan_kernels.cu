@@ -4,23 +4,18 @@
 //       Replaces linearSearchRecords/evaluateWhereClause/checkCondition
 //       (engine/serial/executeEngine-serial.c:854-878, :292-316, :251-289).
 //       Warp-specialised persistent CTAs, one per SM:
-//         P  (1 warp, 1 lane)  streams every referenced column's slice of a tile into shared
-//                              memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier
-//                              complete_tx), S stages deep;
-//         E  (kEvalWarps)      evaluate the compiled WHERE program on the staged tile, one R-bit
-//                              match mask per lane (the operator dispatch happens once per tile,
-//                              the per-row work is load / compare / predicated OR), transpose it
-//                              with __ballot_sync into bitmap words (bit b of word w = row 32w+b)
-//                              and store them.  The bitmap is 1 bit per row: 1/104 of the
-//                              narrowest scan's input traffic.
+//         P  (1 warp, 1 lane)  streams every referenced column's slice of a tile (1024 / 512 / 256 rows) into
+//                              shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx),
+//                              up to 16 stages deep;
+//         E  (16 warps)        each takes a WHOLE tile: a lane owns 32 / 16 / 8 consecutive rows, reads them with
+//                              16-byte shared-memory loads and runs the compiled WHERE program once per tile;
+//                              the lane's match mask is the bitmap word of its rows (bit b of word w = row 32w+b).
 //       Nothing in K1 waits on another CTA, so HBM streaming is never stalled by a scan chain.
 // K1c compact_kernel       order-preserving stream compaction of the bitmap into row ids:
 //       popc per word, block scan, single-pass DECOUPLED LOOK-BACK over 64 Ki-row chunks
 //       (status flag + aggregate / inclusive prefix per chunk), ids staged in shared memory and
 //       written with coalesced stores -- rows come out in exactly table order.  The same bitmap
-//       is DELETE's match mask.  (A first version ran the look-back per 4 Ki-row tile inside K1:
-//       at HBM speed that is >100 descriptors/us, more than a 32-wide look-back window can
-//       follow at L2 latency, and the chain fell behind; see DESIGN.md.)
+//       is DELETE's match mask.
 // K1f scan_fused_kernel    THE SELECT KERNEL: K1's producer / evaluators plus 4 (or 8) compaction warps per CTA that turn
 //       each finished <= 64 Ki-row chunk of the bitmap -- kept in shared memory, never written to HBM -- into
 //       row ids with the same decoupled look-back, beside the scan.  One launch per query; the program comes as a
@@ -78,23 +73,33 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Every spin in this file is bounded: a protocol bug (or a peer that never arrives) ends in a trapped
-// kernel and a CUDA error on the host, never in a hung GPU.  2^31 polls are minutes of waiting.
+// Every spin in this file is bounded by TIME: a protocol bug (or a peer that never arrives) ends in a trapped
+// kernel and a CUDA error on the host after ~2 s, never in a hung GPU.
 constexpr uint32_t kSpinLimit = 0x7fffffffu;
+constexpr unsigned long long kSpinTimeoutNs = 2000000000ull;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = global_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins == kSpinLimit) __trap();
+        if ((++spins & 0xffu) == 0 && global_ns() - t0 > kSpinTimeoutNs) __trap();
     }
 }
 // The same wait for a thread that expects to wait LONG (the TMA producer waits ~1 us per tile for a stage to be
 // released): sleep between polls.  A tight poll loop is 6 instructions per poll; ncu showed the single producer
 // lane issuing 12 % of the whole kernel's instructions that way, on a scheduler it shares with four evaluator warps.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, uint32_t sleep_ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = global_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         __nanosleep(sleep_ns);
-        if (++spins == kSpinLimit) __trap();
+        if ((++spins & 0xffu) == 0 && global_ns() - t0 > kSpinTimeoutNs) __trap();
     }
 }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
@@ -171,14 +176,32 @@ __device__ __forceinline__ uint32_t str_cmp3(RowPtr row, const uint4 *lit, int n
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: TMA-staged scan
+// K1 / K1f / K9: TMA-staged scan with the VECTORISED evaluator
+//
+// Geometry.  A tile is what ONE evaluator warp consumes in one pass of the WHERE program: T = 32 * RPL
+// consecutive rows (RPL = rows per lane = 32, 16 or 8; the largest that leaves >= 3 stages in flight), each lane
+// owning RPL CONSECUTIVE rows.  The producer lane streams a tile's slice of every referenced column into one of
+// S <= 16 shared-memory stages (1-D TMA bulk copies, one mbarrier pair per stage).  STAGE s BELONGS TO EVALUATOR
+// WARP s: tile `seq` of a CTA goes to stage / warp seq % S, so every barrier is produced and consumed strictly in
+// order by one producer and one warp (a stage shared by several warps that run at their own pace cannot be told
+// apart by phase parity: a fast warp would take the barrier's previous phase for its own).  While a warp
+// evaluates its tile the other stages are in flight or being evaluated by their warps.  (Round 1 had one 4096-row tile shared by all 16 warps, 8 rows per lane with a stride of 32 rows, one
+// scalar shared-memory load per row and leaf, the match bits transposed with one ballot per row slot: ncu showed
+// 1.28 warp-instructions per row, ALU pipe 58 % busy, QN at 0.88 of what the same kernel read on wide rows.)
+//
+// Why consecutive rows per lane: (1) a lane's match mask IS the bitmap word of its rows (bit b of word w = row
+// 32 w + b) -- no transposition; (2) cells are read with 16-byte shared-memory loads (4 int / 2 u64 / 16 bool cells
+// per LDS.128); (3) the program is dispatched once per 1024 rows instead of once per 256 / 512.
+// Bank conflicts: lane blocks are RPL * width bytes apart, so reading "unit k" (4 rows) on every lane at the same
+// time would hit the same banks 8 ways.  Lane L therefore reads its units in ROTATED order, unit (k + L) mod U in
+// step k, which makes the 16-byte loads of an int column conflict-free (2-way for u64); text cells rotate by rows.
+// The masks are built in that rotated "slot order" with immediate bit positions and rotated back ONCE per pass.
+// Compare + bit insert is two instructions per row and leaf (ISETP, predicated OR; inline PTX, because the
+// compiler's own choice was SEL + IADD3).
 // ------------------------------------------------------------------------------------------
-constexpr int kEvalWarps = 16;                   // evaluator warps per CTA (4 per scheduler: latency hiding)
-constexpr int kEvalWarpsWide = 8;                // variant for very wide rows (256-row tiles)
-constexpr int kMaxStages = 8;
-constexpr int kRowsPerGroup = 32 * kEvalWarps;   // rows one "row group" covers: a tile is R groups
-constexpr int kMaxR = 8;                         // rows per lane per tile: 1, 2, 4 or 8
-constexpr int kMaxTileRows = kRowsPerGroup * kMaxR;  // 4096 (<= kRowPad: a full tile is always inside the allocation)
+constexpr int kEvalWarps = 16;                   // evaluator warps per CTA (4 per scheduler)
+constexpr int kMaxStages = 16;
+constexpr int kMaxTileRows = 1024;               // 32 lanes x 32 rows (<= kRowPad: a full tile is always inside the allocation)
 
 struct ScanParams {
     const uint8_t *col[NUM_COLS];
@@ -189,7 +212,7 @@ struct ScanParams {
     uint32_t stage_bytes;
     int32_t tile_rows;
     int32_t n_stages;
-    int32_t dynamic_tiles;  // 1: claim tiles from the global counter; 0: tile = cta + k * grid
+    int32_t pad_;
     long long n_rows;
     long long tile_begin;   // this launch covers tiles [tile_begin, n_tiles): a pipelined scan launches
     long long n_tiles;      // K1 once per table segment so that K1c of segment i overlaps K1 of segment i+1
@@ -200,39 +223,8 @@ struct ScanParams {
 struct ScanSmemHeader {
     Program prog;
     alignas(8) uint64_t full[kMaxStages];
-    uint64_t empty[kMaxStages];
-    long long tile_of_stage[kMaxStages];
     unsigned long long cta_count;
 };
-
-// R-bit mask of a per-row predicate, fully unrolled so every shift is an immediate
-template <int R, typename F>
-__device__ __forceinline__ uint32_t rows_mask(F pred) {
-    uint32_t m = 0;
-#pragma unroll
-    for (int j = 0; j < R; ++j) m |= pred(j) ? (1u << j) : 0u;
-    return m;
-}
-
-// numeric leaf: the operator is warp-uniform, so it is dispatched ONCE per evaluation and each case is
-// a straight run of RB (load, compare, predicated OR) triples; ld(j) loads the value of this lane's j-th row
-template <int RB, typename T, typename Ld>
-__device__ __forceinline__ uint32_t cmp_numeric(Ld ld, const T lit, const uint32_t tt) {
-    switch (tt) {
-        case 0b010: return rows_mask<RB>([&](int j) { return ld(j) == lit; });
-        case 0b101: return rows_mask<RB>([&](int j) { return ld(j) != lit; });
-        case 0b100: return rows_mask<RB>([&](int j) { return ld(j) > lit; });
-        case 0b001: return rows_mask<RB>([&](int j) { return ld(j) < lit; });
-        case 0b110: return rows_mask<RB>([&](int j) { return ld(j) >= lit; });
-        case 0b011: return rows_mask<RB>([&](int j) { return ld(j) <= lit; });
-        case 0b111: return (RB >= 32) ? 0xffffffffu : ((1u << RB) - 1u);
-        default: return 0u;
-    }
-}
-
-__device__ __forceinline__ uint32_t diff16(const uint4 v, const uint4 l) {
-    return (v.x ^ l.x) | (v.y ^ l.y) | (v.z ^ l.z) | (v.w ^ l.w);
-}
 
 // After the program has been copied into shared memory: give every leaf its column's stage offset and width, so
 // that evaluating a leaf needs nothing but the leaf record (call between two CTA-wide barriers).
@@ -244,119 +236,236 @@ __device__ __forceinline__ void patch_leaves(Program *sp, const ScanParams &p, u
     }
 }
 
-// Evaluate one leaf for this lane's rows of NT staged tiles at once (NT = 1: rows lrow, lrow+32, ... of the
-// tile at `stage`; NT = 2: also the same rows of the tile at `stage + dB`, which become mask bits R .. 2R-1).
-// Two tiles per call halve the per-tile cost of interpreting the program (~60 % of the evaluators'
-// instructions for a 3-leaf WHERE), so the fused kernel takes two whenever the next stage has already landed.
-template <int R, int NT>
-__device__ __forceinline__ uint32_t eval_leaf_tile(const PLeaf &lf, const Program *sp, const uint8_t *stage,
-                                                   const int dB, const ScanParams &p, int lrow) {
-    constexpr int RB = R * NT;
-    const uint8_t *base = stage + lf.smem_off;  // patched by patch_leaves
+// ---- compare + predicated OR: m |= bit when (x OP lit).  OP is the leaf's 3-bit truth table. ----
+#define QPE_CMP_OR_S32(OPNAME)                                                                                  \
+    asm("{\n\t.reg .pred p;\n\tsetp." OPNAME ".s32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"                   \
+        : "+r"(m)                                                                                               \
+        : "r"(x), "r"(lit), "r"(bit))
+#define QPE_CMP_OR_U64(OPNAME)                                                                                  \
+    asm("{\n\t.reg .pred p;\n\tsetp." OPNAME ".u64 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"                   \
+        : "+r"(m)                                                                                               \
+        : "l"(x), "l"(lit), "r"(bit))
+
+template <int OP>
+__device__ __forceinline__ void cmp_or(uint32_t &m, int32_t x, int32_t lit, uint32_t bit) {
+    if constexpr (OP == 0b010) QPE_CMP_OR_S32("eq");
+    else if constexpr (OP == 0b101) QPE_CMP_OR_S32("ne");
+    else if constexpr (OP == 0b100) QPE_CMP_OR_S32("gt");
+    else if constexpr (OP == 0b001) QPE_CMP_OR_S32("lt");
+    else if constexpr (OP == 0b110) QPE_CMP_OR_S32("ge");
+    else QPE_CMP_OR_S32("le");
+}
+template <int OP>
+__device__ __forceinline__ void cmp_or(uint32_t &m, unsigned long long x, unsigned long long lit, uint32_t bit) {
+    if constexpr (OP == 0b010) QPE_CMP_OR_U64("eq");
+    else if constexpr (OP == 0b101) QPE_CMP_OR_U64("ne");
+    else if constexpr (OP == 0b100) QPE_CMP_OR_U64("hi");
+    else if constexpr (OP == 0b001) QPE_CMP_OR_U64("lo");
+    else if constexpr (OP == 0b110) QPE_CMP_OR_U64("hs");
+    else QPE_CMP_OR_U64("ls");
+}
+// m |= bit when x != 0
+__device__ __forceinline__ void nz_or(uint32_t &m, uint32_t x, uint32_t bit) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(m) : "r"(x), "r"(bit));
+}
+
+__device__ __forceinline__ uint32_t diff16(const uint4 v, const uint4 l) {
+    return (v.x ^ l.x) | (v.y ^ l.y) | (v.z ^ l.z) | (v.w ^ l.w);
+}
+
+template <int RPL>
+__device__ __forceinline__ uint32_t rotl_rpl(uint32_t m, uint32_t s) {  // rotate left by s (0 <= s < RPL) within RPL bits
+    if constexpr (RPL == 32) {
+        return __funnelshift_l(m, m, s);
+    } else {
+        constexpr uint32_t all = (1u << RPL) - 1u;
+        return ((m << s) | (m >> (RPL - s))) & all;
+    }
+}
+
+// Per-lane constants of the rotated access order (computed once per kernel).
+//   numeric cells: step k reads unit (k + lane) mod U (unit = 4 consecutive rows); slot bit b <-> row (b + rot4) mod RPL
+//   text cells:    step j reads row  (j + lane) mod RPL;                            slot bit j <-> row (j + rotr) mod RPL
+template <int RPL>
+struct LaneGeom {
+    static constexpr int U = RPL / 4;
+    uint32_t uoff[U];   // 16 * ((k + lane) mod U): byte offset of step k's unit in an int column's lane block
+    uint32_t rot4;      // 4 * (lane mod U)
+    uint32_t rotr;      // lane mod RPL
+    uint32_t trot;      // text slot order -> numeric slot order: rotate left by (rotr - rot4) mod RPL
+    __device__ __forceinline__ void init(uint32_t lane) {
+#pragma unroll
+        for (int k = 0; k < U; ++k) uoff[k] = ((static_cast<uint32_t>(k) + lane) & (U - 1)) << 4;
+        rot4 = (lane & (U - 1)) << 2;
+        rotr = lane & (RPL - 1);
+        trot = (rotr - rot4) & (RPL - 1);
+    }
+};
+
+template <int RPL, int OP>
+__device__ __forceinline__ uint32_t leaf_i32(const uint8_t *lb, const LaneGeom<RPL> &g, int32_t lit) {
+    uint32_t m0 = 0, m1 = 0;  // two accumulators: half the length of the predicated-OR dependency chain
+#pragma unroll
+    for (int k = 0; k < RPL / 4; ++k) {
+        const int4 v = *reinterpret_cast<const int4 *>(lb + g.uoff[k]);
+        uint32_t &m = (k & 1) ? m1 : m0;
+        cmp_or<OP>(m, v.x, lit, 1u << (4 * k));
+        cmp_or<OP>(m, v.y, lit, 2u << (4 * k));
+        cmp_or<OP>(m, v.z, lit, 4u << (4 * k));
+        cmp_or<OP>(m, v.w, lit, 8u << (4 * k));
+    }
+    return m0 | m1;
+}
+
+template <int RPL, int OP>
+__device__ __forceinline__ uint32_t leaf_u64(const uint8_t *lb, const LaneGeom<RPL> &g, unsigned long long lit) {
+    uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+    for (int k = 0; k < RPL / 4; ++k) {
+        const uint8_t *a = lb + 2u * g.uoff[k];
+        const ulonglong2 v0 = *reinterpret_cast<const ulonglong2 *>(a);
+        const ulonglong2 v1 = *reinterpret_cast<const ulonglong2 *>(a + 16);
+        uint32_t &m = (k & 1) ? m1 : m0;
+        cmp_or<OP>(m, v0.x, lit, 1u << (4 * k));
+        cmp_or<OP>(m, v0.y, lit, 2u << (4 * k));
+        cmp_or<OP>(m, v1.x, lit, 4u << (4 * k));
+        cmp_or<OP>(m, v1.y, lit, 8u << (4 * k));
+    }
+    return m0 | m1;
+}
+
+#define QPE_OP_SWITCH(tt, FN, ...)                                  \
+    switch (tt) {                                                   \
+        case 0b010: return FN<RPL, 0b010>(__VA_ARGS__);             \
+        case 0b101: return FN<RPL, 0b101>(__VA_ARGS__);             \
+        case 0b100: return FN<RPL, 0b100>(__VA_ARGS__);             \
+        case 0b001: return FN<RPL, 0b001>(__VA_ARGS__);             \
+        case 0b110: return FN<RPL, 0b110>(__VA_ARGS__);             \
+        case 0b011: return FN<RPL, 0b011>(__VA_ARGS__);             \
+        case 0b111: return kAll;                                    \
+        default: return 0u;                                         \
+    }
+
+// four cells of 0 / 1 bytes -> their low bits as a nibble (no carries: every product term lands on its own bit)
+__device__ __forceinline__ uint32_t bool4_nibble(uint32_t x) { return (x * 0x01020408u) >> 24; }
+
+// bool column: cells are exactly 0 or 1 (every writer of a device table normalises them); rows are read in ROW order
+// (the whole lane block is 32 / 16 / 8 bytes) and the mask is rotated into slot order at the end
+template <int RPL>
+__device__ __forceinline__ uint32_t leaf_bool(const uint8_t *lb, const LaneGeom<RPL> &g, bool want) {
+    constexpr uint32_t kAll = (RPL >= 32) ? 0xffffffffu : ((1u << RPL) - 1u);
+    uint32_t rows;
+    if constexpr (RPL == 32) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(lb);
+        const uint4 b = *reinterpret_cast<const uint4 *>(lb + 16);
+        rows = bool4_nibble(a.x) | (bool4_nibble(a.y) << 4) | (bool4_nibble(a.z) << 8) | (bool4_nibble(a.w) << 12) |
+               (bool4_nibble(b.x) << 16) | (bool4_nibble(b.y) << 20) | (bool4_nibble(b.z) << 24) | (bool4_nibble(b.w) << 28);
+    } else if constexpr (RPL == 16) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(lb);
+        rows = bool4_nibble(a.x) | (bool4_nibble(a.y) << 4) | (bool4_nibble(a.z) << 8) | (bool4_nibble(a.w) << 12);
+    } else {
+        const uint2 a = *reinterpret_cast<const uint2 *>(lb);
+        rows = bool4_nibble(a.x) | (bool4_nibble(a.y) << 4);
+    }
+    if (!want) rows = ~rows & kAll;
+    // row order -> slot order: slot bit b holds row (b + rot4) mod RPL, i.e. rotate RIGHT by rot4
+    return rotl_rpl<RPL>(rows, (RPL - g.rot4) & (RPL - 1));
+}
+
+// text column (cell = nch x 16 bytes, NUL padded): strcmp order == unsigned byte order over the cell.
+// Step j reads row (j + lane) mod RPL of the lane block (conflict-free 16-byte loads for 16-byte cells).
+template <int RPL>
+__device__ __forceinline__ uint32_t leaf_text(const PLeaf &lf, const Program *sp, const uint8_t *col_stage,
+                                              uint32_t lane, const LaneGeom<RPL> &g) {
+    constexpr uint32_t kAll = (RPL >= 32) ? 0xffffffffu : ((1u << RPL) - 1u);
+    const int nch = lf.nch;
+    const uint32_t w = static_cast<uint32_t>(nch) << 4;
+    const uint32_t span = RPL * w;
+    const uint4 *lit = reinterpret_cast<const uint4 *>(sp->lit_pool + lf.lit_off);
+    const uint8_t *lb = col_stage + lane * span;
+    const uint32_t start = g.rotr * w;
     const uint32_t tt = lf.tt;
-    constexpr uint32_t kAll = (RB >= 32) ? 0xffffffffu : ((1u << RB) - 1u);
-    // byte address of this lane's j-th row of a column with `w`-byte cells (j is a constant after unrolling)
-    auto row_ptr = [&](const uint8_t *c0, int j, uint32_t w) -> const uint8_t * {
-        return (j < R) ? c0 + static_cast<size_t>(j) * 32u * w : c0 + dB + static_cast<size_t>(j - R) * 32u * w;
+    // byte offset of step j's row inside the lane block (j is a constant after unrolling)
+    auto row_off = [&](int j) -> uint32_t {
+        uint32_t o = start + static_cast<uint32_t>(j) * w;
+        return o >= span ? o - span : o;
     };
-    switch (lf.type) {
-        case T_I32: {
-            const uint8_t *c = base + static_cast<size_t>(lrow) * 4u;
-            return cmp_numeric<RB, int32_t>([&](int j) { return *reinterpret_cast<const int32_t *>(row_ptr(c, j, 4)); },
-                                            lf.lit_i32, tt);
-        }
-        case T_U64: {
-            const uint8_t *c = base + static_cast<size_t>(lrow) * 8u;
-            return cmp_numeric<RB, unsigned long long>(
-                [&](int j) { return *reinterpret_cast<const unsigned long long *>(row_ptr(c, j, 8)); }, lf.lit_u64, tt);
-        }
-        case T_BOOL: {
-            // only = and != exist; (cell != 0) == want
-            const uint8_t *c = base + lrow;
-            const bool want = ((tt == 0b010u) == ((lf.lit_i32 & 1) != 0));
-            const uint32_t nz = rows_mask<RB>([&](int j) { return *row_ptr(c, j, 1) != 0; });
-            return want ? nz : (~nz & kAll);
-        }
-        default: {  // T_STR: strcmp order == unsigned byte order over the NUL-padded cell
-            const int nch = lf.nch;
-            const uint32_t w = static_cast<uint32_t>(nch) << 4;
-            const uint4 *lit = reinterpret_cast<const uint4 *>(sp->lit_pool + lf.lit_off);
-            const uint8_t *c = base + static_cast<size_t>(lrow) * w;
-            auto cell = [&](int j) { return reinterpret_cast<const uint4 *>(row_ptr(c, j, w)); };
-            if (tt == 0b010u || tt == 0b101u) {
-                // equality only: OR of XORs, no byte swapping
-                uint32_t ne = 0;
-                if (nch == 1) {
-                    const uint4 l0 = lit[0];
-                    ne = rows_mask<RB>([&](int j) { return diff16(*cell(j), l0) != 0u; });
-                } else {
-                    for (int k = 0; k < nch; ++k) {
-                        const uint4 lk = lit[k];
-                        ne |= rows_mask<RB>([&](int j) { return diff16(cell(j)[k], lk) != 0u; });
-                        if (__all_sync(0xffffffffu, ne == kAll)) break;  // warp-uniform early exit
-                    }
-                }
-                return (tt == 0b010u) ? (~ne & kAll) : ne;
-            }
-            // ordering: three-way compare chunk by chunk, first differing chunk decides
-            uint32_t lt = 0, decided = 0;
-            for (int k = 0; k < nch; ++k) {
-                const uint4 lk = lit[k];
-                const uint32_t b0 = bswap32(lk.x), b1 = bswap32(lk.y), b2 = bswap32(lk.z), b3 = bswap32(lk.w);
-                uint32_t dk = 0, ltk = 0;
+    uint32_t res;
+    if (tt == 0b010u || tt == 0b101u) {
+        // equality only: OR of XORs, no byte swapping
+        uint32_t ne = 0;
+        if (nch == 1) {
+            const uint4 l0 = lit[0];
 #pragma unroll
-                for (int j = 0; j < RB; ++j) {
-                    const uint4 v = cell(j)[k];
-                    const uint32_t a0 = bswap32(v.x), a1 = bswap32(v.y), a2 = bswap32(v.z), a3 = bswap32(v.w);
-                    const bool d0 = a0 != b0, d1 = a1 != b1, d2 = a2 != b2, d3 = a3 != b3;
-                    const bool l = d0 ? (a0 < b0) : d1 ? (a1 < b1) : d2 ? (a2 < b2) : (a3 < b3);
-                    dk |= (d0 | d1 | d2 | d3) ? (1u << j) : 0u;
-                    ltk |= l ? (1u << j) : 0u;
-                }
-                const uint32_t fresh = dk & ~decided;
-                lt |= ltk & fresh;
-                decided |= dk;
-                if (__all_sync(0xffffffffu, decided == kAll)) break;
+            for (int j = 0; j < RPL; ++j) {
+                const uint32_t o = (start + 16u * j) & (RPL * 16u - 1u);
+                nz_or(ne, diff16(*reinterpret_cast<const uint4 *>(lb + o), l0), 1u << j);
             }
-            const uint32_t eq = ~decided & kAll;
-            const uint32_t gt = decided & ~lt;
-            return ((tt & 1u) ? lt : 0u) | ((tt & 2u) ? eq : 0u) | ((tt & 4u) ? gt : 0u);
-        }
-    }
-}
-
-// Transpose this warp's R-bit row masks into R bitmap words (word j = rows [32 j, 32 j + 32) of the warp's slice
-// of a tile) and store them with ONE lane: every ballot result is warp-uniform, so lane 0 holds all R words and
-// writes them as 16-byte vectors (dst is R*4-byte aligned).  The earlier form -- lane j keeps word j, R lanes store
-// one word each -- spent 8 compares + selects per tile on picking the word.
-template <int R>
-__device__ __forceinline__ void store_mask_words(uint32_t acc, uint32_t lane, uint32_t *dst, uint32_t *dst2) {
-    uint32_t w[R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) w[j] = __ballot_sync(0xffffffffu, (acc & (1u << j)) != 0u);
-    if (lane == 0) {
-        if constexpr (R % 4 == 0) {
-#pragma unroll
-            for (int j = 0; j < R; j += 4) {
-                const uint4 v = make_uint4(w[j], w[j + 1], w[j + 2], w[j + 3]);
-                *reinterpret_cast<uint4 *>(dst + j) = v;
-                if (dst2) *reinterpret_cast<uint4 *>(dst2 + j) = v;
-            }
-        } else if constexpr (R == 2) {
-            const uint2 v = make_uint2(w[0], w[1]);
-            *reinterpret_cast<uint2 *>(dst) = v;
-            if (dst2) *reinterpret_cast<uint2 *>(dst2) = v;
         } else {
+            for (int c = 0; c < nch; ++c) {
+                const uint4 lc = lit[c];
 #pragma unroll
-            for (int j = 0; j < R; ++j) {
-                dst[j] = w[j];
-                if (dst2) dst2[j] = w[j];
+                for (int j = 0; j < RPL; ++j)
+                    nz_or(ne, diff16(*reinterpret_cast<const uint4 *>(lb + row_off(j) + 16u * c), lc), 1u << j);
+                if (__all_sync(0xffffffffu, ne == kAll)) break;  // warp-uniform early exit
             }
         }
+        res = (tt == 0b010u) ? (~ne & kAll) : ne;
+    } else {
+        // ordering: three-way compare chunk by chunk, first differing chunk decides
+        uint32_t lt = 0, decided = 0;
+        for (int c = 0; c < nch; ++c) {
+            const uint4 lc = lit[c];
+            const uint32_t b0 = bswap32(lc.x), b1 = bswap32(lc.y), b2 = bswap32(lc.z), b3 = bswap32(lc.w);
+            uint32_t dk = 0, ltk = 0;
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(lb + row_off(j) + 16u * c);
+                const uint32_t a0 = bswap32(v.x), a1 = bswap32(v.y), a2 = bswap32(v.z), a3 = bswap32(v.w);
+                const bool d0 = a0 != b0, d1 = a1 != b1, d2 = a2 != b2, d3 = a3 != b3;
+                const bool l = d0 ? (a0 < b0) : d1 ? (a1 < b1) : d2 ? (a2 < b2) : (a3 < b3);
+                dk |= (d0 | d1 | d2 | d3) ? (1u << j) : 0u;
+                ltk |= l ? (1u << j) : 0u;
+            }
+            const uint32_t fresh = dk & ~decided;
+            lt |= ltk & fresh;
+            decided |= dk;
+            if (__all_sync(0xffffffffu, decided == kAll)) break;
+        }
+        const uint32_t eq = ~decided & kAll;
+        const uint32_t gt = decided & ~lt;
+        res = ((tt & 1u) ? lt : 0u) | ((tt & 2u) ? eq : 0u) | ((tt & 4u) ? gt : 0u);
+    }
+    return rotl_rpl<RPL>(res, g.trot);
+}
+
+template <int RPL>
+__device__ __forceinline__ uint32_t leaf_numeric_i32(const uint8_t *lb, const LaneGeom<RPL> &g, int32_t lit, uint32_t tt) {
+    constexpr uint32_t kAll = (RPL >= 32) ? 0xffffffffu : ((1u << RPL) - 1u);
+    QPE_OP_SWITCH(tt, leaf_i32, lb, g, lit)
+}
+template <int RPL>
+__device__ __forceinline__ uint32_t leaf_numeric_u64(const uint8_t *lb, const LaneGeom<RPL> &g, unsigned long long lit,
+                                                     uint32_t tt) {
+    constexpr uint32_t kAll = (RPL >= 32) ? 0xffffffffu : ((1u << RPL) - 1u);
+    QPE_OP_SWITCH(tt, leaf_u64, lb, g, lit)
+}
+
+// One leaf over this lane's RPL rows of the staged tile; the result is in numeric SLOT order.
+template <int RPL>
+__device__ __forceinline__ uint32_t eval_leaf(const PLeaf &lf, const Program *sp, const uint8_t *stage, uint32_t lane,
+                                              const LaneGeom<RPL> &g) {
+    const uint8_t *base = stage + lf.smem_off;  // patched by patch_leaves
+    switch (lf.type) {
+        case T_I32: return leaf_numeric_i32<RPL>(base + lane * (RPL * 4u), g, lf.lit_i32, lf.tt);
+        case T_U64: return leaf_numeric_u64<RPL>(base + lane * (RPL * 8u), g, lf.lit_u64, lf.tt);
+        case T_BOOL:  // only = and != exist; (cell != 0) == want
+            return leaf_bool<RPL>(base + lane * RPL, g, (lf.tt == 0b010u) == ((lf.lit_i32 & 1) != 0));
+        default: return leaf_text<RPL>(lf, sp, base, lane, g);
     }
 }
 
-// run the compiled WHERE program; returns the R-bit match mask of this lane's rows
+// run the compiled WHERE program; returns the match mask (whatever order the leaves use)
 template <typename LeafFn>
 __device__ __forceinline__ uint32_t run_program(const Program *sp, uint32_t all_mask, LeafFn leaf_fn) {
     uint32_t acc = all_mask;  // empty program == NULL where clause == every row matches
@@ -407,6 +516,37 @@ __device__ __forceinline__ uint32_t run_program(const Program *sp, uint32_t all_
     return acc & all_mask;
 }
 
+// The whole WHERE over one staged tile: this lane's RPL rows as a bitmap (bit b = row first_row + b), rows at or
+// beyond n_rows cleared.  first_row = global row of the lane's first row.
+template <int RPL>
+__device__ __forceinline__ uint32_t eval_tile(const Program *sp, const uint8_t *stage, uint32_t lane,
+                                              const LaneGeom<RPL> &g, long long first_row, long long n_rows) {
+    constexpr uint32_t kAll = (RPL >= 32) ? 0xffffffffu : ((1u << RPL) - 1u);
+    uint32_t acc = run_program(sp, kAll, [&](const PLeaf &lf) { return eval_leaf<RPL>(lf, sp, stage, lane, g); });
+    acc = rotl_rpl<RPL>(acc, g.rot4);  // slot order -> row order
+    const long long left = n_rows - first_row;
+    if (left < RPL) acc = left <= 0 ? 0u : (acc & ((1u << static_cast<uint32_t>(left)) - 1u));
+    return acc;
+}
+
+// a lane's RPL match bits into a bitmap whose first byte holds the tile's first row (shared or global memory)
+template <int RPL>
+__device__ __forceinline__ void store_mask(uint8_t *tile_bitmap, uint32_t lane, uint32_t mask) {
+    if constexpr (RPL == 32) reinterpret_cast<uint32_t *>(tile_bitmap)[lane] = mask;
+    else if constexpr (RPL == 16) reinterpret_cast<uint16_t *>(tile_bitmap)[lane] = static_cast<uint16_t>(mask);
+    else tile_bitmap[lane] = static_cast<uint8_t>(mask);
+}
+
+// producer: the slices of one tile into a stage
+__device__ __forceinline__ void produce_tile(const ScanParams &p, uint8_t *dst, long long tile, int T, uint64_t *bar) {
+    mbar_arrive_expect_tx(bar, p.stage_bytes);
+    for (int r = 0; r < p.n_ref; ++r) {
+        const int c = p.ref_col[r];
+        const uint32_t w = p.width[c];
+        tma_bulk_g2s(dst + p.smem_off[c], p.col[c] + static_cast<size_t>(tile) * T * w, static_cast<uint32_t>(T) * w, bar);
+    }
+}
+
 // warp-wide decoupled look-back: exclusive prefix of `tile` (sum of the aggregates of all
 // earlier tiles).  Lane l inspects tile-1-l; windows of 32 predecessors until a PREFIX is found.
 __device__ __forceinline__ uint32_t warp_lookback(const unsigned long long *desc, long long tile, uint32_t epoch,
@@ -420,9 +560,13 @@ __device__ __forceinline__ uint32_t warp_lookback(const unsigned long long *desc
             unsigned long long d = ld_desc(desc + mine);
             uint32_t flag = static_cast<uint32_t>(d >> 32);
             uint32_t spins = 0;
+            unsigned long long t0 = 0;
             while ((flag >> 2) != epoch) {
                 __nanosleep(64);  // predecessor not published yet: back off instead of hammering L2
-                if (++spins == (kSpinLimit >> 6)) __trap();
+                if ((++spins & 0xffu) == 0) {
+                    if (t0 == 0) t0 = global_ns();
+                    else if (global_ns() - t0 > kSpinTimeoutNs) __trap();
+                }
                 d = ld_desc(desc + mine);
                 flag = static_cast<uint32_t>(d >> 32);
             }
@@ -443,110 +587,72 @@ __device__ __forceinline__ uint32_t warp_lookback(const unsigned long long *desc
     return excl;
 }
 
-template <int EW, int R>
-__global__ void __launch_bounds__(32 * (1 + EW), 1) scan_tma_kernel(const __grid_constant__ ScanParams p) {
+// ------------------------------------------------------------------------------------------
+// K1: scan -> match bitmap (optional) + match count.  Persistent, one CTA per SM; tile seq of CTA b is table
+// tile tile_begin + b + seq * grid, taken by warp seq % S.  Nothing waits on another CTA.
+//
+// SELF-FEEDING WARPS.  There is no producer warp: evaluator warp w owns stage w and its mbarrier, and its lane 0
+// issues the bulk copies of the warp's NEXT tile as soon as the warp has finished reading the current one.  (With
+// one producer lane for the whole CTA, 1024-row tiles were bound by that lane: ~0.43 us per tile whatever its
+// size.)  While a warp waits for its refill, the other warps evaluate; about S - 3 stages are in flight per SM.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <int RPL>
+__global__ void __launch_bounds__(32 * kEvalWarps, 1) scan_tma_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     ScanSmemHeader *sh = reinterpret_cast<ScanSmemHeader *>(smem_raw);
     uint8_t *stages = smem_raw + ((sizeof(ScanSmemHeader) + 127) & ~size_t(127));
+    constexpr int EW = kEvalWarps;
+    constexpr int T = 32 * RPL;
+    constexpr uint32_t kThreads = 32 * EW;
+    const uint32_t tid = threadIdx.x, ew = tid >> 5, lane = tid & 31u;
+    const uint32_t S = static_cast<uint32_t>(p.n_stages);
 
-    const uint32_t tid = threadIdx.x;
-    const uint32_t warp = tid >> 5;
-    const uint32_t lane = tid & 31u;
-    const int S = p.n_stages;
-    constexpr int T = 32 * EW * R;        // rows per tile
-    constexpr int WPT = T >> 5;           // bitmap words per tile
-    constexpr uint32_t kThreads = 32 * (1 + EW);
-
-    // program -> shared memory (uniform reads afterwards), barrier init
+    if (tid == 0) {
+        for (uint32_t s = 0; s < S; ++s) mbar_init(&sh->full[s], 1);
+        sh->cta_count = 0;
+        fence_mbar_init();
+    }
+    __syncthreads();
+    // first tile of every warp: in flight while the program is copied into shared memory
+    uint8_t *stage = stages + static_cast<size_t>(ew) * p.stage_bytes;
+    const long long step = static_cast<long long>(S) * gridDim.x;
+    long long tile = p.tile_begin + blockIdx.x + static_cast<long long>(ew) * gridDim.x;
+    const bool active = ew < S;
+    if (active && lane == 0 && tile < p.n_tiles) produce_tile(p, stage, tile, T, &sh->full[ew]);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(&p.ctl->prog);
         uint4 *dst = reinterpret_cast<uint4 *>(&sh->prog);
         for (uint32_t i = tid; i < sizeof(Program) / 16; i += kThreads) dst[i] = src[i];
-    }
-    if (tid == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&sh->full[s], 1);
-            mbar_init(&sh->empty[s], EW);
-        }
-        sh->cta_count = 0;
-        fence_mbar_init();
     }
     __syncthreads();
     patch_leaves(&sh->prog, p, tid, kThreads);
     __syncthreads();
     const Program *sp = &sh->prog;
 
-    if (warp == 0) {
-        // ===== P: tile claim + TMA producer =====
-        if (lane == 0) {
-            int s = 0;
-            uint32_t phase = 0;
-            for (long long k = 0;; ++k) {
-                mbar_wait_relaxed(&sh->empty[s], phase ^ 1u, 128);
-                // static round-robin keeps the claim off the critical path (a global atomic costs a
-                // full round trip per tile); every CTA is resident (grid <= SM count) and walks its
-                // tiles in increasing order, so the look-back chain always makes progress.
-                const long long tile = p.tile_begin +
-                                       (p.dynamic_tiles ? static_cast<long long>(atomicAdd(&p.ctl->tile_counter, 1u))
-                                                        : static_cast<long long>(blockIdx.x) + k * gridDim.x);
-                if (tile >= p.n_tiles) {
-                    sh->tile_of_stage[s] = -1;
-                    mbar_arrive(&sh->full[s]);
-                    break;
-                }
-                sh->tile_of_stage[s] = tile;
-                mbar_arrive_expect_tx(&sh->full[s], p.stage_bytes);
-                uint8_t *dst = stages + static_cast<size_t>(s) * p.stage_bytes;
-                for (int r = 0; r < p.n_ref; ++r) {
-                    const int c = p.ref_col[r];
-                    const uint32_t w = p.width[c];
-                    tma_bulk_g2s(dst + p.smem_off[c], p.col[c] + static_cast<size_t>(tile) * T * w,
-                                 static_cast<uint32_t>(T) * w, &sh->full[s]);
-                }
-                if (++s == S) {
-                    s = 0;
-                    phase ^= 1u;
-                }
+    LaneGeom<RPL> g;
+    g.init(lane);
+    uint32_t my_count = 0;
+    if (active)
+        for (uint32_t it = 0; tile < p.n_tiles; tile += step, ++it) {
+            mbar_wait(&sh->full[ew], it & 1u);
+            const uint32_t acc = eval_tile<RPL>(sp, stage, lane, g, tile * T + static_cast<long long>(lane) * RPL, p.n_rows);
+            __syncwarp();  // every lane has read the stage: refill it
+            if (lane == 0 && tile + step < p.n_tiles) {
+                fence_proxy_async_smem();
+                produce_tile(p, stage, tile + step, T, &sh->full[ew]);
             }
-        }
-    } else {
-        // ===== E: predicate evaluation =====
-        const int ew = static_cast<int>(warp) - 1;
-        constexpr uint32_t all_mask = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
-        const int lrow = ew * (32 * R) + static_cast<int>(lane);  // first row of this lane inside a tile
-        int s = 0;
-        uint32_t sphase = 0;
-        uint32_t my_count = 0;  // matches seen by this lane's rows (summed per CTA at the end)
-        for (;;) {
-            mbar_wait(&sh->full[s], sphase);
-            const long long tile = sh->tile_of_stage[s];
-            if (tile < 0) break;
-
-            const uint8_t *stage = stages + static_cast<size_t>(s) * p.stage_bytes;
-            uint32_t acc = run_program(sp, all_mask, [&](const PLeaf &lf) {
-                return eval_leaf_tile<R, 1>(lf, sp, stage, 0, p, lrow);
-            });
-            // the stage can be refilled as soon as every evaluator has read it
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh->empty[s]);
-
-            const long long row_base = tile * T + lrow;  // global row of this lane's j = 0
-            if (tile * T + T > p.n_rows)                 // last (partial) tile: drop the padding rows
-                acc &= rows_mask<R>([&](int j) { return row_base + 32ll * j < p.n_rows; });
             my_count += static_cast<uint32_t>(__popc(acc));
-            if (p.out_bitmap) store_mask_words<R>(acc, lane, p.out_bitmap + tile * WPT + ew * R, nullptr);
-            if (++s == S) {
-                s = 0;
-                sphase ^= 1u;
-            }
+            if (p.out_bitmap) store_mask<RPL>(reinterpret_cast<uint8_t *>(p.out_bitmap) + tile * (T / 8), lane, acc);
         }
-        const uint32_t warp_total = __reduce_add_sync(0xffffffffu, my_count);
-        if (lane == 0) atomicAdd(&sh->cta_count, static_cast<unsigned long long>(warp_total));
-    }
+    const uint32_t warp_total = __reduce_add_sync(0xffffffffu, my_count);
+    if (lane == 0 && warp_total) atomicAdd(&sh->cta_count, static_cast<unsigned long long>(warp_total));
     __syncthreads();
     if (tid == 0 && sh->cta_count) atomicAdd(&p.ctl->out_count, sh->cta_count);
 }
-
 
 // ------------------------------------------------------------------------------------------
 // K9: query batch -- up to kMaxBatch WHERE programs over ONE pass of the columns
@@ -565,8 +671,8 @@ struct BatchParams {
     unsigned long long *counts;           // device, n_prog match counts (zeroed by the caller)
 };
 
-template <int EW, int R>
-__global__ void __launch_bounds__(32 * (1 + EW), 1) scan_batch_kernel(const __grid_constant__ BatchParams bp) {
+template <int RPL>
+__global__ void __launch_bounds__(32 * kEvalWarps, 1) scan_batch_kernel(const __grid_constant__ BatchParams bp) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const ScanParams &p = bp.s;
     ScanSmemHeader *sh = reinterpret_cast<ScanSmemHeader *>(smem_raw);  // its own prog slot is unused here
@@ -574,89 +680,50 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_batch_kernel(const __gr
     Program *progs = reinterpret_cast<Program *>(smem_raw + ((sizeof(ScanSmemHeader) + 127) & ~size_t(127)));
     const int Q = bp.n_prog;
     uint8_t *stages = reinterpret_cast<uint8_t *>(progs) + ((static_cast<size_t>(Q) * sizeof(Program) + 127) & ~size_t(127));
-
-    const uint32_t tid = threadIdx.x;
-    const uint32_t warp = tid >> 5;
-    const uint32_t lane = tid & 31u;
-    const int S = p.n_stages;
-    constexpr int T = 32 * EW * R;
-    constexpr int WPT = T >> 5;
-    constexpr uint32_t kThreads = 32 * (1 + EW);
+    constexpr int EW = kEvalWarps;
+    constexpr int T = 32 * RPL;
+    constexpr uint32_t kThreads = 32 * EW;
+    const uint32_t tid = threadIdx.x, ew = tid >> 5, lane = tid & 31u;
+    const uint32_t S = static_cast<uint32_t>(p.n_stages);
+    if (tid < kMaxBatch) s_count[tid] = 0;
+    if (tid == 0) {
+        for (uint32_t s = 0; s < S; ++s) mbar_init(&sh->full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint8_t *stage = stages + static_cast<size_t>(ew) * p.stage_bytes;
+    const long long step = static_cast<long long>(S) * gridDim.x;
+    long long tile = blockIdx.x + static_cast<long long>(ew) * gridDim.x;
+    const bool active = ew < S;
+    if (active && lane == 0 && tile < p.n_tiles) produce_tile(p, stage, tile, T, &sh->full[ew]);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(bp.progs);
         uint4 *dst = reinterpret_cast<uint4 *>(progs);
         for (uint32_t i = tid; i < static_cast<uint32_t>(Q) * (sizeof(Program) / 16); i += kThreads) dst[i] = src[i];
     }
-    if (tid < kMaxBatch) s_count[tid] = 0;
-    if (tid == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&sh->full[s], 1);
-            mbar_init(&sh->empty[s], EW);
-        }
-        fence_mbar_init();
-    }
     __syncthreads();
     for (int q = 0; q < Q; ++q) patch_leaves(progs + q, p, tid, kThreads);
     __syncthreads();
 
-    if (warp == 0) {
-        if (lane == 0) {
-            int s = 0;
-            uint32_t phase = 0;
-            for (long long k = 0;; ++k) {
-                mbar_wait_relaxed(&sh->empty[s], phase ^ 1u, 128);
-                const long long tile = static_cast<long long>(blockIdx.x) + k * gridDim.x;
-                if (tile >= p.n_tiles) {
-                    sh->tile_of_stage[s] = -1;
-                    mbar_arrive(&sh->full[s]);
-                    break;
-                }
-                sh->tile_of_stage[s] = tile;
-                mbar_arrive_expect_tx(&sh->full[s], p.stage_bytes);
-                uint8_t *dst = stages + static_cast<size_t>(s) * p.stage_bytes;
-                for (int r = 0; r < p.n_ref; ++r) {
-                    const int c = p.ref_col[r];
-                    const uint32_t w = p.width[c];
-                    tma_bulk_g2s(dst + p.smem_off[c], p.col[c] + static_cast<size_t>(tile) * T * w,
-                                 static_cast<uint32_t>(T) * w, &sh->full[s]);
-                }
-                if (++s == S) {
-                    s = 0;
-                    phase ^= 1u;
-                }
-            }
-        }
-    } else {
-        const int ew = static_cast<int>(warp) - 1;
-        constexpr uint32_t all_mask = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
-        const int lrow = ew * (32 * R) + static_cast<int>(lane);
-        int s = 0;
-        uint32_t sphase = 0;
-        for (;;) {
-            mbar_wait(&sh->full[s], sphase);
-            const long long tile = sh->tile_of_stage[s];
-            if (tile < 0) break;
-            const uint8_t *stage = stages + static_cast<size_t>(s) * p.stage_bytes;
-            const long long row_base = tile * T + lrow;
-            uint32_t tail = all_mask;
-            if (tile * T + T > p.n_rows) tail = rows_mask<R>([&](int j) { return row_base + 32ll * j < p.n_rows; });
+    LaneGeom<RPL> g;
+    g.init(lane);
+    if (active)
+        for (uint32_t it = 0; tile < p.n_tiles; tile += step, ++it) {
+            mbar_wait(&sh->full[ew], it & 1u);
+            const long long first_row = tile * T + static_cast<long long>(lane) * RPL;
+#pragma unroll 1
             for (int q = 0; q < Q; ++q) {
-                const Program *sp = progs + q;
-                const uint32_t acc = tail & run_program(sp, all_mask, [&](const PLeaf &lf) {
-                                         return eval_leaf_tile<R, 1>(lf, sp, stage, 0, p, lrow);
-                                     });
-                const uint32_t warp_cnt = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(__popc(acc)));
+                const uint32_t a = eval_tile<RPL>(progs + q, stage, lane, g, first_row, p.n_rows);
+                const uint32_t warp_cnt = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(__popc(a)));
                 if (lane == 0 && warp_cnt) atomicAdd(&s_count[q], static_cast<unsigned long long>(warp_cnt));
-                store_mask_words<R>(acc, lane, bp.bitmap[q] + tile * WPT + ew * R, nullptr);
+                store_mask<RPL>(reinterpret_cast<uint8_t *>(bp.bitmap[q]) + tile * (T / 8), lane, a);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh->empty[s]);  // every program has read the stage
-            if (++s == S) {
-                s = 0;
-                sphase ^= 1u;
+            __syncwarp();  // every program has read the stage: refill it
+            if (lane == 0 && tile + step < p.n_tiles) {
+                fence_proxy_async_smem();
+                produce_tile(p, stage, tile + step, T, &sh->full[ew]);
             }
         }
-    }
     __syncthreads();
     if (tid < static_cast<uint32_t>(Q) && s_count[tid]) atomicAdd(&bp.counts[tid], s_count[tid]);
 }
@@ -664,24 +731,22 @@ __global__ void __launch_bounds__(32 * (1 + EW), 1) scan_batch_kernel(const __gr
 // ------------------------------------------------------------------------------------------
 // K1f: fused scan + ordered compaction (one launch, ids leave the SM while the scan is running)
 //
-// Same producer / evaluator roles as K1, plus kFuseCompactWarps COMPACTION warps per CTA.  Work is
-// handed out in CHUNKS of chunk_tiles consecutive tiles (<= 64 Ki rows), chunk c to CTA c % grid, in
-// increasing order.  The evaluators leave the chunk's match bitmap in shared memory (double
-// buffered); the compaction warps popc/scan it, publish the chunk aggregate, run the DECOUPLED
-// LOOK-BACK over the chunk descriptors of the other CTAs (all resident: grid <= SM count, every
-// CTA walks its chunks in increasing order, so the smallest unfinished chunk never waits), expand
-// the bits into row ids in shared memory and store them coalesced at out_ids + prefix -- while the
-// evaluators are already two chunks ahead.  Compared with K1 -> K1c: no second launch, no bitmap
-// round trip through HBM, no barrier-bound compaction pass after the scan (K1c: 7.5 % of a step).
-// The look-back granularity stays one descriptor per chunk (a per-tile chain cannot keep up with
-// HBM), but the chain now advances beside the scan instead of after it.
-// Optional progress words in pinned host memory tell the host when a table segment's ids are
-// complete in HBM, so it can start the device->host copy of that segment during the scan.
+// Self-feeding evaluator warps as in K1, plus CW COMPACTION warps per CTA.  Work is handed out in CHUNKS of
+// chunk_tiles consecutive tiles (<= 64 Ki rows), chunk c to CTA c % grid, in increasing order; tile j of a CTA's
+// k-th chunk is its tile seq = k * chunk_tiles + j and belongs to warp / stage seq % S.  The evaluators leave
+// the chunk's match bitmap in shared memory (double buffered); the compaction warps popc/scan it, publish the
+// chunk aggregate, run the DECOUPLED LOOK-BACK over the chunk descriptors of the other CTAs (all resident:
+// grid <= SM count, every CTA walks its chunks in increasing order, so the smallest unfinished chunk never
+// waits), expand the bits into row ids in shared memory and store them coalesced at out_ids + prefix -- while the
+// evaluators are already two chunks ahead.  Compared with K1 -> K1c: no second launch, no bitmap round trip
+// through HBM, no barrier-bound compaction pass after the scan.
+// The look-back granularity stays one descriptor per chunk (a per-tile chain cannot keep up with HBM),
+// but the chain advances beside the scan instead of after it.
+// Optional progress words in pinned host memory tell the host when a table segment's ids are complete in HBM, so
+// it can start the device->host copy of that segment during the scan.
+// CW = compaction warps per CTA, 4 or 8.  Four are plenty while few rows match; from ~10 % selectivity the
+// evaluators wait for the compaction warps, and eight take over (the engine picks per query, engine.cu).
 // ------------------------------------------------------------------------------------------
-// CW = compaction warps per CTA, 4 or 8.  Four are plenty while few rows match (and measured 3.5 % faster there:
-// 2.07 vs 2.15 ms on 1 B rows at 1 %); from ~10 % selectivity the evaluators wait for the compaction warps
-// (ncu: 18.6 % of all samples in their wait for a free chunk buffer at 50 %), and eight cut 2.79 ms to 2.39 ms.
-// The engine picks per query from the selectivity the previous full scan saw (engine.cu).
 constexpr int kFuseChunkWords = kFuseMaxChunkRows / 32;              // 2048 words
 static_assert(fuse_reserve_bytes(4) == 2 * kFuseChunkWords * 4 + 32 * 32 * 4 * 4, "smem reserve");
 static_assert(fuse_reserve_bytes(8) == 2 * kFuseChunkWords * 4 + 32 * 32 * 8 * 4, "smem reserve");
@@ -706,19 +771,48 @@ struct FusedParams {
 struct FusedSmemHeader {   // sized for the 4-warp variant (16 rounds x 4 warps); the 8-warp one needs 8 x 8
     Program prog;
     alignas(8) uint64_t full[kMaxStages];
-    uint64_t empty[kMaxStages];
     uint64_t cb_full[2];
     uint64_t cb_empty[2];
-    long long tile_of_stage[kMaxStages];
     unsigned long long cta_count;
     uint32_t warp_tot[64];          // [round][compaction warp]
     uint32_t round_base[16 + 1];
     uint32_t excl;
 };
 
-template <int EW, int R, int CW>
-__global__ void __launch_bounds__(32 * (1 + EW + CW), 1)
+// A warp's walk over ITS tiles of the CTA's chunks, in order: tile j of the CTA's k-th chunk has the CTA-wide
+// sequence number k * CT + j, and the tiles with seq % S == w belong to warp w.
+struct WarpTiles {
+    long long chunk;   // current chunk (>= n_chunks: exhausted)
+    uint32_t k;        // its index among this CTA's chunks
+    uint32_t j;        // current tile within the chunk
+    uint32_t nt;       // tiles in the current chunk
+};
+__device__ __forceinline__ uint32_t chunk_tiles_of(long long chunk, uint32_t CT, long long n_tiles) {
+    const long long left = n_tiles - chunk * CT;
+    return static_cast<uint32_t>(left < CT ? left : CT);
+}
+// first tile of warp w in the CTA's k-th chunk
+__device__ __forceinline__ uint32_t first_tile_of(uint32_t w, uint32_t k, uint32_t CT, uint32_t S) {
+    return (w + S - (k * CT) % S) % S;
+}
+// position `wt` on this warp's first tile at or after (chunk, j); false when there is none
+__device__ __forceinline__ bool settle(WarpTiles &wt, uint32_t w, uint32_t CT, uint32_t S, long long n_chunks,
+                                       long long n_tiles, uint32_t grid) {
+    while (wt.chunk < n_chunks) {
+        if (wt.j < wt.nt) return true;
+        wt.chunk += grid;
+        ++wt.k;
+        if (wt.chunk >= n_chunks) break;
+        wt.nt = chunk_tiles_of(wt.chunk, CT, n_tiles);
+        wt.j = first_tile_of(w, wt.k, CT, S);
+    }
+    return false;
+}
+
+template <int RPL, int CW>
+__global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
     scan_fused_kernel(const __grid_constant__ FusedParams fp) {
+    constexpr int EW = kEvalWarps;
     constexpr int kFuseCompactWarps = CW;
     constexpr int kFuseCompactThreads = 32 * CW;                           // 128 | 256
     constexpr int kFuseRounds = kFuseChunkWords / kFuseCompactThreads;     // 16 | 8 words per compaction thread
@@ -728,29 +822,20 @@ __global__ void __launch_bounds__(32 * (1 + EW + CW), 1)
     const ScanParams &p = fp.s;
     FusedSmemHeader *sh = reinterpret_cast<FusedSmemHeader *>(smem_raw);
     uint8_t *stages = smem_raw + ((sizeof(FusedSmemHeader) + 127) & ~size_t(127));
-    const int S = p.n_stages;
+    const uint32_t S = static_cast<uint32_t>(p.n_stages);
     uint32_t *cbuf = reinterpret_cast<uint32_t *>(stages + static_cast<size_t>(S) * p.stage_bytes);  // [2][2048]
-    uint32_t *id_stage = cbuf + 2 * kFuseChunkWords;                                                    // [4096]
+    uint32_t *id_stage = cbuf + 2 * kFuseChunkWords;                                                    // [32 * 32 * CW]
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
     const uint32_t lane = tid & 31u;
-    constexpr int T = 32 * EW * R;   // rows per tile
+    constexpr int T = 32 * RPL;      // rows per tile
     constexpr int WPT = T >> 5;      // bitmap words per tile
-    constexpr uint32_t kThreads = 32 * (1 + EW + kFuseCompactWarps);
-    constexpr bool kDual = (2 * R <= 16);  // two tiles per pass of the program (mask bits 0..2R-1)
-    const int CT = fp.chunk_tiles;
+    constexpr uint32_t kThreads = 32 * (EW + kFuseCompactWarps);
+    const uint32_t CT = static_cast<uint32_t>(fp.chunk_tiles);
 
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(&fp.prog);  // kernel parameter space
-        uint4 *dst = reinterpret_cast<uint4 *>(&sh->prog);
-        for (uint32_t i = tid; i < sizeof(Program) / 16; i += kThreads) dst[i] = src[i];
-    }
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&sh->full[s], 1);
-            mbar_init(&sh->empty[s], EW);
-        }
+        for (uint32_t s = 0; s < S; ++s) mbar_init(&sh->full[s], 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&sh->cb_full[b], EW);
             mbar_init(&sh->cb_empty[b], 1);
@@ -759,148 +844,76 @@ __global__ void __launch_bounds__(32 * (1 + EW + CW), 1)
         fence_mbar_init();
     }
     __syncthreads();
+    // every evaluator warp's first tile: in flight while the program is copied into shared memory
+    const bool active = warp < S;   // evaluator warp that owns a stage
+    uint8_t *stage = stages + static_cast<size_t>(warp < EW ? warp : 0) * p.stage_bytes;
+    WarpTiles nxt;                  // the next tile to FETCH (one ahead of the tile being evaluated)
+    nxt.chunk = blockIdx.x;
+    nxt.k = 0;
+    nxt.nt = nxt.chunk < fp.n_chunks ? chunk_tiles_of(nxt.chunk, CT, p.n_tiles) : 0;
+    nxt.j = warp;                   // first_tile_of(warp, 0, CT, S) for warp < S
+    if (active) {
+        if (settle(nxt, warp, CT, S, fp.n_chunks, p.n_tiles, gridDim.x)) {
+            if (lane == 0) produce_tile(p, stage, nxt.chunk * CT + nxt.j, T, &sh->full[warp]);
+            nxt.j += S;
+        }
+    }
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(&fp.prog);  // kernel parameter space
+        uint4 *dst = reinterpret_cast<uint4 *>(&sh->prog);
+        for (uint32_t i = tid; i < sizeof(Program) / 16; i += kThreads) dst[i] = src[i];
+    }
+    __syncthreads();
     patch_leaves(&sh->prog, p, tid, kThreads);
     __syncthreads();
     const Program *sp = &sh->prog;
 
-    if (warp == 0) {
-        // ===== P: TMA producer, tiles of this CTA's chunks in order =====
-        if (lane == 0) {
-            int s = 0;
-            uint32_t phase = 0;
-            for (long long chunk = blockIdx.x;; chunk += gridDim.x) {
-                const bool done = chunk >= fp.n_chunks;
-                const long long t0 = chunk * CT;
-                const int nt = done ? 1 : static_cast<int>((p.n_tiles - t0 < CT) ? (p.n_tiles - t0) : CT);
-                for (int j = 0; j < nt; ++j) {
-                    mbar_wait_relaxed(&sh->empty[s], phase ^ 1u, 128);
-                    if (done) {
-                        sh->tile_of_stage[s] = -1;
-                        mbar_arrive(&sh->full[s]);
-                    } else {
-                        const long long tile = t0 + j;
-                        sh->tile_of_stage[s] = tile;
-                        mbar_arrive_expect_tx(&sh->full[s], p.stage_bytes);
-                        uint8_t *dst = stages + static_cast<size_t>(s) * p.stage_bytes;
-                        for (int r = 0; r < p.n_ref; ++r) {
-                            const int c = p.ref_col[r];
-                            const uint32_t w = p.width[c];
-                            tma_bulk_g2s(dst + p.smem_off[c], p.col[c] + static_cast<size_t>(tile) * T * w,
-                                         static_cast<uint32_t>(T) * w, &sh->full[s]);
-                        }
-                    }
-                    if (++s == S) {
-                        s = 0;
-                        phase ^= 1u;
-                    }
-                }
-                if (done) break;
-            }
-        }
-    } else if (warp <= EW) {
+    if (warp < EW) {
         // ===== E: predicate evaluation, bitmap words into the chunk buffer =====
-        const int ew = static_cast<int>(warp) - 1;
-        constexpr uint32_t all_mask = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
-        const int lrow = ew * (32 * R) + static_cast<int>(lane);
-        int s = 0;
-        uint32_t sphase = 0;
+        LaneGeom<RPL> g;
+        g.init(lane);
         uint32_t my_count = 0;
-        uint32_t k = 0;  // k-th chunk of this CTA
+        uint32_t k = 0;   // k-th chunk of this CTA
+        uint32_t it = 0;  // tiles this warp has consumed: the phase of ITS stage
         for (long long chunk = blockIdx.x; chunk < fp.n_chunks; chunk += gridDim.x, ++k) {
             const uint32_t buf = k & 1u;
             // the compaction warps must have read this buffer's previous chunk (k - 2)
             mbar_wait(&sh->cb_empty[buf], ((k >> 1) & 1u) ^ 1u);
-            uint32_t *cb = cbuf + buf * kFuseChunkWords;
+            uint8_t *cb = reinterpret_cast<uint8_t *>(cbuf + buf * kFuseChunkWords);
             const long long t0 = chunk * CT;
-            const int nt = static_cast<int>((p.n_tiles - t0 < CT) ? (p.n_tiles - t0) : CT);
-            for (int j = 0; j < nt;) {
-                mbar_wait(&sh->full[s], sphase);
-                const long long tile = t0 + j;
-                const uint8_t *stage = stages + static_cast<size_t>(s) * p.stage_bytes;
-                int s2 = s + 1;
-                uint32_t phase2 = sphase;
-                if (s2 == S) {
-                    s2 = 0;
-                    phase2 ^= 1u;
-                }
-                // Two tiles in one pass of the program when the NEXT stage has already landed (the scan is then
-                // instruction-bound, not waiting for HBM) and a further stage stays in flight (S >= 3).
-                bool dual = false;
-                if (kDual && S >= 3 && j + 1 < nt) {
-                    uint32_t ready = 0;
-                    if (lane == 0) ready = mbar_test(&sh->full[s2], phase2) ? 1u : 0u;
-                    dual = __shfl_sync(0xffffffffu, ready, 0) != 0u;
-                }
-                if (dual) {
-                    if constexpr (kDual) {
-                        mbar_wait(&sh->full[s2], phase2);  // every lane observes the phase (returns at once)
-                        const int dB = (s2 - s) * static_cast<int>(p.stage_bytes);
-                        constexpr uint32_t all2 = (2 * R >= 32) ? 0xffffffffu : ((1u << (2 * R)) - 1u);
-                        uint32_t acc2 = run_program(sp, all2, [&](const PLeaf &lf) {
-                            return eval_leaf_tile<R, 2>(lf, sp, stage, dB, p, lrow);
-                        });
-                        __syncwarp();
+            const uint32_t nt = chunk_tiles_of(chunk, CT, p.n_tiles);
+            if (active)
+                for (uint32_t j = first_tile_of(warp, k, CT, S); j < nt; j += S, ++it) {
+                    mbar_wait(&sh->full[warp], it & 1u);
+                    const long long tile = t0 + j;
+                    const uint32_t acc =
+                        eval_tile<RPL>(sp, stage, lane, g, tile * T + static_cast<long long>(lane) * RPL, p.n_rows);
+                    __syncwarp();  // every lane has read the stage: fetch this warp's next tile into it
+                    if (settle(nxt, warp, CT, S, fp.n_chunks, p.n_tiles, gridDim.x)) {
                         if (lane == 0) {
-                            mbar_arrive(&sh->empty[s]);
-                            mbar_arrive(&sh->empty[s2]);
+                            fence_proxy_async_smem();
+                            produce_tile(p, stage, nxt.chunk * CT + nxt.j, T, &sh->full[warp]);
                         }
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const long long tl = tile + h;
-                            uint32_t acc = (acc2 >> (h * R)) & all_mask;
-                            const long long row_base = tl * T + lrow;
-                            if (tl * T + T > p.n_rows)
-                                acc &= rows_mask<R>([&](int jj) { return row_base + 32ll * jj < p.n_rows; });
-                            my_count += static_cast<uint32_t>(__popc(acc));
-                            store_mask_words<R>(acc, lane, cb + (j + h) * WPT + ew * R,
-                                                p.out_bitmap ? p.out_bitmap + tl * WPT + ew * R : nullptr);
-                        }
+                        nxt.j += S;
                     }
-                    j += 2;
-                    s = s2 + 1;
-                    sphase = phase2;
-                    if (s == S) {
-                        s = 0;
-                        sphase ^= 1u;
-                    }
-                    continue;
+                    my_count += static_cast<uint32_t>(__popc(acc));
+                    store_mask<RPL>(cb + j * (T / 8), lane, acc);
                 }
-                uint32_t acc = run_program(sp, all_mask, [&](const PLeaf &lf) {
-                    return eval_leaf_tile<R, 1>(lf, sp, stage, 0, p, lrow);
-                });
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sh->empty[s]);
-
-                const long long row_base = tile * T + lrow;
-                if (tile * T + T > p.n_rows)
-                    acc &= rows_mask<R>([&](int jj) { return row_base + 32ll * jj < p.n_rows; });
-                my_count += static_cast<uint32_t>(__popc(acc));
-                store_mask_words<R>(acc, lane, cb + j * WPT + ew * R,
-                                    p.out_bitmap ? p.out_bitmap + tile * WPT + ew * R : nullptr);
-                ++j;
-                if (++s == S) {
-                    s = 0;
-                    sphase ^= 1u;
-                }
-            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh->cb_full[buf]);  // release: this warp's words of the chunk are in cb
         }
-        // consume the producer's end marker so that every barrier phase is balanced
-        mbar_wait(&sh->full[s], sphase);
         const uint32_t warp_total = __reduce_add_sync(0xffffffffu, my_count);
-        if (lane == 0) atomicAdd(&sh->cta_count, static_cast<unsigned long long>(warp_total));
+        if (lane == 0 && warp_total) atomicAdd(&sh->cta_count, static_cast<unsigned long long>(warp_total));
     } else {
         // ===== C: ordered compaction of finished chunks =====
-        const uint32_t ct = tid - 32u * (1 + EW);
+        const uint32_t ct = tid - 32u * EW;
         const uint32_t cw = ct >> 5;
-        const uint32_t chunk_rows = static_cast<uint32_t>(CT) * T;
+        const uint32_t chunk_rows = CT * T;
         uint32_t k = 0;
         for (long long chunk = blockIdx.x; chunk < fp.n_chunks; chunk += gridDim.x, ++k) {
             const uint32_t buf = k & 1u;
-            const long long t0 = chunk * CT;
-            const int nt = static_cast<int>((p.n_tiles - t0 < CT) ? (p.n_tiles - t0) : CT);
-            const uint32_t nw = static_cast<uint32_t>(nt) * WPT;
+            const uint32_t nt = chunk_tiles_of(chunk, CT, p.n_tiles);
+            const uint32_t nw = nt * WPT;
             // (one polling warp + a named barrier for the others measured 1.5 % SLOWER than every warp polling)
             mbar_wait_relaxed(&sh->cb_full[buf], (k >> 1) & 1u, fp.poll_ns);
             const uint32_t *cb = cbuf + buf * kFuseChunkWords;
@@ -1091,12 +1104,11 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
         T = T ? T : kMaxTileRows;
         S = S ? S : 2;
     } else if (!T) {
-        // largest tile that still leaves >= 2 stages in flight; else the largest with 1.  Measured (100 M rows,
-        // profiles/r1_perf_history.md): the per-tile fixed work (program dispatch, barrier waits, ballots) costs
-        // more than a third stage buys -- QS 2048x2 6.9 TB/s vs 1024x4 5.3, QD 2048x2 5.4 TB/s vs 1024x4 3.1.
-        static const int kTiles[] = {4096, 2048, 1024, 512, 256};
+        // the largest tile (rows per evaluator warp and pass) that leaves >= 8 stages = 8 evaluating warps, else
+        // >= 4, >= 2, 1: a stage is held by its warp while it evaluates, the others are in flight
+        static const int kTiles[] = {1024, 512, 256};
         int best_T = 0, best_S = 0;
-        for (int want = 2; want >= 1 && !best_T; --want)
+        for (int want = 8; want >= 1 && !best_T; want >>= 1)
             for (int cand : kTiles) {
                 const size_t sb = stage_bytes_for(cand);
                 int fit = static_cast<int>(budget / (sb ? sb : 1));
@@ -1118,8 +1130,8 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
         S = static_cast<int>(budget / (sb ? sb : 1));
         if (S > max_stages) S = max_stages;
     }
-    if ((T != 256 && T != 512 && T != 1024 && T != 2048 && T != 4096) || S < 1 || S > kMaxStages) {
-        if (why) *why = "invalid tile geometry (tile rows must be 256, 512, 1024, 2048 or 4096)";
+    if ((T != 256 && T != 512 && T != 1024) || S < 1 || S > kMaxStages) {
+        if (why) *why = "invalid tile geometry (tile rows must be 256, 512 or 1024, at most 16 stages)";
         return false;
     }
     const size_t stage_bytes = stage_bytes_for(T);
@@ -1165,13 +1177,13 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
     return true;
 }
 
-template <int EW, int R>
+template <int RPL>
 static cudaError_t launch_scan_r(const ScanParams &p, const ScanGeometry &geo, cudaStream_t stream) {
     // per instantiation and device: raise the dynamic shared memory limit only when it grows
     static size_t allowed_by_device[kMaxDevices] = {0};
     size_t &allowed = allowed_by_device[current_device_slot()];
     if (geo.smem_bytes > allowed) {
-        const cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        const cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(geo.smem_bytes));
         if (e != cudaSuccess) return e;
         allowed = geo.smem_bytes;
@@ -1179,7 +1191,7 @@ static cudaError_t launch_scan_r(const ScanParams &p, const ScanGeometry &geo, c
     long long grid = p.n_tiles - p.tile_begin;  // tiles of this launch
     if (grid > geo.grid) grid = geo.grid;
     if (grid < 1) grid = 1;
-    scan_tma_kernel<EW, R><<<static_cast<unsigned>(grid), 32 * (1 + EW), geo.smem_bytes, stream>>>(p);
+    scan_tma_kernel<RPL><<<static_cast<unsigned>(grid), 32 * kEvalWarps, geo.smem_bytes, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -1205,17 +1217,9 @@ static cudaError_t fill_scan_params(const ScanLaunch &L, const ScanGeometry &geo
     if (tx != p.stage_bytes) return cudaErrorInvalidValue;
     p.tile_rows = geo.tile_rows;
     p.n_stages = geo.stages;
-    {
-        static const int dyn = [] {
-            const char *e = std::getenv("QPE_SCAN_DYNAMIC");
-            return (e && e[0] == '1') ? 1 : 0;
-        }();
-        p.dynamic_tiles = dyn;
-    }
     p.n_rows = t.n;
     p.tile_begin = L.tile_begin;
     p.n_tiles = L.tile_end > 0 ? L.tile_end : geo.n_tiles;
-    if (p.tile_begin != 0 || p.n_tiles != geo.n_tiles) p.dynamic_tiles = 0;  // segments use the static walk
     p.ctl = const_cast<QueryCtl *>(L.d_ctl);
     p.out_bitmap = L.out_bitmap;
     return cudaSuccess;
@@ -1226,26 +1230,24 @@ cudaError_t scan_launch(const ScanLaunch &L, const ScanGeometry &geo, cudaStream
     const cudaError_t e = fill_scan_params(L, geo, p);
     if (e != cudaSuccess) return e;
     switch (geo.tile_rows) {
-        case 256: return launch_scan_r<kEvalWarpsWide, 1>(p, geo, stream);
-        case 512: return launch_scan_r<kEvalWarps, 1>(p, geo, stream);
-        case 1024: return launch_scan_r<kEvalWarps, 2>(p, geo, stream);
-        case 2048: return launch_scan_r<kEvalWarps, 4>(p, geo, stream);
-        case 4096: return launch_scan_r<kEvalWarps, 8>(p, geo, stream);
+        case 256: return launch_scan_r<8>(p, geo, stream);
+        case 512: return launch_scan_r<16>(p, geo, stream);
+        case 1024: return launch_scan_r<32>(p, geo, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 
-template <int EW, int R>
+template <int RPL>
 static cudaError_t launch_batch_r(const BatchParams &bp, const ScanGeometry &geo, cudaStream_t stream) {
     static size_t allowed_by_device[kMaxDevices] = {0};
     size_t &allowed = allowed_by_device[current_device_slot()];
     if (geo.smem_bytes > allowed) {
-        const cudaError_t e = cudaFuncSetAttribute(scan_batch_kernel<EW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        const cudaError_t e = cudaFuncSetAttribute(scan_batch_kernel<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(geo.smem_bytes));
         if (e != cudaSuccess) return e;
         allowed = geo.smem_bytes;
     }
-    scan_batch_kernel<EW, R><<<geo.grid, 32 * (1 + EW), geo.smem_bytes, stream>>>(bp);
+    scan_batch_kernel<RPL><<<geo.grid, 32 * kEvalWarps, geo.smem_bytes, stream>>>(bp);
     return cudaGetLastError();
 }
 
@@ -1258,39 +1260,36 @@ cudaError_t batch_launch(const ScanLaunch &L, const ScanGeometry &geo, int n_pro
     BatchParams bp{};
     const cudaError_t e = fill_scan_params(L, geo, bp.s);
     if (e != cudaSuccess) return e;
-    bp.s.dynamic_tiles = 0;
     bp.n_prog = n_prog;
     bp.progs = d_progs;
     for (int q = 0; q < n_prog; ++q) bp.bitmap[q] = d_bitmaps[q];
     bp.counts = d_counts;
     if (geo.n_tiles == 0) return cudaSuccess;
     switch (geo.tile_rows) {
-        case 256: return launch_batch_r<kEvalWarpsWide, 1>(bp, geo, stream);
-        case 512: return launch_batch_r<kEvalWarps, 1>(bp, geo, stream);
-        case 1024: return launch_batch_r<kEvalWarps, 2>(bp, geo, stream);
-        case 2048: return launch_batch_r<kEvalWarps, 4>(bp, geo, stream);
-        case 4096: return launch_batch_r<kEvalWarps, 8>(bp, geo, stream);
+        case 256: return launch_batch_r<8>(bp, geo, stream);
+        case 512: return launch_batch_r<16>(bp, geo, stream);
+        case 1024: return launch_batch_r<32>(bp, geo, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 
-template <int EW, int R, int CW>
+template <int RPL, int CW>
 static cudaError_t launch_fused_r(const FusedParams &fp, const ScanGeometry &geo, cudaStream_t stream) {
     static size_t allowed_by_device[kMaxDevices] = {0};
     size_t &allowed = allowed_by_device[current_device_slot()];
     if (geo.smem_bytes > allowed) {
-        const cudaError_t e = cudaFuncSetAttribute(scan_fused_kernel<EW, R, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        const cudaError_t e = cudaFuncSetAttribute(scan_fused_kernel<RPL, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(geo.smem_bytes));
         if (e != cudaSuccess) return e;
         allowed = geo.smem_bytes;
     }
-    scan_fused_kernel<EW, R, CW><<<geo.grid, 32 * (1 + EW + CW), geo.smem_bytes, stream>>>(fp);
+    scan_fused_kernel<RPL, CW><<<geo.grid, 32 * (kEvalWarps + CW), geo.smem_bytes, stream>>>(fp);
     return cudaGetLastError();
 }
 
-template <int EW, int R>
+template <int RPL>
 static cudaError_t launch_fused_cw(const FusedParams &fp, const ScanGeometry &geo, cudaStream_t stream) {
-    return geo.compact_warps == 8 ? launch_fused_r<EW, R, 8>(fp, geo, stream) : launch_fused_r<EW, R, 4>(fp, geo, stream);
+    return geo.compact_warps == 8 ? launch_fused_r<RPL, 8>(fp, geo, stream) : launch_fused_r<RPL, 4>(fp, geo, stream);
 }
 
 cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStream_t stream) {
@@ -1300,9 +1299,8 @@ cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStre
     if (geo.chunk_tiles < 1 || static_cast<long long>(geo.chunk_tiles) * geo.tile_rows > kFuseMaxChunkRows ||
         (geo.compact_warps != 4 && geo.compact_warps != 8))
         return cudaErrorInvalidValue;
-    fp.s.dynamic_tiles = 0;
     fp.chunk_tiles = geo.chunk_tiles;
-    fp.poll_ns = 256;  // 0 .. 1000 ns measured alike (2.075-2.092 ms on 1 B rows): any sleep that keeps the polls rare
+    fp.poll_ns = 256;  // 0 .. 1000 ns measured alike: any sleep that keeps the polls rare
     fp.n_chunks = geo.n_chunks;
     fp.desc = L.desc;
     fp.epoch = L.epoch;
@@ -1317,11 +1315,9 @@ cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStre
     if (!fp.fctl) return cudaErrorInvalidValue;
     if (fp.n_chunks == 0) return cudaSuccess;
     switch (geo.tile_rows) {
-        case 256: return launch_fused_cw<kEvalWarpsWide, 1>(fp, geo, stream);
-        case 512: return launch_fused_cw<kEvalWarps, 1>(fp, geo, stream);
-        case 1024: return launch_fused_cw<kEvalWarps, 2>(fp, geo, stream);
-        case 2048: return launch_fused_cw<kEvalWarps, 4>(fp, geo, stream);
-        case 4096: return launch_fused_cw<kEvalWarps, 8>(fp, geo, stream);
+        case 256: return launch_fused_cw<8>(fp, geo, stream);
+        case 512: return launch_fused_cw<16>(fp, geo, stream);
+        case 1024: return launch_fused_cw<32>(fp, geo, stream);
         default: return cudaErrorInvalidValue;
     }
 }

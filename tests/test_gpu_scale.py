@@ -93,7 +93,7 @@ def test_ragged_sizes(pkg, n):
     eng.close()
 
 
-@pytest.mark.parametrize("tile,stages", [(256, 2), (512, 4), (1024, 3), (2048, 2), (4096, 1), (2048, 3)])
+@pytest.mark.parametrize("tile,stages", [(256, 2), (256, 16), (512, 4), (512, 1), (1024, 3), (1024, 5)])
 def test_tile_geometries(table_2m, tile, stages):
     eng, o, n = table_2m
     w = '(command_id < 1500000) AND (risk_level >= 2 OR exit_code != 0) AND (user_id < 2000 OR shell_type != "sh")'
