@@ -4,36 +4,49 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is ONE full-scan SELECT ... WHERE over the whole table: K1f (TMA scan + ordered compaction
-with decoupled look-back fused in one launch -> row ids in table order), and at N > 1 the per-GPU
-match-count exchange plus the ordered gather of the row ids to rank 0, in partition order.
+A "step" is ONE full-scan SELECT ... WHERE over the whole table: K1f (self-feeding TMA scan + ordered
+compaction with decoupled look-back fused in one launch -> row ids in table order), and at N > 1 the
+per-GPU match-count exchange plus the ordered gather of the row ids in partition order.
 
 Workload (config.workload): the synthetic command-log table of BASELINE.json configs[4] -- 1 B rows,
 generated on the device by the counter-based generator (csrc/synth.cu, distributions of the
 reference's generate_commands.py), row-range sharded over the N GPUs exactly like the reference's
 MPI partition (engine/mpi/executeEngine-mpi.c:703-715), total work fixed ("scaling": "strong").
 Query QN of SURVEY 8(d): compound AND/OR over command_id (u64), sudo_used (bool), risk_level
-(int) = 13 B/row, ~1 % selectivity.
+(int) = 13 B/row, ~1 % selectivity.  Its matches all sit in the FIRST shard (the table is ordered by
+command_id); `uniform` repeats the measurement with a query whose matches are spread evenly over the shards.
 
-`value`  = rows scanned per second, whole job, result left in HBM on rank 0 (device-resident).
+`value`  = rows scanned per second, whole job, result left packed in HBM on rank 0 (device-resident).
 `e2e`    = the same through the host-facing C-ABI call (SQL text in host memory in, row ids out
            into PINNED HOST memory): per step the compiled query goes host->device and the ids
            come device->host inside the timed region.  The table itself is engine state (it is
            loaded once by initializeEngineGPU, as the reference loads its CSV once).
+           At N > 1 both are measured with TWO queries in flight per rank (`config.queue_depth`: query
+           q + 1 is submitted before query q is waited for -- the host's share of a query and the
+           device->host copy of its ids then run beside the next scan); `sync_value` is the same with
+           one query at a time.  Every step still delivers its own complete result.
 `roofline` = K1f's algorithmic bytes (rows x 13 B read + 4 B per match written) / K1f's own CUDA-event
            time on the engine's stream, vs the measured HBM copy bandwidth of MEASURED_PEAKS.json.
 `cpu_baseline` = the reference's own linearSearchRecords (compiled unmodified under oracle/_ref)
-           on a bounded sample, 1 core (its scan loop is serial in every engine).
+           on a bounded sample, 1 core (its scan loop is serial in every engine);
+`cpu_baseline_omp` = the reference's QPEOMP driver (whole sample-queries.txt run, all host threads).
+`extra`  (N = 1) = the other BASELINE configs under the same driver: the 100 M-row selectivity sweep
+           (clustered and uniform matches), the 1 M-probe batch over 100 M keys, the drop-in API end to end
+           and the index-path sample queries next to the reference.
 
 --impl reference: the reference's serial scan run as one process per host core (query-level
-parallelism, which is how QPEOMP / QPEMPI use cores), same query, bounded sample per step.
+parallelism, which is how QPEOMP / QPEMPI use cores), same query, bounded sample per step.  It loads
+nothing of this repo's product: the sample CSV is made from the committed generator fixture.
 """
 import argparse
 import ctypes as C
 import json
 import math
 import os
+import re
+import shutil
 import statistics
+import subprocess
 import sys
 import tempfile
 import threading
@@ -53,8 +66,28 @@ QUERIES = {
            '(user_id < 2000 OR shell_type != "sh")',
            ["command_id", "risk_level", "exit_code", "user_id", "shell_type"], 36),
 }
+# the same shapes with matches spread UNIFORMLY over the table: the bound is on user_id (drawn per row)
+UNIFORM = {
+    "QN": ("SELECT command_id FROM Commands WHERE (user_id < {X}) AND (sudo_used = FALSE OR risk_level > 3)",
+           ["user_id", "sudo_used", "risk_level"], 9),
+    "QS": ('SELECT command_id FROM Commands WHERE (user_id < {X}) AND (shell_type = "bash" OR host_name = "labpc-01")',
+           ["user_id", "shell_type", "host_name"], 36),
+    "QD": ('SELECT command_id FROM Commands WHERE (user_id < {X}) AND (risk_level >= 2 OR exit_code != 0) AND '
+           '(command_id < 4000000000 OR shell_type != "sh")',
+           ["user_id", "risk_level", "exit_code", "command_id", "shell_type"], 36),
+}
 ALL_COLUMNS = ["command_id", "raw_command", "base_command", "shell_type", "exit_code", "timestamp", "sudo_used",
                "working_directory", "user_id", "user_name", "host_name", "risk_level"]
+
+
+def sample_queries():
+    """(text of the reference's sample-queries.txt, its SELECT statements) -- tests/support.py carries the reference's
+    sample-queries-FULL.txt verbatim; sample-queries.txt is that file without Sample 6 (the DELETE)"""
+    import support
+    text = support.SAMPLE_QUERIES_FULL.replace(
+        "# -- Sample 6:\nDELETE FROM Commands WHERE command_id = 999999;\n\n", "")
+    stmts = [" ".join(x.split()) for x in re.sub(r"#[^\n]*", "", text).split(";")]
+    return text, [x for x in stmts if x.upper().startswith("SELECT")]
 
 
 _REAL_STDOUT = None
@@ -64,6 +97,11 @@ def emit(line):
     f = _REAL_STDOUT or sys.stdout
     f.write(line + "\n")
     f.flush()
+
+
+def log(msg):
+    sys.stderr.write(msg + "\n")
+    sys.stderr.flush()
 
 
 def parse_args():
@@ -77,11 +115,11 @@ def parse_args():
     ap.add_argument("--selectivity", type=float, default=0.01)
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="native", choices=["native", "peer", "nccl"],
-                    help="N > 1: 'native' = csrc/shard.cu: ids stored into rank 0's buffer by the scan kernel over "
-                         "NVLink peer memory, counts exchanged by kernel stores, no host collective per query; "
-                         "'peer' = same stores, count exchange through an NCCL all-gather; 'nccl' = compact "
-                         "locally, then grouped NCCL send/recv")
+    ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the `extra` object (configs[2], [3], API)")
+    ap.add_argument("--extra-rows", type=float, default=1e8, help="rows of the `extra` sweeps / probe index")
+    ap.add_argument("--only-extra", action="store_true", help="development: print only the `extra` object")
+    ap.add_argument("--host-mode", type=int, default=1, choices=[1, 2],
+                    help="N > 1 host result: 1 = staging + copy engine, 2 = the kernel stores into host memory")
     return ap.parse_args()
 
 
@@ -144,13 +182,6 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-class DevArray:
-    """device pointer -> torch tensor (zero copy) through __cuda_array_interface__"""
-
-    def __init__(self, ptr, n, typestr="<i4"):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 def shard_of(total, world, rank):
     """contiguous row ranges, the reference's MPI rule: base = N / G, the first N % G ranks get one more"""
     base, rem = divmod(total, world)
@@ -160,21 +191,44 @@ def shard_of(total, world, rank):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU baseline: the compiled reference's linearSearchRecords on a bounded sample
+# CPU side: sample CSVs and the reference's engines (oracle/_ref, compiled unmodified)
 # ---------------------------------------------------------------------------------------------
+def fixture_csv(rows, path):
+    """A `rows`-row CSV made from the committed generator fixture (tests/golden/commands_2k.csv: 2 000 rows of the
+    reference's own generate_commands.py): its rows repeated with command_id renumbered 1..rows.  Needs nothing of
+    this repo's product (the reference arm must not load libqpegpu.so)."""
+    src = os.path.join(ROOT, "tests", "golden", "commands_2k.csv")
+    with open(src, newline="") as f:
+        lines = f.read().split("\r\n")
+    if len(lines) < 3:   # \n line ends
+        with open(src) as f:
+            lines = f.read().split("\n")
+    header, body = lines[0], [ln for ln in lines[1:] if ln]
+    tails = [ln[ln.index(","):] for ln in body]   # everything after command_id
+    with open(path, "w", newline="") as out:
+        out.write(header + "\r\n")
+        k = 0
+        chunk = []
+        for i in range(rows):
+            chunk.append(f"{i + 1}{tails[k]}")
+            k = k + 1 if k + 1 < len(tails) else 0
+            if len(chunk) == 65536:
+                out.write("\r\n".join(chunk) + "\r\n")
+                chunk = []
+        if chunk:
+            out.write("\r\n".join(chunk) + "\r\n")
+    return path
+
+
 def make_sample_csv(pkg, rows, path):
     eng = pkg.Engine.from_synth(rows, columns=ALL_COLUMNS)
     eng.write_csv(path)
     eng.close()
 
 
-def cpu_baseline(pkg, args, sql_template, target_s=10.0):
+def cpu_baseline(csv, rows, args, sql_template, target_s=10.0):
     import support
-    rows = args.cpu_sample_rows
     sql = sql_template.format(K=max(1, int(rows * args.selectivity)))
-    d = tempfile.mkdtemp(prefix="qpe_cpu_")
-    csv = os.path.join(d, "sample.csv")
-    make_sample_csv(pkg, rows, csv)
     if support.Ref.available():
         ref = support.Ref(csv, num_indexes=0)
         m = C.c_int()
@@ -196,6 +250,53 @@ def cpu_baseline(pkg, args, sql_template, target_s=10.0):
     t = time.perf_counter() - t0
     return {"value": rows * reps / t, "unit": "rows/s", "cores": 1, "kind": "port",
             "sample": f"{rows}-row CSV, oracle port of linearSearchRecords x{reps} ({t:.1f} s), {m} matches/scan"}
+
+
+def _banner(text):
+    vals = {}
+    for key in ("Engine Initialization Time", "Query Execution Time", "Total Execution Time"):
+        m = re.search(key + r"[^0-9]*([0-9.]+) seconds", text)
+        if m:
+            vals[key] = float(m.group(1))
+    return vals
+
+
+def run_cpu_driver(binary, csv, threads=None, timeout=600):
+    """One run of a reference driver (QPESeq / QPEOMP) over sample-queries.txt on a private copy of `csv`."""
+    import support
+    exe = os.path.join(support.REF_DIR, binary)
+    if not os.path.exists(exe):
+        return None
+    wd = tempfile.mkdtemp(prefix="qpe_drv_")
+    try:
+        open(os.path.join(wd, "sample-queries.txt"), "w").write(sample_queries()[0])
+        data = os.path.join(wd, "data.csv")
+        shutil.copyfile(csv, data)
+        cmd = [exe, data] + ([str(threads)] if threads else [])
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, cwd=wd, capture_output=True, timeout=timeout)
+        wall = time.perf_counter() - t0
+        text = r.stdout.decode(errors="replace")
+        return {"rc": r.returncode, "wall_s": wall, "banner": _banner(text)}
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
+def cpu_baseline_omp(csv, rows):
+    """QPEOMP (the reference's OpenMP driver + engine, unmodified) over sample-queries.txt with every host thread,
+    wall-clocked, next to QPESeq on the same file: what north_star asks to be reported beside the GPU numbers."""
+    cores = os.cpu_count() or 1
+    omp = run_cpu_driver("QPEOMP", csv, threads=cores)
+    seq = run_cpu_driver("QPESeq", csv)
+    if omp is None:
+        return {"value": None, "unit": "s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/QPEOMP was not built"}
+    q_omp = omp["banner"].get("Query Execution Time")
+    return {"value": omp["wall_s"], "unit": "s (whole run incl. ingest and index builds)", "cores": cores,
+            "kind": "reference", "query_phase_s": q_omp, "rc": omp["rc"],
+            "qpeseq_wall_s": seq["wall_s"] if seq else None,
+            "qpeseq_query_phase_s": seq["banner"].get("Query Execution Time") if seq else None,
+            "sample": f"{rows}-row CSV, the reference's sample-queries.txt (6 SELECTs + 1 INSERT), thread count argv = {cores}; "
+                      f"its scan loop (linearSearchRecords) is serial, only queries / per-index probes run in parallel"}
 
 
 def _ref_worker(conn, csv, sql):
@@ -222,13 +323,11 @@ def run_reference(args):
     if not support.Ref.available():
         emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libqpe_ref.so was not built"}))
         return 0
-    pkg = support.load_pkg()
     sql_t, cols, bpr = QUERIES[args.query]
     rows = 250_000
     sql = sql_t.format(K=max(1, int(rows * args.selectivity)))
     d = tempfile.mkdtemp(prefix="qpe_ref_")
-    csv = os.path.join(d, "sample.csv")
-    make_sample_csv(pkg, rows, csv)
+    csv = fixture_csv(rows, os.path.join(d, "sample.csv"))
     procs = max(1, min(os.cpu_count() or 1, 64))
     ctx = mp.get_context("spawn")
     workers = []
@@ -258,6 +357,7 @@ def run_reference(args):
         a.send("stop")
     for p, _ in workers:
         p.join(timeout=10)
+    shutil.rmtree(d, ignore_errors=True)
     value = procs * rows * args.steps / dt
     emit(json.dumps({
         "impl": "reference", "metric": "select_where_rows_per_s", "value": value, "unit": "rows/s",
@@ -265,7 +365,8 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": f"{args.query} full-scan SELECT/WHERE, {args.selectivity:g} selectivity, "
                                f"reference serial engine (linearSearchRecords) x {procs} processes, "
-                               f"{rows}-row sample per process per step", "query": sql, "rows_per_step": procs * rows},
+                               f"{rows}-row sample per process per step (rows of the reference generator's fixture)",
+                   "query": sql, "rows_per_step": procs * rows},
         "scan_gbs": value * bpr / 1e9,
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": procs, "kind": "reference",
                          "sample": f"{procs} processes x {rows} rows x {args.steps} steps, {matches} matches/scan"},
@@ -273,6 +374,182 @@ def run_reference(args):
         "gpu_launches": 0,
     }))
     return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# `extra` (N = 1): BASELINE configs[2] and [3], the drop-in API end to end, index-path latencies
+# ---------------------------------------------------------------------------------------------
+def best_scan(eng, sql, reps=4):
+    best = None
+    for _ in range(reps):
+        _, _, st = eng.select_ids_device(sql, force_scan=True)
+        if best is None or st["kernel_ms"] < best["kernel_ms"]:
+            best = st
+    return best
+
+
+def extra_sweep(pkg, rows, peak):
+    """configs[2]: 100 M-row table, QN / QS / QD at 0.01 %, 1 %, 50 %, matches clustered (command_id bound) and
+    uniform (user_id bound); per point K1f's CUDA-event time (best of 4) -> algorithmic GB/s and the fraction of the
+    measured copy peak."""
+    import numpy as np
+    cols = sorted({c for q in list(QUERIES.values()) + list(UNIFORM.values()) for c in q[1]})
+    eng = pkg.Engine.from_synth(rows, columns=cols)
+    # user_id bounds for the uniform variants: quantiles of the column itself (first 4 M rows)
+    uid = np.sort(eng.fetch_column("user_id", 0, min(rows, 4_000_000)))
+    out = []
+    for sel in (0.0001, 0.01, 0.5):
+        for name in ("QN", "QS", "QD"):
+            for kind, (tmpl, _, bpr) in (("clustered", QUERIES[name]), ("uniform", UNIFORM[name])):
+                if kind == "clustered":
+                    sql = tmpl.format(K=max(1, int(rows * sel)))
+                else:
+                    sql = tmpl.format(X=int(uid[min(len(uid) - 1, int(len(uid) * sel))]) + 1)
+                st = best_scan(eng, sql)
+                gbs = st["algo_bytes"] / st["kernel_ms"] / 1e6
+                out.append({"query": name, "matches": kind, "target_selectivity": sel,
+                            "selectivity": st["matches"] / rows, "bytes_per_row": bpr, "kernel_ms": round(st["kernel_ms"], 4),
+                            "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4),
+                            "grows_per_s": round(rows / st["kernel_ms"] / 1e6, 2),
+                            "tile": f"{st['tile_rows']}x{st['stages']}"})
+    eng.close()
+    return {"rows": rows, "kernel": "scan_fused_kernel (K1f), CUDA events on the engine's stream, best of 4",
+            "peak_gbs": peak, "points": out}
+
+
+def extra_probe(pkg, rows, n_probes=1_000_000):
+    """configs[3]: 1 M point / range probes over the 100 M-key command_id (unique u64) and user_id (int, heavy
+    duplicates) indexes: kernel-only (device buffers), end to end with pinned host buffers, with the batch sorted
+    first, and the reference's findRange on a bounded sample."""
+    import numpy as np
+    import support
+    eng = pkg.Engine.from_synth(rows, columns=["command_id", "user_id"], indexes=(("command_id", 0), ("user_id", 1)))
+    rng = np.random.default_rng(12345)
+    out = {"rows": rows, "probes": n_probes, "cases": []}
+    for attr, dtype, keys in (("command_id", np.uint64, rng.integers(0, int(rows * 1.1), n_probes, dtype=np.uint64)),
+                              ("user_id", np.int32, rng.integers(900, 3100, n_probes).astype(np.int32))):
+        lo = pkg.pinned_array(n_probes, dtype)
+        hi = pkg.pinned_array(n_probes, dtype)
+        first = pkg.pinned_array(n_probes, np.uint32)
+        count = pkg.pinned_array(n_probes, np.uint32)
+        for width in (1, 256):
+            lo[:] = keys
+            hi[:] = keys + dtype(width - 1)
+            d_lo, d_hi = pkg.DeviceBuffer(lo.nbytes), pkg.DeviceBuffer(hi.nbytes)
+            d_first, d_count = pkg.DeviceBuffer(4 * n_probes), pkg.DeviceBuffer(4 * n_probes)
+            pkg.load_library().qpe_gpu_copy_to_device(d_lo.ptr, lo.ctypes.data, lo.nbytes)
+            pkg.load_library().qpe_gpu_copy_to_device(d_hi.ptr, hi.ctypes.data, hi.nbytes)
+            case = {"index": attr, "range_width": width}
+            for label, kw, bufs in (("kernel", {}, (d_lo, d_hi, d_first, d_count)),
+                                    ("kernel_sorted", {"sort": True}, (d_lo, d_hi, d_first, d_count)),
+                                    ("e2e_host", {}, (lo, hi, first, count)),
+                                    ("e2e_host_sorted", {"sort": True}, (lo, hi, first, count))):
+                best_dev, best_wall = None, None
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    _, _, st = eng.probe_keys(attr, bufs[0], bufs[1], first=bufs[2], count=bufs[3], **kw)
+                    wall = (time.perf_counter() - t0) * 1e3
+                    best_dev = st["kernel_ms"] if best_dev is None else min(best_dev, st["kernel_ms"])
+                    best_wall = wall if best_wall is None else min(best_wall, wall)
+                case[label] = {"device_ms": round(best_dev, 4), "wall_ms": round(best_wall, 4),
+                               "gprobes_per_s": round(n_probes / (best_dev if label.startswith("kernel") else best_wall) / 1e6, 3)}
+            case["found_rows"] = int(count.astype(np.int64).sum())
+            # unsorted and sorted answers agree
+            f2, c2, _ = eng.probe_keys(attr, lo, hi, sort=True)
+            case["sorted_equals_unsorted"] = bool(np.array_equal(f2, first) and np.array_equal(c2, count))
+            out["cases"].append(case)
+            for b in (d_lo, d_hi, d_first, d_count):
+                b.free()
+    # a parity sample at full size: the row ids of a few answers against a closed form (command_id == row id)
+    f, c, _ = eng.probe_keys("command_id", np.array([5, rows - 1, rows + 7], dtype=np.uint64))
+    ids = [eng.index_slice("command_id", int(a), int(b)).tolist() for a, b in zip(f, c)]
+    out["parity_sample"] = {"keys": [5, rows - 1, rows + 7], "row_ids": ids, "ok": ids == [[5], [rows - 1], []]}
+    eng.close()
+    # CPU: the reference's findRange on a bounded sample (it walks the leaf chain to its end: O(N) per probe)
+    try:
+        if support.Ref.available():
+            d = tempfile.mkdtemp(prefix="qpe_probe_")
+            csv = fixture_csv(200_000, os.path.join(d, "p.csv"))
+            ref = support.Ref(csv, indexes=[("command_id", 0)])
+            lib = ref.lib()
+            lib.ref_time_probe.restype = C.c_double
+            lib.ref_time_probe.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
+            n = 200
+            k = rng.integers(1, 200_000, n, dtype=np.uint64)
+            found = C.c_longlong()
+            t = lib.ref_time_probe(ref.h, 0, k.ctypes.data, k.ctypes.data, n, C.byref(found))
+            ref.close()
+            shutil.rmtree(d, ignore_errors=True)
+            out["cpu_findRange"] = {"probes_per_s": n / t, "cores": 1, "kind": "reference",
+                                    "sample": f"{n} point probes on a 200 000-key ORDER-3 B+ tree (engine/bplus.c findRange), "
+                                              f"{found.value} rows found, {t:.2f} s"}
+    except Exception as e:   # reported, never required
+        out["cpu_findRange"] = {"probes_per_s": None, "sample": f"failed: {e}"}
+    return out
+
+
+def extra_api(pkg, rows=1_000_000):
+    """The reference's actual entry point end to end: executeQuerySelectGPU -> resultSetS -> freeResultSet for the
+    SELECTs of the reference's sample-queries.txt on a `rows`-row CSV, next to executeQuerySelectSerial +
+    freeResultSet on the same file (oracle/_ref harness).  Samples 2, 3, 4, 8 take the index path (K3 + K1g), Samples 1
+    and 7 the scan path (K1f); projection = K7 + K2."""
+    import support
+    d = tempfile.mkdtemp(prefix="qpe_api_")
+    csv = os.path.join(d, "api.csv")
+    make_sample_csv(pkg, rows, csv)
+    out = {"rows": rows, "queries": []}
+    try:
+        t0 = time.perf_counter()
+        eng = pkg.Engine.from_csv(csv)
+        out["gpu_init_s"] = round(time.perf_counter() - t0, 3)
+        ref = None
+        if support.Ref.available():
+            t0 = time.perf_counter()
+            ref = support.Ref(csv)
+            out["ref_init_s"] = round(time.perf_counter() - t0, 3)
+        stmts = sample_queries()[1]
+        names = [1, 2, 3, 4, 7, 8]
+        for k, sql in enumerate(stmts):
+            eng.select_result_time(sql)   # warm-up (pinned result pool, index build)
+            reps = 3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                n_rows = eng.select_result_time(sql)
+            gpu_ms = (time.perf_counter() - t0) * 1e3 / reps
+            ids, st = eng.select_ids(sql)
+            q = {"sample": names[k] if k < len(names) else k + 1, "rows": n_rows, "path": "index" if st["path"] == 1 else "scan",
+                 "gpu_api_ms": round(gpu_ms, 3), "gpu_match_kernel_ms": round(st["kernel_ms"], 4)}
+            if ref is not None:
+                m = C.c_int()
+                t = ref.lib().ref_time_select(ref.h, sql.encode(), 1, C.byref(m))
+                q["ref_api_ms"] = round(t * 1e3, 3)
+                q["rows_equal"] = (m.value == n_rows)
+                q["speedup"] = round(t * 1e3 / gpu_ms, 1)
+            out["queries"].append(q)
+        eng.close()
+        if ref is not None:
+            ref.close()
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    return out
+
+
+def build_extra(pkg, args, peak):
+    extra = {}
+    rows = int(args.extra_rows)
+    for name, fn in (("sweep_100m", lambda: extra_sweep(pkg, rows, peak)),
+                     ("probe_100m", lambda: extra_probe(pkg, rows)),
+                     ("api_1m", lambda: extra_api(pkg))):
+        t0 = time.perf_counter()
+        try:
+            extra[name] = fn()
+        except Exception as e:   # reported, never required for the headline line
+            import traceback
+            log(traceback.format_exc())
+            extra[name] = {"failed": f"{type(e).__name__}: {e}"}
+        extra[name]["wall_s"] = round(time.perf_counter() - t0, 2)
+        log(f"[extra] {name}: {extra[name]['wall_s']} s")
+    return extra
 
 
 # ---------------------------------------------------------------------------------------------
@@ -295,191 +572,251 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     pkg = support.load_pkg()
+    if args.only_extra:
+        emit(json.dumps({"extra": build_extra(pkg, args, peaks()[0])}))
+        return 0
     total = int(args.rows)
     start, n_local = shard_of(total, world, rank)
     sql_t, cols, bpr = QUERIES[args.query]
     sql = sql_t.format(K=max(1, int(total * args.selectivity)))
+    usql_t, ucols, ubpr = UNIFORM[args.query]
+    all_cols = sorted(set(cols) | (set(ucols) if world > 1 else set()))
     t0 = time.perf_counter()
-    eng = pkg.Engine.from_synth(total, n_rows=n_local, row_base=start, columns=cols)
+    eng = pkg.Engine.from_synth(total, n_rows=n_local, row_base=start, columns=all_cols)
     t_gen = time.perf_counter() - t0
-
-    # result buffers: device buffer on rank 0 for the gathered ids, pinned host buffer for e2e
-    from importlib import import_module
-    sharding = import_module("pqps_b200.sharding")
-    cnt0, _, _ = eng.select_ids_device(sql, force_scan=True)
-    if world > 1:
-        total_matches = sum(sharding.exchange_counts(cnt0, dev))
-    else:
-        total_matches = cnt0
-    use_peer = world > 1 and args.gather == "peer"
-    use_native = world > 1 and args.gather == "native"
-    if world > 1:
-        seg_cap = int(max(sharding.exchange_counts(cnt0, dev)) * 1.25) + 4096
-    pg = sharding.PeerGather(pkg, segment_capacity=seg_cap, counts_device=dev) if use_peer else None
-    sg = (sharding.ShardGroup(pkg, eng, segment_capacity=seg_cap, host_capacity=total_matches + 4096,
-                              counts_device=dev) if use_native else None)
-    gathered = (torch.empty(max(total_matches, 1), dtype=torch.int32, device=dev)
-                if (rank == 0 and world > 1 and not use_peer) else None)
-    pinned = torch.empty(max(total_matches, 1), dtype=torch.int32).pin_memory() if rank == 0 else None
-    pinned_np = pinned.numpy().view(np.uint32) if rank == 0 else None
-    launches = [0]
-    scan_ms, compact_ms, kernel_ms, traces = [], [], [], []
     eng_stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+    steps, warmup = args.steps, max(args.warmup, 3)
+    peak, peak_src = peaks()
 
-    def step_device(record=False, pack="device"):
-        """scan + ordered compaction on every GPU, count exchange, ordered gather to rank 0 (device).
-        record=False: no statistics asked for (the engine's CUDA events stay unresolved and are summed after the
-        loop: Engine.timing_totals); record="trace": host-side breakdown of the call (diagnostic pass)."""
-        want = bool(record)
-        if use_native:
-            total_n, counts, st = sg.select(sql, to_host=(pack == "host"), stats=want)
-            n_launch = st.launches if want else 0
-        elif use_peer:
-            total_n, counts, st = pg.run(eng, sql, dev, pack=pack, host_out=pinned_np)
-            n_launch = st["launches"]
-        else:
-            cnt, dptr, st = eng.select_ids_device(sql, force_scan=True, global_ids=(world > 1), stats=want or world > 1)
-            total_n = cnt
-            n_launch = st["launches"] if st else 0
-            if world > 1:
-                mine = torch.as_tensor(DevArray(dptr, max(cnt, 1)), device=dev)[:cnt]
-                total_n, counts, _ = sharding.ordered_gather(mine, gathered)
-        if want:
-            launches[0] = n_launch      # kernels per step (the same every step)
-        if record == "trace":
-            traces.append(eng.last_trace())
-        return total_n
-
-    def step_e2e():
-        """host-facing call: SQL text in host memory -> row ids in pinned host memory"""
-        if world == 1:
-            n, _ = eng.select_ids_into(sql, pinned_np, force_scan=True, stats=False)
-            return n
-        n = step_device(pack="host")
-        if rank == 0:
-            if use_peer or use_native:
-                pass  # peer: the owner copied every segment straight into the pinned host buffer;
-                      # native: every rank delivered its piece into the shared pinned buffer over its own PCIe link
-            else:
-                pinned[:n].copy_(gathered[:n], non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-        return n
-
-    def timed(fn, steps, sampler=None, **kw):
+    def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(loop, n_steps, sampler=None):
+        """time `loop(n_steps)` (which runs exactly n_steps queries): CUDA events on the engine's stream and the
+        host clock, max over ranks; per step"""
+        sync_all()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if sampler:
             sampler.start()
-        t0 = time.perf_counter()
+        t_0 = time.perf_counter()
         ev0.record(eng_stream)      # the engine launches on its own stream: time THERE
-        n = 0
-        for _ in range(steps):
-            n = fn(**kw)
+        n = loop(n_steps)
         ev1.record(eng_stream)
         torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
+        wall = time.perf_counter() - t_0
         clocks = sampler.stop() if sampler else None
         if world > 1:
             dist.barrier()
-        ms = max(ev0.elapsed_time(ev1), 0.0)
-        ms = max(ms, 0.0)
-        t = torch.tensor([ms, wall * 1000.0], dtype=torch.float64, device=dev)
+        t = torch.tensor([max(ev0.elapsed_time(ev1), 0.0), wall * 1000.0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t[0].item() / steps, t[1].item() / steps, n, clocks
+        return max(t[0].item(), t[1].item()) / n_steps, n, clocks
 
-    for _ in range(max(args.warmup, 3)):
-        step_device(record=True)
-        step_e2e()
-    sampler = ClockSampler(local_rank)
-    eng.set_timing(True)   # sum the CUDA-event times of every call of the timed loop, resolved after it
-    ms_step, wall_step, n_matches, clocks = timed(step_device, args.steps, sampler)
-    tot = eng.timing_totals()
-    eng.set_timing(False)
-    assert tot["calls"] == args.steps, tot
-    scan_ms.append(tot["scan_ms"] / tot["calls"])
-    compact_ms.append(tot["compact_ms"] / tot["calls"])
-    gpu_launches = launches[0] * args.steps
-    for _ in range(10):  # diagnostic pass (not timed): where a step's time goes inside the call
-        step_device(record="trace")
-    tr = [statistics.mean(x[k] for x in traces) for k in range(6)]
-    sys.stderr.write(f"[rank {rank}] per step: wall {wall_step:.4f} ms, device events {ms_step:.4f} ms; inside the call: "
-                     f"compile {tr[0]:.4f}, enqueue {tr[1]:.4f}, sync {tr[2]:.4f}, tail {tr[4]:.4f}, whole call {tr[5]:.4f} ms; device: K1f "
-                     f"{statistics.mean(scan_ms):.4f}, post-scan kernel {tot['post_ms'] / tot['calls']:.4f} ms "
-                     f"(means over the timed loop)\n")
-    ms_e2e, wall_e2e, n_e2e, _ = timed(step_e2e, args.steps)
-    assert n_e2e == n_matches
+    out = None
+    if world == 1:
+        # ---- one GPU: the plain engine API ----
+        cnt0, _, st0 = eng.select_ids_device(sql, force_scan=True)
+        pinned = torch.empty(max(cnt0, 1), dtype=torch.int32).pin_memory()
+        pinned_np = pinned.numpy().view(np.uint32)
 
-    # roofline of the dominant kernel: algorithmic bytes of a rank's shard / the kernel's own event time
-    # (max over ranks).  Fused scan (default): one kernel, K1f, reads the columns and writes the ids.
-    k1_ms = statistics.mean(scan_ms)
-    kc_ms = statistics.mean(compact_ms)
-    t = torch.tensor([k1_ms, kc_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    k1_ms, kc_ms = t[0].item(), t[1].item()
-    peak, peak_src = peaks()
+        def loop_device(n):
+            m = 0
+            for _ in range(n):
+                m, _, _ = eng.select_ids_device(sql, force_scan=True, stats=False)
+            return m
+
+        def loop_e2e(n):
+            m = 0
+            for _ in range(n):
+                m, _ = eng.select_ids_into(sql, pinned_np, force_scan=True, stats=False)
+            return m
+
+        loop_device(warmup)
+        loop_e2e(warmup)
+        eng.set_timing(True)
+        ms_step, n_matches, clocks = timed(loop_device, steps, ClockSampler(local_rank))
+        tot = eng.timing_totals()
+        eng.set_timing(False)
+        assert tot["calls"] == steps, tot
+        k1_ms = tot["scan_ms"] / tot["calls"]
+        ms_e2e, n_e2e, _ = timed(loop_e2e, steps)
+        assert n_e2e == n_matches
+        launches = st0["launches"]
+        sync_info = {}
+        uniform = None
+    else:
+        # ---- N GPUs: csrc/shard.cu, two queries in flight ----
+        from importlib import import_module
+        sharding = import_module("pqps_b200.sharding")
+        usql = None
+        cnt0, _, _ = eng.select_ids_device(sql, force_scan=True)
+        counts0 = sharding.exchange_counts(cnt0, dev)
+        # uniform query: user_id bound at the selectivity's quantile of this shard's first rows (same on every rank: rank 0's)
+        uid = np.sort(eng.fetch_column("user_id", 0, min(n_local, 2_000_000)))
+        x = [int(uid[min(len(uid) - 1, int(len(uid) * args.selectivity))])]
+        dist.broadcast_object_list(x, src=0)
+        usql = usql_t.format(X=x[0])
+        ucnt0, _, _ = eng.select_ids_device(usql, force_scan=True)
+        ucounts0 = sharding.exchange_counts(ucnt0, dev)
+        seg_cap = int(max(max(counts0), max(ucounts0)) * 1.25) + 4096
+        host_cap = max(sum(counts0), sum(ucounts0)) + 4096
+        sg = sharding.ShardGroup(pkg, eng, segment_capacity=seg_cap, host_capacity=host_cap, counts_device=dev)
+        sg.set_multipath(args.host_mode)
+
+        def make_loops(statement):
+            def piped(to_host):
+                def loop(n):
+                    sg.submit(statement, to_host)
+                    m = 0
+                    for i in range(n):
+                        if i + 1 < n:
+                            sg.submit(statement, to_host)   # query i + 1 is in flight while query i is waited for
+                        m = sg.wait(stats=False)[0]
+                    return m
+                return loop
+
+            def synced(to_host):
+                def loop(n):
+                    m = 0
+                    for _ in range(n):
+                        m = sg.select(statement, to_host=to_host, stats=False)[0]
+                    return m
+                return loop
+            return piped, synced
+
+        piped, synced = make_loops(sql)
+        _, _, st0 = sg.select(sql, to_host=False, stats=True)
+        launches = st0.launches
+        for to_host in (False, True):
+            piped(to_host)(warmup)
+        eng.set_timing(True)
+        ms_step, n_matches, clocks = timed(piped(False), steps, ClockSampler(local_rank))
+        tot = eng.timing_totals()
+        eng.set_timing(False)
+        assert tot["calls"] == steps, tot
+        k1 = torch.tensor([tot["scan_ms"] / tot["calls"], tot["post_ms"] / tot["calls"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(k1, op=dist.ReduceOp.MAX)
+        k1_ms, post_ms = k1[0].item(), k1[1].item()
+        ms_e2e, n_e2e, _ = timed(piped(True), steps)
+        assert n_e2e == n_matches
+        if rank == 0:   # the delivered ids are the packed device result, bit for bit
+            host_ids = sg.host_result(n_e2e).copy()
+        sg.select(sql, to_host=False, stats=False)
+        if rank == 0:
+            assert np.array_equal(host_ids, sg.device_result(n_matches)), "host result differs from the device result"
+        ms_sync, _, _ = timed(synced(False), steps)
+        ms_e2e_sync, _, _ = timed(synced(True), steps)
+        sync_info = {"sync_ms_per_step": ms_sync, "sync_value": total / (ms_sync * 1e-3),
+                     "e2e_sync_ms_per_step": ms_e2e_sync, "e2e_sync_value": total / (ms_e2e_sync * 1e-3),
+                     "post_scan_kernel_ms": post_ms}
+        # the same with matches spread evenly over the shards: every rank's own ids go out over its own link
+        upiped, _ = make_loops(usql)
+        for to_host in (False, True):
+            upiped(to_host)(warmup)
+        u_ms, u_matches, _ = timed(upiped(False), steps)
+        u_e2e_ms, u_e2e_n, _ = timed(upiped(True), steps)
+        assert u_e2e_n == u_matches
+        uniform = {"query": usql, "bytes_per_row": ubpr, "matches": int(u_matches),
+                   "matches_per_rank": [int(c) for c in sharding.exchange_counts(ucnt0, dev)],
+                   "value": total / (u_ms * 1e-3), "ms_per_step": u_ms,
+                   "e2e": {"value": total / (u_e2e_ms * 1e-3), "ms_per_step": u_e2e_ms, "unit": "rows/s",
+                           "d2h_bytes_per_step": int(4 * u_matches + 8 * world)}}
+        # device -> host rate of one link, every rank at the same time: this rank's 1/world of QN's ids from its HBM
+        # into its part of the shared host buffer (what a delivery moves per query)
+        slice_bytes = 4 * (n_matches // world)
+        link = None
+        if slice_bytes > 0:
+            src = pkg.DeviceBuffer(slice_bytes)
+            dst_ptr = pkg.load_library().qpe_shard_host_result(eng._h) + 4 * (n_matches * rank // world)
+            lib = pkg.load_library()
+            lib.qpe_gpu_copy_to_host(dst_ptr, src.ptr, slice_bytes)
+            sync_all()
+            t_0 = time.perf_counter()
+            for _ in range(10):
+                lib.qpe_gpu_copy_to_host(dst_ptr, src.ptr, slice_bytes)
+            gbs = 10 * slice_bytes / (time.perf_counter() - t_0) / 1e9
+            src.free()
+            g = torch.tensor([gbs], dtype=torch.float64, device=dev)
+            every = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(every, g)
+            link = {"d2h_gbs_per_link": [round(v.item(), 1) for v in every], "bytes_per_copy": slice_bytes,
+                    "how": "blocking cudaMemcpy of this rank's slice into its part of the shared host buffer, x10, all ranks at once"}
+        sync_info["link"] = link
+
+    # roofline of the dominant kernel: algorithmic bytes of a rank's shard / the kernel's own event time (max over ranks)
     shard_rows = shard_of(total, world, 0)[1]
-    fused = kc_ms == 0.0
-    algo_bytes = shard_rows * bpr + (4 * n_matches // world if fused else 0)
+    algo_bytes = shard_rows * bpr + 4 * n_matches // world
     achieved = algo_bytes / (k1_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            if tj.get("query") == args.query and tj.get("rows") and tj.get("fused", False) == fused:
+            if tj.get("query") == args.query and tj.get("rows"):
                 traffic = tj["dram_bytes_per_launch"] * (shard_rows / tj["rows"])
         except Exception:
             pass
 
     if rank == 0:
-        step_s = max(ms_step, wall_step) * 1e-3  # device events and host clock agree; keep the larger
-        e2e_s = max(ms_e2e, wall_e2e) * 1e-3
+        st = eng.last_stats()
         out = {
-            "metric": "select_where_rows_per_s", "value": total / step_s, "unit": "rows/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3,
+            "metric": "select_where_rows_per_s", "value": total / (ms_step * 1e-3), "unit": "rows/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"synthetic {total}-row command-log table (device generator, seed 12345), "
                                    f"row-range sharded over {world} GPU(s)"
-                                   + (", ordered gather = " + {"native": "scan kernel stores into rank 0 over NVLink peer memory, "
-                                                                       "counts exchanged by kernel stores (no host "
-                                                                       "collective per query)",
-                                                             "peer": "K1c stores into rank 0 over NVLink peer memory, "
-                                                                     "NCCL count all-gather",
-                                                             "nccl": "NCCL send/recv"}[args.gather]
-                                      if world > 1 else "")
+                                   + (", ordered gather by kernels over NVLink peer memory (csrc/shard.cu): ids stored into "
+                                      "rank 0's result by the scan kernel, counts exchanged by kernel stores, no host "
+                                      "collective per query; two queries in flight per rank" if world > 1 else "")
                                    + f"; {args.query} full-scan SELECT/WHERE, "
                                    f"{args.selectivity:g} selectivity; inputs ({shard_rows * bpr / 1e9:.1f} GB/GPU) "
                                    f"larger than L2, no flush needed",
                        "rows": total, "rows_per_gpu": shard_rows, "query": sql, "bytes_per_row": bpr,
-                       "matches": int(n_matches), "tile_rows": eng.last_stats()["tile_rows"],
-                       "stages": eng.last_stats()["stages"], "generate_s": round(t_gen, 2)},
-            "scan_gbs": (total * bpr + 4 * n_matches) / step_s / 1e9,
+                       "matches": int(n_matches), "tile_rows": st["tile_rows"], "stages": st["stages"],
+                       "queue_depth": 2 if world > 1 else 1, "generate_s": round(t_gen, 2)},
+            "scan_gbs": (total * bpr + 4 * n_matches) / (ms_step * 1e-3) / 1e9,
             "clocks": clocks,
-            "e2e": {"value": total / e2e_s, "unit": "rows/s", "ms_per_step": e2e_s * 1e3,
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "rows/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(pkg.load_library().qpe_gpu_query_upload_bytes()) * world,
                     "d2h_bytes_per_step": int(4 * n_matches + 8 * world)},
-            "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "hbm", "kernel": "scan_fused_kernel (K1f)" if fused else "scan_tma_kernel (K1)",
-                         "achieved": achieved, "peak": peak,
+            "gpu_launches": int(launches * steps),
+            "roofline": {"bound": "hbm", "kernel": "scan_fused_kernel (K1f)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "k1_ms": k1_ms, "k1c_ms": kc_ms, "algorithmic_bytes_per_launch": algo_bytes},
+                         "k1_ms": k1_ms, "algorithmic_bytes_per_launch": algo_bytes},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                out["cpu_baseline"] = cpu_baseline(pkg, args, sql_t)
-            except Exception as e:  # the baseline is reported, never required
-                out["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": 1, "kind": "reference",
-                                       "sample": f"failed: {e}"}
-        emit(json.dumps(out))
-    if pg is not None:
-        pg.close()
-    if sg is not None:
+        if world > 1:
+            out["e2e"]["sync_value"] = sync_info.pop("e2e_sync_value")
+            out["e2e"]["sync_ms_per_step"] = sync_info.pop("e2e_sync_ms_per_step")
+            out["e2e"]["host_mode"] = args.host_mode
+            out.update(sync_info)
+            out["uniform"] = uniform
+    if world > 1:
         sg.close()
     eng.close()
+    if rank == 0 and world == 1:
+        if not args.no_cpu_baseline:
+            d = tempfile.mkdtemp(prefix="qpe_cpu_")
+            try:
+                csv = os.path.join(d, "sample.csv")
+                make_sample_csv(pkg, args.cpu_sample_rows, csv)
+                try:
+                    out["cpu_baseline"] = cpu_baseline(csv, args.cpu_sample_rows, args, sql_t)
+                except Exception as e:  # the baseline is reported, never required
+                    out["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": 1, "kind": "reference",
+                                           "sample": f"failed: {e}"}
+                try:
+                    out["cpu_baseline_omp"] = cpu_baseline_omp(csv, args.cpu_sample_rows)
+                except Exception as e:
+                    out["cpu_baseline_omp"] = {"value": None, "unit": "s", "cores": os.cpu_count(), "kind": "reference",
+                                               "sample": f"failed: {e}"}
+            finally:
+                shutil.rmtree(d, ignore_errors=True)
+        if not args.no_extra:
+            out["extra"] = build_extra(pkg, args, peak)
+    if rank == 0:
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -134,42 +134,57 @@ void qpe_gpu_device_free(void *p);
 int qpe_gpu_ipc_export(void *device_ptr, unsigned char handle_out[64]);
 void *qpe_gpu_ipc_open(const unsigned char handle[64]);
 void qpe_gpu_ipc_close(void *mapped_ptr);
+int qpe_gpu_copy_to_device(void *dst_device, const void *src_host, size_t bytes);
 int qpe_gpu_copy_to_host(void *dst_host, const void *src_device, size_t bytes);
 int qpe_gpu_copy_device(void *dst_device, const void *src_device, size_t bytes);
 
 /* ---- Row-range sharded table, one process per GPU of one box (csrc/shard.cu) ----------------------
  * What the reference's MPI mode does with MPI_Allreduce / MPI_Allgather(v) (engine/mpi/executeEngine-mpi.c:
  * 703-770), done by the kernels themselves over NVLink peer memory: every rank's scan stores its (global)
- * row ids into its segment of the owner's result buffer, a one-thread-per-rank kernel stores (epoch, count)
- * into every rank's comm block, and the owner packs the segments in partition order = table order.  No
- * host collective and no NCCL call per query; the caller only passes the 64-byte IPC handles around once.
- *   qpe_shard_init(engine, rank, world, handle_out)      allocate this rank's comm block, export it
+ * row ids into its segment of the owner's result buffer (device result) or into its own segment (host result),
+ * a kernel stores (epoch, count) into every rank's comm block, and the owner packs the segments in partition
+ * order = table order / every rank takes its 1/world of the result to the host.  No host collective and no
+ * NCCL call per query; the caller only passes the 64-byte IPC handles around once.
+ *   qpe_shard_init(engine, rank, world, cap, handle_out) allocate this rank's comm block + its own id segments
+ *                                                        (2 x cap ids), export the allocation
  *   qpe_shard_connect(engine, all_handles)               world x 64 bytes in rank order
  *   qpe_shard_set_device_result(engine, owner, segments, cap)  segments = qpe_shard_result_ids(world, cap) ids
  *                                                        in the OWNER's memory (own pointer / qpe_gpu_ipc_open
  *                                                        mapping); the first shard stores straight into the
  *                                                        dense result (its offset is always 0)
- *   qpe_shard_open_host_result(engine, name, cap, create) POSIX shared-memory id buffer all ranks write
- *                                                        their piece into over their own PCIe link
- *   qpe_shard_select / qpe_sql_shard_select              one full-scan SELECT; every rank calls it with the
- *                                                        same statement in the same order */
-int qpe_shard_init(struct engineS *engine, int rank, int world, unsigned char comm_handle_out[64]);
+ *   qpe_shard_open_host_result(engine, name, cap, create) POSIX shared-memory id buffer (2 x cap ids) all ranks
+ *                                                        write their 1/world of a result into over their own
+ *                                                        PCIe link; this rank's parts go to its GPU's NUMA node
+ *   qpe_shard_pin_host_result(engine)                    after every rank has opened it: register it with CUDA
+ *   qpe_shard_submit / qpe_shard_wait                    one full-scan SELECT, enqueued / completed; every rank
+ *                                                        calls them with the same statement in the same order;
+ *                                                        at most two queries in flight
+ *   qpe_shard_select / qpe_sql_shard_select              submit + wait */
+int qpe_shard_init(struct engineS *engine, int rank, int world, unsigned long long segment_capacity,
+                   unsigned char comm_handle_out[64]);
 int qpe_shard_connect(struct engineS *engine, const unsigned char *all_handles);
 unsigned long long qpe_shard_result_ids(int world, unsigned long long segment_capacity);
 int qpe_shard_set_device_result(struct engineS *engine, int owner_rank, unsigned int *segments,
                                 unsigned long long segment_capacity);
 unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *name, unsigned long long capacity,
                                          int create);
+int qpe_shard_pin_host_result(struct engineS *engine);
 /* creator, after every rank has opened the buffer: drop its /dev/shm name (mappings stay valid) */
 int qpe_shard_unlink_host_result(struct engineS *engine);
+/* the packed ids of the most recent device-result / host-result query that qpe_shard_wait completed.  A host result
+ * stays valid until the second qpe_shard_submit after the qpe_shard_wait that returned it. */
 const unsigned int *qpe_shard_device_result(struct engineS *engine);
-/* Host result path: 1 = every rank copies 1/world of the packed result (read from the owner over NVLink) to the
- * host over its OWN PCIe link; 0 = the first shard streams its ids out during its scan, the others copy theirs
- * afterwards; -1 (default) = 1 from eight ranks up.  Every rank must choose the same. */
+const unsigned int *qpe_shard_host_result(struct engineS *engine);
+/* Host result path: 1 (default) = every rank reads its 1/world of the result out of the ranks' segments over NVLink
+ * into its own HBM and the copy engine takes it to the host over this GPU's PCIe link; 2 = the delivery kernel
+ * stores into the mapped host buffer itself.  Every rank must choose the same. */
 int qpe_shard_set_multipath(struct engineS *engine, int mode);
 void qpe_shard_close(struct engineS *engine);
+int qpe_shard_submit(struct engineS *engine, struct whereClauseS *whereClause, int to_host);
+int qpe_shard_wait(struct engineS *engine, unsigned long long *counts_out, qpe_scan_stats *stats);
 int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, int to_host,
                      unsigned long long *counts_out, qpe_scan_stats *stats);
+int qpe_sql_shard_submit(struct engineS *engine, const char *statement, int to_host);
 int qpe_sql_shard_select(struct engineS *engine, const char *statement, int to_host,
                          unsigned long long *counts_out, qpe_scan_stats *stats);
 /* DELETE on the sharded table: every rank deletes its shard's matches, the new shard sizes are all-gathered
@@ -199,6 +214,11 @@ int qpe_gpu_timing_totals(struct engineS *engine, double totals_ms[4], long long
  * [4] tail of the match phase after the synchronisation, [5] whole qpe_sql_shard_select call, [6..7] 0. */
 int qpe_gpu_last_trace(struct engineS *engine, double out[8]);
 
+/* Diagnostics (only with QPE_FUSE_TRACE=1 in the environment): per-CTA %globaltimer stamps of the most recent
+ * fused scan, 8 words per CTA: [0] CTA start, [1] its first tile landed, [2] evaluators done, [3] CTA end,
+ * [5] chunks it processed.  Returns the number of CTAs written (0 when tracing is off). */
+int qpe_gpu_fused_trace(struct engineS *engine, unsigned long long *out, int max_ctas);
+
 /* Write the whole table as a CSV in the data generator's format (header line, QUOTE_MINIMAL
  * quoting, \r\n line ends, sudo_used as true/false: data-generation/generate_commands.py:812-816)
  * so that the reference's loader and ours can both ingest it.  Every column must be resident. */
@@ -208,6 +228,19 @@ int qpe_gpu_write_csv(struct engineS *engine, const char *path);
  * (num_rows + 31) / 32 words. */
 int qpe_gpu_match_mask(struct engineS *engine, struct whereClauseS *whereClause, unsigned int *bitmap,
                        size_t n_words, unsigned long long *count_out, qpe_scan_stats *stats);
+
+/* Batched probes with PLAIN key arrays (unsigned long long for a u64 index, int for an int index) -- the end-to-end
+ * form of findRange / find_rows (engine/bplus.c:282-314, :361-411) for many probes at once.  hi == NULL: point
+ * probes (hi = lo).  lo / hi and first / count may be host pointers (ideally from qpe_gpu_host_alloc: pinned memory is
+ * copied in place, chunk by chunk, beside the probe kernel; pageable memory goes through a bounce buffer) or device
+ * pointers (no copies).  flags: QPE_PROBE_SORT = sort the batch by its lower keys on the device first, probe in key
+ * order and scatter the answers back.  stats->kernel_ms is the device time of the whole batch, copies included. */
+#define QPE_PROBE_SORT 1
+int qpe_gpu_probe_keys(struct engineS *engine, const char *attribute, const void *lo, const void *hi, size_t n_queries,
+                       unsigned int *first, unsigned int *count, int flags, qpe_scan_stats *stats);
+/* pinned host memory for probe batches and id lists (release with qpe_gpu_host_free) */
+void *qpe_gpu_host_alloc(size_t bytes);
+void qpe_gpu_host_free(void *p);
 
 /* Batched inclusive-range probes [lo[q], hi[q]] on the index of `attribute` (point lookup:
  * lo == hi).  first[q] / count[q] delimit the answer inside the index order

@@ -144,6 +144,32 @@ double ref_time_select(struct engineS *e, const char *sql, int reps, int *matche
     return t1 - t0;
 }
 
+/* wall seconds of `n` findRange calls (engine/bplus.c:282-314) on the engine's index number `index_no`, with the
+ * caller-allocated result arrays sized to the table as executeQuerySelectSerial sizes them (:438-439);
+ * lo / hi are unsigned 64-bit (index type 0) or int (index type 1) keys; *found = rows found over all calls */
+double ref_time_probe(struct engineS *e, int index_no, const unsigned long long *lo, const unsigned long long *hi,
+                      int n, long long *found) {
+    if (index_no < 0 || index_no >= e->num_indexes) return -1.0;
+    node *root = e->bplus_tree_roots[index_no];
+    const FieldType type = e->attribute_types[index_no];
+    KEY_T *keys = malloc(sizeof(KEY_T) * (size_t)(e->num_records > 0 ? e->num_records : 1));
+    ROW_PTR *rows = malloc(sizeof(ROW_PTR) * (size_t)(e->num_records > 0 ? e->num_records : 1));
+    long long total = 0;
+    double t0 = now_s();
+    for (int i = 0; i < n; i++) {
+        KEY_T a, b;
+        a.type = b.type = (type == FIELD_UINT64) ? KEY_UINT64 : KEY_INT;
+        if (type == FIELD_UINT64) { a.v.u64 = lo[i]; b.v.u64 = hi[i]; }
+        else { a.v.i32 = (int)lo[i]; b.v.i32 = (int)hi[i]; }
+        total += findRange(root, a, b, false, keys, rows);
+    }
+    double t1 = now_s();
+    free(keys);
+    free(rows);
+    if (found) *found = total;
+    return t1 - t0;
+}
+
 /* the whereClauseS list the reference's tokenizer + parser + convert_conditions build for `sql`,
  * rendered as text (same rendering as qpe_sql_where_to_text in the product's front end);
  * also reports the parsed command. Caller frees. */

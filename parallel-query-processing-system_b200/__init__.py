@@ -42,6 +42,25 @@ class QpeError(RuntimeError):
     pass
 
 
+def pinned_array(n: int, dtype) -> np.ndarray:
+    """numpy array over pinned host memory from qpe_gpu_host_alloc (copied to / from the device in place, without a
+    bounce buffer); released when the array is garbage collected"""
+    lib = load_library()
+    dt = np.dtype(dtype)
+    nbytes = max(int(n) * dt.itemsize, 16)
+    p = lib.qpe_gpu_host_alloc(nbytes)
+    if not p:
+        raise QpeError("qpe_gpu_host_alloc failed: " + (lib.qpe_gpu_last_error() or b"").decode())
+
+    class _Owner:
+        def __del__(self, p=p, lib=lib):
+            lib.qpe_gpu_host_free(p)
+
+    buf = (C.c_uint8 * nbytes).from_address(p)
+    buf._owner = _Owner()
+    return np.frombuffer(buf, dtype=dt, count=int(n))
+
+
 class ScanStats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("total_ms", C.c_double), ("rows_scanned", C.c_longlong),
                 ("candidates", C.c_longlong), ("matches", C.c_longlong), ("algo_bytes", C.c_longlong),
@@ -94,6 +113,9 @@ def load_library() -> C.CDLL:
         "qpe_gpu_num_rows": (ll, [vp]),
         "qpe_gpu_row_base": (ull, [vp]),
         "qpe_gpu_probe_batch": (i, [vp, cp, C.POINTER(KeyT), C.POINTER(KeyT), sz, vp, vp, pstats]),
+        "qpe_gpu_probe_keys": (i, [vp, cp, vp, vp, sz, vp, vp, i, pstats]),
+        "qpe_gpu_host_alloc": (vp, [sz]),
+        "qpe_gpu_host_free": (None, [vp]),
         "qpe_gpu_index_slice": (i, [vp, cp, C.c_uint, C.c_uint, vp]),
         "qpe_gpu_index_slice_keys": (i, [vp, cp, C.c_uint, C.c_uint, vp]),
         "qpe_gpu_fetch_column": (i, [vp, cp, ll, ll, vp, C.POINTER(C.c_uint)]),
@@ -102,6 +124,7 @@ def load_library() -> C.CDLL:
         "qpe_gpu_stream": (vp, [vp]),
         "qpe_gpu_query_upload_bytes": (C.c_uint, []),
         "qpe_gpu_last_trace": (i, [vp, C.POINTER(C.c_double)]),
+        "qpe_gpu_fused_trace": (i, [vp, vp, i]),
         "qpe_gpu_set_timing": (i, [vp, i]),
         "qpe_gpu_timing_totals": (i, [vp, C.POINTER(C.c_double), C.POINTER(ll)]),
         "qpe_gpu_copy_from_device": (i, [vp, vp, sz]),
@@ -126,12 +149,17 @@ def load_library() -> C.CDLL:
         "qpe_gpu_ipc_open": (vp, [C.c_char_p]),
         "qpe_gpu_ipc_close": (None, [vp]),
         "qpe_gpu_copy_to_host": (i, [vp, vp, sz]),
-        "qpe_shard_init": (i, [vp, i, i, C.c_char_p]),
+        "qpe_gpu_copy_to_device": (i, [vp, vp, sz]),
+        "qpe_shard_init": (i, [vp, i, i, ull, C.c_char_p]),
         "qpe_shard_connect": (i, [vp, C.c_char_p]),
         "qpe_shard_set_device_result": (i, [vp, i, vp, ull]),
         "qpe_shard_result_ids": (ull, [i, ull]),
         "qpe_shard_open_host_result": (vp, [vp, cp, ull, i]),
         "qpe_shard_device_result": (vp, [vp]),
+        "qpe_shard_host_result": (vp, [vp]),
+        "qpe_shard_pin_host_result": (i, [vp]),
+        "qpe_shard_wait": (i, [vp, C.POINTER(ull), pstats]),
+        "qpe_sql_shard_submit": (i, [vp, cp, i]),
         "qpe_shard_close": (None, [vp]),
         "qpe_shard_unlink_host_result": (i, [vp]),
         "qpe_shard_set_multipath": (i, [vp, i]),
@@ -300,6 +328,12 @@ class Engine:
         self._check(self._lib.qpe_gpu_last_trace(self._h, out), "last_trace")
         return list(out)
 
+    def fused_trace(self) -> np.ndarray:
+        """per-CTA time stamps of the most recent fused scan (QPE_FUSE_TRACE=1), shape (ctas, 8), ns"""
+        buf = np.zeros((1024, 8), dtype=np.uint64)
+        n = self._lib.qpe_gpu_fused_trace(self._h, buf.ctypes.data, 1024)
+        return buf[:n]
+
     def last_stats(self) -> dict:
         st = ScanStats()
         self._check(self._lib.qpe_gpu_last_stats(self._h, C.byref(st)), "last_stats")
@@ -328,6 +362,18 @@ class Engine:
             names = [r.columnNames[j].decode() for j in range(r.numColumns)]
             rows = [[r.data[i][j].decode(errors="replace") for j in range(r.numColumns)] for i in range(r.numRecords)]
             return names, rows, r.queryTime
+        finally:
+            self._lib.freeResultSet(res)
+
+    def select_result_time(self, statement: str) -> int:
+        """executeQuerySelectGPU -> resultSetS -> freeResultSet without touching the cells (timing aid): rows returned"""
+        res = self._lib.qpe_sql_select(self._h, statement.encode())
+        if not res:
+            raise QpeError("not a SELECT statement: " + statement)
+        try:
+            if not res.contents.success:
+                raise QpeError("SELECT failed: " + (self._lib.qpe_gpu_last_error() or b"").decode())
+            return int(res.contents.numRecords)
         finally:
             self._lib.freeResultSet(res)
 
@@ -485,6 +531,24 @@ class Engine:
                                            count.ctypes.data, C.byref(st))
         self._check(rc, "probe_batch")
         return first[:q], count[:q], st.as_dict()
+
+    def probe_keys(self, attribute: str, lo, hi=None, sort: bool = False, first=None, count=None):
+        """Batched probes with plain key arrays (qpe_gpu_probe_keys).  lo / hi: numpy arrays (uint64 for a u64 index,
+        int32 for an int index; pinned ones from `pinned_array` are copied in place) or DeviceBuffer; hi=None: point
+        probes.  first / count: numpy uint32 arrays or DeviceBuffer to receive the answers (allocated when None).
+        Returns (first, count, stats dict)."""
+        def ptr(x):
+            return x.ptr if isinstance(x, DeviceBuffer) else x.ctypes.data
+        q = (lo.n_bytes // (8 if attribute == "command_id" else 4)) if isinstance(lo, DeviceBuffer) else len(lo)
+        if first is None:
+            first = np.empty(q, dtype=np.uint32)
+        if count is None:
+            count = np.empty(q, dtype=np.uint32)
+        st = ScanStats()
+        rc = self._lib.qpe_gpu_probe_keys(self._h, attribute.encode(), ptr(lo), ptr(hi) if hi is not None else None, q,
+                                          ptr(first), ptr(count), 1 if sort else 0, C.byref(st))
+        self._check(rc, "probe_keys")
+        return first, count, st.as_dict()
 
     def index_slice(self, attribute: str, first: int, count: int) -> np.ndarray:
         out = np.zeros(max(count, 1), dtype=np.uint32)

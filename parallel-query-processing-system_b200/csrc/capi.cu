@@ -1116,6 +1116,10 @@ int qpe_gpu_copy_device(void *dst_device, const void *src_device, size_t bytes) 
     if (bytes == 0) return 0;
     return cuda_ok(cudaMemcpy(dst_device, src_device, bytes, cudaMemcpyDeviceToDevice), "device copy") ? 0 : -4;
 }
+int qpe_gpu_copy_to_device(void *dst_device, const void *src_host, size_t bytes) {
+    if (bytes == 0) return 0;
+    return cuda_ok(cudaMemcpy(dst_device, src_host, bytes, cudaMemcpyHostToDevice), "copy to device") ? 0 : -4;
+}
 int qpe_gpu_copy_to_host(void *dst_host, const void *src_device, size_t bytes) {
     if (bytes == 0) return 0;
     return cuda_ok(cudaMemcpy(dst_host, src_device, bytes, cudaMemcpyDeviceToHost), "copy to host") ? 0 : -4;
@@ -1168,6 +1172,17 @@ int qpe_gpu_last_trace(struct engineS *engine, double out[8]) {
     engine_resolve_timing(g);
     for (int k = 0; k < 8; ++k) out[k] = g->trace[k];
     return 0;
+}
+
+int qpe_gpu_fused_trace(struct engineS *engine, unsigned long long *out, int max_ctas) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    if (!g || !out || !g->d_trace || g->last.grid <= 0) return 0;
+    cudaSetDevice(g->device);
+    const int n = g->last.grid < max_ctas ? g->last.grid : max_ctas;
+    if (!cuda_ok(cudaMemcpy(out, g->d_trace, sizeof(unsigned long long) * 8 * n, cudaMemcpyDeviceToHost), "download trace"))
+        return 0;
+    return n;
 }
 
 int qpe_gpu_write_csv(struct engineS *engine, const char *path) {

@@ -169,6 +169,7 @@ void engine_destroy(GpuEngine *g) {
     for (auto &ix : g->idx) index_free(&ix);
     if (g->d_ctl) cudaFree(g->d_ctl);
     if (g->d_fctl) cudaFree(g->d_fctl);
+    if (g->d_trace) cudaFree(g->d_trace);
     if (g->h_ctl) cudaFreeHost(g->h_ctl);
     if (g->h_progress) cudaFreeHost(g->h_progress);
     if (g->d_tile_desc) cudaFree(g->d_tile_desc);
@@ -187,6 +188,8 @@ void engine_destroy(GpuEngine *g) {
     if (g->d_probe_count) cudaFree(g->d_probe_count);
     if (g->h_probe_keys) cudaFreeHost(g->h_probe_keys);
     if (g->h_probe_out) cudaFreeHost(g->h_probe_out);
+    if (g->d_probe_scratch) cudaFree(g->d_probe_scratch);
+    if (g->h_probe_bounce) cudaFreeHost(g->h_probe_bounce);
     for (int i = 0; i < GpuEngine::kTimingRing; ++i)
         for (int k = 0; k < 4; ++k)
             if (g->ring[i].ev[k]) cudaEventDestroy(g->ring[i].ev[k]);
@@ -287,6 +290,8 @@ static bool ensure_index(GpuEngine *g, DevIndex *ix, int *launches) {
     if (!ix->usable || !ix->dirty) return true;
     return cuda_ok(index_build(ix, g->table, g->stream, launches), "index rebuild");
 }
+
+bool index_ready(GpuEngine *g, DevIndex *ix, int *launches) { return ensure_index(g, ix, launches); }
 
 bool engine_ensure_ids(GpuEngine *g, int64_t n) {
     if (n <= g->ids_cap && g->d_ids) return true;
@@ -534,11 +539,11 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
             // ~3 us a stage takes to be refilled and consumed), not by bytes
             bool planned = scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, kFusedMaxStages, &fg, &fwhy, 4);
             if (planned && want_cw == 8) {
-                // eight compaction warps need 16 KB more shared memory: only when that costs no tile rows or stages
+                // eight compaction warps need 16 KB more shared memory: only when that costs no tile rows and at most a quarter of the stages
                 ScanGeometry g8{};
                 const char *why8 = nullptr;
                 if (scan_plan(t, hc->prog, g->force_tile_rows, g->force_stages, kFusedMaxStages, &g8, &why8, 8) &&
-                    g8.tile_rows == fg.tile_rows && g8.stages == fg.stages)
+                    g8.tile_rows == fg.tile_rows && g8.stages * 4 >= fg.stages * 3)
                     fg = g8;
             }
             if (planned) {
@@ -567,6 +572,9 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
                 }
                 // no upload: K1f takes the program as a kernel parameter and resets its own control words
                 F.d_fctl = g->d_fctl;
+                static const bool want_trace = std::getenv("QPE_FUSE_TRACE") != nullptr;
+                if (want_trace && !g->d_trace) cudaMalloc(&g->d_trace, 8 * 8 * 1024);
+                F.trace = want_trace ? g->d_trace : nullptr;
                 g->count_dev = &g->d_fctl->final_count;
                 // a plain (unsharded) scan: the kernel's last CTA writes the count into mapped host memory
                 if (!g->count_mapped) {
@@ -830,6 +838,115 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     g->last_bm_count = hc->out_count;
     if (count) *count = hc->out_count;
     return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1f without the synchronisation: compile + plan + launch on the engine's stream and return.  The sharded
+// SELECT (shard.cu) enqueues its count exchange / delivery kernels right behind and may enqueue the NEXT
+// query before it waits for this one.  The match count ends up in g->d_fctl->final_count (device).
+// ------------------------------------------------------------------------------------------
+static GpuEngine::TimingSlot *take_timing_slot(GpuEngine *g) {
+    GpuEngine::TimingSlot *slot = &g->ring[g->ring_head];
+    g->ring_head = (g->ring_head + 1) % GpuEngine::kTimingRing;
+    if (slot->pending && g->accumulate_timing) resolve_slot(g, slot, nullptr);
+    slot->pending = false;
+    if (g->cur_slot && g->cur_slot->pending && !g->accumulate_timing) g->cur_slot->pending = false;  // never asked for
+    return slot;
+}
+
+bool engine_fused_enqueue(GpuEngine *g, const struct whereClauseS *wc, uint32_t *out_ids, uint64_t out_cap,
+                          uint32_t id_base, FusedEnqueue *fe) {
+    cudaSetDevice(g->device);
+    const DevTable &t = g->table;
+    fe->slot = nullptr;
+    fe->launched = false;
+    fe->geo = ScanGeometry{};
+    fe->bytes_per_row = 0;
+    uint32_t widths[NUM_COLS];
+    for (int c = 0; c < NUM_COLS; ++c) widths[c] = t.col[c].width;
+    Program *prog = &g->h_ctl->prog;  // copied into the kernel's parameter block by the launch: reusable at once
+    const std::string err = compile_where(wc, widths, prog, false);
+    if (!err.empty()) {
+        set_error(err);
+        return false;
+    }
+    for (int c = 0; c < NUM_COLS; ++c)
+        if (prog->col_mask & (1u << c)) {
+            if (!t.resident(c)) {
+                set_error(std::string("WHERE references column '") + kCols[c].name + "' which is not resident on the device");
+                return false;
+            }
+            fe->bytes_per_row += t.col[c].width;
+        }
+    GpuEngine::TimingSlot *slot = take_timing_slot(g);
+    fe->slot = slot;
+    if (t.n == 0) {
+        // an empty shard still takes part: its count is 0
+        cudaEventRecord(slot->ev[0], g->stream);
+        if (!cuda_ok(cudaMemsetAsync(&g->d_fctl->final_count, 0, sizeof(unsigned long long), g->stream), "reset count"))
+            return false;
+        cudaEventRecord(slot->ev[1], g->stream);
+        cudaEventRecord(slot->ev[2], g->stream);
+        return true;
+    }
+    const char *why = nullptr;
+    ScanGeometry fg{};
+    if (!scan_plan(t, *prog, g->force_tile_rows, g->force_stages, kFusedMaxStages, &fg, &why, 4)) {
+        set_error(std::string("this WHERE cannot be staged by the scan kernel: ") + (why ? why : "row too wide"));
+        return false;
+    }
+    if (g->fuse_cw == 8) {
+        ScanGeometry g8{};
+        const char *why8 = nullptr;
+        if (scan_plan(t, *prog, g->force_tile_rows, g->force_stages, kFusedMaxStages, &g8, &why8, 8) &&
+            g8.tile_rows == fg.tile_rows && g8.stages * 4 >= fg.stages * 3)
+            fg = g8;
+    }
+    if (!ensure_desc(g, fg.n_chunks)) return false;
+    FusedLaunch F{};
+    F.scan.table = &t;
+    F.scan.d_ctl = g->d_ctl;
+    F.scan.h_prog = prog;
+    F.desc = g->d_tile_desc;
+    F.epoch = next_epoch(g);
+    F.id_base = id_base;
+    F.out_ids = out_ids;
+    F.out_cap = out_cap;
+    F.d_fctl = g->d_fctl;
+    cudaEventRecord(slot->ev[0], g->stream);
+    if (!cuda_ok(fused_launch(F, fg, g->stream), "fused scan kernel launch")) return false;
+    cudaEventRecord(slot->ev[1], g->stream);
+    cudaEventRecord(slot->ev[2], g->stream);
+    fe->geo = fg;
+    fe->launched = true;
+    return true;
+}
+
+// bookkeeping once the match count of an enqueued fused scan is known (statistics, compaction-warp choice)
+void engine_fused_finish(GpuEngine *g, const FusedEnqueue &fe, uint64_t matches, int extra_launches, double t_begin_ms) {
+    ScanStats st;
+    st.path = 0;
+    st.rows_scanned = g->table.n;
+    st.matches = static_cast<int64_t>(matches);
+    st.launches = (fe.launched ? 1 : 0) + extra_launches;
+    st.tile_rows = fe.geo.tile_rows;
+    st.stages = fe.geo.stages;
+    st.grid = fe.geo.grid;
+    st.algo_bytes = st.rows_scanned * fe.bytes_per_row + 4 * st.matches;
+    st.total_ms = now_ms() - t_begin_ms;
+    if (st.rows_scanned > 0) g->fuse_cw = (st.matches * 8 > st.rows_scanned) ? 8 : 4;
+    g->last = st;
+    if (fe.slot) {
+        g->cur_slot = fe.slot;
+        fe.slot->pending = true;
+        fe.slot->staged = fe.launched;
+        fe.slot->two_kernels = false;
+        fe.slot->has_post = true;
+        g->ev0 = fe.slot->ev[0];
+        g->ev_mid = fe.slot->ev[1];
+        g->ev1 = fe.slot->ev[2];
+        g->ev_post = fe.slot->ev[3];
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -59,6 +59,7 @@ struct GpuEngine {
 
     // per-query scratch
     FusedCtl *d_fctl = nullptr;  // K1f's self-resetting control words
+    unsigned long long *d_trace = nullptr;  // QPE_FUSE_TRACE=1: per-CTA time stamps of the last K1f (diagnostics)
     const unsigned long long *count_dev = nullptr;  // device word holding the match count of the scan just enqueued
     QueryCtl *d_ctl = nullptr;
     QueryCtl *h_ctl = nullptr;  // pinned
@@ -96,6 +97,11 @@ struct GpuEngine {
     uint32_t *d_probe_first = nullptr, *d_probe_count = nullptr;
     unsigned long long *h_probe_keys = nullptr;  // pinned: lo[kMaxSegments], hi[kMaxSegments]
     uint32_t *h_probe_out = nullptr;             // pinned: first[kMaxSegments], count[kMaxSegments]
+    // batched probes (probe_batch.cu): grow-only device scratch and pinned bounce buffer
+    void *d_probe_scratch = nullptr;
+    size_t probe_scratch_bytes = 0;
+    void *h_probe_bounce = nullptr;
+    size_t probe_bounce_bytes = 0;
 
     // host-side breakdown of the last match phase (ms): [0] parse/compile, [1] enqueue (copies + launches),
     // [2] stream synchronisation, [3] device time ev1 -> end of the post-match kernels, [4] tail of the
@@ -129,6 +135,8 @@ bool engine_append(GpuEngine *g, const record &r);
 bool engine_upload(GpuEngine *g, const HostColumns &hc);  // replaces the table
 bool engine_add_index(GpuEngine *g, const char *name, int attributeType);
 bool engine_ensure_ids(GpuEngine *g, int64_t n);
+// bring a (usable) index up to date with the table before it is probed
+bool index_ready(GpuEngine *g, DevIndex *ix, int *launches);
 // resolve the event times of the most recent match phase into g->last (no-op when already done)
 void engine_resolve_timing(GpuEngine *g);
 // resolve every pending slot into the accumulators (accumulate_timing)
@@ -137,6 +145,18 @@ void engine_resolve_all(GpuEngine *g);
 // match phase. On success the ids are in g->d_ids[0 .. *count) (unless count_only).
 bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, bool invert, bool count_only,
                   bool want_bitmap, uint64_t *count);
+
+// K1f enqueued WITHOUT a synchronisation (sharded SELECT, shard.cu): compile + plan + launch, the count stays in
+// g->d_fctl->final_count.  engine_fused_finish does the bookkeeping once the caller knows the count.
+struct FusedEnqueue {
+    ScanGeometry geo;
+    int64_t bytes_per_row = 0;
+    GpuEngine::TimingSlot *slot = nullptr;  // its ev[3] is free for the caller's post-scan kernels
+    bool launched = false;                   // false: empty shard (count 0), nothing launched
+};
+bool engine_fused_enqueue(GpuEngine *g, const struct whereClauseS *wc, uint32_t *out_ids, uint64_t out_cap,
+                          uint32_t id_base, FusedEnqueue *fe);
+void engine_fused_finish(GpuEngine *g, const FusedEnqueue &fe, uint64_t matches, int extra_launches, double t_begin_ms);
 
 // K9: the match phase of up to kMaxBatch full-scan queries in ONE pass over the columns.  On success the ids of
 // query q are g->d_ids[offsets[q] .. offsets[q + 1]) in table order.  Every query must be a full-scan query

@@ -765,6 +765,7 @@ struct FusedParams {
     unsigned long long *progress;   // mapped pinned host memory: [seg] = epoch << 32 | ids complete through seg
     unsigned long long *host_count; // mapped pinned host memory: the match count, written by the last CTA (or null)
     FusedCtl *fctl;                 // this kernel's own control words (self-resetting)
+    unsigned long long *trace;      // diagnostics (QPE_FUSE_TRACE=1): 8 words per CTA of %globaltimer stamps, or null
     Program prog;                   // the compiled WHERE, by value: no upload precedes the launch
 };
 
@@ -835,6 +836,7 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
     const uint32_t CT = static_cast<uint32_t>(fp.chunk_tiles);
 
     if (tid == 0) {
+        if (fp.trace) fp.trace[blockIdx.x * 8 + 0] = global_ns();
         for (uint32_t s = 0; s < S; ++s) mbar_init(&sh->full[s], 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&sh->cb_full[b], EW);
@@ -885,6 +887,7 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
             if (active)
                 for (uint32_t j = first_tile_of(warp, k, CT, S); j < nt; j += S, ++it) {
                     mbar_wait(&sh->full[warp], it & 1u);
+                    if (fp.trace && it == 0 && tid == 0) fp.trace[blockIdx.x * 8 + 1] = global_ns();
                     const long long tile = t0 + j;
                     const uint32_t acc =
                         eval_tile<RPL>(sp, stage, lane, g, tile * T + static_cast<long long>(lane) * RPL, p.n_rows);
@@ -904,6 +907,10 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
         }
         const uint32_t warp_total = __reduce_add_sync(0xffffffffu, my_count);
         if (lane == 0 && warp_total) atomicAdd(&sh->cta_count, static_cast<unsigned long long>(warp_total));
+        if (fp.trace && tid == 0) {
+            fp.trace[blockIdx.x * 8 + 2] = global_ns();
+            fp.trace[blockIdx.x * 8 + 5] = k;
+        }
     } else {
         // ===== C: ordered compaction of finished chunks =====
         const uint32_t ct = tid - 32u * EW;
@@ -1028,6 +1035,7 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
     }
     __syncthreads();
     if (tid == 0) {
+        if (fp.trace) fp.trace[blockIdx.x * 8 + 3] = global_ns();
         FusedCtl *fc = fp.fctl;
         if (sh->cta_count) atomicAdd(&fc->out_count, sh->cta_count);
         // The last CTA to get here hands the total over (device word for the sharded post-scan kernel, mapped host
@@ -1151,22 +1159,23 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
     geo->chunk_tiles = 0;
     geo->n_chunks = 0;
     if (fused) {
-        // chunk = the largest power-of-two run of tiles (<= 64 Ki rows) whose last, partly filled round of
-        // CTAs costs < 3 %; halving stops at 8 Ki rows (shorter chunks publish descriptors faster than
-        // a look-back window can follow at HBM speed)
-        int ct = kFuseMaxChunkRows / T;
-        int best_ct = ct;
-        double best_loss = 1e9;
-        for (; ct >= 1 && static_cast<long long>(ct) * T >= 8192; ct >>= 1) {
+        // Chunk size: 64 Ki rows unless a smaller one finishes sooner.  Per round of chunks a CTA needs the longer of
+        // its scan time (rows x bytes per row at ~47 GB/s per SM) and the compaction warps' per-chunk latency
+        // (~6 us: barrier, scan, look-back, expansion; measured with tools/k1f_trace.py -- a 25 M-row table cut into
+        // 8 Ki-row chunks ran at 2.2 TB/s, every round waiting for the compaction).  Small tables take smaller chunks
+        // only to put more SMs to work.
+        int best_ct = kFuseMaxChunkRows / T;
+        double best_us = 1e30;
+        for (int ct = kFuseMaxChunkRows / T; ct >= 1 && static_cast<long long>(ct) * T >= 8192; ct >>= 1) {
             const int64_t nc = (geo->n_tiles + ct - 1) / ct;
             const int64_t g = nc < n_sm ? nc : n_sm;
             const int64_t rounds = (nc + g - 1) / (g > 0 ? g : 1);
-            const double loss = nc > 0 ? static_cast<double>(rounds * g) / static_cast<double>(nc) - 1.0 : 0.0;
-            if (loss < best_loss - 1e-9) {
-                best_loss = loss;
+            const double scan_us = static_cast<double>(ct) * T * static_cast<double>(bpr > 0 ? bpr : 1) / 47e3;
+            const double us = static_cast<double>(rounds) * (scan_us > 6.0 ? scan_us : 6.0);
+            if (us < best_us * 0.97) {  // a smaller chunk must win by 3 %
+                best_us = us;
                 best_ct = ct;
             }
-            if (loss < 0.03) break;
         }
         geo->chunk_tiles = best_ct;
         geo->n_chunks = (geo->n_tiles + best_ct - 1) / best_ct;
@@ -1311,6 +1320,7 @@ cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStre
     fp.progress = L.progress;
     fp.host_count = L.host_count;
     fp.fctl = L.d_fctl;
+    fp.trace = L.trace;
     fp.prog = *L.scan.h_prog;
     if (!fp.fctl) return cudaErrorInvalidValue;
     if (fp.n_chunks == 0) return cudaSuccess;

@@ -1,80 +1,122 @@
 // shard.cu -- a row-range sharded table: one process per GPU, full-scan SELECT with the ordered
-// gather fused into the kernels over peer memory.
+// gather done by kernels over peer memory, and up to TWO queries in flight per rank.
 //
 // What the reference does in MPI mode (engine/mpi/executeEngine-mpi.c:703-770): block partition of
 // the rows, every rank evaluates its slice, MPI_Allreduce / MPI_Allgather of the per-rank counts,
 // MPI_Allgatherv of the per-rank pieces in partition order.  Here, per query (no host collective,
 // no NCCL call, no send/recv on the data path):
 //
-//   every rank      K1f scans its shard; the ids (already global: + first row of the shard) are
-//                   stored by the compaction warps either into the rank's segment of the OWNER's
-//                   result buffer -- peer memory mapped through CUDA IPC, so the ids cross NVLink
-//                   as the kernel's own coalesced stores, during the scan -- or into the rank's own
-//                   HBM (host result);
-//   every rank      post_kernel: one system-scope release store of (epoch, match count) into
-//                   EVERY rank's comm block (peer stores) = the count exchange;
-//   owner           post_kernel: waits for all counts of this epoch (acquire loads of its own comm
-//                   block), then moves the segments of ranks 1.. behind rank 0's ids -- rank 0's
-//                   offset is always 0, so ITS scan stores straight into the dense result and is never
-//                   moved -- giving one dense id list in partition order, which is table order;
-//   host result     a host buffer shared by all ranks (POSIX shared memory, registered with CUDA in every
-//                   process).  Up to 7 ranks: the first shard streams its ids out during its scan (its
-//                   offset is 0), every other rank learns the counts of the lower ranks the same way and
-//                   copies its ids to its exact offset over ITS OWN PCIe link.  From 8 ranks ("multipath"):
-//                   the ids land in the owner's HBM as for a device result and every rank pulls 1/world of
-//                   the packed list over NVLink and copies that out over its own link.
+//   every rank      K1f scans its shard; the ids are already global (+ first row of the shard).
+//
+//   DEVICE RESULT   (ids packed in the owner's HBM).  The compaction warps store the ids into the rank's segment of
+//                   the OWNER's result memory -- peer memory mapped through CUDA IPC, so the ids cross NVLink as the
+//                   scan kernel's own coalesced stores, during the scan; the first shard's offset is always 0, so ITS
+//                   scan stores straight into the dense result.  post_kernel: one system-scope release store of
+//                   (epoch, match count) into EVERY rank's comm block = the count exchange; every rank waits for
+//                   all counts of the epoch (acquire loads of its own block); the owner moves the segments of ranks
+//                   1.. behind rank 0's ids.
+//
+//   HOST RESULT     (ids in a host buffer shared by all ranks: POSIX shared memory, registered with CUDA in every
+//                   process, each rank's part of it placed on the NUMA node of that rank's GPU).  The ids stay in the
+//                   rank's OWN segment (own HBM, mapped by every other rank).  deliver_kernel: the same count
+//                   exchange, then rank j takes the j-th 1/world of the RESULT -- whichever ranks' segments it spans
+//                   -- reading it over NVLink straight from those segments (no pack, no flag, no second hop) into a
+//                   local staging buffer, from where the copy engine takes it to the host over this GPU's own PCIe
+//                   link (or, mode 2, the kernel stores it into the mapped host buffer itself).  Every link carries
+//                   1/world of the result whatever its distribution over the shards.
+//
+//   TWO IN FLIGHT   qpe_shard_submit enqueues scan + exchange / delivery kernel and returns; qpe_shard_wait waits for
+//                   the counts (a mapped host word written by the kernel: no stream synchronisation), finishes the
+//                   host copy and returns the per-rank counts.  A caller that submits query q + 1 before it waits for
+//                   q hides the host's share of a query (launch, wake-up) behind the scans and lets the host copy of q
+//                   run beside the scan of q + 1.  Every buffer a query touches exists twice (epoch parity).
+//
+//   ERRORS          are collective: a rank that cannot run its scan (WHERE does not compile, row ids beyond 32 bits,
+//                   row too wide to stage) still publishes a failure marker instead of a count, and every decision
+//                   that follows (overflow of a segment / of the host buffer) is taken from the exchanged counts, so
+//                   all ranks take the same branch and nobody is left waiting.  A wait that times out (~20 s) sets a
+//                   status word instead of trapping.
+//
 //   DELETE          qpe_shard_delete: local mask + stable compaction per shard, the new shard sizes
 //                   all-gathered through the same comm blocks, shards renumbered.
 //
-// Slots are double buffered by epoch parity: no rank finishes query e before every rank has
-// published its count of e, so a rank is never more than one query ahead of another.
-// Every wait is bounded (trap, never a hung GPU).  NCCL / torch.distributed is only used by the
-// caller to hand the IPC handles around at start-up.
+// Why a rank is never more than one query ahead of another: no rank's exchange of query e completes before every rank
+// has published its count of e, and a rank publishes e + 1 only after its exchange of e (stream order).  So the slot,
+// segment and staging sets of parity e & 1 are free again when query e + 2 is enqueued.
+// NCCL / torch.distributed is only used by the caller to hand the IPC handles around at start-up.
 
 #include "engine.cuh"
 
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
 namespace qpe {
 
 constexpr int kMaxRanks = 16;
+constexpr unsigned long long kCountFailed = 0xffffffffull;   // published instead of a count: this rank could not scan
+constexpr int kHostWords = kMaxRanks + 2;                     // per parity: counts, [kMaxRanks] = epoch flag, [+1] = status
 
-struct ShardComm {                      // device memory of one rank, mapped by all the others
+struct ShardComm {                      // device memory of one rank, mapped by all the others; followed by its segments
     unsigned long long count[2][kMaxRanks];  // [epoch parity][source rank] = epoch << 32 | match count
-    unsigned long long packed[2];            // [epoch parity] = epoch whose dense result the owner has packed
+    unsigned int ctas_done[2];               // [epoch parity] CTAs of the post-scan kernel that have finished
+    unsigned int pad_[2];
 };
+constexpr size_t kCommBytes = (sizeof(ShardComm) + 255) & ~size_t(255);
 
 struct ShardHostHeader {                // start of the shared host buffer
     volatile unsigned long long done[kMaxRanks][8];  // [rank][0] = epoch whose ids rank has delivered (64 B apart)
+};
+constexpr size_t kHostHeaderBytes = (sizeof(ShardHostHeader) + 4095) & ~size_t(4095);
+
+struct ShardPending {
+    bool active = false;
+    bool local_ok = false;              // this rank's scan was enqueued (else it published the failure marker)
+    int to_host = 0;
+    uint32_t epoch = 0;
+    double t_begin = 0;
+    FusedEnqueue fe;
+    std::string local_error;
 };
 
 struct ShardState {
     int rank = 0, world = 1;
     ShardComm *comm[kMaxRanks] = {nullptr};  // [rank] = own allocation, others = IPC mappings
-    uint32_t epoch = 0;
-    // device result: segments in the owner's memory (own pointer on the owner, IPC mapping elsewhere)
-    int owner = 0;
-    // result memory (owner's; own pointer on the owner, IPC mapping elsewhere), per epoch parity:
-    //   [ dense result: world x seg_cap ids | segments of ranks 1 .. world-1: seg_cap ids each ]
-    uint32_t *seg_base = nullptr;
+    uint32_t *seg[kMaxRanks] = {nullptr};    // [r] = rank r's own segments: 2 parities x seg_cap ids (behind its comm block)
     uint64_t seg_cap = 0;
+    uint32_t epoch = 0;
+    // device result: memory in the owner's HBM (own pointer on the owner, IPC mapping elsewhere), per epoch parity:
+    //   [ dense result: world x dev_cap ids | segments of ranks 1 .. world-1: dev_cap ids each ]
+    int owner = 0;
+    uint32_t *dev_base = nullptr;
+    uint64_t dev_cap = 0;
     uint32_t last_parity = 0;           // parity of the most recent device-result query
-    int multipath = -1;                 // host result over every rank's PCIe link: -1 = auto (world >= 8), 0, 1
-    // host result
-    void *host_map = nullptr;           // shared mapping: ShardHostHeader, then the ids
+    int host_mode = 1;                  // host result: 1 = staging + copy engine, 2 = the kernel stores into host memory
+    // host result: shared mapping = header, then 2 parities x host_cap ids
+    void *host_map = nullptr;
     size_t host_bytes = 0;
-    uint64_t host_cap = 0;              // ids
+    uint64_t host_cap = 0;
+    uint32_t *host_ids = nullptr;       // first parity's ids (host pointer)
+    uint32_t *host_ids_dev = nullptr;   // device alias (after qpe_shard_pin_host_result)
+    bool host_pinned = false;
     char host_name[96] = {0};
     bool host_creator = false;
-    // per-query counts as seen by this rank (mapped pinned host memory, written by post_kernel)
-    unsigned long long *h_counts = nullptr;
-    unsigned long long *d_counts = nullptr;
+    uint32_t last_host_parity = 0;
+    uint32_t *staging[2] = {nullptr, nullptr};   // this rank's slice of the result before it goes to the host
+    uint64_t staging_cap = 0;
+    cudaEvent_t ev_post[2] = {nullptr, nullptr};  // post-scan kernel of parity p has finished (stream2 waits for it)
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    // per-query words written by the post-scan kernel (mapped pinned host memory), per parity
+    unsigned long long *h_words = nullptr;
+    unsigned long long *d_words = nullptr;
+    ShardPending pending[2];
+    int n_pending = 0;
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
@@ -85,14 +127,24 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long shard_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
-// wait until the slot carries `epoch`; bounded (about 20 s), then trap
-__device__ __forceinline__ unsigned long long wait_slot(const unsigned long long *slot, uint32_t epoch) {
+// wait until the slot carries `epoch`; bounded by time (~20 s): then *timed_out is set and the stale word returned
+__device__ __forceinline__ unsigned long long wait_slot(const unsigned long long *slot, uint32_t epoch, int *timed_out) {
     unsigned long long v = ld_acquire_sys(slot);
+    if (static_cast<uint32_t>(v >> 32) == epoch) return v;
+    const unsigned long long t0 = shard_now_ns();
     uint32_t spins = 0;
     while (static_cast<uint32_t>(v >> 32) != epoch) {
-        __nanosleep(200);
-        if (++spins == 100000000u) __trap();
+        __nanosleep(100);
+        if ((++spins & 0x3ffu) == 0 && shard_now_ns() - t0 > 20000000000ull) {
+            *timed_out = 1;
+            return v;
+        }
         v = ld_acquire_sys(slot);
     }
     return v;
@@ -101,23 +153,20 @@ __device__ __forceinline__ unsigned long long wait_slot(const unsigned long long
 struct PeerPtrs {
     ShardComm *comm[kMaxRanks];
 };
+struct PeerSegs {
+    const uint32_t *seg[kMaxRanks];   // every rank's segment of THIS query's parity
+};
 
-// ids per parity set: the dense area, then one segment per rank >= 1
+// ids per parity set of the device result: the dense area, then one segment per rank >= 1
 __host__ __device__ inline unsigned long long set_ids(int world, unsigned long long seg_cap) {
     return static_cast<unsigned long long>(2 * world - 1) * seg_cap;
 }
 
-// The ONE kernel that follows the scan on every rank (same stream):
-//   1. count exchange: thread r of CTA 0 stores (epoch, this rank's match count) into rank r's comm block;
-//   2. every CTA waits (thread 0, acquire loads of this rank's own comm block) for all counts of the epoch;
-//      CTA 0 also hands them to the host through mapped pinned memory;
-//   3. pack != 0 (owner, device result): the segments of ranks 1.. are moved to their offsets in the dense
-//      result, 4 independent loads in flight per thread (the move is latency-bound otherwise).
-__global__ void __launch_bounds__(256) post_kernel(const unsigned long long *count, PeerPtrs peers, int rank, int world,
-                                                   uint32_t epoch, unsigned long long *host_counts, int pack,
-                                                   uint32_t *set, unsigned long long seg_cap) {
-    __shared__ unsigned long long s_off[kMaxRanks + 1];
-    const unsigned long long my = *reinterpret_cast<const volatile unsigned long long *>(count);
+// The count exchange, common to both post-scan kernels.  Thread r < world of CTA 0 stores (epoch, count) into rank r's
+// comm block; thread r < world of EVERY CTA waits for rank r's count in this rank's own block.  On return s_cnt[r]
+// holds the counts (kCountFailed = that rank failed / timed out) -- after a __syncthreads().
+__device__ __forceinline__ void exchange_counts_dev(unsigned long long my, const PeerPtrs &peers, int rank, int world,
+                                                    uint32_t epoch, unsigned long long *s_cnt, int *s_timeout) {
     if (blockIdx.x == 0 && threadIdx.x < world) {
         __threadfence_system();  // this rank's id stores (peer memory included) are visible before the count is
         st_release_sys(&peers.comm[threadIdx.x]->count[epoch & 1u][rank],
@@ -125,78 +174,22 @@ __global__ void __launch_bounds__(256) post_kernel(const unsigned long long *cou
     }
     if (threadIdx.x < world) {
         const int r = threadIdx.x;
-        const unsigned long long c =
-            (r == rank) ? (my & 0xffffffffull) : (wait_slot(&peers.comm[rank]->count[epoch & 1u][r], epoch) & 0xffffffffull);
-        s_off[r + 1] = c;
-        if (blockIdx.x == 0) host_counts[r] = c;
-    }
-    __syncthreads();
-    if (!pack) return;
-    if (threadIdx.x == 0) {
-        unsigned long long o = 0;
-        for (int r = 0; r < world; ++r) {
-            const unsigned long long c = s_off[r + 1];
-            s_off[r] = o;
-            o += c;
+        int to = 0;
+        unsigned long long c = my & 0xffffffffull;
+        if (r != rank) {
+            c = wait_slot(&peers.comm[rank]->count[epoch & 1u][r], epoch, &to) & 0xffffffffull;
+            if (to) {
+                c = kCountFailed;
+                *s_timeout = 1;
+            }
         }
-        s_off[world] = o;
-    }
-    __syncthreads();
-    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-    const unsigned long long t0 = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
-    for (int r = 1; r < world; ++r) {
-        const unsigned long long n = s_off[r + 1] - s_off[r];
-        if (n > seg_cap || s_off[r] + n > static_cast<unsigned long long>(world) * seg_cap) continue;  // host reports it
-        const uint32_t *__restrict__ src = set + (static_cast<unsigned long long>(world) + (r - 1)) * seg_cap;
-        uint32_t *__restrict__ dst = set + s_off[r];
-        unsigned long long i = t0;
-        for (; i + 3 * stride < n; i += 4 * stride) {
-            const uint32_t a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride),
-                           d = __ldcs(src + i + 3 * stride);
-            dst[i] = a;
-            dst[i + stride] = b;
-            dst[i + 2 * stride] = c;
-            dst[i + 3 * stride] = d;
-        }
-        for (; i < n; i += stride) dst[i] = src[i];
+        s_cnt[r] = c;
     }
 }
 
-// A plain all-gather of one 32-bit value per rank through the comm blocks (same slots, same epoch protocol as
-// the post-scan kernel): thread r stores (epoch, value) into rank r's block, then waits for rank r's value.
-__global__ void exchange_kernel(PeerPtrs peers, int rank, int world, uint32_t epoch, unsigned long long value,
-                                unsigned long long *host_values) {
-    const int r = threadIdx.x;
-    if (r >= world) return;
-    __threadfence_system();
-    st_release_sys(&peers.comm[r]->count[epoch & 1u][rank],
-                   (static_cast<unsigned long long>(epoch) << 32) | (value & 0xffffffffull));
-    host_values[r] = (r == rank) ? (value & 0xffffffffull)
-                                 : (wait_slot(&peers.comm[rank]->count[epoch & 1u][r], epoch) & 0xffffffffull);
-}
-
-// owner, after its pack: tell every rank that the dense result of this epoch is complete
-__global__ void packed_flag_kernel(PeerPtrs peers, int world, uint32_t epoch) {
-    const int r = threadIdx.x;
-    if (r >= world) return;
-    __threadfence_system();
-    st_release_sys(&peers.comm[r]->packed[epoch & 1u], static_cast<unsigned long long>(epoch));
-}
-// every other rank: wait for it (bounded) before reading the owner's memory
-__global__ void packed_wait_kernel(const ShardComm *mine, uint32_t epoch) {
-    if (threadIdx.x != 0) return;
-    uint32_t spins = 0;
-    while (ld_acquire_sys(&mine->packed[epoch & 1u]) != static_cast<unsigned long long>(epoch)) {
-        __nanosleep(200);
-        if (++spins == 100000000u) __trap();
-    }
-}
-
-// this rank's slice of the packed result: owner's HBM -> (NVLink) -> local HBM, 4 independent loads in flight per
-// thread; the copy engine then takes it to the host over this GPU's own PCIe link.  (A cudaMemcpy straight from the
-// peer mapping to the host measured 12 GB/s per rank.)
-__global__ void __launch_bounds__(256) pull_slice_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
-                                                         unsigned long long n) {
+// copy n ids, 4 independent loads in flight per thread (a plain grid-stride copy over NVLink / within HBM is
+// latency-bound: 78 us -> 17 us for 9.4 M ids)
+__device__ __forceinline__ void copy_ids(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, unsigned long long n) {
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
     for (; i + 3 * stride < n; i += 4 * stride) {
@@ -210,13 +203,163 @@ __global__ void __launch_bounds__(256) pull_slice_kernel(const uint32_t *__restr
     for (; i < n; i += stride) dst[i] = src[i];
 }
 
+// hand the counts to the host (mapped pinned memory): words[r] = count, words[kMaxRanks + 1] = status, and LAST
+// words[kMaxRanks] = epoch, which is what the host waits for
+__device__ __forceinline__ void publish_to_host(unsigned long long *words, const unsigned long long *s_cnt, int world,
+                                                uint32_t epoch, int timed_out) {
+    for (int r = 0; r < world; ++r) words[r] = s_cnt[r];
+    words[kMaxRanks + 1] = timed_out ? 1ull : 0ull;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(words + kMaxRanks) = static_cast<unsigned long long>(epoch);
+    __threadfence_system();
+}
+
+// DEVICE RESULT: the ONE kernel that follows the scan on every rank (same stream):
+//   1. count exchange;
+//   2. pack != 0 (owner): the segments of ranks 1.. are moved to their offsets in the dense result;
+//   3. the last CTA to finish hands the counts to the host.
+// count == nullptr: this rank could not scan and publishes the failure marker.
+__global__ void __launch_bounds__(256) post_kernel(const unsigned long long *count, PeerPtrs peers, int rank, int world,
+                                                   uint32_t epoch, unsigned long long *host_words, int pack,
+                                                   uint32_t *set, unsigned long long seg_cap) {
+    __shared__ unsigned long long s_cnt[kMaxRanks];
+    __shared__ unsigned long long s_off[kMaxRanks + 1];
+    __shared__ int s_timeout, s_ok;
+    if (threadIdx.x == 0) s_timeout = 0;
+    __syncthreads();
+    const unsigned long long my = count ? *reinterpret_cast<const volatile unsigned long long *>(count) : kCountFailed;
+    exchange_counts_dev(my, peers, rank, world, epoch, s_cnt, &s_timeout);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long o = 0;
+        int ok = 1;
+        for (int r = 0; r < world; ++r) {
+            const unsigned long long c = s_cnt[r];
+            if (c == kCountFailed || c > seg_cap) ok = 0;
+            s_off[r] = o;
+            o += c;
+        }
+        s_off[world] = o;
+        s_ok = ok;
+    }
+    __syncthreads();
+    if (pack && s_ok) {
+        for (int r = 1; r < world; ++r) {
+            const unsigned long long n = s_off[r + 1] - s_off[r];
+            copy_ids(set + (static_cast<unsigned long long>(world) + (r - 1)) * seg_cap, set + s_off[r], n);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int *done = &peers.comm[rank]->ctas_done[epoch & 1u];
+        if (atomicAdd(done, 1u) == gridDim.x - 1u) {
+            *done = 0u;
+            __threadfence();
+            publish_to_host(host_words, s_cnt, world, epoch, s_timeout);
+        }
+    }
+}
+
+// HOST RESULT: count exchange, then this rank's 1/world of the RESULT is read from whichever ranks' segments it spans
+// (NVLink peer loads) into `dst` = local staging (mode 1: the counts go to the host at once, so that it can queue the
+// copy engine behind this kernel) or the mapped host buffer itself (mode 2: the counts go to the host when the last
+// CTA has stored its ids).
+__global__ void __launch_bounds__(256) deliver_kernel(const unsigned long long *count, PeerPtrs peers, PeerSegs segs, int rank,
+                                                      int world, uint32_t epoch, unsigned long long *host_words,
+                                                      uint32_t *dst, unsigned long long seg_cap,
+                                                      unsigned long long host_cap, unsigned long long dst_cap,
+                                                      int direct) {
+    __shared__ unsigned long long s_cnt[kMaxRanks];
+    __shared__ unsigned long long s_off[kMaxRanks + 1];
+    __shared__ int s_timeout, s_ok;
+    if (threadIdx.x == 0) s_timeout = 0;
+    __syncthreads();
+    const unsigned long long my = count ? *reinterpret_cast<const volatile unsigned long long *>(count) : kCountFailed;
+    exchange_counts_dev(my, peers, rank, world, epoch, s_cnt, &s_timeout);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long o = 0;
+        int ok = 1;
+        for (int r = 0; r < world; ++r) {
+            const unsigned long long c = s_cnt[r];
+            if (c == kCountFailed || c > seg_cap) ok = 0;
+            s_off[r] = o;
+            o += c;
+        }
+        s_off[world] = o;
+        if (o > host_cap) ok = 0;
+        s_ok = ok;
+        if (!direct && blockIdx.x == 0) publish_to_host(host_words, s_cnt, world, epoch, s_timeout);
+    }
+    __syncthreads();
+    if (s_ok) {
+        const unsigned long long total = s_off[world];
+        const unsigned long long lo = total * rank / world, hi = total * (rank + 1) / world;
+        // staging holds the slice from its first id on; the host array is addressed by result position
+        uint32_t *d0 = direct ? dst : dst - lo;
+        if (direct || hi - lo <= dst_cap)
+            for (int r = 0; r < world; ++r) {
+                const unsigned long long a = s_off[r] > lo ? s_off[r] : lo;
+                const unsigned long long b = s_off[r + 1] < hi ? s_off[r + 1] : hi;
+                if (a < b) copy_ids(segs.seg[r] + (a - s_off[r]), d0 + a, b - a);
+            }
+    }
+    if (!direct) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        unsigned int *done = &peers.comm[rank]->ctas_done[epoch & 1u];
+        if (atomicAdd(done, 1u) == gridDim.x - 1u) {
+            *done = 0u;
+            __threadfence();
+            publish_to_host(host_words, s_cnt, world, epoch, s_timeout);
+        }
+    }
+}
+
+// A plain all-gather of one 32-bit value per rank through the comm blocks (same slots, same epoch protocol as
+// the post-scan kernels): thread r stores (epoch, value) into rank r's block, then waits for rank r's value.
+__global__ void exchange_kernel(PeerPtrs peers, int rank, int world, uint32_t epoch, unsigned long long value,
+                                unsigned long long *host_values) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    __threadfence_system();
+    st_release_sys(&peers.comm[r]->count[epoch & 1u][rank],
+                   (static_cast<unsigned long long>(epoch) << 32) | (value & 0xffffffffull));
+    int to = 0;
+    host_values[r] = (r == rank) ? (value & 0xffffffffull)
+                                 : (wait_slot(&peers.comm[rank]->count[epoch & 1u][r], epoch, &to) & 0xffffffffull);
+    if (to) host_values[kMaxRanks + 1] = 1ull;
+}
+
 static ShardState *shard_of(GpuEngine *g) { return static_cast<ShardState *>(g->shard); }
+
+static void release_host_result(ShardState *s) {
+    if (!s->host_map) return;
+    if (s->host_pinned) cudaHostUnregister(s->host_map);
+    munmap(s->host_map, s->host_bytes);
+    if (s->host_creator) shm_unlink(s->host_name);
+    for (int p = 0; p < 2; ++p) {
+        if (s->staging[p]) cudaFree(s->staging[p]);
+        s->staging[p] = nullptr;
+    }
+    s->staging_cap = 0;
+    s->host_map = nullptr;
+    s->host_ids = nullptr;
+    s->host_ids_dev = nullptr;
+    s->host_pinned = false;
+    s->host_bytes = 0;
+    s->host_cap = 0;
+    s->host_creator = false;
+}
 
 void shard_destroy(GpuEngine *g) {
     ShardState *s = shard_of(g);
     if (!s) return;
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
+    cudaStreamSynchronize(g->stream2);
     for (int r = 0; r < s->world; ++r) {
         if (!s->comm[r]) continue;
         if (r == s->rank)
@@ -224,14 +367,75 @@ void shard_destroy(GpuEngine *g) {
         else
             cudaIpcCloseMemHandle(s->comm[r]);
     }
-    if (s->h_counts) cudaFreeHost(s->h_counts);
-    if (s->host_map) {
-        cudaHostUnregister(s->host_map);
-        munmap(s->host_map, s->host_bytes);
-        if (s->host_creator) shm_unlink(s->host_name);
+    if (s->h_words) cudaFreeHost(s->h_words);
+    release_host_result(s);
+    for (int p = 0; p < 2; ++p) {
+        if (s->ev_post[p]) cudaEventDestroy(s->ev_post[p]);
+        if (s->ev_copy[p]) cudaEventDestroy(s->ev_copy[p]);
     }
     delete s;
     g->shard = nullptr;
+}
+
+// NUMA node of this process's GPU (from sysfs), -1 when it cannot be told
+static int gpu_numa_node(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char *c = bus; *c; ++c)
+        if (*c >= 'A' && *c <= 'Z') *c = static_cast<char>(*c - 'A' + 'a');
+    char path[128];
+    std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = std::fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (std::fscanf(f, "%d", &node) != 1) node = -1;
+    std::fclose(f);
+    return node;
+}
+
+// Place [p, p + bytes) on `node` (mbind, then first touch by this process).  Best effort: without the system call
+// (or on a single-node box) the pages simply land where the first touch puts them.
+static void place_on_node(void *p, size_t bytes, int node) {
+    if (bytes == 0) return;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~uintptr_t(4095);
+    const uintptr_t e = (reinterpret_cast<uintptr_t>(p) + bytes + 4095) & ~uintptr_t(4095);
+#ifdef SYS_mbind
+    if (node >= 0 && node < 64) {
+        unsigned long mask = 1ul << node;
+        (void)syscall(SYS_mbind, reinterpret_cast<void *>(a), static_cast<unsigned long>(e - a), 1 /* MPOL_PREFERRED */, &mask,
+                      sizeof(mask) * 8 + 1, 0u);
+    }
+#endif
+    volatile char *c = reinterpret_cast<volatile char *>(a);
+    for (uintptr_t o = 0; o < e - a; o += 4096) c[o] = 0;
+}
+
+// wait (spinning on mapped host memory) until the post-scan kernel of `epoch` has handed its counts over
+static int wait_host_words(GpuEngine *g, ShardState *s, uint32_t epoch) {
+    volatile unsigned long long *w = s->h_words + static_cast<size_t>(epoch & 1u) * kHostWords;
+    unsigned long long spins = 0;
+    while (w[kMaxRanks] != epoch) {
+        if ((++spins & 0xfffu) == 0) {
+            const cudaError_t q = cudaStreamQuery(g->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) {
+                cuda_ok(q, "sharded SELECT kernels");
+                return -4;
+            }
+            if (q == cudaSuccess && w[kMaxRanks] != epoch) {
+                set_error("sharded SELECT: the post-scan kernel finished without handing the counts over");
+                return -4;
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (w[kMaxRanks + 1] != 0) {
+        set_error("sharded SELECT: a rank never published its count (timed out after ~20 s)");
+        return -4;
+    }
+    return 0;
 }
 
 }  // namespace qpe
@@ -240,12 +444,15 @@ using namespace qpe;
 
 extern "C" {
 
-int qpe_shard_init(struct engineS *engine, int rank, int world, unsigned char comm_handle_out[64]) {
+/* Allocates this rank's comm block and its OWN id segments (2 parities x segment_capacity ids, one allocation) and
+ * returns the CUDA IPC handle of it for the other ranks.  segment_capacity must be the same on every rank. */
+int qpe_shard_init(struct engineS *engine, int rank, int world, unsigned long long segment_capacity,
+                   unsigned char comm_handle_out[64]) {
     std::lock_guard<std::mutex> lk(g_api_mutex);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
-    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) {
-        set_error("qpe_shard_init: rank / world out of range (at most 16 ranks)");
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || segment_capacity == 0) {
+        set_error("qpe_shard_init: rank / world out of range (at most 16 ranks) or no segment capacity");
         return -5;
     }
     if (g->shard) shard_destroy(g);
@@ -253,13 +460,22 @@ int qpe_shard_init(struct engineS *engine, int rank, int world, unsigned char co
     ShardState *s = new ShardState();
     s->rank = rank;
     s->world = world;
-    bool ok = cuda_ok(cudaMalloc(&s->comm[rank], sizeof(ShardComm)), "cudaMalloc comm") &&
-              cuda_ok(cudaMemset(s->comm[rank], 0, sizeof(ShardComm)), "cudaMemset comm") &&
-              cuda_ok(cudaHostAlloc(&s->h_counts, sizeof(unsigned long long) * kMaxRanks, cudaHostAllocMapped),
+    s->seg_cap = segment_capacity;
+    const size_t bytes = kCommBytes + 2 * static_cast<size_t>(segment_capacity) * sizeof(uint32_t) + 256;
+    void *block = nullptr;
+    bool ok = cuda_ok(cudaMalloc(&block, bytes), "cudaMalloc comm + segments") &&
+              cuda_ok(cudaMemset(block, 0, kCommBytes), "cudaMemset comm") &&
+              cuda_ok(cudaHostAlloc(&s->h_words, sizeof(unsigned long long) * 2 * kHostWords, cudaHostAllocMapped),
                       "cudaHostAlloc counts") &&
-              cuda_ok(cudaHostGetDevicePointer(&s->d_counts, s->h_counts, 0), "cudaHostGetDevicePointer");
+              cuda_ok(cudaHostGetDevicePointer(&s->d_words, s->h_words, 0), "cudaHostGetDevicePointer");
+    if (ok) std::memset(s->h_words, 0, sizeof(unsigned long long) * 2 * kHostWords);
+    s->comm[rank] = static_cast<ShardComm *>(block);
+    if (block) s->seg[rank] = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(block) + kCommBytes);
+    for (int p = 0; p < 2 && ok; ++p)
+        ok = cuda_ok(cudaEventCreateWithFlags(&s->ev_post[p], cudaEventDisableTiming), "cudaEventCreate") &&
+             cuda_ok(cudaEventCreateWithFlags(&s->ev_copy[p], cudaEventDisableTiming), "cudaEventCreate");
     cudaIpcMemHandle_t h;
-    ok = ok && cuda_ok(cudaIpcGetMemHandle(&h, s->comm[rank]), "cudaIpcGetMemHandle");
+    ok = ok && cuda_ok(cudaIpcGetMemHandle(&h, block), "cudaIpcGetMemHandle");
     g->shard = s;
     if (!ok) {
         shard_destroy(g);
@@ -284,12 +500,14 @@ int qpe_shard_connect(struct engineS *engine, const unsigned char *all_handles) 
         if (s->comm[r]) {  // connected before: drop the old mapping
             cudaIpcCloseMemHandle(s->comm[r]);
             s->comm[r] = nullptr;
+            s->seg[r] = nullptr;
         }
         cudaIpcMemHandle_t h;
         std::memcpy(&h, all_handles + 64 * r, 64);
         void *p = nullptr;
         if (!cuda_ok(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle comm")) return -4;
         s->comm[r] = static_cast<ShardComm *>(p);
+        s->seg[r] = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(p) + kCommBytes);
     }
     return 0;
 }
@@ -312,35 +530,37 @@ int qpe_shard_set_device_result(struct engineS *engine, int owner_rank, unsigned
         return -1;
     }
     s->owner = owner_rank;
-    s->seg_base = segments;
-    s->seg_cap = segment_capacity;
+    s->dev_base = segments;
+    s->dev_cap = segment_capacity;
     return 0;
 }
 
-/* Host result: a buffer of `capacity` ids shared by all ranks of the box.  create != 0 on exactly one
- * rank (it creates /dev/shm/<name>), the others open it afterwards.  Returns the host pointer of the
- * id array in this process (NULL on failure). */
+/* Host result: a buffer of 2 x `capacity` ids (two queries can be in flight) shared by all ranks of the box.
+ * create != 0 on exactly one rank (it creates /dev/shm/<name>), the others open it afterwards.  This maps the buffer
+ * and places THIS rank's parts of it on the NUMA node of its GPU; qpe_shard_pin_host_result, called once every
+ * rank has opened it, registers it with CUDA.  Returns the host pointer of the first id array (NULL on failure);
+ * the second follows `capacity` ids behind. */
 unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *name, unsigned long long capacity,
                                          int create) {
     std::lock_guard<std::mutex> lk(g_api_mutex);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
-    if (!s || !name || std::strlen(name) >= sizeof(s->host_name)) {
-        set_error("qpe_shard_open_host_result: call qpe_shard_init first / bad name");
+    if (!s || !name || std::strlen(name) >= sizeof(s->host_name) || capacity == 0) {
+        set_error("qpe_shard_open_host_result: call qpe_shard_init first / bad name / no capacity");
         return nullptr;
     }
     cudaSetDevice(g->device);
+    if (s->n_pending) {
+        set_error("qpe_shard_open_host_result: queries are still in flight");
+        return nullptr;
+    }
     if (s->host_map) {  // opened before: release the old buffer first
         cudaStreamSynchronize(g->stream);
-        cudaHostUnregister(s->host_map);
-        munmap(s->host_map, s->host_bytes);
-        if (s->host_creator) shm_unlink(s->host_name);
-        s->host_map = nullptr;
-        s->host_bytes = 0;
-        s->host_cap = 0;
-        s->host_creator = false;
+        cudaStreamSynchronize(g->stream2);
+        release_host_result(s);
     }
-    const size_t bytes = sizeof(ShardHostHeader) + sizeof(uint32_t) * (capacity + 16);
+    const uint64_t cap = (capacity + 1023) & ~uint64_t(1023);  // parity 1 starts page aligned
+    const size_t bytes = kHostHeaderBytes + sizeof(uint32_t) * (2 * cap + 16);
     const int fd = shm_open(name, create ? (O_CREAT | O_RDWR | O_TRUNC) : O_RDWR, 0600);
     if (fd < 0) {
         set_error(std::string("shm_open failed for ") + name);
@@ -358,29 +578,60 @@ unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *nam
         return nullptr;
     }
     if (create) std::memset(p, 0, sizeof(ShardHostHeader));
-    if (!cuda_ok(cudaHostRegister(p, bytes, cudaHostRegisterPortable), "cudaHostRegister shared result")) {
-        munmap(p, bytes);
-        return nullptr;
-    }
     s->host_map = p;
     s->host_bytes = bytes;
-    s->host_cap = capacity;
+    s->host_cap = cap;
     s->host_creator = create != 0;
+    s->host_ids = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(p) + kHostHeaderBytes);
     std::strncpy(s->host_name, name, sizeof(s->host_name) - 1);
-    return reinterpret_cast<unsigned int *>(static_cast<uint8_t *>(p) + sizeof(ShardHostHeader));
+    // rank j delivers the j-th 1/world of every result: put that part of both id arrays next to its GPU
+    const int node = gpu_numa_node(g->device);
+    for (int par = 0; par < 2; ++par) {
+        const uint64_t lo = cap * s->rank / s->world, hi = cap * (s->rank + 1) / s->world;
+        place_on_node(s->host_ids + par * cap + lo, (hi - lo) * sizeof(uint32_t), node);
+    }
+    // staging for this rank's slice (mode 1)
+    s->staging_cap = cap / s->world + 1024;
+    for (int par = 0; par < 2; ++par)
+        if (!cuda_ok(cudaMalloc(&s->staging[par], s->staging_cap * sizeof(uint32_t)), "cudaMalloc staging")) {
+            release_host_result(s);
+            return nullptr;
+        }
+    return s->host_ids;
 }
 
-/* Host result path: -1 = automatic (every rank's PCIe link from 8 ranks up), 0 = the first shard streams during its
- * scan and the others copy afterwards, 1 = always over every link.  Every rank must choose the same. */
+/* Once every rank has opened (and placed) the shared buffer: register it with CUDA in this process. */
+int qpe_shard_pin_host_result(struct engineS *engine) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    if (!s || !s->host_map) {
+        set_error("qpe_shard_pin_host_result: open the host result first");
+        return -1;
+    }
+    if (s->host_pinned) return 0;
+    cudaSetDevice(g->device);
+    if (!cuda_ok(cudaHostRegister(s->host_map, s->host_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped),
+                 "cudaHostRegister shared result"))
+        return -4;
+    s->host_pinned = true;
+    void *d = nullptr;
+    if (!cuda_ok(cudaHostGetDevicePointer(&d, s->host_ids, 0), "cudaHostGetDevicePointer shared result")) return -4;
+    s->host_ids_dev = static_cast<uint32_t *>(d);
+    return 0;
+}
+
+/* Host result path: 1 = every rank stages its 1/world of the result in its HBM and the copy engine takes it to the
+ * host (default), 2 = the delivery kernel stores into the mapped host buffer itself.  Every rank must choose the same. */
 int qpe_shard_set_multipath(struct engineS *engine, int mode) {
     std::lock_guard<std::mutex> lk(g_api_mutex);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
-    if (!s || mode < -1 || mode > 1) {
-        set_error("qpe_shard_set_multipath: call qpe_shard_init first; mode is -1, 0 or 1");
+    if (!s || (mode != 1 && mode != 2) || s->n_pending) {
+        set_error("qpe_shard_set_multipath: call qpe_shard_init first; mode is 1 or 2; no query may be in flight");
         return -1;
     }
-    s->multipath = mode;
+    s->host_mode = mode;
     return 0;
 }
 
@@ -401,7 +652,14 @@ int qpe_shard_unlink_host_result(struct engineS *engine) {
 const unsigned int *qpe_shard_device_result(struct engineS *engine) {
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
-    return (s && s->seg_base) ? s->seg_base + s->last_parity * set_ids(s->world, s->seg_cap) : nullptr;
+    return (s && s->dev_base) ? s->dev_base + s->last_parity * set_ids(s->world, s->dev_cap) : nullptr;
+}
+
+/* the id array the most recent host-result query (qpe_shard_wait) was delivered into */
+const unsigned int *qpe_shard_host_result(struct engineS *engine) {
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    return (s && s->host_ids) ? s->host_ids + s->last_host_parity * s->host_cap : nullptr;
 }
 
 void qpe_shard_close(struct engineS *engine) {
@@ -410,146 +668,186 @@ void qpe_shard_close(struct engineS *engine) {
     if (g) shard_destroy(g);
 }
 
-/* One sharded full-scan SELECT; every rank of the group calls it with the same statement, in the same
- * order.  to_host == 0: the ids end up packed in the owner's HBM (qpe_shard_device_result);
- * to_host != 0: in the shared host buffer.  counts_out[world] = per-rank match counts (partition
- * order); the result is their concatenation = table order.  Returns -5 if a rank's ids did not fit. */
-int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, int to_host,
-                     unsigned long long *counts_out, qpe_scan_stats *stats) {
+/* Enqueue one sharded full-scan SELECT and return; every rank of the group calls it with the same statement, in the
+ * same order, and qpe_shard_wait once per submit, in the same order.  At most two queries may be in flight.
+ * to_host == 0: the ids end up packed in the owner's HBM (qpe_shard_device_result); to_host != 0: in the shared host
+ * buffer (qpe_shard_host_result).  A rank whose scan cannot be enqueued still takes part (it publishes a failure
+ * marker) and learns the error from qpe_shard_wait, like every other rank. */
+int qpe_shard_submit(struct engineS *engine, struct whereClauseS *whereClause, int to_host) {
     std::lock_guard<std::mutex> lk(g_api_mutex);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
     if (!s) {
-        set_error("qpe_shard_select: call qpe_shard_init / qpe_shard_connect first");
+        set_error("qpe_shard_submit: call qpe_shard_init / qpe_shard_connect first");
         return -1;
     }
-    if (to_host ? !s->host_map : !s->seg_base) {
-        set_error(to_host ? "qpe_shard_select: no host result buffer" : "qpe_shard_select: no device result segments");
+    if (to_host ? !(s->host_map && s->host_pinned) : !s->dev_base) {
+        set_error(to_host ? "qpe_shard_submit: no (pinned) host result buffer" : "qpe_shard_submit: no device result memory");
         return -1;
     }
-    if (g->table.row_base + static_cast<uint64_t>(g->table.n) > 0xffffffffull) {
-        set_error("global row ids do not fit 32 bits");
-        return -5;
+    if (s->n_pending >= 2) {
+        set_error("qpe_shard_submit: two queries are already in flight (call qpe_shard_wait)");
+        return -1;
     }
     cudaSetDevice(g->device);
     if (++s->epoch == 0) s->epoch = 1;
-    const uint32_t epoch = s->epoch;
+    const uint32_t epoch = s->epoch, par = epoch & 1u;
+    ShardPending &pq = s->pending[par];
+    pq = ShardPending();
+    pq.active = true;
+    pq.to_host = to_host;
+    pq.epoch = epoch;
+    pq.t_begin = now_ms();
+    ++s->n_pending;
     PeerPtrs peers{};
     for (int r = 0; r < s->world; ++r) peers.comm[r] = s->comm[r];
 
-    // Host result over EVERY rank's PCIe link ("multipath"): the ids first land in the owner's HBM exactly as for
-    // a device result, then each rank copies 1/world of the packed list (read over NVLink from the owner) to the
-    // shared host buffer over its own link.  It pays when one link's copy of the whole result far outlasts a shard's
-    // scan.  Measured (1 B rows, 9.45 M ids = 38 MB, all from the first shard): 8 ranks 0.845 -> 0.748 ms per query;
-    // 4 ranks 0.849 -> 1.07 ms (the small per-rank copies reach only ~13-20 GB/s each, and the first shard's
-    // streaming copy hides most of itself under a 0.56 ms scan), hence automatic from 8 ranks up.  Otherwise the
-    // first shard streams its ids out during the scan and the others copy theirs afterwards.
-    const bool multi = to_host && s->world > 1 && s->seg_base != nullptr &&
-                       (s->multipath == 1 || (s->multipath < 0 && s->world >= 8));
-    const bool to_segments = !to_host || multi;
-    // the kernels that follow the scan on the engine's stream, before its single synchronisation
-    uint32_t *set = to_segments ? s->seg_base + (epoch & 1u) * set_ids(s->world, s->seg_cap) : nullptr;
-    const int pack = (to_segments && s->rank == s->owner && s->world > 1) ? 1 : 0;
-    g->post_match = [&]() -> bool {
-        post_kernel<<<pack ? 148 * 8 : 1, 256, 0, g->stream>>>(g->count_dev, peers, s->rank, s->world, epoch, s->d_counts,
-                                                               pack, set, s->seg_cap);
-        if (multi) {
-            if (s->rank == s->owner)
-                packed_flag_kernel<<<1, 32, 0, g->stream>>>(peers, s->world, epoch);
-            else
-                packed_wait_kernel<<<1, 32, 0, g->stream>>>(s->comm[s->rank], epoch);
-        }
-        return cuda_ok(cudaGetLastError(), "shard post-scan kernel launch");
-    };
-    if (to_segments) {
-        // the first shard's offset in the result is always 0: its scan writes the dense result in place
-        g->out_override = s->rank == 0 ? set : set + (static_cast<size_t>(s->world) + (s->rank - 1)) * s->seg_cap;
-        g->out_override_cap = s->seg_cap;
-        s->last_parity = epoch & 1u;
-    }
-    uint32_t *host_ids =
-        to_host ? reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(s->host_map) + sizeof(ShardHostHeader)) : nullptr;
-    if (to_host && !multi && s->rank == 0) {
-        // the first shard's offset is always 0: its ids are copied out segment by segment DURING the scan
-        g->host_out = host_ids;
-        g->host_out_cap = s->host_cap;
-    }
-    g->id_base_override = static_cast<uint32_t>(g->table.row_base);
-    g->id_base_always = true;
-    g->count_mapped = &s->h_counts[s->rank];  // the post kernel hands the count over: no separate download
-    uint64_t m = 0;
-    const bool ok = engine_match(g, whereClause, true, false, false, false, &m);
-    g->post_match = nullptr;
-    g->count_mapped = nullptr;
-    const bool delivered = g->host_out != nullptr && g->host_out_done;
-    g->host_out = nullptr;
-    g->host_out_cap = 0;
-    g->out_override = nullptr;
-    g->out_override_cap = 0;
-    g->id_base_override = 0;
-    g->id_base_always = false;
-    if (!ok) return -2;
-    if (g->last.path != 0 || (g->table.n > 0 && g->last.tile_rows == 0)) {
-        // every rank takes the same branch (same statement, same column widths), so nobody is left waiting
-        set_error("qpe_shard_select: this WHERE cannot be staged by the scan kernel (too wide for shared memory)");
-        return -6;
-    }
-    g->last.launches += multi ? 2 : 1;
-
-    int rc = 0;
-    unsigned long long before = 0, total = 0;
-    for (int r = 0; r < s->world; ++r) {
-        const unsigned long long c = s->h_counts[r];
-        if (counts_out) counts_out[r] = c;
-        if (r < s->rank) before += c;
-        total += c;
-        if (to_segments && c > s->seg_cap) rc = -5;
-    }
+    // where this rank's scan stores its ids
+    uint32_t *out = nullptr;
+    uint64_t out_cap = 0;
+    uint32_t *set = nullptr;
     if (to_host) {
-        ShardHostHeader *hh = static_cast<ShardHostHeader *>(s->host_map);
-        if (multi) {
-            // this rank's 1/world of the packed result: owner's HBM -> (NVLink) -> this GPU -> (its PCIe) -> host
-            const unsigned long long lo = total * s->rank / s->world, hi = total * (s->rank + 1) / s->world;
-            if (total > s->host_cap) rc = -5;
-            if (rc == 0 && hi > lo) {
-                const uint32_t *src = set + lo;
-                if (s->rank != s->owner) {
-                    if (!engine_ensure_ids(g, static_cast<int64_t>(hi - lo))) return -4;
-                    pull_slice_kernel<<<148 * 4, 256, 0, g->stream>>>(set + lo, g->d_ids, hi - lo);
-                    if (!cuda_ok(cudaGetLastError(), "shard slice kernel launch")) return -4;
-                    g->last.launches += 1;
-                    src = g->d_ids;
-                }
-                if (!cuda_ok(cudaMemcpyAsync(host_ids + lo, src, (hi - lo) * 4, cudaMemcpyDeviceToHost, g->stream),
-                             "download ids") ||
-                    !cuda_ok(cudaStreamSynchronize(g->stream), "download ids"))
-                    return -4;
-            }
-        } else if (before + m > s->host_cap) {
-            rc = -5;
-        } else if (m && !delivered) {
-            if (!cuda_ok(cudaMemcpyAsync(host_ids + before, g->d_ids, m * 4, cudaMemcpyDeviceToHost, g->stream),
-                         "download ids") ||
-                !cuda_ok(cudaStreamSynchronize(g->stream), "download ids"))
-                return -4;
+        out = s->seg[s->rank] + static_cast<size_t>(par) * s->seg_cap;  // own segment, read by the other ranks
+        out_cap = s->seg_cap;
+    } else {
+        set = s->dev_base + par * set_ids(s->world, s->dev_cap);
+        // the first shard's offset in the result is always 0: its scan writes the dense result in place
+        out = s->rank == 0 ? set : set + (static_cast<size_t>(s->world) + (s->rank - 1)) * s->dev_cap;
+        out_cap = s->dev_cap;
+    }
+    bool local_ok = true;
+    if (g->table.row_base + static_cast<uint64_t>(g->table.n) > 0xffffffffull) {
+        set_error("global row ids do not fit 32 bits");
+        local_ok = false;
+    }
+    if (local_ok) local_ok = engine_fused_enqueue(g, whereClause, out, out_cap, static_cast<uint32_t>(g->table.row_base), &pq.fe);
+    if (!local_ok) pq.local_error = last_error_cstr();
+    pq.local_ok = local_ok;
+    const unsigned long long *count = local_ok ? &g->d_fctl->final_count : nullptr;
+    unsigned long long *words = s->d_words + static_cast<size_t>(par) * kHostWords;
+    if (to_host) {
+        PeerSegs segs{};
+        for (int r = 0; r < s->world; ++r) segs.seg[r] = s->seg[r] + static_cast<size_t>(par) * s->seg_cap;
+        const bool direct = s->host_mode == 2;
+        uint32_t *dst = direct ? s->host_ids_dev + static_cast<size_t>(par) * s->host_cap : s->staging[par];
+        deliver_kernel<<<148 * 4, 256, 0, g->stream>>>(count, peers, segs, s->rank, s->world, epoch, words, dst, s->seg_cap,
+                                                       s->host_cap, s->staging_cap, direct ? 1 : 0);
+    } else {
+        const int pack = (s->rank == s->owner && s->world > 1) ? 1 : 0;
+        post_kernel<<<pack ? 148 * 8 : 1, 256, 0, g->stream>>>(count, peers, s->rank, s->world, epoch, words, pack, set,
+                                                               s->dev_cap);
+    }
+    const bool launched = cuda_ok(cudaGetLastError(), "shard post-scan kernel launch");
+    if (pq.fe.slot) cudaEventRecord(pq.fe.slot->ev[3], g->stream);
+    cudaEventRecord(s->ev_post[par], g->stream);
+    if (!launched) {
+        // nothing was published: the other ranks will time out; report it here at once
+        pq.active = false;
+        --s->n_pending;
+        return -4;
+    }
+    return 0;
+}
+
+/* Wait for the OLDEST query in flight.  counts_out[world] = per-rank match counts (partition order); the result is
+ * their concatenation = table order.  Returns 0, -5 if a rank's ids did not fit its segment or the result did not fit
+ * the host buffer (every rank returns it; nothing was written past a buffer), -2 / -6 if a rank could not run its scan
+ * (every rank returns it), -4 on a CUDA error or a rank that never arrived. */
+int qpe_shard_wait(struct engineS *engine, unsigned long long *counts_out, qpe_scan_stats *stats) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    if (!s || s->n_pending == 0) {
+        set_error("qpe_shard_wait: no query in flight");
+        return -1;
+    }
+    cudaSetDevice(g->device);
+    // the oldest pending query: with two in flight it is the one with the smaller epoch
+    ShardPending *pq = nullptr;
+    for (int p = 0; p < 2; ++p)
+        if (s->pending[p].active && (!pq || static_cast<int32_t>(s->pending[p].epoch - pq->epoch) < 0)) pq = &s->pending[p];
+    const uint32_t epoch = pq->epoch, par = epoch & 1u;
+    int rc = wait_host_words(g, s, epoch);
+    pq->active = false;
+    --s->n_pending;
+    if (rc != 0) return rc;
+    const volatile unsigned long long *w = s->h_words + static_cast<size_t>(par) * kHostWords;
+    unsigned long long total = 0;
+    bool failed = false, overflow = false;
+    const unsigned long long cap = pq->to_host ? s->seg_cap : s->dev_cap;
+    for (int r = 0; r < s->world; ++r) {
+        const unsigned long long c = w[r];
+        if (c == kCountFailed) {
+            failed = true;
+            if (counts_out) counts_out[r] = 0;
+            continue;
         }
+        if (counts_out) counts_out[r] = c;
+        if (c > cap) overflow = true;
+        total += c;
+    }
+    if (pq->to_host && total > s->host_cap) overflow = true;
+    const unsigned long long mine = pq->local_ok ? w[s->rank] : 0;
+    int extra = 1;
+    if (pq->to_host) {
+        ShardHostHeader *hh = static_cast<ShardHostHeader *>(s->host_map);
+        uint32_t *host_ids = s->host_ids + static_cast<size_t>(par) * s->host_cap;
+        if (!failed && !overflow && s->host_mode == 1) {
+            // this rank's 1/world of the result: local staging -> (its own PCIe link) -> host, on the copy stream, so
+            // that the next query's scan (already enqueued on the main stream) runs beside it
+            const unsigned long long lo = total * s->rank / s->world, hi = total * (s->rank + 1) / s->world;
+            if (hi > lo) {
+                cudaStreamWaitEvent(g->stream2, s->ev_post[par], 0);
+                if (!cuda_ok(cudaMemcpyAsync(host_ids + lo, s->staging[par], (hi - lo) * sizeof(uint32_t),
+                                             cudaMemcpyDeviceToHost, g->stream2),
+                             "download ids") ||
+                    !cuda_ok(cudaEventRecord(s->ev_copy[par], g->stream2), "download ids") ||
+                    !cuda_ok(cudaEventSynchronize(s->ev_copy[par]), "download ids"))
+                    rc = -4;
+            }
+        }
+        // (mode 2: the kernel stored the ids and fenced before it handed the counts over)
         __atomic_store_n(&hh->done[s->rank][0], static_cast<unsigned long long>(epoch), __ATOMIC_RELEASE);
-        if (s->rank == s->owner) {
+        if (s->rank == s->owner && rc == 0) {
             // the result is complete when every rank has delivered its piece
             for (int r = 0; r < s->world; ++r) {
                 unsigned long long spins = 0;
-                while (__atomic_load_n(&hh->done[r][0], __ATOMIC_ACQUIRE) != epoch) {
+                // (>= : with two queries in flight rank r may already have delivered the next one)
+                while (static_cast<int32_t>(static_cast<uint32_t>(__atomic_load_n(&hh->done[r][0], __ATOMIC_ACQUIRE)) - epoch) < 0) {
                     if (++spins > 4000000000ull) {
-                        set_error("qpe_shard_select: a rank never delivered its ids");
+                        set_error("qpe_shard_wait: a rank never delivered its ids");
                         return -4;
                     }
                 }
             }
         }
+        s->last_host_parity = par;
+    } else {
+        s->last_parity = par;
     }
-    if (rc == -5) set_error("a rank's ids did not fit the result buffer (nothing was written past it)");
+    engine_fused_finish(g, pq->fe, mine, extra, pq->t_begin);
+    if (rc != 0) return rc;
+    if (failed) {
+        if (pq->local_ok)
+            set_error("qpe_shard_select: another rank could not run its scan");
+        else
+            set_error(pq->local_error);
+        return pq->local_ok ? -2 : -6;
+    }
+    if (overflow) {
+        set_error("a rank's ids did not fit its segment / the result buffer (nothing was written past it)");
+        return -5;
+    }
     if (stats) qpe_gpu_last_stats(engine, stats);
-    return rc;
+    return 0;
+}
+
+/* One sharded full-scan SELECT, start to finish (submit + wait). */
+int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, int to_host,
+                     unsigned long long *counts_out, qpe_scan_stats *stats) {
+    const int rc = qpe_shard_submit(engine, whereClause, to_host);
+    if (rc != 0) return rc;
+    return qpe_shard_wait(engine, counts_out, stats);
 }
 
 /* DELETE on a sharded table (the MPI engine's executeQueryDeleteMPI, engine/mpi/executeEngine-mpi.c:703-770:
@@ -567,21 +865,35 @@ int qpe_shard_delete(struct engineS *engine, struct whereClauseS *whereClause, u
         set_error("qpe_shard_delete: call qpe_shard_init / qpe_shard_connect first");
         return -1;
     }
+    if (s->n_pending) {
+        set_error("qpe_shard_delete: queries are still in flight");
+        return -1;
+    }
     cudaSetDevice(g->device);
     int64_t deleted = 0;
-    if (!engine_delete(g, whereClause, &deleted)) return -2;
+    // a rank whose DELETE fails still takes part in both exchanges (it publishes its old size and 0 deleted rows)
+    const bool local_ok = engine_delete(g, whereClause, &deleted);
+    const std::string local_error = local_ok ? std::string() : std::string(last_error_cstr());
     PeerPtrs peers{};
     for (int r = 0; r < s->world; ++r) peers.comm[r] = s->comm[r];
     unsigned long long rows_before = 0, rows_total = 0, deleted_total = 0;
-    const unsigned long long mine[2] = {static_cast<unsigned long long>(g->table.n), static_cast<unsigned long long>(deleted)};
+    const unsigned long long mine[2] = {static_cast<unsigned long long>(g->table.n),
+                                        static_cast<unsigned long long>(local_ok ? deleted : 0)};
     for (int pass = 0; pass < 2; ++pass) {
         if (++s->epoch == 0) s->epoch = 1;
-        exchange_kernel<<<1, 32, 0, g->stream>>>(peers, s->rank, s->world, s->epoch, mine[pass], s->d_counts);
+        unsigned long long *words = s->d_words + static_cast<size_t>(s->epoch & 1u) * kHostWords;
+        volatile unsigned long long *hw = s->h_words + static_cast<size_t>(s->epoch & 1u) * kHostWords;
+        hw[kMaxRanks + 1] = 0;
+        exchange_kernel<<<1, 32, 0, g->stream>>>(peers, s->rank, s->world, s->epoch, mine[pass], words);
         if (!cuda_ok(cudaGetLastError(), "shard exchange kernel launch") ||
             !cuda_ok(cudaStreamSynchronize(g->stream), "shard exchange"))
             return -4;
+        if (hw[kMaxRanks + 1] != 0) {
+            set_error("qpe_shard_delete: a rank never published its value (timed out)");
+            return -4;
+        }
         for (int r = 0; r < s->world; ++r) {
-            const unsigned long long v = s->h_counts[r];
+            const unsigned long long v = hw[r];
             if (pass == 0) {
                 rows_total += v;
                 if (r < s->rank) rows_before += v;
@@ -593,6 +905,10 @@ int qpe_shard_delete(struct engineS *engine, struct whereClauseS *whereClause, u
     g->table.row_base = rows_before;
     if (deleted_total_out) *deleted_total_out = deleted_total;
     if (rows_total_out) *rows_total_out = rows_total;
+    if (!local_ok) {
+        set_error(local_error);
+        return -2;
+    }
     return 0;
 }
 

@@ -621,6 +621,12 @@ int qpe_sql_shard_select(struct engineS *engine, const char *statement, int to_h
     return rc;
 }
 
+int qpe_sql_shard_submit(struct engineS *engine, const char *statement, int to_host) {
+    const ParsedWhere &pw = parse_cached(statement);
+    if (!pw.ok) return -7;
+    return qpe_shard_submit(engine, pw.wc, to_host);
+}
+
 int qpe_sql_select_segments(struct engineS *engine, const char *statement, int global_ids, int *used_index_out,
                             int *n_segments_out, size_t seg_counts_out[32], long long **keys_out,
                             unsigned int **ids_out) {

@@ -249,9 +249,12 @@ class PeerGather:
 
 class ShardGroup:
     """A row-range sharded table driven natively (csrc/shard.cu): per query NO host collective and no NCCL
-    call.  Every rank's scan kernel stores its global row ids into the owner's result buffer over NVLink
-    peer memory, a tiny kernel stores (epoch, count) into every rank's comm block, the owner packs the
-    segments in partition order.  `torch.distributed` is used once, here, to pass the IPC handles around."""
+    call.  Device result: every rank's scan kernel stores its global row ids into the owner's result buffer over
+    NVLink peer memory, a kernel stores (epoch, count) into every rank's comm block, the owner packs the segments
+    in partition order.  Host result: the ids stay in the rank's own segment, and every rank takes ITS 1/world of
+    the result (read over NVLink from whichever segments it spans) to the shared host buffer over its own PCIe link.
+    Up to two queries can be in flight (`submit` / `wait`).  `torch.distributed` is used once, here, to pass the
+    IPC handles around."""
 
     def __init__(self, pkg, engine, segment_capacity: int, host_capacity: int = 0, owner: int = 0, group=None,
                  counts_device="cpu"):
@@ -262,13 +265,14 @@ class ShardGroup:
         self.world = dist.get_world_size(group)
         self.lib = pkg.load_library()
         lib, h = self.lib, engine._h
+        # every rank must lay its segments out identically: agree on the largest request
+        self.seg_cap = max(exchange_counts(int(max(segment_capacity, 1)), counts_device, group))
         buf = C.create_string_buffer(64)
-        engine._check(lib.qpe_shard_init(h, self.rank, self.world, buf), "qpe_shard_init")
+        engine._check(lib.qpe_shard_init(h, self.rank, self.world, self.seg_cap, buf), "qpe_shard_init")
         handles = [None] * self.world
         dist.all_gather_object(handles, buf.raw, group=group)
         engine._check(lib.qpe_shard_connect(h, b"".join(handles)), "qpe_shard_connect")
         # device result memory in the owner's HBM (dense result + one segment per rank >= 1, two parities)
-        self.seg_cap = max(exchange_counts(int(max(segment_capacity, 1)), counts_device, group))
         self.buffer = None
         obj = [None]
         if self.rank == owner:
@@ -279,12 +283,12 @@ class ShardGroup:
         if self.rank != owner:
             self.seg_ptr = pkg.ipc_open(obj[0])
         engine._check(lib.qpe_shard_set_device_result(h, owner, self.seg_ptr, self.seg_cap), "set_device_result")
-        # host result: one shared-memory id buffer, every rank delivers its piece over its own PCIe link
-        self.host_ids = None
+        # host result: one shared-memory id buffer, every rank delivers its 1/world of a result over its own PCIe link
         self.host_cap = max(exchange_counts(int(host_capacity), counts_device, group))
         if self.host_cap > 0:
             name = [f"/qpe_shard_{os.getpid()}_{id(self) & 0xffff:x}" if self.rank == owner else None]
             dist.broadcast_object_list(name, src=owner, group=group)
+            p = 1
             if self.rank == owner:
                 p = lib.qpe_shard_open_host_result(h, name[0].encode(), self.host_cap, 1)
             dist.barrier(group=group)
@@ -292,33 +296,58 @@ class ShardGroup:
                 p = lib.qpe_shard_open_host_result(h, name[0].encode(), self.host_cap, 0)
             if not p:
                 raise pkg.QpeError("shared host result: " + (lib.qpe_gpu_last_error() or b"").decode())
-            import numpy as np
-            self.host_ids = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(self.host_cap,))
+            dist.barrier(group=group)   # every rank has placed its part of the buffer: now pin it
+            engine._check(lib.qpe_shard_pin_host_result(h), "qpe_shard_pin_host_result")
         self._counts = (C.c_ulonglong * 16)()
         self._stats = pkg.ScanStats()
         self._C = C
         self._pstats = C.byref(self._stats)
-        self._fn, self._h = lib.qpe_sql_shard_select, engine._h
+        self._h = engine._h
         self._last_sql, self._last_bytes = None, None
         dist.barrier(group=group)
         if self.host_cap > 0 and self.rank == owner:
             lib.qpe_shard_unlink_host_result(h)   # every rank has it mapped: no name left in /dev/shm
 
-    def select(self, statement: str, to_host: bool = False, stats: bool = True):
-        """One sharded full-scan SELECT (every rank calls it).  Returns (total, per-rank counts, ScanStats).
-        to_host=False: ids packed in the owner's HBM (`device_result`); True: in `host_ids` on every rank.
-        stats=False: no statistics (None); the event times stay unresolved (Engine.set_timing / timing_totals)."""
+    def _encode(self, statement: str) -> bytes:
         if statement is not self._last_sql:      # the same statement object again: no re-encoding
             self._last_sql, self._last_bytes = statement, statement.encode()
-        rc = self._fn(self._h, self._last_bytes, 1 if to_host else 0, self._counts, self._pstats if stats else None)
+        return self._last_bytes
+
+    def submit(self, statement: str, to_host: bool = False):
+        """Enqueue one sharded full-scan SELECT (every rank calls it, same statement, same order); at most two may
+        be in flight.  `wait` completes them in submission order."""
+        rc = self.lib.qpe_sql_shard_submit(self._h, self._encode(statement), 1 if to_host else 0)
         if rc != 0:
-            self.engine._check(rc, "qpe_shard_select")
+            self.engine._check(rc, "qpe_shard_submit")
+
+    def wait(self, stats: bool = True):
+        """Complete the oldest query in flight: (total, per-rank counts, ScanStats / None)."""
+        rc = self.lib.qpe_shard_wait(self._h, self._counts, self._pstats if stats else None)
+        if rc != 0:
+            self.engine._check(rc, "qpe_shard_wait")
         counts = self._counts[:self.world]
         return sum(counts), counts, (self._stats if stats else None)
 
+    def select(self, statement: str, to_host: bool = False, stats: bool = True):
+        """One sharded full-scan SELECT, start to finish.  Returns (total, per-rank counts, ScanStats).
+        to_host=False: ids packed in the owner's HBM (`device_result`); True: in the shared host buffer
+        (`host_result`).  stats=False: no statistics (None); the event times stay unresolved."""
+        self.submit(statement, to_host)
+        return self.wait(stats)
+
     def set_multipath(self, mode: int):
-        """host result over every rank's PCIe link: -1 auto (from 8 ranks up), 0 off, 1 on; same on every rank"""
+        """host result: 1 = staging in HBM + copy engine (default), 2 = the kernel stores into host memory"""
         self.engine._check(self.lib.qpe_shard_set_multipath(self.engine._h, mode), "qpe_shard_set_multipath")
+
+    def host_result(self, total: int):
+        """the ids of the most recent host-result query `wait` completed (a view of the shared buffer: valid until
+        the second `submit` after that `wait`)"""
+        import numpy as np
+        C = self._C
+        p = self.lib.qpe_shard_host_result(self._h)
+        if not p or total <= 0:
+            return np.zeros(0, dtype=np.uint32)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(int(total),))
 
     def delete(self, statement: str):
         """DELETE on the sharded table (every rank calls it): (rows deleted, rows left) over all shards.  The
@@ -338,7 +367,6 @@ class ShardGroup:
 
     def close(self):
         dist.barrier(group=self.group)
-        self.host_ids = None
         self.lib.qpe_shard_close(self.engine._h)
         if self.rank != self.owner:
             self.pkg.ipc_close(self.seg_ptr)

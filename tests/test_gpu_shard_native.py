@@ -25,6 +25,7 @@ QUERIES = ["SELECT command_id FROM Commands WHERE (command_id < 1700000) AND (su
            "SELECT command_id FROM Commands WHERE (sudo_used = TRUE) OR (risk_level < 2)"]
 COLS = ["command_id", "sudo_used", "risk_level"]
 DELETE_SQL = "DELETE FROM Commands WHERE (risk_level = 2) OR (command_id < 1000)"
+TINY_SQL = "SELECT command_id FROM Commands WHERE (command_id > 2499900)"
 
 
 def _free_port():
@@ -46,9 +47,9 @@ def _worker(rank, world, port, ret):
     start, n = sharding.shard_range(TOTAL, world, rank)
     eng = pkg.Engine.from_synth(TOTAL, n_rows=n, row_base=start, columns=COLS)
     grp = sharding.ShardGroup(pkg, eng, segment_capacity=n + 1, host_capacity=TOTAL)
-    # both host-result paths: the first shard streaming during its scan (2 ranks) and every rank copying its
-    # 1/world of the packed result out of the owner's memory (3 ranks; automatic only from 8 ranks up)
-    grp.set_multipath(1 if world == 3 else 0)
+    # both host-result paths: every rank stages its 1/world of the result and the copy engine takes it to the host
+    # (2 ranks), and the delivery kernel storing into the mapped host buffer itself (3 ranks)
+    grp.set_multipath(2 if world == 3 else 1)
     out = []
     # every query twice in a row (device result then host result), then the whole list again: epochs and
     # the two parities of every buffer get reused with different contents
@@ -58,7 +59,18 @@ def _worker(rank, world, port, ret):
             dev_ids = grp.device_result(total).copy() if rank == 0 else None
             total_h, counts_h, _ = grp.select(q, to_host=True)
             if rank == 0:
-                out.append((total, counts, dev_ids, total_h, counts_h, grp.host_ids[:total_h].copy()))
+                out.append((total, counts, dev_ids, total_h, counts_h, grp.host_result(total_h).copy()))
+    # two queries in flight: submit q + 1 before waiting for q, device and host results alternating
+    piped = []
+    plan = [(q, k % 2 == 1) for k, q in enumerate(QUERIES + QUERIES[::-1])]
+    grp.submit(*plan[0])
+    for k, (q, to_host) in enumerate(plan):
+        if k + 1 < len(plan):
+            grp.submit(*plan[k + 1])
+        total, counts, _ = grp.wait()
+        if rank == 0:
+            ids = grp.host_result(total).copy() if to_host else grp.device_result(total).copy()
+            piped.append((q, total, counts, ids))
     # sharded DELETE (local compaction + renumbering through the comm blocks), then the same queries again:
     # global row ids must be positions in the table AFTER the delete
     deleted, left = grp.delete(DELETE_SQL)
@@ -68,9 +80,23 @@ def _worker(rank, world, port, ret):
         ids = grp.device_result(total).copy() if rank == 0 else None
         after.append((total, ids))
     grp.close()
+    # errors are collective: a segment too small for a rank's ids fails on EVERY rank (and nothing hangs);
+    # the group keeps working afterwards
+    small = sharding.ShardGroup(pkg, eng, segment_capacity=1000, host_capacity=4000)
+    errors = []
+    for to_host in (False, True):
+        try:
+            small.select(QUERIES[0], to_host=to_host)
+            errors.append("no error")
+        except pkg.QpeError as e:
+            errors.append(str(e))
+    tiny_total, _, _ = small.select(TINY_SQL, to_host=True)
+    all_errors = [None] * world
+    dist.all_gather_object(all_errors, (errors, tiny_total))
+    small.close()
     eng.close()
     if rank == 0:
-        ret.put((out, deleted, left, after))
+        ret.put((out, deleted, left, after, piped, all_errors))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -84,7 +110,7 @@ def test_native_shard_select_equals_single_engine(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
     for p in procs:
         p.start()
-    results, deleted, left, after = ret.get(timeout=600)
+    results, deleted, left, after, piped, all_errors = ret.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -96,9 +122,16 @@ def test_native_shard_select_equals_single_engine(world):
         assert len(counts) == world and sum(counts) == total and counts == counts_h
         assert np.array_equal(dev_ids, want), q
         assert np.array_equal(host_ids, want), q
+    for q, total, counts, ids in piped:
+        want, _ = whole.select_ids(q, force_scan=True)
+        assert total == len(want) and sum(counts) == total and np.array_equal(ids, want), "two in flight: " + q
     # the same DELETE on the whole table, then the same queries
     out = whole.run(DELETE_SQL, 5)
     assert f"Rows affected: {deleted}" in out and whole.num_rows == left == TOTAL - deleted
+    tiny_want, _ = whole.select_ids(TINY_SQL, force_scan=True)
+    for errors, tiny_total in all_errors:   # every rank saw the same failures, and the same success afterwards
+        assert len(errors) == 2 and all("rc=-5" in e for e in errors), errors
+        assert tiny_total == len(tiny_want) > 0
     for q, (total, ids) in zip(QUERIES, after):
         want, _ = whole.select_ids(q, force_scan=True)
         assert total == len(want) and np.array_equal(ids, want), "after DELETE: " + q
