@@ -691,14 +691,22 @@ def run_ours(args):
         launches = st0.launches
         for to_host in (False, True):
             piped(to_host)(warmup)
+        # one query at a time: K1f's own CUDA-event time (a pipelined scan starts under the previous query's
+        # exchange kernel and is not timed on its own), and the sync numbers
         eng.set_timing(True)
-        ms_step, n_matches, clocks = timed(piped(False), steps, ClockSampler(local_rank))
+        ms_sync, _, _ = timed(synced(False), steps)
         tot = eng.timing_totals()
         eng.set_timing(False)
         assert tot["calls"] == steps, tot
-        k1 = torch.tensor([tot["scan_ms"] / tot["calls"], tot["post_ms"] / tot["calls"]], dtype=torch.float64, device=dev)
-        dist.all_reduce(k1, op=dist.ReduceOp.MAX)
-        k1_ms, post_ms = k1[0].item(), k1[1].item()
+        mine = torch.tensor([tot["scan_ms"] / tot["calls"], tot["post_ms"] / tot["calls"]], dtype=torch.float64, device=dev)
+        every = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(every, mine)
+        k1_by_rank = [round(v[0].item(), 4) for v in every]
+        post_by_rank = [round(v[1].item(), 4) for v in every]
+        k1_ms = max(k1_by_rank)
+        ms_e2e_sync, _, _ = timed(synced(True), steps)
+        # two queries in flight
+        ms_step, n_matches, clocks = timed(piped(False), steps, ClockSampler(local_rank))
         ms_e2e, n_e2e, _ = timed(piped(True), steps)
         assert n_e2e == n_matches
         if rank == 0:   # the delivered ids are the packed device result, bit for bit
@@ -706,11 +714,9 @@ def run_ours(args):
         sg.select(sql, to_host=False, stats=False)
         if rank == 0:
             assert np.array_equal(host_ids, sg.device_result(n_matches)), "host result differs from the device result"
-        ms_sync, _, _ = timed(synced(False), steps)
-        ms_e2e_sync, _, _ = timed(synced(True), steps)
         sync_info = {"sync_ms_per_step": ms_sync, "sync_value": total / (ms_sync * 1e-3),
                      "e2e_sync_ms_per_step": ms_e2e_sync, "e2e_sync_value": total / (ms_e2e_sync * 1e-3),
-                     "post_scan_kernel_ms": post_ms}
+                     "k1f_ms_by_rank": k1_by_rank, "post_scan_kernel_ms_by_rank": post_by_rank}
         # the same with matches spread evenly over the shards: every rank's own ids go out over its own link
         upiped, _ = make_loops(usql)
         for to_host in (False, True):

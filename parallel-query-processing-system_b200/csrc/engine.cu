@@ -855,7 +855,7 @@ static GpuEngine::TimingSlot *take_timing_slot(GpuEngine *g) {
 }
 
 bool engine_fused_enqueue(GpuEngine *g, const struct whereClauseS *wc, uint32_t *out_ids, uint64_t out_cap,
-                          uint32_t id_base, FusedEnqueue *fe) {
+                          uint32_t id_base, FusedEnqueue *fe, bool overlap_previous) {
     cudaSetDevice(g->device);
     const DevTable &t = g->table;
     fe->slot = nullptr;
@@ -878,15 +878,18 @@ bool engine_fused_enqueue(GpuEngine *g, const struct whereClauseS *wc, uint32_t 
             }
             fe->bytes_per_row += t.col[c].width;
         }
-    GpuEngine::TimingSlot *slot = take_timing_slot(g);
+    // an overlapped scan is not timed: an event between it and the stream's previous kernel would serialise the two
+    GpuEngine::TimingSlot *slot = overlap_previous ? nullptr : take_timing_slot(g);
     fe->slot = slot;
     if (t.n == 0) {
         // an empty shard still takes part: its count is 0
-        cudaEventRecord(slot->ev[0], g->stream);
+        if (slot) cudaEventRecord(slot->ev[0], g->stream);
         if (!cuda_ok(cudaMemsetAsync(&g->d_fctl->final_count, 0, sizeof(unsigned long long), g->stream), "reset count"))
             return false;
-        cudaEventRecord(slot->ev[1], g->stream);
-        cudaEventRecord(slot->ev[2], g->stream);
+        if (slot) {
+            cudaEventRecord(slot->ev[1], g->stream);
+            cudaEventRecord(slot->ev[2], g->stream);
+        }
         return true;
     }
     const char *why = nullptr;
@@ -913,10 +916,13 @@ bool engine_fused_enqueue(GpuEngine *g, const struct whereClauseS *wc, uint32_t 
     F.out_ids = out_ids;
     F.out_cap = out_cap;
     F.d_fctl = g->d_fctl;
-    cudaEventRecord(slot->ev[0], g->stream);
+    F.pdl = overlap_previous;
+    if (slot) cudaEventRecord(slot->ev[0], g->stream);
     if (!cuda_ok(fused_launch(F, fg, g->stream), "fused scan kernel launch")) return false;
-    cudaEventRecord(slot->ev[1], g->stream);
-    cudaEventRecord(slot->ev[2], g->stream);
+    if (slot) {
+        cudaEventRecord(slot->ev[1], g->stream);
+        cudaEventRecord(slot->ev[2], g->stream);
+    }
     fe->geo = fg;
     fe->launched = true;
     return true;
@@ -936,6 +942,7 @@ void engine_fused_finish(GpuEngine *g, const FusedEnqueue &fe, uint64_t matches,
     st.total_ms = now_ms() - t_begin_ms;
     if (st.rows_scanned > 0) g->fuse_cw = (st.matches * 8 > st.rows_scanned) ? 8 : 4;
     g->last = st;
+    if (!fe.slot) g->cur_slot = nullptr;  // an overlapped (untimed) scan: no event times to resolve for it
     if (fe.slot) {
         g->cur_slot = fe.slot;
         fe.slot->pending = true;

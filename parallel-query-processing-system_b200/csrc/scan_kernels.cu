@@ -1283,7 +1283,7 @@ cudaError_t batch_launch(const ScanLaunch &L, const ScanGeometry &geo, int n_pro
 }
 
 template <int RPL, int CW>
-static cudaError_t launch_fused_r(const FusedParams &fp, const ScanGeometry &geo, cudaStream_t stream) {
+static cudaError_t launch_fused_r(const FusedParams &fp, const ScanGeometry &geo, cudaStream_t stream, bool pdl) {
     static size_t allowed_by_device[kMaxDevices] = {0};
     size_t &allowed = allowed_by_device[current_device_slot()];
     if (geo.smem_bytes > allowed) {
@@ -1292,13 +1292,28 @@ static cudaError_t launch_fused_r(const FusedParams &fp, const ScanGeometry &geo
         if (e != cudaSuccess) return e;
         allowed = geo.smem_bytes;
     }
+    if (pdl) {
+        // programmatic dependent launch: this scan may start while the kernel before it in the stream (the previous
+        // query's count exchange / delivery, which has nothing to hand to it) is still running
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(geo.grid);
+        cfg.blockDim = dim3(32 * (kEvalWarps + CW));
+        cfg.dynamicSmemBytes = geo.smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, scan_fused_kernel<RPL, CW>, fp);
+    }
     scan_fused_kernel<RPL, CW><<<geo.grid, 32 * (kEvalWarps + CW), geo.smem_bytes, stream>>>(fp);
     return cudaGetLastError();
 }
 
 template <int RPL>
-static cudaError_t launch_fused_cw(const FusedParams &fp, const ScanGeometry &geo, cudaStream_t stream) {
-    return geo.compact_warps == 8 ? launch_fused_r<RPL, 8>(fp, geo, stream) : launch_fused_r<RPL, 4>(fp, geo, stream);
+static cudaError_t launch_fused_cw(const FusedParams &fp, const ScanGeometry &geo, cudaStream_t stream, bool pdl) {
+    return geo.compact_warps == 8 ? launch_fused_r<RPL, 8>(fp, geo, stream, pdl) : launch_fused_r<RPL, 4>(fp, geo, stream, pdl);
 }
 
 cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStream_t stream) {
@@ -1325,9 +1340,9 @@ cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStre
     if (!fp.fctl) return cudaErrorInvalidValue;
     if (fp.n_chunks == 0) return cudaSuccess;
     switch (geo.tile_rows) {
-        case 256: return launch_fused_cw<8>(fp, geo, stream);
-        case 512: return launch_fused_cw<16>(fp, geo, stream);
-        case 1024: return launch_fused_cw<32>(fp, geo, stream);
+        case 256: return launch_fused_cw<8>(fp, geo, stream, L.pdl);
+        case 512: return launch_fused_cw<16>(fp, geo, stream, L.pdl);
+        case 1024: return launch_fused_cw<32>(fp, geo, stream, L.pdl);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -90,6 +90,7 @@ struct FusedLaunch {
     unsigned long long *host_count;  // mapped pinned host word (device alias) that receives the match count, or null
     FusedCtl *d_fctl;                // device, zeroed once at engine creation
     unsigned long long *trace;       // diagnostics: 8 words per CTA (device), or null
+    bool pdl;                        // programmatic dependent launch: may overlap the previous kernel of the stream
 };
 size_t fused_param_bytes();          // bytes of K1f's kernel parameter block (carries the compiled program)
 cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStream_t stream);

@@ -54,6 +54,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -117,6 +118,7 @@ struct ShardState {
     unsigned long long *d_words = nullptr;
     ShardPending pending[2];
     int n_pending = 0;
+    bool last_was_post = false;         // the engine stream's most recent kernel is a post-scan kernel of this file
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
@@ -225,6 +227,8 @@ __global__ void __launch_bounds__(256) post_kernel(const unsigned long long *cou
     __shared__ unsigned long long s_cnt[kMaxRanks];
     __shared__ unsigned long long s_off[kMaxRanks + 1];
     __shared__ int s_timeout, s_ok;
+    // the next query's scan (a programmatic dependent launch) needs nothing from this kernel: let it start now
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) s_timeout = 0;
     __syncthreads();
     const unsigned long long my = count ? *reinterpret_cast<const volatile unsigned long long *>(count) : kCountFailed;
@@ -262,9 +266,9 @@ __global__ void __launch_bounds__(256) post_kernel(const unsigned long long *cou
 }
 
 // HOST RESULT: count exchange, then this rank's 1/world of the RESULT is read from whichever ranks' segments it spans
-// (NVLink peer loads) into `dst` = local staging (mode 1: the counts go to the host at once, so that it can queue the
-// copy engine behind this kernel) or the mapped host buffer itself (mode 2: the counts go to the host when the last
-// CTA has stored its ids).
+// (NVLink peer loads) into `dst` = local staging (mode 1: the host then queues the copy engine) or the mapped host
+// buffer itself (mode 2).  The counts go to the host when the last CTA has stored its ids, so the host needs no
+// event between this kernel and the next query's scan to know that the slice is complete.
 __global__ void __launch_bounds__(256) deliver_kernel(const unsigned long long *count, PeerPtrs peers, PeerSegs segs, int rank,
                                                       int world, uint32_t epoch, unsigned long long *host_words,
                                                       uint32_t *dst, unsigned long long seg_cap,
@@ -273,6 +277,8 @@ __global__ void __launch_bounds__(256) deliver_kernel(const unsigned long long *
     __shared__ unsigned long long s_cnt[kMaxRanks];
     __shared__ unsigned long long s_off[kMaxRanks + 1];
     __shared__ int s_timeout, s_ok;
+    // the next query's scan (a programmatic dependent launch) needs nothing from this kernel: let it start now
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) s_timeout = 0;
     __syncthreads();
     const unsigned long long my = count ? *reinterpret_cast<const volatile unsigned long long *>(count) : kCountFailed;
@@ -290,7 +296,6 @@ __global__ void __launch_bounds__(256) deliver_kernel(const unsigned long long *
         s_off[world] = o;
         if (o > host_cap) ok = 0;
         s_ok = ok;
-        if (!direct && blockIdx.x == 0) publish_to_host(host_words, s_cnt, world, epoch, s_timeout);
     }
     __syncthreads();
     if (s_ok) {
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(256) deliver_kernel(const unsigned long long *
                 if (a < b) copy_ids(segs.seg[r] + (a - s_off[r]), d0 + a, b - a);
             }
     }
-    if (!direct) return;
+    // the last CTA to finish hands the counts to the host: the slice is then complete in `dst`
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
@@ -720,7 +725,13 @@ int qpe_shard_submit(struct engineS *engine, struct whereClauseS *whereClause, i
         set_error("global row ids do not fit 32 bits");
         local_ok = false;
     }
-    if (local_ok) local_ok = engine_fused_enqueue(g, whereClause, out, out_cap, static_cast<uint32_t>(g->table.row_base), &pq.fe);
+    // With a query already in flight the stream's last kernel is ITS count exchange / delivery kernel, which hands
+    // nothing to this scan (other parity of every buffer): the scan is launched as a programmatic dependent, so its
+    // CTAs move in while that kernel is still waiting for the other ranks / moving ids.
+    static const bool no_pdl = std::getenv("QPE_SHARD_NO_PDL") != nullptr;
+    const bool overlap = s->n_pending >= 2 && s->last_was_post && !no_pdl;
+    if (local_ok)
+        local_ok = engine_fused_enqueue(g, whereClause, out, out_cap, static_cast<uint32_t>(g->table.row_base), &pq.fe, overlap);
     if (!local_ok) pq.local_error = last_error_cstr();
     pq.local_ok = local_ok;
     const unsigned long long *count = local_ok ? &g->d_fctl->final_count : nullptr;
@@ -738,8 +749,9 @@ int qpe_shard_submit(struct engineS *engine, struct whereClauseS *whereClause, i
                                                                s->dev_cap);
     }
     const bool launched = cuda_ok(cudaGetLastError(), "shard post-scan kernel launch");
-    if (pq.fe.slot) cudaEventRecord(pq.fe.slot->ev[3], g->stream);
-    cudaEventRecord(s->ev_post[par], g->stream);
+    s->last_was_post = launched;
+    // (no event may sit between this kernel and the next query's scan if that scan is to overlap it)
+    if (pq.fe.slot && !overlap) cudaEventRecord(pq.fe.slot->ev[3], g->stream);
     if (!launched) {
         // nothing was published: the other ranks will time out; report it here at once
         pq.active = false;
@@ -797,7 +809,6 @@ int qpe_shard_wait(struct engineS *engine, unsigned long long *counts_out, qpe_s
             // that the next query's scan (already enqueued on the main stream) runs beside it
             const unsigned long long lo = total * s->rank / s->world, hi = total * (s->rank + 1) / s->world;
             if (hi > lo) {
-                cudaStreamWaitEvent(g->stream2, s->ev_post[par], 0);
                 if (!cuda_ok(cudaMemcpyAsync(host_ids + lo, s->staging[par], (hi - lo) * sizeof(uint32_t),
                                              cudaMemcpyDeviceToHost, g->stream2),
                              "download ids") ||
@@ -871,6 +882,7 @@ int qpe_shard_delete(struct engineS *engine, struct whereClauseS *whereClause, u
     }
     cudaSetDevice(g->device);
     int64_t deleted = 0;
+    s->last_was_post = false;
     // a rank whose DELETE fails still takes part in both exchanges (it publishes its old size and 0 deleted rows)
     const bool local_ok = engine_delete(g, whereClause, &deleted);
     const std::string local_error = local_ok ? std::string() : std::string(last_error_cstr());
