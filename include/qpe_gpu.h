@@ -169,6 +169,8 @@ int qpe_shard_set_device_result(struct engineS *engine, int owner_rank, unsigned
 unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *name, unsigned long long capacity,
                                          int create);
 int qpe_shard_pin_host_result(struct engineS *engine);
+/* NUMA node of this rank's GPU (-1 unknown); *how_out: bit 0 = mbind accepted, bit 1 = first touch under that node's CPUs */
+int qpe_shard_numa(struct engineS *engine, int *how_out);
 /* creator, after every rank has opened the buffer: drop its /dev/shm name (mappings stay valid) */
 int qpe_shard_unlink_host_result(struct engineS *engine);
 /* the packed ids of the most recent device-result / host-result query that qpe_shard_wait completed.  A host result

@@ -158,6 +158,7 @@ def load_library() -> C.CDLL:
         "qpe_shard_device_result": (vp, [vp]),
         "qpe_shard_host_result": (vp, [vp]),
         "qpe_shard_pin_host_result": (i, [vp]),
+        "qpe_shard_numa": (i, [vp, C.POINTER(i)]),
         "qpe_shard_wait": (i, [vp, C.POINTER(ull), pstats]),
         "qpe_sql_shard_submit": (i, [vp, cp, i]),
         "qpe_shard_close": (None, [vp]),

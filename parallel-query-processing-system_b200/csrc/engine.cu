@@ -189,6 +189,8 @@ void engine_destroy(GpuEngine *g) {
     if (g->h_probe_keys) cudaFreeHost(g->h_probe_keys);
     if (g->h_probe_out) cudaFreeHost(g->h_probe_out);
     if (g->d_probe_scratch) cudaFree(g->d_probe_scratch);
+    if (g->d_dml_scratch) cudaFree(g->d_dml_scratch);
+    if (g->h_row_stage) cudaFreeHost(g->h_row_stage);
     if (g->h_probe_bounce) cudaFreeHost(g->h_probe_bounce);
     for (int i = 0; i < GpuEngine::kTimingRing; ++i)
         for (int k = 0; k < 4; ++k)
@@ -1291,6 +1293,17 @@ bool engine_download_all(GpuEngine *g, HostColumns *out) {
 // ------------------------------------------------------------------------------------------
 // DELETE: stable compaction of every column by the keep list (K1 with the inverted program)
 // ------------------------------------------------------------------------------------------
+static bool ensure_dml_scratch(GpuEngine *g, size_t bytes) {
+    if (bytes <= g->dml_scratch_bytes && g->d_dml_scratch) return true;
+    if (g->d_dml_scratch) cudaFree(g->d_dml_scratch);
+    g->d_dml_scratch = nullptr;
+    g->dml_scratch_bytes = 0;
+    const size_t cap = bytes + bytes / 8 + 4096;
+    if (!cuda_ok(cudaMalloc(&g->d_dml_scratch, cap), "cudaMalloc DML scratch")) return false;
+    g->dml_scratch_bytes = cap;
+    return true;
+}
+
 bool engine_delete(GpuEngine *g, const struct whereClauseS *wc, int64_t *deleted) {
     cudaSetDevice(g->device);
     uint64_t kept = 0;
@@ -1299,21 +1312,66 @@ bool engine_delete(GpuEngine *g, const struct whereClauseS *wc, int64_t *deleted
     const int64_t n_old = g->table.n;
     *deleted = n_old - static_cast<int64_t>(kept);
     if (*deleted == 0) return true;
+    // K5: stable compaction of every column by the keep list (ids ascending: ids[k] >= k), IN PLACE, a block of output
+    // rows at a time through a scratch buffer -- the block's source rows all lie at or behind the block's first row,
+    // where nothing has been overwritten yet.  No allocation, no per-column synchronisation.
+    constexpr int64_t kBlockRows = int64_t(4) << 20;
+    uint32_t max_w = 1;
+    for (int c = 0; c < NUM_COLS; ++c)
+        if (g->table.col[c].d && g->table.col[c].width > max_w) max_w = g->table.col[c].width;
+    // indexes that are up to date are maintained (entries of deleted rows dropped, the others renumbered) instead of
+    // being re-sorted: remap[old row] = new row
+    bool any_index = false;
+    size_t idx_scratch = 0;
+    for (auto &ix : g->idx)
+        if (ix.usable && !ix.dirty) {
+            any_index = true;
+            const size_t b = index_scratch_bytes(ix, ix.n);
+            if (b > idx_scratch) idx_scratch = b;
+        }
+    const size_t col_scratch =
+        ((static_cast<size_t>(kBlockRows < static_cast<int64_t>(kept) ? kBlockRows : static_cast<int64_t>(kept)) * max_w + 255) & ~size_t(255)) + 256;
+    const size_t remap_bytes = any_index ? ((static_cast<size_t>(n_old) * 4 + 255) & ~size_t(255)) : 0;
+    const size_t need = remap_bytes + (idx_scratch > col_scratch ? idx_scratch : col_scratch) + 512;
+    if (!ensure_dml_scratch(g, need)) return false;
+    uint8_t *scratch = static_cast<uint8_t *>(g->d_dml_scratch);
+    uint32_t *d_remap = reinterpret_cast<uint32_t *>(scratch);
+    uint8_t *work = scratch + remap_bytes;
+    unsigned int *d_counter = reinterpret_cast<unsigned int *>(work + (need - remap_bytes - 256));   // last 256 bytes
+    unsigned long long *d_total = reinterpret_cast<unsigned long long *>(d_counter + 2);
+    if (any_index) {
+        if (!cuda_ok(index_build_remap(g->d_ids, static_cast<long long>(kept), n_old, d_remap, g->stream), "remap kernel launch"))
+            return false;
+        for (auto &ix : g->idx) {
+            if (!ix.usable || ix.dirty) continue;
+            if (!ensure_desc(g, index_filter_tiles(ix.n))) return false;
+            int launches = 0;
+            if (!cuda_ok(index_apply_delete(&ix, d_remap, static_cast<long long>(kept), work, g->d_tile_desc, d_counter, d_total,
+                                            next_epoch(g), g->stream, &launches),
+                         "index maintenance (DELETE)"))
+                return false;
+        }
+    }
     for (int c = 0; c < NUM_COLS; ++c) {
         DevColumn &dc = g->table.col[c];
         if (!dc.d) continue;
-        DevColumn nc;
-        if (!column_alloc(&nc, dc.width, dc.cap, g->stream)) return false;
-        if (!cuda_ok(gather_launch(dc.d, dc.width, g->d_ids, static_cast<int64_t>(kept), nc.d, g->stream),
-                     "compaction kernel launch"))
+        for (int64_t r0 = 0; r0 < static_cast<int64_t>(kept); r0 += kBlockRows) {
+            const int64_t r1 = (r0 + kBlockRows < static_cast<int64_t>(kept)) ? r0 + kBlockRows : static_cast<int64_t>(kept);
+            if (!cuda_ok(gather_launch(dc.d, dc.width, g->d_ids + r0, r1 - r0, work, g->stream), "compaction kernel launch") ||
+                !cuda_ok(cudaMemcpyAsync(dc.d + static_cast<size_t>(r0) * dc.width, work, static_cast<size_t>(r1 - r0) * dc.width,
+                                         cudaMemcpyDeviceToDevice, g->stream),
+                         "compaction copy"))
+                return false;
+        }
+        // rows behind the new end stay zero (a tile may be read past the last row)
+        const int64_t tail = n_old - static_cast<int64_t>(kept);
+        if (!cuda_ok(cudaMemsetAsync(dc.d + static_cast<size_t>(kept) * dc.width, 0, static_cast<size_t>(tail) * dc.width, g->stream),
+                     "compaction tail"))
             return false;
-        if (!cuda_ok(cudaStreamSynchronize(g->stream), "compaction sync")) return false;
-        cudaFree(dc.d);
-        dc = nc;
     }
+    if (!cuda_ok(cudaStreamSynchronize(g->stream), "compaction sync")) return false;
     g->table.n = static_cast<int64_t>(kept);
     g->head.num_records = static_cast<int>(kept);
-    for (auto &ix : g->idx) ix.dirty = true;  // (key ASC, pos DESC) is a pure function of the table
     return true;
 }
 
@@ -1344,6 +1402,10 @@ bool engine_append(GpuEngine *g, const record &r) {
     cudaSetDevice(g->device);
     const uint8_t *rb = reinterpret_cast<const uint8_t *>(&r);
     const int64_t n = g->table.n;
+    // the new row's cells, one after the other in a pinned staging block; ONE synchronisation for the whole row
+    constexpr size_t kCellSlot = 512 + 16;
+    if (!g->h_row_stage && !cuda_ok(cudaMallocHost(&g->h_row_stage, kCellSlot * NUM_COLS), "cudaMallocHost row stage")) return false;
+    std::memset(g->h_row_stage, 0, kCellSlot * NUM_COLS);
     for (int c = 0; c < NUM_COLS; ++c) {
         DevColumn &dc = g->table.col[c];
         if (!dc.d) {
@@ -1362,8 +1424,7 @@ bool engine_append(GpuEngine *g, const record &r) {
         if (need_w != dc.width || need_cap) {
             if (!grow_column(g, c, need_w, need_cap ? cap_for(n + 1) : dc.cap)) return false;
         }
-        uint8_t cell[512 + 16];
-        std::memset(cell, 0, sizeof cell);
+        uint8_t *cell = g->h_row_stage + kCellSlot * c;
         if (kCols[c].type == T_STR)
             std::memcpy(cell, rb + kCols[c].rec_offset, len);
         else if (kCols[c].type == T_BOOL)
@@ -1374,12 +1435,26 @@ bool engine_append(GpuEngine *g, const record &r) {
                                      g->table.col[c].width, cudaMemcpyHostToDevice, g->stream),
                      "append cell"))
             return false;
-        if (!cuda_ok(cudaStreamSynchronize(g->stream), "append sync")) return false;  // cell is a stack buffer
     }
     g->table.n = n + 1;
     g->head.num_records = static_cast<int>(n + 1);
-    for (auto &ix : g->idx) ix.dirty = true;
-    return true;
+    // insert() of the reference (engine/bplus.c:723-740), per index: the new row enters at the FRONT of its key run.
+    // One K3 probe + one shift of the tail, no re-sort (an index that is not built yet stays "dirty" and is built on use).
+    size_t idx_scratch = 0;
+    for (auto &ix : g->idx)
+        if (ix.usable && !ix.dirty) {
+            const size_t b = index_scratch_bytes(ix, ix.n);
+            if (b > idx_scratch) idx_scratch = b;
+        }
+    bool ok = true;
+    if (idx_scratch && !ensure_dml_scratch(g, idx_scratch + 256)) ok = false;
+    for (auto &ix : g->idx) {
+        if (!ok) break;
+        int launches = 0;
+        ok = cuda_ok(index_insert_row(&ix, g->table, n, g->d_dml_scratch, g->d_probe_first, g->d_probe_count, g->stream, &launches),
+                     "index maintenance (INSERT)");
+    }
+    return cuda_ok(cudaStreamSynchronize(g->stream), "append sync") && ok;
 }
 
 }  // namespace qpe

@@ -102,6 +102,10 @@ struct GpuEngine {
     size_t probe_scratch_bytes = 0;
     void *h_probe_bounce = nullptr;
     size_t probe_bounce_bytes = 0;
+    // DML (engine_delete / engine_append): grow-only device scratch (column block / index tail / remap), pinned row stage
+    void *d_dml_scratch = nullptr;
+    size_t dml_scratch_bytes = 0;
+    uint8_t *h_row_stage = nullptr;
 
     // host-side breakdown of the last match phase (ms): [0] parse/compile, [1] enqueue (copies + launches),
     // [2] stream synchronisation, [3] device time ev1 -> end of the post-match kernels, [4] tail of the

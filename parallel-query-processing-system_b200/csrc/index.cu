@@ -57,33 +57,77 @@ void index_free(DevIndex *ix) {
     if (ix->keys) cudaFree(ix->keys);
     if (ix->perm) cudaFree(ix->perm);
     for (int l = 0; l < kMaxIndexLevels; ++l)
-        if (ix->level[l]) cudaFree(ix->level[l]);
+        if (ix->level_buf[l]) cudaFree(ix->level_buf[l]);
     ix->keys = nullptr;
     ix->perm = nullptr;
-    for (int l = 0; l < kMaxIndexLevels; ++l) ix->level[l] = nullptr;
+    for (int l = 0; l < kMaxIndexLevels; ++l) {
+        ix->level[l] = nullptr;
+        ix->level_buf[l] = nullptr;
+        ix->level_cap[l] = 0;
+        ix->level_cnt[l] = 0;
+    }
     ix->n_levels = 0;
     ix->cap = 0;
     ix->n = 0;
 }
 
+// keys / perm for `cap` entries and every separator level such a tree can have (height h holds every 16^(h+1)-th key)
+template <typename K>
+static cudaError_t alloc_index(DevIndex *ix, long long n) {
+    if (ix->cap >= n && ix->keys != nullptr) return cudaSuccess;
+    index_free(ix);
+    const long long cap = n + n / 8 + 1024;
+    cudaError_t e;
+    if ((e = cudaMalloc(&ix->keys, static_cast<size_t>(cap) * sizeof(K))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&ix->perm, static_cast<size_t>(cap) * sizeof(uint32_t))) != cudaSuccess) return e;
+    long long below = cap;
+    for (int h = 0; h < kMaxIndexLevels && below > kFanout; ++h) {
+        const long long cnt = (below + kFanout - 1) / kFanout;
+        if ((e = cudaMalloc(&ix->level_buf[h], static_cast<size_t>(cnt) * sizeof(K))) != cudaSuccess) return e;
+        ix->level_cap[h] = cnt;
+        below = cnt;
+    }
+    ix->cap = cap;
+    return cudaSuccess;
+}
+
+// separator levels for the current ix->n keys, finest first into level_buf[], then viewed coarsest first
+template <typename K>
+static cudaError_t build_levels(DevIndex *ix, cudaStream_t stream, int *launches) {
+    const K *below = static_cast<const K *>(ix->keys);
+    long long n_below = ix->n;
+    int nl = 0;
+    long long cnt[kMaxIndexLevels];
+    while (n_below > kFanout && nl < kMaxIndexLevels) {
+        const long long n_level = (n_below + kFanout - 1) / kFanout;
+        if (!ix->level_buf[nl] || n_level > ix->level_cap[nl]) return cudaErrorInvalidValue;
+        K *lvl = static_cast<K *>(ix->level_buf[nl]);
+        sample_level_kernel<K><<<grid_for(n_level, 256), 256, 0, stream>>>(below, n_below, lvl, n_level);
+        ++*launches;
+        cnt[nl] = n_level;
+        ++nl;
+        below = lvl;
+        n_below = n_level;
+    }
+    for (int l = 0; l < kMaxIndexLevels; ++l) {
+        ix->level[l] = nullptr;
+        ix->level_cnt[l] = 0;
+    }
+    for (int l = 0; l < nl; ++l) {
+        ix->level[l] = ix->level_buf[nl - 1 - l];
+        ix->level_cnt[l] = cnt[nl - 1 - l];
+    }
+    ix->n_levels = nl;
+    ix->fanout = kFanout;
+    return cudaGetLastError();
+}
+
 template <typename K>
 static cudaError_t build_typed(DevIndex *ix, const K *col, long long n, cudaStream_t stream, int *launches) {
     cudaError_t e;
-    // (re)allocate
-    if (ix->cap < n || ix->keys == nullptr) {
-        index_free(ix);
-        long long cap = n + n / 8 + 1024;
-        if ((e = cudaMalloc(&ix->keys, static_cast<size_t>(cap) * sizeof(K))) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&ix->perm, static_cast<size_t>(cap) * sizeof(uint32_t))) != cudaSuccess) return e;
-        ix->cap = cap;
-    }
-    for (int l = 0; l < kMaxIndexLevels; ++l)
-        if (ix->level[l]) {
-            cudaFree(ix->level[l]);
-            ix->level[l] = nullptr;
-        }
-    ix->n_levels = 0;
+    if ((e = alloc_index<K>(ix, n)) != cudaSuccess) return e;
     ix->n = n;
+    ix->n_levels = 0;
     ix->fanout = kFanout;
     if (n == 0) return cudaSuccess;
 
@@ -100,36 +144,12 @@ static cudaError_t build_typed(DevIndex *ix, const K *col, long long n, cudaStre
     if ((e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16)) != cudaSuccess) return e;
     e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_rev, static_cast<K *>(ix->keys), pos_rev, ix->perm, n, 0,
                                         static_cast<int>(sizeof(K) * 8), stream);
-    if (e != cudaSuccess) return e;
-
-    // separator levels, finest first, then reversed so level[0] is the coarsest
-    void *lv[kMaxIndexLevels];
-    long long cnt[kMaxIndexLevels];
-    int nl = 0;
-    const K *below = static_cast<const K *>(ix->keys);
-    long long n_below = n;
-    while (n_below > kFanout && nl < kMaxIndexLevels) {
-        const long long n_level = (n_below + kFanout - 1) / kFanout;
-        K *lvl = nullptr;
-        if ((e = cudaMalloc(&lvl, static_cast<size_t>(n_level) * sizeof(K))) != cudaSuccess) return e;
-        sample_level_kernel<K><<<grid_for(n_level, 256), 256, 0, stream>>>(below, n_below, lvl, n_level);
-        ++*launches;
-        lv[nl] = lvl;
-        cnt[nl] = n_level;
-        ++nl;
-        below = lvl;
-        n_below = n_level;
-    }
-    for (int l = 0; l < nl; ++l) {
-        ix->level[l] = lv[nl - 1 - l];
-        ix->level_cnt[l] = cnt[nl - 1 - l];
-    }
-    ix->n_levels = nl;
-    e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = build_levels<K>(ix, stream, launches);
+    const cudaError_t es = cudaStreamSynchronize(stream);
     cudaFree(keys_rev);
     cudaFree(pos_rev);
     cudaFree(tmp);
-    return e;
+    return e != cudaSuccess ? e : es;
 }
 
 cudaError_t index_build(DevIndex *ix, const DevTable &t, cudaStream_t stream, int *launches) {
@@ -149,6 +169,249 @@ cudaError_t index_build(DevIndex *ix, const DevTable &t, cudaStream_t stream, in
         e = build_typed<int>(ix, reinterpret_cast<const int *>(c.d), t.n, stream, launches);
     if (e == cudaSuccess) ix->dirty = false;
     return e;
+}
+
+// ------------------------------------------------------------------------------------------
+// Index maintenance without a re-sort (the reference's insert / delete, engine/bplus.c:723-740,
+// :1022-1051, called per row from executeEngine-serial.c:599-614, :661-665).
+//
+// INSERT: the new row is the table's LAST row, so among equal keys it goes to the FRONT of its key run
+// (position DESC): slot p = lower_bound(keys, key).  K3 finds p (it stays on the device), the tail [p, n) moves one
+// slot to the right through a scratch copy, the entry is written, the separator levels are re-sampled.
+// DELETE: the table's stable compaction renumbers row r to remap[r] (monotonic), so the (key ASC, position DESC) order
+// of the surviving entries is unchanged: one ordered filter pass (ballot / popc + decoupled look-back per 2 Ki entries)
+// drops the deleted rows' entries and writes the new row ids.
+// Both are O(n) streaming passes per index and allocate nothing.
+// ------------------------------------------------------------------------------------------
+template <typename K>
+__global__ void tail_to_scratch_kernel(const K *__restrict__ keys, const uint32_t *__restrict__ perm, long long n,
+                                       const uint32_t *__restrict__ p_ptr, K *__restrict__ s_keys,
+                                       uint32_t *__restrict__ s_perm) {
+    const long long p = *p_ptr;
+    for (long long i = p + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        s_keys[i - p] = keys[i];
+        s_perm[i - p] = perm[i];
+    }
+}
+template <typename K>
+__global__ void insert_entry_kernel(K *__restrict__ keys, uint32_t *__restrict__ perm, long long n,
+                                    const uint32_t *__restrict__ p_ptr, const K *__restrict__ s_keys,
+                                    const uint32_t *__restrict__ s_perm, const K *__restrict__ key_ptr, uint32_t row) {
+    const long long p = *p_ptr;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        keys[p] = *key_ptr;
+        perm[p] = row;
+    }
+    for (long long i = p + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        keys[i + 1] = s_keys[i - p];
+        perm[i + 1] = s_perm[i - p];
+    }
+}
+
+size_t index_scratch_bytes(const DevIndex &ix, long long n_entries) {
+    const size_t ksz = ix.type == T_U64 ? 8 : 4;
+    return ((static_cast<size_t>(n_entries) * ksz + 255) & ~size_t(255)) + ((static_cast<size_t>(n_entries) * 4 + 255) & ~size_t(255)) + 256;
+}
+
+template <typename K>
+static cudaError_t insert_typed(DevIndex *ix, const K *col, long long row, void *scratch, uint32_t *d_first,
+                                uint32_t *d_count, cudaStream_t stream, int *launches) {
+    const long long n = ix->n;  // entries before the insert
+    K *keys = static_cast<K *>(ix->keys);
+    const K *key_ptr = col + row;  // the new row's key, read on the device
+    cudaError_t e = index_probe(*ix, key_ptr, key_ptr, 1, d_first, d_count, stream);  // first = lower_bound(key)
+    if (e != cudaSuccess) return e;
+    ++*launches;
+    K *s_keys = static_cast<K *>(scratch);
+    uint32_t *s_perm = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(scratch) + ((static_cast<size_t>(n) * sizeof(K) + 255) & ~size_t(255)));
+    if (n > 0) {
+        tail_to_scratch_kernel<K><<<grid_for(n, 256), 256, 0, stream>>>(keys, ix->perm, n, d_first, s_keys, s_perm);
+        ++*launches;
+    }
+    insert_entry_kernel<K><<<grid_for(n > 0 ? n : 1, 256), 256, 0, stream>>>(keys, ix->perm, n, d_first, s_keys, s_perm, key_ptr,
+                                                                         static_cast<uint32_t>(row));
+    ++*launches;
+    ix->n = n + 1;
+    return build_levels<K>(ix, stream, launches);
+}
+
+cudaError_t index_insert_row(DevIndex *ix, const DevTable &t, long long row, void *scratch, uint32_t *d_first,
+                             uint32_t *d_count, cudaStream_t stream, int *launches) {
+    int dummy = 0;
+    if (!launches) launches = &dummy;
+    if (!ix->usable || ix->dirty) return cudaSuccess;   // nothing to maintain: built on next use
+    if (ix->n + 1 > ix->cap) {                          // out of head-room: rebuild (allocates)
+        ix->dirty = true;
+        return cudaSuccess;
+    }
+    const DevColumn &c = t.col[ix->col];
+    if (!c.d) return cudaErrorInvalidValue;
+    if (ix->type == T_U64)
+        return insert_typed<unsigned long long>(ix, reinterpret_cast<const unsigned long long *>(c.d), row, scratch, d_first,
+                                                d_count, stream, launches);
+    return insert_typed<int>(ix, reinterpret_cast<const int *>(c.d), row, scratch, d_first, d_count, stream, launches);
+}
+
+// remap[old row] = new row, 0xffffffff for a deleted row: scatter of the keep list (remap pre-set to 0xff)
+__global__ void remap_kernel(const uint32_t *__restrict__ keep, long long n_keep, uint32_t *__restrict__ remap) {
+    for (long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < n_keep;
+         j += static_cast<long long>(gridDim.x) * blockDim.x)
+        remap[keep[j]] = static_cast<uint32_t>(j);
+}
+cudaError_t index_build_remap(const uint32_t *d_keep, long long n_keep, long long n_old, uint32_t *d_remap,
+                              cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(d_remap, 0xff, static_cast<size_t>(n_old) * 4, stream);
+    if (e != cudaSuccess) return e;
+    if (n_keep > 0) remap_kernel<<<grid_for(n_keep, 256), 256, 0, stream>>>(d_keep, n_keep, d_remap);
+    return cudaGetLastError();
+}
+
+constexpr int kIdxFilterThreads = 256;
+constexpr int kIdxFilterItems = 8;
+constexpr int kIdxFilterTile = kIdxFilterThreads * kIdxFilterItems;  // 2048 entries per CTA
+
+__device__ __forceinline__ unsigned long long ix_ld_desc(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ix_st_desc(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ordered filter of the index entries: tiles are claimed in order (atomic counter), so every predecessor of a tile is
+// resident or finished and the look-back cannot deadlock.  desc[tile] = epoch << 34 | state << 32 | value.
+template <typename K>
+__global__ void __launch_bounds__(kIdxFilterThreads)
+    index_filter_kernel(const K *__restrict__ keys, const uint32_t *__restrict__ perm, long long n,
+                        const uint32_t *__restrict__ remap, K *__restrict__ out_keys, uint32_t *__restrict__ out_perm,
+                        unsigned long long *__restrict__ desc, unsigned int *__restrict__ tile_counter,
+                        unsigned long long *__restrict__ total_out, uint32_t epoch) {
+    __shared__ long long s_tile;
+    __shared__ uint32_t s_wcnt[kIdxFilterItems][kIdxFilterThreads / 32];
+    __shared__ uint32_t s_woff[kIdxFilterItems][kIdxFilterThreads / 32];
+    __shared__ uint32_t s_excl;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    constexpr int kWarps = kIdxFilterThreads / 32;
+    const long long n_tiles = (n + kIdxFilterTile - 1) / kIdxFilterTile;
+    if (tid == 0) s_tile = static_cast<long long>(atomicAdd(tile_counter, 1u));
+    __syncthreads();
+    const long long tile = s_tile;
+    if (tile >= n_tiles) return;
+    K key[kIdxFilterItems];
+    uint32_t nid[kIdxFilterItems];
+    uint32_t bal[kIdxFilterItems];
+#pragma unroll
+    for (int it = 0; it < kIdxFilterItems; ++it) {
+        const long long i = tile * kIdxFilterTile + it * kIdxFilterThreads + tid;
+        uint32_t v = 0xffffffffu;
+        key[it] = K(0);
+        if (i < n) {
+            key[it] = keys[i];
+            v = __ldg(remap + perm[i]);
+        }
+        nid[it] = v;
+        bal[it] = __ballot_sync(0xffffffffu, v != 0xffffffffu);
+        if (lane == 0) s_wcnt[it][warp] = __popc(bal[it]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive offsets of the (item, warp) groups in entry order, tile total, look-back
+        uint32_t run = 0;
+        for (int g0 = 0; g0 < kIdxFilterItems * kWarps; g0 += 32) {
+            const int gi = g0 + static_cast<int>(lane);
+            const uint32_t c = gi < kIdxFilterItems * kWarps ? s_wcnt[gi / kWarps][gi % kWarps] : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= static_cast<uint32_t>(d)) inc += t;
+            }
+            if (gi < kIdxFilterItems * kWarps) s_woff[gi / kWarps][gi % kWarps] = run + inc - c;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        const uint32_t total = run;
+        const unsigned long long tag = static_cast<unsigned long long>(epoch) << 34;
+        if (lane == 0) ix_st_desc(desc + tile, tag | (static_cast<unsigned long long>(tile == 0 ? 2u : 1u) << 32) | total);
+        uint32_t excl = 0;
+        long long idx = tile - 1;
+        while (idx >= 0) {
+            const long long mine = idx - static_cast<long long>(lane);
+            uint32_t state = 2u, val = 0;
+            if (mine >= 0) {
+                unsigned long long d = ix_ld_desc(desc + mine);
+                while ((d >> 34) != epoch) {
+                    __nanosleep(64);
+                    d = ix_ld_desc(desc + mine);
+                }
+                state = static_cast<uint32_t>(d >> 32) & 3u;
+                val = static_cast<uint32_t>(d);
+            }
+            const uint32_t pm = __ballot_sync(0xffffffffu, state == 2u);
+            uint32_t contrib = val;
+            if (pm) {
+                const uint32_t first = static_cast<uint32_t>(__ffs(pm) - 1);
+                if (lane > first) contrib = 0;
+            }
+            excl += __reduce_add_sync(0xffffffffu, contrib);
+            if (pm) break;
+            idx -= 32;
+        }
+        if (lane == 0) {
+            ix_st_desc(desc + tile, tag | (2ull << 32) | (excl + total));
+            s_excl = excl;
+            if (tile == n_tiles - 1) *total_out = static_cast<unsigned long long>(excl) + total;
+        }
+    }
+    __syncthreads();
+    const uint32_t excl = s_excl;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int it = 0; it < kIdxFilterItems; ++it)
+        if ((bal[it] >> lane) & 1u) {
+            const uint32_t o = excl + s_woff[it][warp] + __popc(bal[it] & lt);
+            out_keys[o] = key[it];
+            out_perm[o] = nid[it];
+        }
+}
+
+template <typename K>
+static cudaError_t delete_typed(DevIndex *ix, const uint32_t *d_remap, long long n_new, void *scratch,
+                                unsigned long long *desc, unsigned int *d_counter, unsigned long long *d_total,
+                                uint32_t epoch, cudaStream_t stream, int *launches) {
+    const long long n = ix->n;
+    K *keys = static_cast<K *>(ix->keys);
+    K *s_keys = static_cast<K *>(scratch);
+    uint32_t *s_perm = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(scratch) + ((static_cast<size_t>(n) * sizeof(K) + 255) & ~size_t(255)));
+    cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    const long long n_tiles = (n + kIdxFilterTile - 1) / kIdxFilterTile;
+    if (n_tiles > 0) {
+        index_filter_kernel<K><<<static_cast<unsigned>(n_tiles), kIdxFilterThreads, 0, stream>>>(
+            keys, ix->perm, n, d_remap, s_keys, s_perm, desc, d_counter, d_total, epoch);
+        ++*launches;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        // every surviving entry belongs to a surviving row: the count is the new table size
+        if ((e = cudaMemcpyAsync(keys, s_keys, static_cast<size_t>(n_new) * sizeof(K), cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(ix->perm, s_perm, static_cast<size_t>(n_new) * 4, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
+    }
+    ix->n = n_new;
+    return build_levels<K>(ix, stream, launches);
+}
+
+long long index_filter_tiles(long long n) { return (n + kIdxFilterTile - 1) / kIdxFilterTile; }
+
+cudaError_t index_apply_delete(DevIndex *ix, const uint32_t *d_remap, long long n_new, void *scratch,
+                               unsigned long long *desc, unsigned int *d_counter, unsigned long long *d_total,
+                               uint32_t epoch, cudaStream_t stream, int *launches) {
+    int dummy = 0;
+    if (!launches) launches = &dummy;
+    if (!ix->usable || ix->dirty) return cudaSuccess;
+    if (ix->type == T_U64)
+        return delete_typed<unsigned long long>(ix, d_remap, n_new, scratch, desc, d_counter, d_total, epoch, stream, launches);
+    return delete_typed<int>(ix, d_remap, n_new, scratch, desc, d_counter, d_total, epoch, stream, launches);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -159,8 +159,12 @@ struct DevIndex {
     // group of `fanout` entries of the level below (the finest level groups entries of `keys`).
     int n_levels = 0;
     int fanout = 16;
-    void *level[kMaxIndexLevels] = {nullptr};
+    void *level[kMaxIndexLevels] = {nullptr};      // views into level_buf, coarsest first
     int64_t level_cnt[kMaxIndexLevels] = {0};
+    // the level buffers themselves, by HEIGHT above the key array (0 = finest), sized once for `cap` entries so that
+    // INSERT / DELETE maintenance never allocates
+    void *level_buf[kMaxIndexLevels] = {nullptr};
+    int64_t level_cap[kMaxIndexLevels] = {0};
 };
 
 struct ScanStats {

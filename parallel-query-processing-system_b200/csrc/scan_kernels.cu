@@ -992,9 +992,10 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
                     named_bar_sync(1, kFuseCompactThreads);
                     for (uint32_t i = ct; i < total; i += kFuseCompactThreads) out[i] = id_stage[i];
                 } else {
-                    // dense chunk: a round (128 words, <= 4096 ids) at a time through the stage.  (Expanding
-                    // word by word with lane-parallel direct stores was measured slower: 2.4 x the
-                    // instructions, and they compete with the evaluators for issue slots.)
+                    // dense chunk: a round (128 / 256 words, <= 4096 / 8192 ids) at a time through the stage.  (Expanding
+                    // word by word with lane-parallel direct stores -- one coalesced store per 32-row word, no barriers --
+                    // was measured again in round 2, with the light evaluators: still slower, 2.46 vs 2.36 ms for QN at
+                    // 50 % on 1 B rows, 0.309 vs 0.294 ms on 100 M.)
 #pragma unroll
                     for (int r = 0; r < kFuseRounds; ++r) {
                         const uint32_t base = sh->round_base[r];

@@ -48,6 +48,7 @@
 #include "engine.cuh"
 
 #include <fcntl.h>
+#include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/syscall.h>
@@ -119,6 +120,7 @@ struct ShardState {
     ShardPending pending[2];
     int n_pending = 0;
     bool last_was_post = false;         // the engine stream's most recent kernel is a post-scan kernel of this file
+    int numa_node = -1, numa_how = 0;   // where this rank's part of the host buffer was placed, and by what (1 mbind, 2 affinity)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
@@ -401,21 +403,60 @@ static int gpu_numa_node(int device) {
     return node;
 }
 
-// Place [p, p + bytes) on `node` (mbind, then first touch by this process).  Best effort: without the system call
-// (or on a single-node box) the pages simply land where the first touch puts them.
-static void place_on_node(void *p, size_t bytes, int node) {
-    if (bytes == 0) return;
+// Place [p, p + bytes) on `node`: first touch by this thread while it is pinned to that node's CPUs (the default
+// first-touch policy then allocates there; mbind is tried as well, but containers usually filter that system call).
+// Best effort: on a single-node box, or when the node cannot be told, the pages land wherever the first touch puts them.
+static int place_on_node(void *p, size_t bytes, int node) {
+    if (bytes == 0) return 0;
     const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~uintptr_t(4095);
     const uintptr_t e = (reinterpret_cast<uintptr_t>(p) + bytes + 4095) & ~uintptr_t(4095);
+    int how = 0;
+    cpu_set_t old_set, node_set;
+    bool pinned = false;
+    if (node >= 0) {
 #ifdef SYS_mbind
-    if (node >= 0 && node < 64) {
-        unsigned long mask = 1ul << node;
-        (void)syscall(SYS_mbind, reinterpret_cast<void *>(a), static_cast<unsigned long>(e - a), 1 /* MPOL_PREFERRED */, &mask,
-                      sizeof(mask) * 8 + 1, 0u);
-    }
+        if (node < 64) {
+            unsigned long mask = 1ul << node;
+            if (syscall(SYS_mbind, reinterpret_cast<void *>(a), static_cast<unsigned long>(e - a), 1 /* MPOL_PREFERRED */, &mask,
+                        sizeof(mask) * 8 + 1, 0u) == 0)
+                how |= 1;
+        }
 #endif
+        char path[96];
+        std::snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+        FILE *f = std::fopen(path, "r");
+        if (f) {
+            CPU_ZERO(&node_set);
+            int lo = 0, hi = 0, n = 0;
+            char sep = 0;
+            while (std::fscanf(f, "%d", &lo) == 1) {
+                hi = lo;
+                const int c = std::fgetc(f);
+                if (c == '-') {
+                    if (std::fscanf(f, "%d", &hi) != 1) hi = lo;
+                    sep = static_cast<char>(std::fgetc(f));
+                } else {
+                    sep = static_cast<char>(c);
+                }
+                for (int k = lo; k <= hi && k < CPU_SETSIZE; ++k) {
+                    CPU_SET(k, &node_set);
+                    ++n;
+                }
+                if (sep != ',') break;
+            }
+            std::fclose(f);
+            if (n > 0 && sched_getaffinity(0, sizeof old_set, &old_set) == 0 &&
+                sched_setaffinity(0, sizeof node_set, &node_set) == 0) {
+                pinned = true;
+                how |= 2;
+            }
+        }
+    }
+    madvise(reinterpret_cast<void *>(a), e - a, MADV_HUGEPAGE);  // helps only where shmem huge pages are "advise"
     volatile char *c = reinterpret_cast<volatile char *>(a);
     for (uintptr_t o = 0; o < e - a; o += 4096) c[o] = 0;
+    if (pinned) sched_setaffinity(0, sizeof old_set, &old_set);
+    return how;
 }
 
 // wait (spinning on mapped host memory) until the post-scan kernel of `epoch` has handed its counts over
@@ -591,9 +632,10 @@ unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *nam
     std::strncpy(s->host_name, name, sizeof(s->host_name) - 1);
     // rank j delivers the j-th 1/world of every result: put that part of both id arrays next to its GPU
     const int node = gpu_numa_node(g->device);
+    s->numa_node = node;
     for (int par = 0; par < 2; ++par) {
         const uint64_t lo = cap * s->rank / s->world, hi = cap * (s->rank + 1) / s->world;
-        place_on_node(s->host_ids + par * cap + lo, (hi - lo) * sizeof(uint32_t), node);
+        s->numa_how = place_on_node(s->host_ids + par * cap + lo, (hi - lo) * sizeof(uint32_t), node);
     }
     // staging for this rank's slice (mode 1)
     s->staging_cap = cap / s->world + 1024;
@@ -665,6 +707,15 @@ const unsigned int *qpe_shard_host_result(struct engineS *engine) {
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
     return (s && s->host_ids) ? s->host_ids + s->last_host_parity * s->host_cap : nullptr;
+}
+
+/* NUMA node of this rank's GPU (-1: unknown) and how its part of the host buffer was placed there: bit 0 = mbind
+ * accepted, bit 1 = first touch under that node's CPU affinity. */
+int qpe_shard_numa(struct engineS *engine, int *how_out) {
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    if (how_out) *how_out = s ? s->numa_how : 0;
+    return s ? s->numa_node : -1;
 }
 
 void qpe_shard_close(struct engineS *engine) {
