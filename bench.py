@@ -664,6 +664,11 @@ def run_ours(args):
         host_cap = max(sum(counts0), sum(ucounts0)) + 4096
         sg = sharding.ShardGroup(pkg, eng, segment_capacity=seg_cap, host_capacity=host_cap, counts_device=dev)
         sg.set_multipath(args.host_mode)
+        # every rank's device->host rate with all links busy; a host result is then cut in proportion
+        rates = sg.balance_links()
+        link = {"d2h_gbs_per_link": [round(r, 1) for r in rates], "total_gbs": round(sum(rates), 1),
+                "how": "blocking cudaMemcpy of 4 MiB from this rank's HBM into its part of the shared host buffer, x6, all "
+                       "ranks at once; every rank then delivers a share of each host result proportional to its rate"}
 
         def make_loops(statement):
             def piped(to_host):
@@ -729,26 +734,6 @@ def run_ours(args):
                    "value": total / (u_ms * 1e-3), "ms_per_step": u_ms,
                    "e2e": {"value": total / (u_e2e_ms * 1e-3), "ms_per_step": u_e2e_ms, "unit": "rows/s",
                            "d2h_bytes_per_step": int(4 * u_matches + 8 * world)}}
-        # device -> host rate of one link, every rank at the same time: this rank's 1/world of QN's ids from its HBM
-        # into its part of the shared host buffer (what a delivery moves per query)
-        slice_bytes = 4 * (n_matches // world)
-        link = None
-        if slice_bytes > 0:
-            src = pkg.DeviceBuffer(slice_bytes)
-            dst_ptr = pkg.load_library().qpe_shard_host_result(eng._h) + 4 * (n_matches * rank // world)
-            lib = pkg.load_library()
-            lib.qpe_gpu_copy_to_host(dst_ptr, src.ptr, slice_bytes)
-            sync_all()
-            t_0 = time.perf_counter()
-            for _ in range(10):
-                lib.qpe_gpu_copy_to_host(dst_ptr, src.ptr, slice_bytes)
-            gbs = 10 * slice_bytes / (time.perf_counter() - t_0) / 1e9
-            src.free()
-            g = torch.tensor([gbs], dtype=torch.float64, device=dev)
-            every = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
-            dist.all_gather(every, g)
-            link = {"d2h_gbs_per_link": [round(v.item(), 1) for v in every], "bytes_per_copy": slice_bytes,
-                    "how": "blocking cudaMemcpy of this rank's slice into its part of the shared host buffer, x10, all ranks at once"}
         sync_info["link"] = link
 
     # roofline of the dominant kernel: algorithmic bytes of a rank's shard / the kernel's own event time (max over ranks)

@@ -116,8 +116,9 @@ int qpe_sql_scan_count(struct engineS *engine, const char *statement, unsigned l
 
 /* Index path of a SHARDED table.  For every (top-level condition x index) segment of the WHERE, in the
  * reference's generation order (executeEngine-serial.c:358-459), the rows of THIS shard that pass the
- * whole WHERE, in (key ASC, local position DESC) order, with their keys (u64 keys as long long bits,
- * int keys sign-extended).  The caller merges the shards per segment: concatenate from the highest
+ * whole WHERE, in (key ASC, local position DESC) order, with their ORDER keys (u64 keys with the top bit
+ * flipped, so that a signed 64-bit sort orders them as the B+ tree's unsigned compare does; int keys
+ * sign-extended).  The caller merges the shards per segment: concatenate from the highest
  * rank to the lowest and sort stably by key = (key ASC, global position DESC), the reference's order.
  * *used_index_out = 0 when no index applies (use the scan path).  keys_out / ids_out are malloc'ed
  * (qpe_gpu_free), concatenated over the segments; seg_counts_out[s] = rows of segment s (<= 32). */
@@ -181,6 +182,8 @@ const unsigned int *qpe_shard_host_result(struct engineS *engine);
  * into its own HBM and the copy engine takes it to the host over this GPU's PCIe link; 2 = the delivery kernel
  * stores into the mapped host buffer itself.  Every rank must choose the same. */
 int qpe_shard_set_multipath(struct engineS *engine, int mode);
+/* shares of a host result per rank, proportional to `weights` (measured link rates); same numbers on every rank */
+int qpe_shard_set_link_weights(struct engineS *engine, const double *weights, int n);
 void qpe_shard_close(struct engineS *engine);
 int qpe_shard_submit(struct engineS *engine, struct whereClauseS *whereClause, int to_host);
 int qpe_shard_wait(struct engineS *engine, unsigned long long *counts_out, qpe_scan_stats *stats);

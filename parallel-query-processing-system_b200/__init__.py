@@ -164,6 +164,7 @@ def load_library() -> C.CDLL:
         "qpe_shard_close": (None, [vp]),
         "qpe_shard_unlink_host_result": (i, [vp]),
         "qpe_shard_set_multipath": (i, [vp, i]),
+        "qpe_shard_set_link_weights": (i, [vp, C.POINTER(C.c_double), i]),
         "qpe_sql_shard_select": (i, [vp, cp, i, C.POINTER(ull), pstats]),
         "qpe_sql_shard_delete": (i, [vp, cp, C.POINTER(ull), C.POINTER(ull)]),
         "qpe_sql_select": (C.POINTER(ResultSet), [vp, cp]),

@@ -1076,11 +1076,15 @@ int qpe_gpu_select_segments(struct engineS *engine, struct whereClauseS *whereCl
     }
     const uint32_t base = global_ids ? static_cast<uint32_t>(g->table.row_base) : 0u;
     size_t o = 0;
-    for (const SegmentResult &r : segs)
+    for (const SegmentResult &r : segs) {
+        // keys are handed out as ORDER keys: a u64 key has its top bit flipped, so that the caller's signed 64-bit
+        // sort orders them as the B+ tree's unsigned compare does (recordSchema.c:88-127), keys >= 2^63 included
+        const bool u64 = r.key_col >= 0 && kCols[r.key_col].type == T_U64;
         for (size_t k = 0; k < r.ids.size(); ++k, ++o) {
-            keys[o] = r.keys[k];
+            keys[o] = u64 ? static_cast<long long>(static_cast<unsigned long long>(r.keys[k]) ^ 0x8000000000000000ull) : r.keys[k];
             ids[o] = r.ids[k] + base;
         }
+    }
     if (keys_out) *keys_out = keys; else std::free(keys);
     if (ids_out) *ids_out = ids; else std::free(ids);
     return 0;

@@ -190,6 +190,7 @@ void engine_destroy(GpuEngine *g) {
     if (g->h_probe_out) cudaFreeHost(g->h_probe_out);
     if (g->d_probe_scratch) cudaFree(g->d_probe_scratch);
     if (g->d_dml_scratch) cudaFree(g->d_dml_scratch);
+    if (g->d_segs) cudaFree(g->d_segs);
     if (g->h_row_stage) cudaFreeHost(g->h_row_stage);
     if (g->h_probe_bounce) cudaFreeHost(g->h_probe_bounce);
     for (int i = 0; i < GpuEngine::kTimingRing; ++i)
@@ -351,7 +352,15 @@ static int plan_segments(const GpuEngine *g, const struct whereClauseS *wc, Segm
             const FieldType type = g->head.attribute_types[i];
             if (type != FIELD_UINT64 && type != FIELD_INT) continue;  // bool / string: unsupported (:425-429)
             const DevIndex &ix = g->idx[i];
-            if (!ix.usable) continue;
+            if (!ix.usable) {
+                // declared u64 / int, so the reference WOULD take the index path here (:366-424) and return its order;
+                // this engine cannot probe it (declared type differs from the column's, or the column is not
+                // resident): say so instead of silently answering in table order
+                *too_many = true;
+                set_error(std::string("index on '") + w->attribute + "' cannot be probed (declared type differs from the "
+                          "column's type, or the column is not resident): the reference would use it for this WHERE");
+                return -1;
+            }
             const char *op = w->op_ ? w->op_ : "";
             const char *val = w->value ? w->value : "";
             SegmentPlan s{};
@@ -457,6 +466,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     const DevTable &t = g->table;
     g->last_bm_words = 0;
     bool post_done = false;
+    bool index_synced = false;  // the index path has already synchronised (count and candidates are on the host)
     const unsigned long long *count_src = g->count_mapped;  // where the match count arrives without a download (or null)
     g->count_dev = &g->d_ctl->out_count;                    // (K1f: its own control block, set below)
     {
@@ -498,6 +508,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     if (!force_scan && !invert) {
         bool too_many = false;
         n_seg = plan_segments(g, wc, segs, kMaxSegments, &too_many);
+        if (n_seg < 0) return false;  // an index the reference would use cannot be probed (error set)
         if (too_many) {
             set_error("too many (condition x index) segments in one WHERE clause");
             return false;
@@ -745,78 +756,71 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
         int launches = 0;
         for (int s = 0; s < n_seg; ++s)
             if (!ensure_index(g, &g->idx[segs[s].index_slot], &launches)) return false;
-        if (!upload_query()) return false;
-        cudaEventRecord(g->ev0, g->stream);
+        // K3s (all segments' probes, one launch, keys as kernel parameters) -> segment table in device memory -> K1g
+        // (persistent, reads the table there): ONE synchronisation per indexed SELECT.  The host only knows an upper
+        // bound of the candidates (the sum of the probed indexes' sizes); the id buffer holds a table's worth of ids,
+        // as the reference's candidate array does (:342), and a result that does not fit is run again with room.
+        const DevIndex *ixs[kMaxSegments];
+        unsigned long long lo[kMaxSegments], hi[kMaxSegments];
+        long long bound = 0;
         for (int s = 0; s < n_seg; ++s) {
+            ixs[s] = &g->idx[segs[s].index_slot];
+            bound += ixs[s]->n;
             if (segs[s].is_u64) {
-                g->h_probe_keys[s] = segs[s].lo_u64;
-                g->h_probe_keys[kMaxSegments + s] = segs[s].hi_u64;
+                lo[s] = segs[s].lo_u64;
+                hi[s] = segs[s].hi_u64;
             } else {
-                int32_t lo = segs[s].lo_i32, hi = segs[s].hi_i32;
-                g->h_probe_keys[s] = 0;
-                g->h_probe_keys[kMaxSegments + s] = 0;
-                std::memcpy(&g->h_probe_keys[s], &lo, 4);
-                std::memcpy(&g->h_probe_keys[kMaxSegments + s], &hi, 4);
+                lo[s] = static_cast<uint32_t>(segs[s].lo_i32);
+                hi[s] = static_cast<uint32_t>(segs[s].hi_i32);
             }
         }
-        if (!cuda_ok(cudaMemcpyAsync(g->d_probe_lo, g->h_probe_keys, sizeof(unsigned long long) * n_seg,
-                                     cudaMemcpyHostToDevice, g->stream),
-                     "upload probe keys") ||
-            !cuda_ok(cudaMemcpyAsync(g->d_probe_hi, g->h_probe_keys + kMaxSegments, sizeof(unsigned long long) * n_seg,
-                                     cudaMemcpyHostToDevice, g->stream),
-                     "upload probe keys"))
-            return false;
-        for (int s = 0; s < n_seg; ++s) {
-            // keys of segment s sit in 8-byte slots: int keys use the low 4 bytes of their slot
-            const DevIndex &ix = g->idx[segs[s].index_slot];
-            if (!cuda_ok(index_probe(ix, g->d_probe_lo + s, g->d_probe_hi + s, 1, g->d_probe_first + s,
-                                     g->d_probe_count + s, g->stream),
-                         "probe kernel launch"))
+        if (!g->d_segs && !cuda_ok(cudaMalloc(&g->d_segs, sizeof(CandSegments)), "cudaMalloc segment table")) return false;
+        if (!ensure_desc(g, filter_tiles(bound))) return false;
+        if (!count_only && !engine_ensure_ids(g, t.n > 0 ? t.n : 1)) return false;
+        long long n_cand = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if (!upload_query()) return false;
+            cudaEventRecord(g->ev0, g->stream);
+            if (!cuda_ok(index_probe_segments(ixs, lo, hi, n_seg, g->d_segs, g->stream), "probe kernel launch")) return false;
+            if (!cuda_ok(filter_launch(t, g->d_ctl, CandSegments{}, g->d_tile_desc, next_epoch(g), count_only ? nullptr : g->d_ids,
+                                       g->stream, g->d_segs, bound, static_cast<unsigned long long>(g->ids_cap)),
+                         "filter kernel launch"))
                 return false;
-            ++launches;
+            cudaEventRecord(g->ev1, g->stream);
+            launches += 2;
+            if (!cuda_ok(cudaMemcpyAsync(&g->h_probe_out[0], &g->d_segs->vstart[n_seg], sizeof(long long), cudaMemcpyDeviceToHost, g->stream),
+                         "download candidates") ||
+                !cuda_ok(cudaMemcpyAsync(&hc->out_count, &g->d_ctl->out_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, g->stream),
+                         "download count") ||
+                !cuda_ok(cudaStreamSynchronize(g->stream), "match sync"))
+                return false;
+            std::memcpy(&n_cand, &g->h_probe_out[0], sizeof(long long));
+            if (count_only || static_cast<int64_t>(hc->out_count) <= g->ids_cap) break;
+            // more survivors than a table's worth of ids (duplicated segments): make room, run once more
+            if (attempt == 1 || !engine_ensure_ids(g, static_cast<int64_t>(hc->out_count))) {
+                set_error("indexed SELECT: result does not fit the id buffer");
+                return false;
+            }
+            hc->tile_counter = 0;
+            hc->out_count = 0;
         }
-        if (!cuda_ok(cudaMemcpyAsync(g->h_probe_out, g->d_probe_first, sizeof(uint32_t) * n_seg, cudaMemcpyDeviceToHost,
-                                     g->stream),
-                     "download probe") ||
-            !cuda_ok(cudaMemcpyAsync(g->h_probe_out + kMaxSegments, g->d_probe_count, sizeof(uint32_t) * n_seg,
-                                     cudaMemcpyDeviceToHost, g->stream),
-                     "download probe") ||
-            !cuda_ok(cudaStreamSynchronize(g->stream), "probe sync"))
-            return false;
-        CandSegments cs{};
-        cs.n_seg = n_seg;
-        cs.vstart[0] = 0;
-        for (int s = 0; s < n_seg; ++s) {
-            const DevIndex &ix = g->idx[segs[s].index_slot];
-            cs.perm[s] = ix.perm;
-            cs.first[s] = g->h_probe_out[s];
-            cs.vstart[s + 1] = cs.vstart[s] + g->h_probe_out[kMaxSegments + s];
-        }
-        const long long n_cand = cs.vstart[n_seg];
         st.candidates = n_cand;
         st.rows_scanned = n_cand;
-        if (!ensure_desc(g, filter_tiles(n_cand))) return false;
-        if (!count_only && !engine_ensure_ids(g, n_cand)) return false;
-        if (!cuda_ok(filter_launch(t, g->d_ctl, cs, g->d_tile_desc, next_epoch(g), count_only ? nullptr : g->d_ids,
-                                   g->stream),
-                     "filter kernel launch"))
-            return false;
-        if (n_cand > 0) ++launches;
-        cudaEventRecord(g->ev1, g->stream);
         st.launches = launches;
+        index_synced = true;
     }
 
     if (g->post_match && !post_done) {
         if (!g->post_match()) return false;
         cudaEventRecord(g->ev_post, g->stream);
     }
-    if (!count_src && !cuda_ok(cudaMemcpyAsync(&hc->out_count, g->count_dev, sizeof(unsigned long long),
-                                               cudaMemcpyDeviceToHost, g->stream),
-                               "download count"))
+    if (!index_synced && !count_src &&
+        !cuda_ok(cudaMemcpyAsync(&hc->out_count, g->count_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, g->stream),
+                 "download count"))
         return false;
     const double t_enq = now_ms();
-    if (!cuda_ok(cudaStreamSynchronize(g->stream), "match sync")) return false;
-    if (count_src) hc->out_count = *static_cast<const volatile unsigned long long *>(count_src);
+    if (!index_synced && !cuda_ok(cudaStreamSynchronize(g->stream), "match sync")) return false;
+    if (count_src && !index_synced) hc->out_count = *static_cast<const volatile unsigned long long *>(count_src);
     const double t_sync = now_ms();
     g->trace[0] = t_compiled - t_begin;
     g->trace[1] = t_enq - t_compiled;
@@ -1169,6 +1173,7 @@ bool engine_match_segments(GpuEngine *g, const struct whereClauseS *wc, std::vec
     SegmentPlan segs[kMaxSegments];
     bool too_many = false;
     const int n_seg = plan_segments(g, wc, segs, kMaxSegments, &too_many);
+    if (n_seg < 0) return false;
     if (too_many) {
         set_error("too many (condition x index) segments in one WHERE clause");
         return false;

@@ -97,6 +97,7 @@ struct GpuEngine {
     uint32_t *d_probe_first = nullptr, *d_probe_count = nullptr;
     unsigned long long *h_probe_keys = nullptr;  // pinned: lo[kMaxSegments], hi[kMaxSegments]
     uint32_t *h_probe_out = nullptr;             // pinned: first[kMaxSegments], count[kMaxSegments]
+    CandSegments *d_segs = nullptr;              // the candidate-segment table K3s leaves for K1g (index path)
     // batched probes (probe_batch.cu): grow-only device scratch and pinned bounce buffer
     void *d_probe_scratch = nullptr;
     size_t probe_scratch_bytes = 0;

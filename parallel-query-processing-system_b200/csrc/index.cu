@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include "index.cuh"
+#include "scan_kernels.cuh"
 
 namespace qpe {
 
@@ -493,6 +494,104 @@ __global__ void __launch_bounds__(256) probe_kernel(const __grid_constant__ Prob
                 }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3s: the probes of ONE indexed SELECT -- one warp per (top-level condition x index) segment, possibly over
+// different indexes and key types, keys passed as kernel parameters -- leaving the candidate-segment table
+// (first entry and running total per segment: executeEngine-serial.c:358-459 concatenates the findRange results
+// in this order) in device memory for K1g.  The host never sees first / count: no synchronisation between
+// the probes and the filter.
+// ------------------------------------------------------------------------------------------
+struct SegProbeOne {
+    const void *keys;
+    const uint32_t *perm;
+    long long n;
+    const void *level[kMaxIndexLevels];
+    long long level_cnt[kMaxIndexLevels];
+    unsigned long long lo, hi;   // int keys: the value in the low 32 bits
+    int n_levels;
+    int is_u64;
+};
+struct SegProbeParams {
+    int n_seg;
+    int pad;
+    CandSegments *out;
+    SegProbeOne seg[kMaxSegments];
+};
+
+template <typename K>
+__device__ __forceinline__ long long descend_half(const SegProbeOne &sg, K key, bool upper, uint32_t sub, uint32_t half) {
+    long long g = 0;
+    for (int l = 0; l <= sg.n_levels; ++l) {  // warp-uniform trip count
+        const bool leaf = (l == sg.n_levels);
+        const K *arr = static_cast<const K *>(leaf ? sg.keys : sg.level[l]);
+        const long long cnt = leaf ? sg.n : sg.level_cnt[l];
+        const long long i = g * kFanout + sub;
+        const K v = i < cnt ? __ldg(arr + i) : K(0);
+        const bool less = i < cnt && (upper ? v <= key : v < key);
+        const uint32_t b = (__ballot_sync(0xffffffffu, less) >> (16u * half)) & 0xffffu;
+        const int r = __popc(b);
+        g = g * kFanout + (leaf ? r : (r > 0 ? r - 1 : 0));
+    }
+    return g;
+}
+
+__global__ void __launch_bounds__(32 * kMaxSegments) probe_segments_kernel(const __grid_constant__ SegProbeParams p) {
+    __shared__ long long s_first[kMaxSegments], s_count[kMaxSegments];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t sub = lane & 15u, half = lane >> 4;   // lanes 0-15: lower_bound(lo), lanes 16-31: upper_bound(hi)
+    if (warp < static_cast<uint32_t>(p.n_seg)) {
+        const SegProbeOne &sg = p.seg[warp];
+        long long pos;
+        if (sg.is_u64)
+            pos = descend_half<unsigned long long>(sg, half ? sg.hi : sg.lo, half != 0, sub, half);
+        else
+            pos = descend_half<int>(sg, static_cast<int>(static_cast<uint32_t>(half ? sg.hi : sg.lo)), half != 0, sub, half);
+        const long long lo_pos = __shfl_sync(0xffffffffu, pos, 0), hi_pos = __shfl_sync(0xffffffffu, pos, 16);
+        if (lane == 0) {
+            s_first[warp] = lo_pos;
+            s_count[warp] = hi_pos > lo_pos ? hi_pos - lo_pos : 0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        CandSegments *o = p.out;
+        o->n_seg = p.n_seg;
+        long long run = 0;
+        o->vstart[0] = 0;
+        for (int s = 0; s < p.n_seg; ++s) {
+            o->perm[s] = p.seg[s].perm;
+            o->first[s] = s_first[s];
+            run += s_count[s];
+            o->vstart[s + 1] = run;
+        }
+    }
+}
+
+cudaError_t index_probe_segments(const DevIndex *const *ix, const unsigned long long *lo, const unsigned long long *hi,
+                                 int n_seg, CandSegments *d_out, cudaStream_t stream) {
+    if (n_seg < 1 || n_seg > kMaxSegments) return cudaErrorInvalidValue;
+    SegProbeParams p{};
+    p.n_seg = n_seg;
+    p.out = d_out;
+    for (int s = 0; s < n_seg; ++s) {
+        const DevIndex &x = *ix[s];
+        SegProbeOne &o = p.seg[s];
+        o.keys = x.keys;
+        o.perm = x.perm;
+        o.n = x.n;
+        o.n_levels = x.n_levels;
+        for (int l = 0; l < x.n_levels; ++l) {
+            o.level[l] = x.level[l];
+            o.level_cnt[l] = x.level_cnt[l];
+        }
+        o.lo = lo[s];
+        o.hi = hi[s];
+        o.is_u64 = x.type == T_U64 ? 1 : 0;
+    }
+    probe_segments_kernel<<<1, 32 * n_seg, 0, stream>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t index_probe(const DevIndex &ix, const void *d_lo, const void *d_hi, long long q, uint32_t *d_first,

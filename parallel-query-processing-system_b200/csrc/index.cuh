@@ -16,6 +16,12 @@ void index_free(DevIndex *ix);
 cudaError_t index_probe(const DevIndex &ix, const void *d_lo, const void *d_hi, long long q, uint32_t *d_first,
                         uint32_t *d_count, cudaStream_t stream);
 
+// K3s: all probes of one indexed SELECT in ONE launch (one warp per segment; ix[s] / lo[s] / hi[s] per segment, int
+// keys in the low 32 bits), leaving the candidate-segment table for K1g in device memory (*d_out)
+struct CandSegments;
+cudaError_t index_probe_segments(const DevIndex *const *ix, const unsigned long long *lo, const unsigned long long *hi,
+                                 int n_seg, CandSegments *d_out, cudaStream_t stream);
+
 // ---- maintenance without a re-sort (no allocation; `scratch` holds index_scratch_bytes(ix, ix.n) bytes) ----
 size_t index_scratch_bytes(const DevIndex &ix, long long n_entries);
 // INSERT: table row `row` (the table's last row) enters the index at the front of its key run.  d_first / d_count:

@@ -1517,13 +1517,13 @@ int64_t filter_tiles(long long n) { return (n + kFilterTile - 1) / kFilterTile; 
 struct FilterParams {
     const uint8_t *col[NUM_COLS];
     uint32_t width[NUM_COLS];
-    CandSegments segs;
-    long long n_cand;
-    long long n_tiles;
+    CandSegments segs;            // host-known segments (identity list) ...
+    const CandSegments *d_segs;   // ... or the table K3s left on the device (index path: no host round trip)
     QueryCtl *ctl;
     unsigned long long *tile_desc;
     uint32_t epoch;
     uint32_t *out_ids;
+    unsigned long long out_cap;   // nothing is stored at or beyond it (the count is still exact)
 };
 
 __device__ __forceinline__ uint32_t eval_leaf_row(const PLeaf &lf, const Program *sp, const FilterParams &p,
@@ -1559,6 +1559,9 @@ __device__ __forceinline__ uint32_t eval_leaf_row(const PLeaf &lf, const Program
     }
 }
 
+// Persistent CTAs: tiles of 1 Ki candidates are claimed IN ORDER from an atomic counter (every predecessor of a tile is
+// finished or being worked on by a resident CTA, so the look-back cannot deadlock); the number of candidates is read
+// from the segment table, which on the index path was written by the probe kernel just before -- the host never sees it.
 __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_constant__ FilterParams p) {
     __shared__ Program s_prog;
     __shared__ long long s_tile;
@@ -1572,78 +1575,101 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_con
         uint4 *dst = reinterpret_cast<uint4 *>(&s_prog);
         for (uint32_t i = tid; i < sizeof(Program) / 16; i += kFilterThreads) dst[i] = src[i];
     }
-    if (tid == 0) s_tile = static_cast<long long>(atomicAdd(&p.ctl->tile_counter, 1u));
-    __syncthreads();
-    const long long tile = s_tile;
-    if (tile >= p.n_tiles) return;  // cannot happen with grid == n_tiles; kept for safety
+    const CandSegments &S = p.d_segs ? *p.d_segs : p.segs;
+    const int n_seg = S.n_seg;
+    const long long n_cand = S.vstart[n_seg];
+    const long long n_tiles = (n_cand + kFilterTile - 1) / kFilterTile;
     const Program *sp = &s_prog;
-
     constexpr int kWarps = kFilterThreads / 32;
-    uint32_t rows[kFilterItems];
+    for (;;) {
+        __syncthreads();  // the previous tile's shared words have been read; (first pass) the program is in place
+        if (tid == 0) s_tile = static_cast<long long>(atomicAdd(&p.ctl->tile_counter, 1u));
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= n_tiles) return;
+
+        uint32_t rows[kFilterItems];
 #pragma unroll
-    for (int it = 0; it < kFilterItems; ++it) {
-        const long long i = tile * kFilterTile + it * kFilterThreads + tid;
-        uint32_t row = 0;
-        bool valid = i < p.n_cand;
-        if (valid) {
-            int sg = 0;
-            while (sg + 1 < p.segs.n_seg && i >= p.segs.vstart[sg + 1]) ++sg;
-            const long long k = p.segs.first[sg] + (i - p.segs.vstart[sg]);
-            row = p.segs.perm[sg] ? __ldg(p.segs.perm[sg] + k) : static_cast<uint32_t>(k);
+        for (int it = 0; it < kFilterItems; ++it) {
+            const long long i = tile * kFilterTile + it * kFilterThreads + tid;
+            uint32_t row = 0;
+            bool valid = i < n_cand;
+            if (valid) {
+                int sg = 0;
+                while (sg + 1 < n_seg && i >= S.vstart[sg + 1]) ++sg;
+                const long long k = S.first[sg] + (i - S.vstart[sg]);
+                row = S.perm[sg] ? __ldg(S.perm[sg] + k) : static_cast<uint32_t>(k);
+            }
+            rows[it] = row;
+            const uint32_t acc = run_program(sp, 1u, [&](const PLeaf &lf) { return eval_leaf_row(lf, sp, p, row); });
+            const uint32_t bal = __ballot_sync(0xffffffffu, valid && (acc & 1u));
+            if (lane == 0) s_words[it * kWarps + warp] = bal;
         }
-        rows[it] = row;
-        const uint32_t acc = run_program(sp, 1u, [&](const PLeaf &lf) { return eval_leaf_row(lf, sp, p, row); });
-        const uint32_t bal = __ballot_sync(0xffffffffu, valid && (acc & 1u));
-        if (lane == 0) s_words[it * kWarps + warp] = bal;
-    }
-    __syncthreads();
-    // block scan over the 32 words by warp 0, then publish + look back
-    if (warp == 0) {
-        const uint32_t word = s_words[lane];
-        const uint32_t pc = __popc(word);
-        uint32_t inc = pc;
+        __syncthreads();
+        // block scan over the 32 words by warp 0, then publish + look back
+        if (warp == 0) {
+            const uint32_t word = s_words[lane];
+            const uint32_t pc = __popc(word);
+            uint32_t inc = pc;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t tmp = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= static_cast<uint32_t>(d)) inc += tmp;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t tmp = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= static_cast<uint32_t>(d)) inc += tmp;
+            }
+            s_woff[lane] = inc - pc;
+            const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+            if (lane == 0) st_desc(p.tile_desc + tile, make_desc(p.epoch, tile == 0 ? kStatePrefix : kStateAgg, total));
+            const uint32_t excl = warp_lookback(p.tile_desc, tile, p.epoch, lane);
+            if (lane == 0) {
+                st_desc(p.tile_desc + tile, make_desc(p.epoch, kStatePrefix, excl + total));
+                if (tile == n_tiles - 1) p.ctl->out_count = static_cast<unsigned long long>(excl) + total;
+                s_total = total;
+                s_excl = excl;
+            }
         }
-        s_woff[lane] = inc - pc;
-        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        if (lane == 0) st_desc(p.tile_desc + tile, make_desc(p.epoch, tile == 0 ? kStatePrefix : kStateAgg, total));
-        const uint32_t excl = warp_lookback(p.tile_desc, tile, p.epoch, lane);
-        if (lane == 0) {
-            st_desc(p.tile_desc + tile, make_desc(p.epoch, kStatePrefix, excl + total));
-            if (tile == p.n_tiles - 1) p.ctl->out_count = static_cast<unsigned long long>(excl) + total;
-            s_total = total;
-            s_excl = excl;
-        }
-    }
-    __syncthreads();
-    if (p.out_ids == nullptr || s_total == 0) return;
-    const uint32_t excl = s_excl;
+        __syncthreads();
+        if (p.out_ids == nullptr || s_total == 0) continue;
+        const uint32_t excl = s_excl;
 #pragma unroll
-    for (int it = 0; it < kFilterItems; ++it) {
-        const uint32_t w = s_words[it * kWarps + warp];
-        if ((w >> lane) & 1u) p.out_ids[excl + s_woff[it * kWarps + warp] + __popc(w & lanemask_lt())] = rows[it];
+        for (int it = 0; it < kFilterItems; ++it) {
+            const uint32_t w = s_words[it * kWarps + warp];
+            if ((w >> lane) & 1u) {
+                const unsigned long long o = static_cast<unsigned long long>(excl) + s_woff[it * kWarps + warp] + __popc(w & lanemask_lt());
+                if (o < p.out_cap) p.out_ids[o] = rows[it];
+            }
+        }
     }
 }
 
 cudaError_t filter_launch(const DevTable &t, const QueryCtl *d_ctl, const CandSegments &segs,
-                          unsigned long long *tile_desc, uint32_t epoch, uint32_t *out_ids, cudaStream_t stream) {
+                          unsigned long long *tile_desc, uint32_t epoch, uint32_t *out_ids, cudaStream_t stream,
+                          const CandSegments *d_segs, long long max_candidates, unsigned long long out_cap) {
     FilterParams p{};
     for (int c = 0; c < NUM_COLS; ++c) {
         p.col[c] = t.col[c].d;
         p.width[c] = t.col[c].width;
     }
     p.segs = segs;
-    p.n_cand = segs.vstart[segs.n_seg];
-    p.n_tiles = filter_tiles(p.n_cand);
+    p.d_segs = d_segs;
     p.ctl = const_cast<QueryCtl *>(d_ctl);
     p.tile_desc = tile_desc;
     p.epoch = epoch;
     p.out_ids = out_ids;
-    if (p.n_tiles == 0) return cudaSuccess;
-    filter_kernel<<<static_cast<unsigned>(p.n_tiles), kFilterThreads, 0, stream>>>(p);
+    p.out_cap = out_cap;
+    // with the segment table on the device the host only knows an upper bound of the candidates
+    const long long bound = d_segs ? max_candidates : segs.vstart[segs.n_seg];
+    long long grid = filter_tiles(bound);
+    if (grid == 0) return cudaSuccess;
+    static int wave = 0;
+    if (wave == 0) {
+        int dev = 0, n_sm = 148, per_sm = 4;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter_kernel, kFilterThreads, 0);
+        wave = n_sm * (per_sm > 0 ? per_sm : 1);
+    }
+    if (grid > wave) grid = wave;
+    filter_kernel<<<static_cast<unsigned>(grid), kFilterThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

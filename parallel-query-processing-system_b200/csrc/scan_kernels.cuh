@@ -118,9 +118,13 @@ struct CandSegments {
     long long first[kMaxSegments];       // first entry of the slice within perm
     long long vstart[kMaxSegments + 1];  // prefix of slice lengths (virtual candidate index)
 };
+// d_segs != nullptr: the segment table is read from device memory (written by index_probe_segments just before, no
+// host round trip); max_candidates then bounds the grid, and segs is ignored.  Nothing is stored at or beyond
+// out_cap (the count in ctl->out_count is still exact).
 cudaError_t filter_launch(const DevTable &t, const QueryCtl *d_ctl, const CandSegments &segs,
-                          unsigned long long *tile_desc, uint32_t epoch, uint32_t *out_ids,
-                          cudaStream_t stream);
+                          unsigned long long *tile_desc, uint32_t epoch, uint32_t *out_ids, cudaStream_t stream,
+                          const CandSegments *d_segs = nullptr, long long max_candidates = 0,
+                          unsigned long long out_cap = ~0ull);
 int64_t filter_tiles(long long n_candidates);
 
 // K2: projection gather  out[k] = column[ids[k]]  (width bytes per row)

@@ -120,6 +120,9 @@ struct ShardState {
     ShardPending pending[2];
     int n_pending = 0;
     bool last_was_post = false;         // the engine stream's most recent kernel is a post-scan kernel of this file
+    // share of a host result each rank delivers, as cumulative fractions of 2^20 (equal shares unless
+    // qpe_shard_set_link_weights: PCIe links of one box can differ by 2x when all of them copy at once)
+    uint32_t slice_cum[kMaxRanks + 1] = {0};
     int numa_node = -1, numa_how = 0;   // where this rank's part of the host buffer was placed, and by what (1 mbind, 2 affinity)
 };
 
@@ -160,6 +163,12 @@ struct PeerPtrs {
 struct PeerSegs {
     const uint32_t *seg[kMaxRanks];   // every rank's segment of THIS query's parity
 };
+struct SliceCum {
+    uint32_t cum[kMaxRanks + 1];      // rank j delivers result positions [total * cum[j] >> 20, total * cum[j + 1] >> 20)
+};
+__host__ __device__ inline unsigned long long slice_bound(unsigned long long total, uint32_t cum) {
+    return (total * cum) >> 20;       // total < 2^32, cum <= 2^20: no overflow
+}
 
 // ids per parity set of the device result: the dense area, then one segment per rank >= 1
 __host__ __device__ inline unsigned long long set_ids(int world, unsigned long long seg_cap) {
@@ -215,7 +224,6 @@ __device__ __forceinline__ void publish_to_host(unsigned long long *words, const
     words[kMaxRanks + 1] = timed_out ? 1ull : 0ull;
     __threadfence_system();
     *reinterpret_cast<volatile unsigned long long *>(words + kMaxRanks) = static_cast<unsigned long long>(epoch);
-    __threadfence_system();
 }
 
 // DEVICE RESULT: the ONE kernel that follows the scan on every rank (same stream):
@@ -249,11 +257,16 @@ __global__ void __launch_bounds__(256) post_kernel(const unsigned long long *cou
         s_ok = ok;
     }
     __syncthreads();
-    if (pack && s_ok) {
-        for (int r = 1; r < world; ++r) {
-            const unsigned long long n = s_off[r + 1] - s_off[r];
-            copy_ids(set + (static_cast<unsigned long long>(world) + (r - 1)) * seg_cap, set + s_off[r], n);
-        }
+    // nothing to move (one CTA, or every other rank's count is 0: all matches in the first shard): CTA 0 hands the
+    // counts over at once, nobody counts CTAs
+    const bool moving = pack && s_ok && gridDim.x > 1 && s_off[world] > s_off[1];
+    if (!moving) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) publish_to_host(host_words, s_cnt, world, epoch, s_timeout);
+        return;
+    }
+    for (int r = 1; r < world; ++r) {
+        const unsigned long long n = s_off[r + 1] - s_off[r];
+        copy_ids(set + (static_cast<unsigned long long>(world) + (r - 1)) * seg_cap, set + s_off[r], n);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -275,7 +288,7 @@ __global__ void __launch_bounds__(256) deliver_kernel(const unsigned long long *
                                                       int world, uint32_t epoch, unsigned long long *host_words,
                                                       uint32_t *dst, unsigned long long seg_cap,
                                                       unsigned long long host_cap, unsigned long long dst_cap,
-                                                      int direct) {
+                                                      int direct, SliceCum sc) {
     __shared__ unsigned long long s_cnt[kMaxRanks];
     __shared__ unsigned long long s_off[kMaxRanks + 1];
     __shared__ int s_timeout, s_ok;
@@ -302,7 +315,7 @@ __global__ void __launch_bounds__(256) deliver_kernel(const unsigned long long *
     __syncthreads();
     if (s_ok) {
         const unsigned long long total = s_off[world];
-        const unsigned long long lo = total * rank / world, hi = total * (rank + 1) / world;
+        const unsigned long long lo = slice_bound(total, sc.cum[rank]), hi = slice_bound(total, sc.cum[rank + 1]);
         // staging holds the slice from its first id on; the host array is addressed by result position
         uint32_t *d0 = direct ? dst : dst - lo;
         if (direct || hi - lo <= dst_cap)
@@ -507,6 +520,7 @@ int qpe_shard_init(struct engineS *engine, int rank, int world, unsigned long lo
     s->rank = rank;
     s->world = world;
     s->seg_cap = segment_capacity;
+    for (int r = 0; r <= world; ++r) s->slice_cum[r] = static_cast<uint32_t>((static_cast<unsigned long long>(r) << 20) / world);
     const size_t bytes = kCommBytes + 2 * static_cast<size_t>(segment_capacity) * sizeof(uint32_t) + 256;
     void *block = nullptr;
     bool ok = cuda_ok(cudaMalloc(&block, bytes), "cudaMalloc comm + segments") &&
@@ -638,7 +652,7 @@ unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *nam
         s->numa_how = place_on_node(s->host_ids + par * cap + lo, (hi - lo) * sizeof(uint32_t), node);
     }
     // staging for this rank's slice (mode 1)
-    s->staging_cap = cap / s->world + 1024;
+    s->staging_cap = cap;  // any share of a result fits (qpe_shard_set_link_weights may give a fast link most of it)
     for (int par = 0; par < 2; ++par)
         if (!cuda_ok(cudaMalloc(&s->staging[par], s->staging_cap * sizeof(uint32_t)), "cudaMalloc staging")) {
             release_host_result(s);
@@ -679,6 +693,34 @@ int qpe_shard_set_multipath(struct engineS *engine, int mode) {
         return -1;
     }
     s->host_mode = mode;
+    return 0;
+}
+
+/* Shares of a host result per rank, proportional to `weights` (e.g. the device->host rate of every rank's PCIe link
+ * measured with all links busy).  Every rank must pass the same numbers.  Equal shares by default. */
+int qpe_shard_set_link_weights(struct engineS *engine, const double *weights, int n) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    if (!s || n != s->world || s->n_pending) {
+        set_error("qpe_shard_set_link_weights: one weight per rank, no query in flight");
+        return -1;
+    }
+    double sum = 0;
+    for (int r = 0; r < n; ++r) {
+        if (!(weights[r] > 0)) {
+            set_error("qpe_shard_set_link_weights: weights must be positive");
+            return -5;
+        }
+        sum += weights[r];
+    }
+    double run = 0;
+    s->slice_cum[0] = 0;
+    for (int r = 0; r < n; ++r) {
+        run += weights[r];
+        s->slice_cum[r + 1] = static_cast<uint32_t>(run / sum * 1048576.0 + 0.5);
+    }
+    s->slice_cum[n] = 1u << 20;
     return 0;
 }
 
@@ -792,8 +834,10 @@ int qpe_shard_submit(struct engineS *engine, struct whereClauseS *whereClause, i
         for (int r = 0; r < s->world; ++r) segs.seg[r] = s->seg[r] + static_cast<size_t>(par) * s->seg_cap;
         const bool direct = s->host_mode == 2;
         uint32_t *dst = direct ? s->host_ids_dev + static_cast<size_t>(par) * s->host_cap : s->staging[par];
+        SliceCum sc{};
+        for (int r = 0; r <= s->world; ++r) sc.cum[r] = s->slice_cum[r];
         deliver_kernel<<<148 * 4, 256, 0, g->stream>>>(count, peers, segs, s->rank, s->world, epoch, words, dst, s->seg_cap,
-                                                       s->host_cap, s->staging_cap, direct ? 1 : 0);
+                                                       s->host_cap, s->staging_cap, direct ? 1 : 0, sc);
     } else {
         const int pack = (s->rank == s->owner && s->world > 1) ? 1 : 0;
         post_kernel<<<pack ? 148 * 8 : 1, 256, 0, g->stream>>>(count, peers, s->rank, s->world, epoch, words, pack, set,
@@ -858,8 +902,8 @@ int qpe_shard_wait(struct engineS *engine, unsigned long long *counts_out, qpe_s
         if (!failed && !overflow && s->host_mode == 1) {
             // this rank's 1/world of the result: local staging -> (its own PCIe link) -> host, on the copy stream, so
             // that the next query's scan (already enqueued on the main stream) runs beside it
-            const unsigned long long lo = total * s->rank / s->world, hi = total * (s->rank + 1) / s->world;
-            if (hi > lo) {
+            const unsigned long long lo = slice_bound(total, s->slice_cum[s->rank]), hi = slice_bound(total, s->slice_cum[s->rank + 1]);
+            if (hi > lo && hi - lo <= s->staging_cap) {
                 if (!cuda_ok(cudaMemcpyAsync(host_ids + lo, s->staging[par], (hi - lo) * sizeof(uint32_t),
                                              cudaMemcpyDeviceToHost, g->stream2),
                              "download ids") ||

@@ -82,7 +82,8 @@ def ordered_gather(local_ids: torch.Tensor, out: Optional[torch.Tensor] = None, 
 
 def merge_index_segments(local_segments, device="cpu", dst: int = 0, group=None):
     """Cross-shard merge of an index-path SELECT.  `local_segments` = this rank's
-    [(keys int64, global ids), ...] per segment, each (key ASC, local position DESC).  For every
+    [(order keys int64, global ids), ...] per segment, each (key ASC, local position DESC); u64 keys arrive with
+    their top bit flipped (Engine.select_segments), so the signed sort below is the tree's unsigned order.  For every
     segment the shards are concatenated from the HIGHEST rank to the lowest and sorted stably by
     key, which yields (key ASC, global position DESC): exactly the leaf-chain order of one B+ tree
     over the whole table (engine/bplus.c:282-358).  Segments are then concatenated in
@@ -334,6 +335,33 @@ class ShardGroup:
         (`host_result`).  stats=False: no statistics (None); the event times stay unresolved."""
         self.submit(statement, to_host)
         return self.wait(stats)
+
+    def balance_links(self, nbytes: int = 4 << 20, reps: int = 6):
+        """Measure every rank's device->host rate into ITS part of the shared buffer with all links busy at once, and
+        give each rank a share of every host result in proportion (the PCIe links of one box can differ by 2x under
+        load: a result cut into equal parts waits for the slowest).  Every rank calls it; returns the rates (GB/s)."""
+        import time
+        lib, h = self.lib, self._h
+        C = self._C
+        src = self.pkg.DeviceBuffer(nbytes)
+        cap = (self.host_cap + 1023) & ~1023
+        dst = lib.qpe_shard_host_result(h) + 4 * (cap * self.rank // self.world)
+        nbytes = min(nbytes, 4 * (cap // self.world))
+        lib.qpe_gpu_copy_to_host(dst, src.ptr, nbytes)
+        dist.barrier(group=self.group)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            lib.qpe_gpu_copy_to_host(dst, src.ptr, nbytes)
+        rate = reps * nbytes / (time.perf_counter() - t0) / 1e9
+        src.free()
+        rates = [None] * self.world
+        dist.all_gather_object(rates, float(rate), group=self.group)
+        # a link never gets less than a quarter of an equal share: the measurement is short
+        floor = 0.25 * sum(rates) / self.world
+        w = (C.c_double * self.world)(*[max(r, floor) for r in rates])
+        self.engine._check(lib.qpe_shard_set_link_weights(h, w, self.world), "qpe_shard_set_link_weights")
+        dist.barrier(group=self.group)
+        return rates
 
     def set_multipath(self, mode: int):
         """host result: 1 = staging in HBM + copy engine (default), 2 = the kernel stores into host memory"""

@@ -50,6 +50,8 @@ def _worker(rank, world, port, ret):
     # both host-result paths: every rank stages its 1/world of the result and the copy engine takes it to the host
     # (2 ranks), and the delivery kernel storing into the mapped host buffer itself (3 ranks)
     grp.set_multipath(2 if world == 3 else 1)
+    if world == 3:
+        grp.balance_links(nbytes=1 << 20, reps=2)    # unequal shares of a host result (whatever the links measure)
     out = []
     # every query twice in a row (device result then host result), then the whole list again: epochs and
     # the two parities of every buffer get reused with different contents

@@ -12,10 +12,11 @@ import support  # noqa: E402
 pkg = support.load_pkg()
 Q = "SELECT command_id FROM Commands WHERE (command_id < {K}) AND (sudo_used = FALSE OR risk_level > 3)"
 sizes = [int(float(x)) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["25e6", "50e6", "125e6", "250e6", "500e6"])]
+sel = float(sys.argv[2]) if len(sys.argv) > 2 else 0.01
 rows = []
 for n in sizes:
     eng = pkg.Engine.from_synth(n, columns=["command_id", "sudo_used", "risk_level"])
-    sql = Q.format(K=max(1, n // 100))
+    sql = Q.format(K=max(1, int(n * sel)))
     best = None
     for rep in range(6):
         cnt, dptr, st = eng.select_ids_device(sql, force_scan=True)
