@@ -13,7 +13,10 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__grid_size", "launch__shared_mem_per_block_dynamic", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max", "lts__t_sector_hit_rate.pct",
         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_ld.ratio",
+        "l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_st.ratio",
+        "l1tex__t_sector_hit_rate.pct", "dram__throughput.avg.pct_of_peak_sustained_elapsed"]
 STALL = "smsp__average_warps_issue_stalled_"
 
 
