@@ -645,7 +645,39 @@ def run_ours(args):
         assert n_e2e == n_matches
         launches = st0["launches"]
         sync_info = {}
+        # the uniform-match query of the N > 1 runs, on one GPU (so that its scaling can be read off the per-N lines)
         uniform = None
+        try:
+            ueng = pkg.Engine.from_synth(total, columns=ucols)
+            uid = np.sort(ueng.fetch_column("user_id", 0, 2_000_000))
+            usql = usql_t.format(X=int(uid[min(len(uid) - 1, int(len(uid) * args.selectivity))]))
+            ucnt, _, _ = ueng.select_ids_device(usql, force_scan=True)
+            upinned = np.empty(max(ucnt, 1), dtype=np.uint32)
+            upin = torch.from_numpy(upinned.view(np.int32)).pin_memory().numpy().view(np.uint32)
+            ustream = torch.cuda.ExternalStream(ueng.stream, device=dev)
+
+            def utimed(fn):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t_0 = time.perf_counter()
+                e0.record(ustream)
+                for _ in range(steps):
+                    fn()
+                e1.record(ustream)
+                torch.cuda.synchronize()
+                return max(e0.elapsed_time(e1), (time.perf_counter() - t_0) * 1e3) / steps
+
+            for _ in range(warmup):
+                ueng.select_ids_device(usql, force_scan=True, stats=False)
+                ueng.select_ids_into(usql, upin, force_scan=True, stats=False)
+            u_ms = utimed(lambda: ueng.select_ids_device(usql, force_scan=True, stats=False))
+            u_e2e = utimed(lambda: ueng.select_ids_into(usql, upin, force_scan=True, stats=False))
+            uniform = {"query": usql, "bytes_per_row": ubpr, "matches": int(ucnt), "value": total / (u_ms * 1e-3),
+                       "ms_per_step": u_ms, "e2e": {"value": total / (u_e2e * 1e-3), "ms_per_step": u_e2e, "unit": "rows/s",
+                                                    "d2h_bytes_per_step": int(4 * ucnt + 8)}}
+            ueng.close()
+        except Exception as e:   # reported, never required
+            uniform = {"failed": f"{type(e).__name__}: {e}"}
     else:
         # ---- N GPUs: csrc/shard.cu, two queries in flight ----
         from importlib import import_module
@@ -782,6 +814,7 @@ def run_ours(args):
             out["e2e"]["sync_ms_per_step"] = sync_info.pop("e2e_sync_ms_per_step")
             out["e2e"]["host_mode"] = args.host_mode
             out.update(sync_info)
+        if uniform is not None:
             out["uniform"] = uniform
     if world > 1:
         sg.close()
