@@ -243,6 +243,14 @@ int qpe_gpu_match_mask(struct engineS *engine, struct whereClauseS *whereClause,
 #define QPE_PROBE_SORT 1
 int qpe_gpu_probe_keys(struct engineS *engine, const char *attribute, const void *lo, const void *hi, size_t n_queries,
                        unsigned int *first, unsigned int *count, int flags, qpe_scan_stats *stats);
+/* K4 on its own: the stable LSD radix sort behind the index build (the reference builds the same (key ASC, position
+ * DESC) leaf order by inserting row after row: engine/serial/buildEngine-serial.c:46-53 -> engine/bplus.c:723-740) and
+ * behind QPE_PROBE_SORT.  keys: n keys of key_bytes (4 or 8) in host memory, ordered as unsigned or (signed_keys) two's
+ * complement values.  mode 0: pairs (keys[i], vals[i]); 1: (keys[i], i); 2: the input read backwards, (keys[n-1-i],
+ * n-1-i) -- equal keys then come out in DESCENDING position order.  passes_out: digit passes run (byte positions equal
+ * in all keys are skipped); kernel_ms_out: device time of the sort. */
+int qpe_gpu_sort_pairs(const void *keys, const unsigned int *vals, size_t n, int key_bytes, int signed_keys, int mode,
+                       void *keys_out, unsigned int *vals_out, int *passes_out, double *kernel_ms_out);
 /* pinned host memory for probe batches and id lists (release with qpe_gpu_host_free) */
 void *qpe_gpu_host_alloc(size_t bytes);
 void qpe_gpu_host_free(void *p);

@@ -114,6 +114,7 @@ def load_library() -> C.CDLL:
         "qpe_gpu_row_base": (ull, [vp]),
         "qpe_gpu_probe_batch": (i, [vp, cp, C.POINTER(KeyT), C.POINTER(KeyT), sz, vp, vp, pstats]),
         "qpe_gpu_probe_keys": (i, [vp, cp, vp, vp, sz, vp, vp, i, pstats]),
+        "qpe_gpu_sort_pairs": (i, [vp, vp, sz, i, i, i, vp, vp, C.POINTER(i), C.POINTER(C.c_double)]),
         "qpe_gpu_host_alloc": (vp, [sz]),
         "qpe_gpu_host_free": (None, [vp]),
         "qpe_gpu_index_slice": (i, [vp, cp, C.c_uint, C.c_uint, vp]),
@@ -223,6 +224,32 @@ def ipc_close(ptr: int):
 
 def gpu_available() -> bool:
     return bool(load_library().qpe_gpu_available())
+
+
+def sort_pairs(keys, vals=None, mode: int = 0, signed: Optional[bool] = None):
+    """K4 on its own (qpe_gpu_sort_pairs): stable radix sort of (key, payload) pairs on the GPU.  keys: uint64 / uint32 /
+    int32 / int64 array; mode 0 = (keys[i], vals[i]), 1 = (keys[i], i), 2 = the input read backwards (keys[n-1-i], n-1-i).
+    Returns (sorted keys, payloads, digit passes run, device ms)."""
+    keys = np.ascontiguousarray(keys)
+    if keys.dtype not in (np.uint64, np.int64, np.uint32, np.int32):
+        raise QpeError("sort_pairs: keys must be 32- or 64-bit integers")
+    if signed is None:
+        signed = keys.dtype.kind == "i"
+    n = keys.shape[0]
+    if mode == 0:
+        vals = np.ascontiguousarray(vals, dtype=np.uint32)
+        if vals.shape[0] != n:
+            raise QpeError("sort_pairs: keys and vals differ in length")
+    keys_out = np.empty_like(keys)
+    vals_out = np.empty(n, dtype=np.uint32)
+    passes, ms = C.c_int(0), C.c_double(0)
+    rc = load_library().qpe_gpu_sort_pairs(keys.ctypes.data if n else None, vals.ctypes.data if (mode == 0 and n) else None, n,
+                                           keys.dtype.itemsize, 1 if signed else 0, mode,
+                                           keys_out.ctypes.data if n else None, vals_out.ctypes.data if n else None,
+                                           C.byref(passes), C.byref(ms))
+    if rc != 0:
+        raise QpeError(f"sort_pairs failed (rc={rc}): " + (load_library().qpe_gpu_last_error() or b"").decode())
+    return keys_out, vals_out, passes.value, ms.value
 
 
 def _index_args(indexes):

@@ -432,7 +432,7 @@ struct engineS *qpe_gpu_engine_from_records(const record *rows, long long n_rows
 }
 
 void destroyEngineGPU(struct engineS *engine) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    std::lock_guard<std::mutex> lk(g_api_mutex);  // (the engine's own mutex dies with it; no call may be running on it)
     if (engine == nullptr) {
         std::fprintf(stderr, "Attempted to destroy a NULL engine pointer\n");  // executeEngine-serial.c:811
         return;
@@ -449,7 +449,7 @@ void destroyEngineGPU(struct engineS *engine) {
 struct resultSetS *executeQuerySelectGPU(struct engineS *engine, const char **selectItems, int numSelectItems,
                                          const char *tableName, struct whereClauseS *whereClause) {
     (void)tableName;  // ignored by every reference engine
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     struct resultSetS *res = new_result();
     GpuEngine *g = as_engine(engine);
     if (!g) {
@@ -479,7 +479,7 @@ struct resultSetS *executeQuerySelectGPU(struct engineS *engine, const char **se
 struct resultSetS *executeQueryDeleteGPU(struct engineS *engine, const char *tableName,
                                          struct whereClauseS *whereClause) {
     (void)tableName;
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     struct resultSetS *res = new_result();
     GpuEngine *g = as_engine(engine);
     if (!g) {
@@ -503,7 +503,7 @@ struct resultSetS *executeQueryDeleteGPU(struct engineS *engine, const char *tab
 
 bool executeQueryInsertGPU(struct engineS *engine, const char *tableName, const record *r) {
     (void)tableName;
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g || !r) return false;
     // validation of executeEngine-serial.c:544-551
@@ -529,7 +529,7 @@ bool executeQueryInsertGPU(struct engineS *engine, const char *tableName, const 
 bool addAttributeIndexGPU(struct engineS *engine, const char *tableName, const char *attributeName,
                           int attributeType) {
     (void)tableName;
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return true;
     // the reference returns FALSE when the index was created (inverted test, :833-840)
@@ -537,7 +537,7 @@ bool addAttributeIndexGPU(struct engineS *engine, const char *tableName, const c
 }
 
 bool makeIndexGPU(struct engineS *engine, const char *indexName, int attributeType) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return false;
     return engine_add_index(g, indexName, attributeType);
@@ -608,7 +608,7 @@ long long qpe_gpu_num_rows(const struct engineS *engine) {
 
 int qpe_gpu_select_ids_device(struct engineS *engine, struct whereClauseS *whereClause, int flags,
                               unsigned long long *count_out, const unsigned int **d_ids_out, qpe_scan_stats *stats) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     uint64_t m = 0;
@@ -638,7 +638,7 @@ int qpe_gpu_select_ids_device(struct engineS *engine, struct whereClauseS *where
  * full-scan queries that reference the same set of columns are evaluated together, up to 8 programs per pass. */
 int qpe_gpu_select_ids_batch(struct engineS *engine, struct whereClauseS *const *whereClauses, int n_queries,
                              unsigned int **ids_out, size_t *n_out, qpe_scan_stats *stats) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     if (n_queries < 0 || (n_queries > 0 && (!whereClauses || !ids_out || !n_out))) {
@@ -735,7 +735,7 @@ int qpe_gpu_select_ids_batch(struct engineS *engine, struct whereClauseS *const 
 
 int qpe_gpu_select_ids(struct engineS *engine, struct whereClauseS *whereClause, unsigned int **ids_out, size_t *n_out,
                        qpe_scan_stats *stats) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     const double t0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -780,7 +780,7 @@ static unsigned int *device_alias_of_host(void *p) {
 // copy engine while the scan of the following segments is still running.
 int qpe_gpu_select_ids_into(struct engineS *engine, struct whereClauseS *whereClause, int flags, unsigned int *ids,
                             size_t cap, size_t *n_out, qpe_scan_stats *stats) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     const double t0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -823,7 +823,7 @@ int qpe_gpu_select_ids_into(struct engineS *engine, struct whereClauseS *whereCl
 
 int qpe_gpu_match_mask(struct engineS *engine, struct whereClauseS *whereClause, unsigned int *bitmap, size_t n_words,
                        unsigned long long *count_out, qpe_scan_stats *stats) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     const size_t need = static_cast<size_t>((g->table.n + 31) / 32);
@@ -841,7 +841,7 @@ int qpe_gpu_match_mask(struct engineS *engine, struct whereClauseS *whereClause,
 
 int qpe_gpu_probe_batch(struct engineS *engine, const char *attribute, const KEY_T *lo, const KEY_T *hi,
                         size_t n_queries, unsigned int *first, unsigned int *count, qpe_scan_stats *stats) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     cudaSetDevice(g->device);
@@ -905,7 +905,7 @@ int qpe_gpu_probe_batch(struct engineS *engine, const char *attribute, const KEY
 
 int qpe_gpu_index_slice(struct engineS *engine, const char *attribute, unsigned int first, unsigned int count,
                         unsigned int *row_ids_out) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     cudaSetDevice(g->device);
@@ -929,7 +929,7 @@ int qpe_gpu_index_slice(struct engineS *engine, const char *attribute, unsigned 
 
 int qpe_gpu_index_slice_keys(struct engineS *engine, const char *attribute, unsigned int first, unsigned int count,
                              long long *keys_out) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     cudaSetDevice(g->device);
@@ -959,7 +959,7 @@ int qpe_gpu_index_slice_keys(struct engineS *engine, const char *attribute, unsi
 
 int qpe_gpu_fetch_column(struct engineS *engine, const char *attribute, long long first_row, long long n_rows, void *out,
                          unsigned int *width_out) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     cudaSetDevice(g->device);
@@ -989,7 +989,7 @@ int qpe_gpu_fetch_column(struct engineS *engine, const char *attribute, long lon
 // ---- split scan: count first, compaction later to a caller-chosen (possibly peer) destination ----
 int qpe_gpu_scan_count(struct engineS *engine, struct whereClauseS *whereClause, unsigned long long *count_out,
                        qpe_scan_stats *stats) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     uint64_t m = 0;
@@ -1003,7 +1003,7 @@ int qpe_gpu_scan_count(struct engineS *engine, struct whereClauseS *whereClause,
 int qpe_gpu_select_ids_to(struct engineS *engine, struct whereClauseS *whereClause, unsigned int *dst_device,
                           unsigned long long dst_capacity, int global_ids, unsigned long long *count_out,
                           qpe_scan_stats *stats) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     uint32_t base = 0;
@@ -1033,7 +1033,7 @@ int qpe_gpu_select_ids_to(struct engineS *engine, struct whereClauseS *whereClau
 }
 
 int qpe_gpu_compact_to(struct engineS *engine, unsigned int *dst_device, int global_ids, qpe_scan_stats *stats) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     uint32_t base = 0;
@@ -1053,7 +1053,7 @@ int qpe_gpu_compact_to(struct engineS *engine, unsigned int *dst_device, int glo
 int qpe_gpu_select_segments(struct engineS *engine, struct whereClauseS *whereClause, int global_ids,
                             int *used_index_out, int *n_segments_out, size_t seg_counts_out[32], long long **keys_out,
                             unsigned int **ids_out) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     std::vector<SegmentResult> segs;
@@ -1142,7 +1142,7 @@ int qpe_gpu_last_stats(struct engineS *engine, qpe_scan_stats *stats) {
 }
 
 int qpe_gpu_set_timing(struct engineS *engine, int accumulate) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     engine_resolve_all(g);
@@ -1153,7 +1153,7 @@ int qpe_gpu_set_timing(struct engineS *engine, int accumulate) {
 }
 
 int qpe_gpu_timing_totals(struct engineS *engine, double totals_ms[4], long long *calls_out) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     engine_resolve_all(g);
@@ -1179,7 +1179,7 @@ int qpe_gpu_last_trace(struct engineS *engine, double out[8]) {
 }
 
 int qpe_gpu_fused_trace(struct engineS *engine, unsigned long long *out, int max_ctas) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g || !out || !g->d_trace || g->last.grid <= 0) return 0;
     cudaSetDevice(g->device);
@@ -1190,7 +1190,7 @@ int qpe_gpu_fused_trace(struct engineS *engine, unsigned long long *out, int max
 }
 
 int qpe_gpu_write_csv(struct engineS *engine, const char *path) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     HostColumns hc;
@@ -1256,7 +1256,7 @@ void *qpe_gpu_stream(struct engineS *engine) {
 }
 
 int qpe_gpu_set_pipeline(struct engineS *engine, int segments) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     if (segments < 0 || segments > kMaxPipeSegments) {
@@ -1268,7 +1268,7 @@ int qpe_gpu_set_pipeline(struct engineS *engine, int segments) {
 }
 
 int qpe_gpu_set_tile(struct engineS *engine, int tile_rows, int stages) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     g->force_tile_rows = tile_rows;

@@ -22,6 +22,7 @@ constexpr uint64_t kResultMagic = 0x5150455245533031ull;  // "QPERES01"
 struct GpuEngine {
     struct engineS head;  // MUST stay first: callers hold `struct engineS *`
     uint64_t magic = kEngineMagic;
+    std::mutex mu;        // serialises the calls on THIS engine (EngineLock)
     int device = 0;
     cudaStream_t stream = nullptr;   // K1 and everything else (highest priority)
     cudaStream_t stream2 = nullptr;  // K1c of a pipelined scan (lowest priority: fills the SMs beside K1)
@@ -120,7 +121,19 @@ struct GpuEngine {
     ScanStats last;
 };
 
-extern std::mutex g_api_mutex;  // the engine is not re-entrant (one stream, one scratch set)
+extern std::mutex g_api_mutex;  // engine creation / destruction, and calls on a handle that is not an engine
+// An engine is not re-entrant (one stream, one scratch set): calls on ONE engine are serialised by its own mutex,
+// calls on different engines of a process run side by side (a QPEOMP-style driver with one engine per thread).
+struct EngineLock {
+    std::unique_lock<std::mutex> lk;
+    explicit EngineLock(const struct engineS *e) {
+        const GpuEngine *g = reinterpret_cast<const GpuEngine *>(e);
+        if (g && g->magic == kEngineMagic)
+            lk = std::unique_lock<std::mutex>(const_cast<GpuEngine *>(g)->mu);
+        else
+            lk = std::unique_lock<std::mutex>(g_api_mutex);
+    }
+};
 GpuEngine *as_engine(struct engineS *e);  // nullptr (and error set) if e is not one of ours
 void set_error(const std::string &msg);
 double now_ms();

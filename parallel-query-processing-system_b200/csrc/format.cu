@@ -12,8 +12,6 @@
 
 #include "scan_kernels.cuh"
 
-#include <cub/device/device_scan.cuh>
-
 namespace qpe {
 
 namespace {
@@ -115,8 +113,8 @@ cudaError_t format_launch(const uint8_t *col, int col_type, uint32_t cell_width,
 //
 // executeQueryDeleteSerial rewrites the WHOLE data file after every DELETE, one fprintf per row
 // (engine/serial/executeEngine-serial.c:683-706): "%llu,%s,%s,%s,%d,%s,%d,%s,%d,%s,%s,%d\n", no header, no
-// quoting, sudo_used as 0/1.  Here: csv_len_kernel (bytes of every row) -> exclusive scan (cub::DeviceScan, a
-// library primitive off the query path, like the index build's radix sort) -> csv_write_kernel (a CTA renders
+// quoting, sudo_used as 0/1.  Here: csv_len_kernel (bytes of every row) -> exclusive scan (our own three launches:
+// sums of 4096-entry blocks, one CTA scanning the sums, blocks scanned from their sums) -> csv_write_kernel (a CTA renders
 // its 128 rows into shared memory at their offsets and copies the contiguous text out with 16-byte stores);
 // the host then writes the file with ONE write().  Bound: HBM (all columns read twice) + PCIe + the file write.
 // ------------------------------------------------------------------------------------------
@@ -257,11 +255,107 @@ __global__ void __launch_bounds__(kCsvRows) csv_write_kernel(const CsvCols t, lo
 
 }  // namespace
 
+// ---- exclusive scan of 64-bit values, in place: block sums -> scan of the sums (one CTA) -> blocks from their sums ----
+namespace {
+constexpr int kScanThreads = 512, kScanItems = 8, kScanBlock = kScanThreads * kScanItems;
+
+// exclusive scan of one 64-bit value per thread over the CTA; *total = the CTA's sum.  Every thread calls it.
+__device__ __forceinline__ unsigned long long cta_exclusive_scan_u64(unsigned long long v, unsigned long long *s_warp,
+                                                                     unsigned long long *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
+    unsigned long long x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = lane < n_warps ? s_warp[lane] : 0ull;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) w += y;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    const unsigned long long before = warp > 0 ? s_warp[warp - 1] : 0ull;
+    *total = s_warp[n_warps - 1];
+    __syncthreads();
+    return before + x - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(const unsigned long long *__restrict__ data,
+                                                                       long long n, unsigned long long *__restrict__ sums) {
+    __shared__ unsigned long long s_warp[32];
+    const long long base = blockIdx.x * static_cast<long long>(kScanBlock);
+    unsigned long long v = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        const long long idx = base + i * kScanThreads + threadIdx.x;
+        if (idx < n) v += data[idx];
+    }
+    unsigned long long total = 0;
+    cta_exclusive_scan_u64(v, s_warp, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned long long *__restrict__ sums, long long n_blocks) {
+    __shared__ unsigned long long s_warp[32];
+    unsigned long long running = 0;
+    for (long long base = 0; base < n_blocks; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const unsigned long long v = i < n_blocks ? sums[i] : 0ull;
+        unsigned long long total = 0;
+        const unsigned long long before = cta_exclusive_scan_u64(v, s_warp, &total);
+        if (i < n_blocks) sums[i] = running + before;
+        running += total;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(unsigned long long *__restrict__ data, long long n,
+                                                                  const unsigned long long *__restrict__ sums) {
+    __shared__ unsigned long long s_warp[32];
+    // a thread owns kScanItems consecutive entries
+    const long long first = blockIdx.x * static_cast<long long>(kScanBlock) + threadIdx.x * kScanItems;
+    unsigned long long v[kScanItems];
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        v[i] = first + i < n ? data[first + i] : 0ull;
+        mine += v[i];
+    }
+    unsigned long long total = 0;
+    unsigned long long run = sums[blockIdx.x] + cta_exclusive_scan_u64(mine, s_warp, &total);
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        if (first + i < n) data[first + i] = run;
+        run += v[i];
+    }
+}
+
+cudaError_t exclusive_scan_u64(unsigned long long *d_data, long long n, unsigned long long *d_sums, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const long long n_blocks = (n + kScanBlock - 1) / kScanBlock;
+    scan_block_sums_kernel<<<static_cast<unsigned int>(n_blocks), kScanThreads, 0, stream>>>(d_data, n, d_sums);
+    scan_sums_kernel<<<1, 1024, 0, stream>>>(d_sums, n_blocks);
+    scan_apply_kernel<<<static_cast<unsigned int>(n_blocks), kScanThreads, 0, stream>>>(d_data, n, d_sums);
+    return cudaGetLastError();
+}
+}  // namespace
+
 // Phase 1: row lengths + scan.  d_offs holds n + 1 entries; after the call d_offs[i] = byte offset of row i and
-// d_offs[n] = total bytes.  scan_tmp / scan_tmp_bytes: cub scratch (call with scan_tmp == nullptr to size it).
+// d_offs[n] = total bytes.  scan_tmp / scan_tmp_bytes: scratch of the scan (call with scan_tmp == nullptr to size it).
 cudaError_t csv_measure(const DevTable &t, unsigned long long *d_offs, void *scan_tmp, size_t *scan_tmp_bytes,
                         cudaStream_t stream) {
-    if (!scan_tmp) return cub::DeviceScan::ExclusiveSum(nullptr, *scan_tmp_bytes, d_offs, d_offs, t.n + 1, stream);
+    const size_t need = static_cast<size_t>((t.n + 1 + kScanBlock - 1) / kScanBlock) * sizeof(unsigned long long) + 256;
+    if (!scan_tmp) {
+        *scan_tmp_bytes = need;
+        return cudaSuccess;
+    }
+    if (*scan_tmp_bytes < need) return cudaErrorInvalidValue;
     CsvCols cc;
     for (int c = 0; c < NUM_COLS; ++c) {
         cc.col[c] = t.col[c].d;
@@ -271,7 +365,7 @@ cudaError_t csv_measure(const DevTable &t, unsigned long long *d_offs, void *sca
     csv_len_kernel<<<static_cast<unsigned int>(blocks), kCsvRows, 0, stream>>>(cc, t.n, d_offs);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    return cub::DeviceScan::ExclusiveSum(scan_tmp, *scan_tmp_bytes, d_offs, d_offs, t.n + 1, stream);
+    return exclusive_scan_u64(d_offs, t.n + 1, static_cast<unsigned long long *>(scan_tmp), stream);
 }
 
 // Phase 2: the text of rows [r0, r1) into d_out, whose first byte is file offset base_off = d_offs[r0]

@@ -14,30 +14,22 @@
 // contiguously, coarsest level <= kFanout entries.  A node is kFanout consecutive separators =
 // one 128-byte line for u64 keys (64 bytes for int keys).
 //
-// Build: one stable LSD radix sort of the keys taken in REVERSE table order (stable + reversed
-// input == position-descending among equal keys).  The sort is cub::DeviceRadixSort (library
-// primitive); gather-in-reverse and the level construction are ours.
+// Build (K4): one stable LSD radix sort of the keys taken in REVERSE table order (stable + reversed
+// input == position-descending among equal keys) -- our own sort (radix_sort.cu): its first pass reads the table
+// column backwards with the position as payload, byte positions that are the same in every key are skipped --
+// then the separator levels are sampled.
 
-#include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "index.cuh"
+#include "radix_sort.cuh"
 #include "scan_kernels.cuh"
 
 namespace qpe {
 
 constexpr int kFanout = 16;
-
-template <typename K>
-__global__ void reverse_keys_kernel(const K *__restrict__ col, long long n, K *__restrict__ keys_rev,
-                                    uint32_t *__restrict__ pos_rev) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long src = n - 1 - i;
-        keys_rev[i] = col[src];
-        pos_rev[i] = static_cast<uint32_t>(src);
-    }
-}
 
 template <typename K>
 __global__ void sample_level_kernel(const K *__restrict__ below, long long n_below, K *__restrict__ level,
@@ -132,24 +124,16 @@ static cudaError_t build_typed(DevIndex *ix, const K *col, long long n, cudaStre
     ix->fanout = kFanout;
     if (n == 0) return cudaSuccess;
 
-    K *keys_rev = nullptr;
-    uint32_t *pos_rev = nullptr;
-    void *tmp = nullptr;
-    size_t tmp_bytes = 0;
-    if ((e = cudaMalloc(&keys_rev, static_cast<size_t>(n) * sizeof(K))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&pos_rev, static_cast<size_t>(n) * sizeof(uint32_t))) != cudaSuccess) return e;
-    reverse_keys_kernel<K><<<grid_for(n, 256), 256, 0, stream>>>(col, n, keys_rev, pos_rev);
-    ++*launches;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_rev, static_cast<K *>(ix->keys), pos_rev, ix->perm, n, 0,
-                                    static_cast<int>(sizeof(K) * 8), stream);
-    if ((e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16)) != cudaSuccess) return e;
-    e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_rev, static_cast<K *>(ix->keys), pos_rev, ix->perm, n, 0,
-                                        static_cast<int>(sizeof(K) * 8), stream);
+    // int keys order as signed values; the sort itself works on the unsigned bit patterns
+    using U = typename std::conditional<sizeof(K) == 8, unsigned long long, uint32_t>::type;
+    void *scratch = nullptr;
+    const size_t scratch_bytes = radix_sort_scratch_bytes(n, static_cast<int>(sizeof(K)));
+    if ((e = cudaMalloc(&scratch, scratch_bytes)) != cudaSuccess) return e;
+    e = radix_sort_pairs<U>(reinterpret_cast<const U *>(col), nullptr, kSortReverseIota, std::is_signed<K>::value,
+                            static_cast<U *>(ix->keys), ix->perm, n, scratch, scratch_bytes, stream, launches);
     if (e == cudaSuccess) e = build_levels<K>(ix, stream, launches);
     const cudaError_t es = cudaStreamSynchronize(stream);
-    cudaFree(keys_rev);
-    cudaFree(pos_rev);
-    cudaFree(tmp);
+    cudaFree(scratch);
     return e != cudaSuccess ? e : es;
 }
 

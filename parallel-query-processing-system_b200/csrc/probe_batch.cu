@@ -14,21 +14,16 @@
 //                        probed in key order -- neighbouring probes then walk the same separator nodes, and the leaf
 //                        level is touched front to back like a merge -- and the answers are scattered back to the
 //                        caller's order.
-#include <cub/device/device_radix_sort.cuh>
 
 #include <chrono>
 #include <cstring>
 
 #include "engine.cuh"
+#include "radix_sort.cuh"
 #include "executeEngine-gpu.h"
 
 namespace qpe {
 
-__global__ void iota_kernel(uint32_t *out, long long n) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
-        out[i] = static_cast<uint32_t>(i);
-}
 template <typename K>
 __global__ void gather_keys_kernel(const K *__restrict__ src, const uint32_t *__restrict__ slot, K *__restrict__ dst,
                                    long long n) {
@@ -87,19 +82,6 @@ static PtrKind kind_of(const void *p) {
     return kPageable;
 }
 
-template <typename K>
-static cudaError_t sort_by_key(void *tmp, size_t &tmp_bytes, const K *keys_in, K *keys_out, const uint32_t *slot_in,
-                               uint32_t *slot_out, long long n, cudaStream_t stream) {
-    return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, slot_in, slot_out, n, 0,
-                                           static_cast<int>(sizeof(K) * 8), stream);
-}
-// int keys order as SIGNED values: flip the sign bit around the unsigned radix sort
-__global__ void flip_sign_kernel(uint32_t *k, long long n) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
-        k[i] ^= 0x80000000u;
-}
-
 }  // namespace qpe
 
 using namespace qpe;
@@ -117,7 +99,7 @@ void qpe_gpu_host_free(void *p) {
 
 int qpe_gpu_probe_keys(struct engineS *engine, const char *attribute, const void *lo, const void *hi, size_t n_queries,
                        unsigned int *first, unsigned int *count, int flags, qpe_scan_stats *stats) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     cudaSetDevice(g->device);
@@ -153,13 +135,7 @@ int qpe_gpu_probe_keys(struct engineS *engine, const char *attribute, const void
     // device scratch: lo | hi | first | count | (sort) keys_sorted | hi_sorted | slot | slot_sorted | first_s | count_s | tmp
     const size_t kq = (static_cast<size_t>(Q) * ksz + 255) & ~size_t(255);
     const size_t wq = (static_cast<size_t>(Q) * 4 + 255) & ~size_t(255);
-    size_t tmp_bytes = 0;
-    if (sorted) {
-        if (ix.type == T_U64)
-            sort_by_key<unsigned long long>(nullptr, tmp_bytes, nullptr, nullptr, nullptr, nullptr, Q, g->stream);
-        else
-            sort_by_key<uint32_t>(nullptr, tmp_bytes, nullptr, nullptr, nullptr, nullptr, Q, g->stream);
-    }
+    const size_t tmp_bytes = sorted ? radix_sort_scratch_bytes(Q, static_cast<int>(ksz)) : 0;
     const size_t need = 2 * kq + 2 * wq + (sorted ? 2 * kq + 4 * wq + tmp_bytes + 256 : 0);
     if (!ensure_probe_scratch(g, need)) return -4;
     uint8_t *sp = static_cast<uint8_t *>(g->d_probe_scratch);
@@ -237,22 +213,21 @@ int qpe_gpu_probe_keys(struct engineS *engine, const char *attribute, const void
         uint32_t *first_s = reinterpret_cast<uint32_t *>(sort_base + 2 * kq + 2 * wq);
         uint32_t *count_s = reinterpret_cast<uint32_t *>(sort_base + 2 * kq + 3 * wq);
         void *tmp = sort_base + 2 * kq + 4 * wq;
-        iota_kernel<<<grid_for(Q, 256), 256, 0, g->stream>>>(slot_in, Q);
+        // K4 (radix_sort.cu): by lower key, payload = the probe's slot; int keys order as signed values
+        (void)slot_in;
         if (ix.type == T_U64) {
-            ok = ok && cuda_ok(sort_by_key<unsigned long long>(tmp, tmp_bytes, static_cast<const unsigned long long *>(d_lo),
-                                                               static_cast<unsigned long long *>(keys_s), slot_in, slot_s, Q, g->stream),
+            ok = ok && cuda_ok(radix_sort_pairs<unsigned long long>(static_cast<const unsigned long long *>(d_lo), nullptr, kSortIota,
+                                                                    false, static_cast<unsigned long long *>(keys_s), slot_s, Q, tmp,
+                                                                    tmp_bytes, g->stream, &launches),
                                "probe sort");
             if (!point)
                 gather_keys_kernel<unsigned long long><<<grid_for(Q, 256), 256, 0, g->stream>>>(
                     static_cast<const unsigned long long *>(d_hi), slot_s, static_cast<unsigned long long *>(hi_s), Q);
         } else {
-            // signed order: sort keys ^ 0x80000000 as unsigned on a copy, flip back
-            ok = ok && cuda_ok(cudaMemcpyAsync(hi_s, d_lo, in_bytes, cudaMemcpyDeviceToDevice, g->stream), "probe sort");
-            flip_sign_kernel<<<grid_for(Q, 256), 256, 0, g->stream>>>(static_cast<uint32_t *>(hi_s), Q);
-            ok = ok && cuda_ok(sort_by_key<uint32_t>(tmp, tmp_bytes, static_cast<const uint32_t *>(hi_s),
-                                                     static_cast<uint32_t *>(keys_s), slot_in, slot_s, Q, g->stream),
+            ok = ok && cuda_ok(radix_sort_pairs<uint32_t>(static_cast<const uint32_t *>(d_lo), nullptr, kSortIota, true,
+                                                          static_cast<uint32_t *>(keys_s), slot_s, Q, tmp, tmp_bytes, g->stream,
+                                                          &launches),
                                "probe sort");
-            flip_sign_kernel<<<grid_for(Q, 256), 256, 0, g->stream>>>(static_cast<uint32_t *>(keys_s), Q);
             if (!point)
                 gather_keys_kernel<int><<<grid_for(Q, 256), 256, 0, g->stream>>>(static_cast<const int *>(d_hi), slot_s,
                                                                               static_cast<int *>(hi_s), Q);
@@ -260,7 +235,7 @@ int qpe_gpu_probe_keys(struct engineS *engine, const char *attribute, const void
         ok = ok && cuda_ok(index_probe(ix, keys_s, point ? keys_s : hi_s, Q, first_s, count_s, g->stream), "probe kernel launch");
         scatter_answers_kernel<<<grid_for(Q, 256), 256, 0, g->stream>>>(first_s, count_s, slot_s, o_first, o_count, Q);
         ok = ok && cuda_ok(cudaGetLastError(), "probe sort kernels");
-        launches += 5;
+        launches += point ? 2 : 3;
         if (!dev_out) {
             ok = ok && cuda_ok(cudaMemcpyAsync(h_first, o_first, out_bytes, cudaMemcpyDeviceToHost, g->stream), "probe d2h");
             ok = ok && cuda_ok(cudaMemcpyAsync(h_count, o_count, out_bytes, cudaMemcpyDeviceToHost, g->stream), "probe d2h");
@@ -284,6 +259,65 @@ int qpe_gpu_probe_keys(struct engineS *engine, const char *attribute, const void
         stats->algo_bytes = Q * 2 * (ix.n_levels + 1) * ix.fanout * static_cast<long long>(ksz) +
                             Q * static_cast<long long>(2 * ksz + 8);
     }
+    return ok ? 0 : -4;
+}
+
+/* K4 on its own (csrc/radix_sort.cu): n (key, payload) pairs from host arrays, sorted by key ascending, stable.
+ * See qpe_gpu.h.  Runs on the current device with buffers of its own -- no engine involved. */
+int qpe_gpu_sort_pairs(const void *keys, const unsigned int *vals, size_t n, int key_bytes, int signed_keys, int mode,
+                       void *keys_out, unsigned int *vals_out, int *passes_out, double *kernel_ms_out) {
+    if ((key_bytes != 4 && key_bytes != 8) || mode < 0 || mode > 2 || (n && (!keys || !keys_out || !vals_out)) ||
+        (mode == kSortPairs && n && !vals) || n > 0xffffffffull) {
+        set_error("qpe_gpu_sort_pairs: bad arguments");
+        return -1;
+    }
+    if (passes_out) *passes_out = 0;
+    if (kernel_ms_out) *kernel_ms_out = 0;
+    if (n == 0) return 0;
+    const long long N = static_cast<long long>(n);
+    const size_t kb = n * static_cast<size_t>(key_bytes), vb = n * 4;
+    const size_t scratch_bytes = radix_sort_scratch_bytes(N, key_bytes);
+    void *d_kin = nullptr, *d_kout = nullptr, *d_scratch = nullptr;
+    uint32_t *d_vin = nullptr, *d_vout = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int launches = 0, passes = 0;
+    bool ok = cuda_ok(cudaMalloc(&d_kin, kb), "cudaMalloc sort keys") && cuda_ok(cudaMalloc(&d_kout, kb), "cudaMalloc sort keys") &&
+              cuda_ok(cudaMalloc(&d_vout, vb), "cudaMalloc sort payload") &&
+              cuda_ok(cudaMalloc(&d_scratch, scratch_bytes), "cudaMalloc sort scratch") &&
+              cuda_ok(cudaMemcpy(d_kin, keys, kb, cudaMemcpyHostToDevice), "sort h2d") &&
+              cuda_ok(cudaEventCreate(&e0), "event") && cuda_ok(cudaEventCreate(&e1), "event");
+    if (ok && mode == kSortPairs)
+        ok = cuda_ok(cudaMalloc(&d_vin, vb), "cudaMalloc sort payload") &&
+             cuda_ok(cudaMemcpy(d_vin, vals, vb, cudaMemcpyHostToDevice), "sort h2d");
+    if (ok) {
+        cudaEventRecord(e0, nullptr);
+        const cudaError_t e =
+            key_bytes == 8
+                ? radix_sort_pairs<unsigned long long>(static_cast<const unsigned long long *>(d_kin), d_vin,
+                                                       static_cast<SortInput>(mode), signed_keys != 0,
+                                                       static_cast<unsigned long long *>(d_kout), d_vout, N, d_scratch,
+                                                       scratch_bytes, nullptr, &launches, &passes)
+                : radix_sort_pairs<uint32_t>(static_cast<const uint32_t *>(d_kin), d_vin, static_cast<SortInput>(mode),
+                                             signed_keys != 0, static_cast<uint32_t *>(d_kout), d_vout, N, d_scratch,
+                                             scratch_bytes, nullptr, &launches, &passes);
+        cudaEventRecord(e1, nullptr);
+        ok = cuda_ok(e, "radix sort") && cuda_ok(cudaDeviceSynchronize(), "radix sort") &&
+             cuda_ok(cudaMemcpy(keys_out, d_kout, kb, cudaMemcpyDeviceToHost), "sort d2h") &&
+             cuda_ok(cudaMemcpy(vals_out, d_vout, vb, cudaMemcpyDeviceToHost), "sort d2h");
+        if (ok && kernel_ms_out) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            *kernel_ms_out = ms;
+        }
+        if (passes_out) *passes_out = passes;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(d_kin);
+    cudaFree(d_kout);
+    cudaFree(d_vin);
+    cudaFree(d_vout);
+    cudaFree(d_scratch);
     return ok ? 0 : -4;
 }
 

@@ -31,6 +31,7 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <mutex>
 
 namespace qpe {
 
@@ -732,7 +733,7 @@ __global__ void __launch_bounds__(32 * kEvalWarps, 1) scan_batch_kernel(const __
 // K1f: fused scan + ordered compaction (one launch, ids leave the SM while the scan is running)
 //
 // Self-feeding evaluator warps as in K1, plus CW COMPACTION warps per CTA.  Work is handed out in CHUNKS of
-// chunk_tiles consecutive tiles (<= 64 Ki rows), chunk c to CTA c % grid, in increasing order; tile j of a CTA's
+// chunk_tiles consecutive tiles (<= 64 Ki rows), each CTA taking the next unclaimed chunk (tickets), so in increasing order; tile j of a CTA's
 // k-th chunk is its tile seq = k * chunk_tiles + j and belongs to warp / stage seq % S.  The evaluators leave
 // the chunk's match bitmap in shared memory (double buffered); the compaction warps popc/scan it, publish the
 // chunk aggregate, run the DECOUPLED LOOK-BACK over the chunk descriptors of the other CTAs (all resident:
@@ -778,10 +779,18 @@ struct FusedSmemHeader {   // sized for the 4-warp variant (16 rounds x 4 warps)
     uint32_t warp_tot[64];          // [round][compaction warp]
     uint32_t round_base[16 + 1];
     uint32_t excl;
+    // the chunks this CTA has claimed: [k & 7] = (k + 1) << 32 | chunk index of its k-th chunk.  Evaluator warps are
+    // never more than three chunks apart and the compaction warps at most two behind them, so eight slots suffice.
+    alignas(8) unsigned long long chunk_ring[8];
 };
 
 // A warp's walk over ITS tiles of the CTA's chunks, in order: tile j of the CTA's k-th chunk has the CTA-wide
 // sequence number k * CT + j, and the tiles with seq % S == w belong to warp w.
+// WHICH chunk is the CTA's k-th is decided at run time: chunk b for k = 0, after that the next unclaimed one (a ticket
+// from FusedCtl::next_chunk).  SMs do not all stream at the same rate (+-3 % on a B200: r2_k1f_cta_trace.txt, static
+// assignment left the fast ones idle for the last ~25 us of a 125 M-row scan); tickets keep every SM busy to the end.
+// A CTA's chunks still increase with k and all CTAs are resident, so the look-back never waits for an unstarted chunk:
+// the smallest unfinished chunk is either being worked on or is the next one of a CTA that only waits for smaller ones.
 struct WarpTiles {
     long long chunk;   // current chunk (>= n_chunks: exhausted)
     uint32_t k;        // its index among this CTA's chunks
@@ -796,13 +805,33 @@ __device__ __forceinline__ uint32_t chunk_tiles_of(long long chunk, uint32_t CT,
 __device__ __forceinline__ uint32_t first_tile_of(uint32_t w, uint32_t k, uint32_t CT, uint32_t S) {
     return (w + S - (k * CT) % S) % S;
 }
+// the CTA's k-th chunk (k >= 1 was claimed by the warp that fetched tile 0 of chunk k - 1, some tiles ago; the wait is
+// bounded by time like every spin of this file)
+__device__ __forceinline__ long long chunk_of(const unsigned long long *ring, uint32_t k) {
+    const volatile unsigned long long *slot = ring + (k & 7u);
+    unsigned long long v = *slot;
+    if (static_cast<uint32_t>(v >> 32) != k + 1u) {
+        const unsigned long long t0 = global_ns();
+        do {
+            __nanosleep(20);
+            v = *slot;
+            if (global_ns() - t0 > 2000000000ull) __trap();
+        } while (static_cast<uint32_t>(v >> 32) != k + 1u);
+    }
+    return static_cast<long long>(static_cast<uint32_t>(v));
+}
+// one lane: take the next ticket for the CTA's k-th chunk and publish it to the CTA
+__device__ __forceinline__ void claim_chunk(unsigned long long *ring, uint32_t k, FusedCtl *fc, uint32_t grid) {
+    const uint32_t c = atomicAdd(&fc->next_chunk, 1u) + grid;
+    *reinterpret_cast<volatile unsigned long long *>(ring + (k & 7u)) = (static_cast<unsigned long long>(k + 1u) << 32) | c;
+}
 // position `wt` on this warp's first tile at or after (chunk, j); false when there is none
 __device__ __forceinline__ bool settle(WarpTiles &wt, uint32_t w, uint32_t CT, uint32_t S, long long n_chunks,
-                                       long long n_tiles, uint32_t grid) {
+                                       long long n_tiles, const unsigned long long *ring) {
     while (wt.chunk < n_chunks) {
         if (wt.j < wt.nt) return true;
-        wt.chunk += grid;
         ++wt.k;
+        wt.chunk = chunk_of(ring, wt.k);
         if (wt.chunk >= n_chunks) break;
         wt.nt = chunk_tiles_of(wt.chunk, CT, n_tiles);
         wt.j = first_tile_of(w, wt.k, CT, S);
@@ -843,6 +872,8 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
             mbar_init(&sh->cb_empty[b], 1);
         }
         sh->cta_count = 0;
+        for (int i = 1; i < 8; ++i) sh->chunk_ring[i] = 0ull;
+        sh->chunk_ring[0] = (1ull << 32) | blockIdx.x;   // the CTA's first chunk needs no ticket
         fence_mbar_init();
     }
     __syncthreads();
@@ -855,8 +886,12 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
     nxt.nt = nxt.chunk < fp.n_chunks ? chunk_tiles_of(nxt.chunk, CT, p.n_tiles) : 0;
     nxt.j = warp;                   // first_tile_of(warp, 0, CT, S) for warp < S
     if (active) {
-        if (settle(nxt, warp, CT, S, fp.n_chunks, p.n_tiles, gridDim.x)) {
-            if (lane == 0) produce_tile(p, stage, nxt.chunk * CT + nxt.j, T, &sh->full[warp]);
+        if (settle(nxt, warp, CT, S, fp.n_chunks, p.n_tiles, sh->chunk_ring)) {
+            if (lane == 0) {
+                produce_tile(p, stage, nxt.chunk * CT + nxt.j, T, &sh->full[warp]);
+                // whoever fetches a chunk's first tile claims the CTA's next chunk
+                if (nxt.j == 0) claim_chunk(sh->chunk_ring, nxt.k + 1u, fp.fctl, gridDim.x);
+            }
             nxt.j += S;
         }
     }
@@ -877,7 +912,7 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
         uint32_t my_count = 0;
         uint32_t k = 0;   // k-th chunk of this CTA
         uint32_t it = 0;  // tiles this warp has consumed: the phase of ITS stage
-        for (long long chunk = blockIdx.x; chunk < fp.n_chunks; chunk += gridDim.x, ++k) {
+        for (long long chunk = blockIdx.x; chunk < fp.n_chunks; chunk = chunk_of(sh->chunk_ring, ++k)) {
             const uint32_t buf = k & 1u;
             // the compaction warps must have read this buffer's previous chunk (k - 2)
             mbar_wait(&sh->cb_empty[buf], ((k >> 1) & 1u) ^ 1u);
@@ -892,10 +927,11 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
                     const uint32_t acc =
                         eval_tile<RPL>(sp, stage, lane, g, tile * T + static_cast<long long>(lane) * RPL, p.n_rows);
                     __syncwarp();  // every lane has read the stage: fetch this warp's next tile into it
-                    if (settle(nxt, warp, CT, S, fp.n_chunks, p.n_tiles, gridDim.x)) {
+                    if (settle(nxt, warp, CT, S, fp.n_chunks, p.n_tiles, sh->chunk_ring)) {
                         if (lane == 0) {
                             fence_proxy_async_smem();
                             produce_tile(p, stage, nxt.chunk * CT + nxt.j, T, &sh->full[warp]);
+                            if (nxt.j == 0) claim_chunk(sh->chunk_ring, nxt.k + 1u, fp.fctl, gridDim.x);
                         }
                         nxt.j += S;
                     }
@@ -917,7 +953,7 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
         const uint32_t cw = ct >> 5;
         const uint32_t chunk_rows = CT * T;
         uint32_t k = 0;
-        for (long long chunk = blockIdx.x; chunk < fp.n_chunks; chunk += gridDim.x, ++k) {
+        for (long long chunk = blockIdx.x; chunk < fp.n_chunks; chunk = chunk_of(sh->chunk_ring, ++k)) {
             const uint32_t buf = k & 1u;
             const uint32_t nt = chunk_tiles_of(chunk, CT, p.n_tiles);
             const uint32_t nw = nt * WPT;
@@ -1047,19 +1083,26 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
             const unsigned long long total = atomicExch(&fc->out_count, 0ull);
             fc->final_count = total;
             fc->ctas_done = 0u;
+            fc->next_chunk = 0u;
             for (int i = 0; i < kMaxProgressSegments; ++i) fc->seg_stored[i] = 0u;
             if (fp.host_count) {
                 *reinterpret_cast<volatile unsigned long long *>(fp.host_count) = total;
                 __threadfence_system();
             }
         }
+        // Launched as a programmatic dependent (sharded SELECT, two queries in flight) this grid must not COMPLETE
+        // before the kernel it overlapped has: the stream's next kernel (this query's count exchange) tells the other
+        // ranks that everything before it on this rank is done.  A no-op for an ordinary launch.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
     }
 }
 
 size_t fused_param_bytes() { return sizeof(FusedParams); }
 
-// function attributes are per device: cache what was set per (instantiation, device)
+// function attributes are per device: cache what was set per (instantiation, device); engines of different threads
+// may launch at the same time, so the caches are updated under a lock
 constexpr int kMaxDevices = 64;
+static std::mutex g_attr_mutex;
 static int current_device_slot() {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1192,12 +1235,14 @@ static cudaError_t launch_scan_r(const ScanParams &p, const ScanGeometry &geo, c
     // per instantiation and device: raise the dynamic shared memory limit only when it grows
     static size_t allowed_by_device[kMaxDevices] = {0};
     size_t &allowed = allowed_by_device[current_device_slot()];
+    std::unique_lock<std::mutex> attr_lock(g_attr_mutex);
     if (geo.smem_bytes > allowed) {
         const cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(geo.smem_bytes));
         if (e != cudaSuccess) return e;
         allowed = geo.smem_bytes;
     }
+    attr_lock.unlock();
     long long grid = p.n_tiles - p.tile_begin;  // tiles of this launch
     if (grid > geo.grid) grid = geo.grid;
     if (grid < 1) grid = 1;
@@ -1251,12 +1296,14 @@ template <int RPL>
 static cudaError_t launch_batch_r(const BatchParams &bp, const ScanGeometry &geo, cudaStream_t stream) {
     static size_t allowed_by_device[kMaxDevices] = {0};
     size_t &allowed = allowed_by_device[current_device_slot()];
+    std::unique_lock<std::mutex> attr_lock(g_attr_mutex);
     if (geo.smem_bytes > allowed) {
         const cudaError_t e = cudaFuncSetAttribute(scan_batch_kernel<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(geo.smem_bytes));
         if (e != cudaSuccess) return e;
         allowed = geo.smem_bytes;
     }
+    attr_lock.unlock();
     scan_batch_kernel<RPL><<<geo.grid, 32 * kEvalWarps, geo.smem_bytes, stream>>>(bp);
     return cudaGetLastError();
 }
@@ -1287,12 +1334,14 @@ template <int RPL, int CW>
 static cudaError_t launch_fused_r(const FusedParams &fp, const ScanGeometry &geo, cudaStream_t stream, bool pdl) {
     static size_t allowed_by_device[kMaxDevices] = {0};
     size_t &allowed = allowed_by_device[current_device_slot()];
+    std::unique_lock<std::mutex> attr_lock(g_attr_mutex);
     if (geo.smem_bytes > allowed) {
         const cudaError_t e = cudaFuncSetAttribute(scan_fused_kernel<RPL, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(geo.smem_bytes));
         if (e != cudaSuccess) return e;
         allowed = geo.smem_bytes;
     }
+    attr_lock.unlock();
     if (pdl) {
         // programmatic dependent launch: this scan may start while the kernel before it in the stream (the previous
         // query's count exchange / delivery, which has nothing to hand to it) is still running

@@ -25,7 +25,7 @@ struct FusedCtl {
     unsigned long long out_count;    // running sum of the CTAs' counts; zero between queries
     unsigned long long final_count;  // the last query's match count (read by the sharded post-scan kernel)
     unsigned int ctas_done;          // zero between queries
-    unsigned int pad_;
+    unsigned int next_chunk;         // tickets handed out by the dynamic chunk assignment (ticket t = chunk grid + t); zero between queries
     unsigned int seg_stored[kMaxProgressSegments];  // chunks of table segment s whose ids are stored; zero between queries
 };
 

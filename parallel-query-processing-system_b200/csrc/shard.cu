@@ -40,9 +40,13 @@
 //   DELETE          qpe_shard_delete: local mask + stable compaction per shard, the new shard sizes
 //                   all-gathered through the same comm blocks, shards renumbered.
 //
-// Why a rank is never more than one query ahead of another: no rank's exchange of query e completes before every rank
-// has published its count of e, and a rank publishes e + 1 only after its exchange of e (stream order).  So the slot,
-// segment and staging sets of parity e & 1 are free again when query e + 2 is enqueued.
+// Why the buffers of parity e & 1 are free again when the scan of query e + 2 starts: that scan is released by this rank's
+// post-scan kernel of e + 1 only AFTER every rank's count of e + 1 has arrived (griddepcontrol.launch_dependents
+// follows the exchange), a rank publishes its count of e + 1 only after its scan of e + 1 has completed, and that scan
+// -- a programmatic dependent of the post-scan kernel of e -- ends with griddepcontrol.wait, i.e. not before that kernel
+// (the last reader of the other ranks' segments of e) has completed.  Releasing the scan at the START of the post-scan
+// kernel, as the first version did, let a fast rank overwrite a segment a slow rank was still delivering (caught by
+// the 3-processes-on-one-GPU test, where the time slicing makes ranks arbitrarily slow).
 // NCCL / torch.distributed is only used by the caller to hand the IPC handles around at start-up.
 
 #include "engine.cuh"
@@ -237,13 +241,16 @@ __global__ void __launch_bounds__(256) post_kernel(const unsigned long long *cou
     __shared__ unsigned long long s_cnt[kMaxRanks];
     __shared__ unsigned long long s_off[kMaxRanks + 1];
     __shared__ int s_timeout, s_ok;
-    // the next query's scan (a programmatic dependent launch) needs nothing from this kernel: let it start now
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) s_timeout = 0;
     __syncthreads();
     const unsigned long long my = count ? *reinterpret_cast<const volatile unsigned long long *>(count) : kCountFailed;
     exchange_counts_dev(my, peers, rank, world, epoch, s_cnt, &s_timeout);
     __syncthreads();
+    // The next query's scan (a programmatic dependent launch) needs nothing from this kernel and may start now -- but
+    // not earlier: it overwrites the segments of the query BEFORE this one (same parity), which the other ranks'
+    // post-scan kernels of that query read.  Every rank's count of THIS query has arrived, so every rank has finished
+    // that kernel (its stream order); and the count word of this rank's own scan has been read.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) {
         unsigned long long o = 0;
         int ok = 1;
@@ -292,13 +299,16 @@ __global__ void __launch_bounds__(256) deliver_kernel(const unsigned long long *
     __shared__ unsigned long long s_cnt[kMaxRanks];
     __shared__ unsigned long long s_off[kMaxRanks + 1];
     __shared__ int s_timeout, s_ok;
-    // the next query's scan (a programmatic dependent launch) needs nothing from this kernel: let it start now
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) s_timeout = 0;
     __syncthreads();
     const unsigned long long my = count ? *reinterpret_cast<const volatile unsigned long long *>(count) : kCountFailed;
     exchange_counts_dev(my, peers, rank, world, epoch, s_cnt, &s_timeout);
     __syncthreads();
+    // The next query's scan (a programmatic dependent launch) needs nothing from this kernel and may start now -- but
+    // not earlier: it overwrites the segments of the query BEFORE this one (same parity), which the other ranks'
+    // post-scan kernels of that query read.  Every rank's count of THIS query has arrived, so every rank has finished
+    // that kernel (its stream order); and the count word of this rank's own scan has been read.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) {
         unsigned long long o = 0;
         int ok = 1;
@@ -507,7 +517,7 @@ extern "C" {
  * returns the CUDA IPC handle of it for the other ranks.  segment_capacity must be the same on every rank. */
 int qpe_shard_init(struct engineS *engine, int rank, int world, unsigned long long segment_capacity,
                    unsigned char comm_handle_out[64]) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (!g) return -1;
     if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || segment_capacity == 0) {
@@ -547,7 +557,7 @@ int qpe_shard_init(struct engineS *engine, int rank, int world, unsigned long lo
 
 /* all_handles: world x 64 bytes, in rank order (what every rank's qpe_shard_init returned) */
 int qpe_shard_connect(struct engineS *engine, const unsigned char *all_handles) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
     if (!s) {
@@ -582,7 +592,7 @@ unsigned long long qpe_shard_result_ids(int world, unsigned long long segment_ca
 
 int qpe_shard_set_device_result(struct engineS *engine, int owner_rank, unsigned int *segments,
                                 unsigned long long segment_capacity) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
     if (!s) {
@@ -602,7 +612,7 @@ int qpe_shard_set_device_result(struct engineS *engine, int owner_rank, unsigned
  * the second follows `capacity` ids behind. */
 unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *name, unsigned long long capacity,
                                          int create) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
     if (!s || !name || std::strlen(name) >= sizeof(s->host_name) || capacity == 0) {
@@ -663,7 +673,7 @@ unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *nam
 
 /* Once every rank has opened (and placed) the shared buffer: register it with CUDA in this process. */
 int qpe_shard_pin_host_result(struct engineS *engine) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
     if (!s || !s->host_map) {
@@ -685,7 +695,7 @@ int qpe_shard_pin_host_result(struct engineS *engine) {
 /* Host result path: 1 = every rank stages its 1/world of the result in its HBM and the copy engine takes it to the
  * host (default), 2 = the delivery kernel stores into the mapped host buffer itself.  Every rank must choose the same. */
 int qpe_shard_set_multipath(struct engineS *engine, int mode) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
     if (!s || (mode != 1 && mode != 2) || s->n_pending) {
@@ -699,7 +709,7 @@ int qpe_shard_set_multipath(struct engineS *engine, int mode) {
 /* Shares of a host result per rank, proportional to `weights` (e.g. the device->host rate of every rank's PCIe link
  * measured with all links busy).  Every rank must pass the same numbers.  Equal shares by default. */
 int qpe_shard_set_link_weights(struct engineS *engine, const double *weights, int n) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
     if (!s || n != s->world || s->n_pending) {
@@ -727,7 +737,7 @@ int qpe_shard_set_link_weights(struct engineS *engine, const double *weights, in
 /* Creator only, once every rank has opened the shared host buffer: remove its name from /dev/shm (the mappings
  * stay valid), so that nothing is left behind if a process dies. */
 int qpe_shard_unlink_host_result(struct engineS *engine) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
     if (!s) return -1;
@@ -761,7 +771,7 @@ int qpe_shard_numa(struct engineS *engine, int *how_out) {
 }
 
 void qpe_shard_close(struct engineS *engine) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     if (g) shard_destroy(g);
 }
@@ -772,7 +782,7 @@ void qpe_shard_close(struct engineS *engine) {
  * buffer (qpe_shard_host_result).  A rank whose scan cannot be enqueued still takes part (it publishes a failure
  * marker) and learns the error from qpe_shard_wait, like every other rank. */
 int qpe_shard_submit(struct engineS *engine, struct whereClauseS *whereClause, int to_host) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
     if (!s) {
@@ -861,7 +871,7 @@ int qpe_shard_submit(struct engineS *engine, struct whereClauseS *whereClause, i
  * the host buffer (every rank returns it; nothing was written past a buffer), -2 / -6 if a rank could not run its scan
  * (every rank returns it), -4 on a CUDA error or a rank that never arrived. */
 int qpe_shard_wait(struct engineS *engine, unsigned long long *counts_out, qpe_scan_stats *stats) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
     if (!s || s->n_pending == 0) {
@@ -964,7 +974,7 @@ int qpe_shard_select(struct engineS *engine, struct whereClauseS *whereClause, i
  * Every rank calls it with the same statement.  No data file is touched (a sharded table has none). */
 int qpe_shard_delete(struct engineS *engine, struct whereClauseS *whereClause, unsigned long long *deleted_total_out,
                      unsigned long long *rows_total_out) {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
     if (!s) {

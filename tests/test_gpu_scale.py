@@ -274,3 +274,38 @@ def test_insert_delete_on_synthetic_table_vs_oracle(pkg, tmp_path):
     ids, _ = eng.select_ids("SELECT command_id FROM Commands WHERE user_id = 1001")
     assert ids[0] == eng.num_rows - 1   # newest row first among equal keys
     eng.close()
+
+
+def test_two_engines_run_side_by_side(pkg):
+    """calls on DIFFERENT engines of one process are not serialised against each other (an engine has its own lock,
+    stream and scratch): two threads, one engine each -- the QPEOMP pattern (QPEOMP.c:234-335) with an engine per
+    thread -- must each get exactly their own results"""
+    import threading
+    sizes = (700_001, 1_300_003)
+    cols = NUM_COLS + ["shell_type"]
+    engines = [pkg.Engine.from_synth(n, columns=cols, indexes=(("user_id", 1),)) for n in sizes]
+    oracles = [Oracle.from_columns({c: e.fetch_column(c) for c in cols}) for e in engines]
+    wheres = ['(command_id < 300000) AND (sudo_used = FALSE OR risk_level > 3)', 'user_id = 1001 OR (exit_code = 127)',
+              '(shell_type = "zsh") AND (risk_level >= 4)', '(exit_code != 0)']
+    want = [[o.select_ids(w, (("user_id", 1),))[0] for w in wheres] for o in oracles]
+    errors = []
+
+    def work(k):
+        try:
+            for rep in range(25):
+                for w, expect in zip(wheres, want[k]):
+                    ids, _ = engines[k].select_ids(f"SELECT command_id FROM Commands WHERE {w}")
+                    if not np.array_equal(ids, expect):
+                        errors.append((k, rep, w))
+                        return
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in engines:
+        e.close()
+    assert not errors, errors[:3]
