@@ -782,6 +782,10 @@ struct FusedSmemHeader {   // sized for the 4-warp variant (16 rounds x 4 warps)
     // the chunks this CTA has claimed: [k & 7] = (k + 1) << 32 | chunk index of its k-th chunk.  Evaluator warps are
     // never more than three chunks apart and the compaction warps at most two behind them, so eight slots suffice.
     alignas(8) unsigned long long chunk_ring[8];
+    // per chunk buffer: matches counted by the evaluator warps that have finished the chunk, and how many have.  The
+    // LAST warp to finish a chunk publishes the chunk's aggregate itself (see the evaluator loop).
+    uint32_t chunk_cnt[2];
+    uint32_t chunk_arr[2];
 };
 
 // A warp's walk over ITS tiles of the CTA's chunks, in order: tile j of the CTA's k-th chunk has the CTA-wide
@@ -805,7 +809,7 @@ __device__ __forceinline__ uint32_t chunk_tiles_of(long long chunk, uint32_t CT,
 __device__ __forceinline__ uint32_t first_tile_of(uint32_t w, uint32_t k, uint32_t CT, uint32_t S) {
     return (w + S - (k * CT) % S) % S;
 }
-// the CTA's k-th chunk (k >= 1 was claimed by the warp that fetched tile 0 of chunk k - 1, some tiles ago; the wait is
+// the CTA's k-th chunk (k >= 1 was claimed by the warp that fetched the claim tile of chunk k - 1, some tiles ago; the wait is
 // bounded by time like every spin of this file)
 __device__ __forceinline__ long long chunk_of(const unsigned long long *ring, uint32_t k) {
     const volatile unsigned long long *slot = ring + (k & 7u);
@@ -820,6 +824,10 @@ __device__ __forceinline__ long long chunk_of(const unsigned long long *ring, ui
     }
     return static_cast<long long>(static_cast<uint32_t>(v));
 }
+// The tile of a chunk whose fetch triggers the claim of the CTA's next chunk: two rounds of the stages before the
+// chunk's end (~8 us ahead of the first warp that needs the answer, the ticket takes ~1-2 us) rather than its first
+// tile -- a chunk claimed early is a chunk a faster SM cannot take at the end of the scan.
+__device__ __forceinline__ uint32_t claim_tile_of(uint32_t nt, uint32_t S) { return nt > 2u * S ? nt - 2u * S : 0u; }
 // one lane: take the next ticket for the CTA's k-th chunk and publish it to the CTA
 __device__ __forceinline__ void claim_chunk(unsigned long long *ring, uint32_t k, FusedCtl *fc, uint32_t grid) {
     const uint32_t c = atomicAdd(&fc->next_chunk, 1u) + grid;
@@ -873,6 +881,8 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
         }
         sh->cta_count = 0;
         for (int i = 1; i < 8; ++i) sh->chunk_ring[i] = 0ull;
+        sh->chunk_cnt[0] = sh->chunk_cnt[1] = 0u;
+        sh->chunk_arr[0] = sh->chunk_arr[1] = 0u;
         sh->chunk_ring[0] = (1ull << 32) | blockIdx.x;   // the CTA's first chunk needs no ticket
         fence_mbar_init();
     }
@@ -889,8 +899,8 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
         if (settle(nxt, warp, CT, S, fp.n_chunks, p.n_tiles, sh->chunk_ring)) {
             if (lane == 0) {
                 produce_tile(p, stage, nxt.chunk * CT + nxt.j, T, &sh->full[warp]);
-                // whoever fetches a chunk's first tile claims the CTA's next chunk
-                if (nxt.j == 0) claim_chunk(sh->chunk_ring, nxt.k + 1u, fp.fctl, gridDim.x);
+                // whoever fetches a chunk's claim tile takes the CTA's next chunk
+                if (nxt.j == claim_tile_of(nxt.nt, S)) claim_chunk(sh->chunk_ring, nxt.k + 1u, fp.fctl, gridDim.x);
             }
             nxt.j += S;
         }
@@ -912,13 +922,17 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
         uint32_t my_count = 0;
         uint32_t k = 0;   // k-th chunk of this CTA
         uint32_t it = 0;  // tiles this warp has consumed: the phase of ITS stage
+        unsigned long long t_wait_empty = 0;  // diagnostics: time warp 0 waited for a free chunk buffer
         for (long long chunk = blockIdx.x; chunk < fp.n_chunks; chunk = chunk_of(sh->chunk_ring, ++k)) {
             const uint32_t buf = k & 1u;
             // the compaction warps must have read this buffer's previous chunk (k - 2)
+            const unsigned long long tw0 = (fp.trace && tid == 0) ? global_ns() : 0ull;
             mbar_wait(&sh->cb_empty[buf], ((k >> 1) & 1u) ^ 1u);
+            if (fp.trace && tid == 0) t_wait_empty += global_ns() - tw0;
             uint8_t *cb = reinterpret_cast<uint8_t *>(cbuf + buf * kFuseChunkWords);
             const long long t0 = chunk * CT;
             const uint32_t nt = chunk_tiles_of(chunk, CT, p.n_tiles);
+            uint32_t chunk_count = 0;  // this lane's matches in this chunk
             if (active)
                 for (uint32_t j = first_tile_of(warp, k, CT, S); j < nt; j += S, ++it) {
                     mbar_wait(&sh->full[warp], it & 1u);
@@ -931,34 +945,54 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
                         if (lane == 0) {
                             fence_proxy_async_smem();
                             produce_tile(p, stage, nxt.chunk * CT + nxt.j, T, &sh->full[warp]);
-                            if (nxt.j == 0) claim_chunk(sh->chunk_ring, nxt.k + 1u, fp.fctl, gridDim.x);
+                            if (nxt.j == claim_tile_of(nxt.nt, S)) claim_chunk(sh->chunk_ring, nxt.k + 1u, fp.fctl, gridDim.x);
                         }
                         nxt.j += S;
                     }
-                    my_count += static_cast<uint32_t>(__popc(acc));
+                    chunk_count += static_cast<uint32_t>(__popc(acc));
                     store_mask<RPL>(cb + j * (T / 8), lane, acc);
                 }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh->cb_full[buf]);  // release: this warp's words of the chunk are in cb
+            my_count += chunk_count;
+            // The chunk's AGGREGATE is published here, by the last evaluator warp to finish the chunk, not by the
+            // compaction warps: those take the CTA's chunks one after the other, so an aggregate they published had
+            // to wait for the look-back of the chunk before it -- which was waiting for other CTAs' aggregates, held
+            // up the same way.  Measured (tools/k1f_trace.py): 11.8 us of look-back per 17.5 us chunk, a convoy.
+            const uint32_t warp_chunk = __reduce_add_sync(0xffffffffu, chunk_count);
+            __syncwarp();  // every lane's bitmap words are written before lane 0 arrives
+            if (lane == 0) {
+                if (warp_chunk) atomicAdd(&sh->chunk_cnt[buf], warp_chunk);
+                __threadfence_block();
+                if (atomicAdd(&sh->chunk_arr[buf], 1u) == static_cast<uint32_t>(EW) - 1u) {
+                    __threadfence_block();
+                    const uint32_t total = atomicExch(&sh->chunk_cnt[buf], 0u);
+                    sh->chunk_arr[buf] = 0u;
+                    st_desc(fp.desc + chunk, make_desc(fp.epoch, chunk == 0 ? kStatePrefix : kStateAgg, total));
+                }
+                mbar_arrive(&sh->cb_full[buf]);  // release: this warp's words of the chunk are in cb
+            }
         }
         const uint32_t warp_total = __reduce_add_sync(0xffffffffu, my_count);
         if (lane == 0 && warp_total) atomicAdd(&sh->cta_count, static_cast<unsigned long long>(warp_total));
         if (fp.trace && tid == 0) {
             fp.trace[blockIdx.x * 8 + 2] = global_ns();
             fp.trace[blockIdx.x * 8 + 5] = k;
+            fp.trace[blockIdx.x * 8 + 4] = t_wait_empty;
         }
     } else {
         // ===== C: ordered compaction of finished chunks =====
         const uint32_t ct = tid - 32u * EW;
         const uint32_t cw = ct >> 5;
         const uint32_t chunk_rows = CT * T;
+        unsigned long long t_lookback = 0, t_expand = 0, t_wait_full = 0;  // diagnostics (QPE_FUSE_TRACE)
         uint32_t k = 0;
         for (long long chunk = blockIdx.x; chunk < fp.n_chunks; chunk = chunk_of(sh->chunk_ring, ++k)) {
             const uint32_t buf = k & 1u;
             const uint32_t nt = chunk_tiles_of(chunk, CT, p.n_tiles);
             const uint32_t nw = nt * WPT;
             // (one polling warp + a named barrier for the others measured 1.5 % SLOWER than every warp polling)
+            const unsigned long long tf0 = (fp.trace && ct == 0) ? global_ns() : 0ull;
             mbar_wait_relaxed(&sh->cb_full[buf], (k >> 1) & 1u, fp.poll_ns);
+            if (fp.trace && ct == 0) t_wait_full += global_ns() - tf0;
             const uint32_t *cb = cbuf + buf * kFuseChunkWords;
             // 1. words -> registers, popc, warp-inclusive scan per round
             uint32_t word[kFuseRounds], off[kFuseRounds];
@@ -993,11 +1027,10 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
                 }
                 if (lane < kFuseRounds) sh->round_base[lane] = inc - rt;
                 const uint32_t total = __shfl_sync(0xffffffffu, inc, kFuseRounds - 1);
-                if (lane == 0) {
-                    sh->round_base[kFuseRounds] = total;
-                    st_desc(fp.desc + chunk, make_desc(fp.epoch, chunk == 0 ? kStatePrefix : kStateAgg, total));
-                }
+                if (lane == 0) sh->round_base[kFuseRounds] = total;  // (the aggregate was published by the evaluators)
+                const unsigned long long tl0 = (fp.trace && ct == 0) ? global_ns() : 0ull;
                 const uint32_t excl = warp_lookback(fp.desc, chunk, fp.epoch, lane);
+                if (fp.trace && ct == 0) t_lookback += global_ns() - tl0;
                 if (lane == 0) {
                     st_desc(fp.desc + chunk, make_desc(fp.epoch, kStatePrefix, excl + total));
                     sh->excl = excl;
@@ -1006,6 +1039,7 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
             named_bar_sync(1, kFuseCompactThreads);
             const uint32_t total = sh->round_base[kFuseRounds];
             const uint32_t excl = sh->excl;
+            const unsigned long long tx0 = (fp.trace && ct == 0) ? global_ns() : 0ull;
             // 3. expand the bits into row ids, staged in shared memory, coalesced stores
             if (total != 0 && static_cast<unsigned long long>(excl) + total <= fp.out_cap) {
                 uint32_t *out = fp.out_ids + excl;
@@ -1053,6 +1087,7 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
                 }
             }
             named_bar_sync(1, kFuseCompactThreads);  // stage / scan scratch are free again; this chunk's stores are issued
+            if (fp.trace && ct == 0) t_expand += global_ns() - tx0;
             // 4. progress: the last chunk of a table segment to finish publishes the segment to the host
             if (fp.seg_chunks > 0 && ct == 0) {
                 __threadfence();
@@ -1068,6 +1103,10 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
                         (static_cast<unsigned long long>(fp.epoch) << 32) | static_cast<uint32_t>(d);
                 }
             }
+        }
+        if (fp.trace && ct == 0) {
+            fp.trace[blockIdx.x * 8 + 6] = t_lookback;
+            fp.trace[blockIdx.x * 8 + 7] = (t_expand << 32) | (t_wait_full & 0xffffffffull);
         }
     }
     __syncthreads();
@@ -1207,7 +1246,10 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
         // its scan time (rows x bytes per row at ~47 GB/s per SM) and the compaction warps' per-chunk latency
         // (~6 us: barrier, scan, look-back, expansion; measured with tools/k1f_trace.py -- a 25 M-row table cut into
         // 8 Ki-row chunks ran at 2.2 TB/s, every round waiting for the compaction).  Small tables take smaller chunks
-        // only to put more SMs to work.
+        // only to put more SMs to work.  (With the chunks handed out by tickets the last round is shared out evenly, and
+        // a model that charges (chunks per SM + 1) x chunk time prefers 32 Ki-row chunks for a 125 M-row shard and 16 Ki
+        // for 40 B rows -- measured, that is SLOWER: 295 vs 258 us and 0.78 vs 0.58 ms; a chunk costs ~3 us that its
+        // scan does not hide once it lasts less than ~15 us.  So the rule stays as it was.)
         int best_ct = kFuseMaxChunkRows / T;
         double best_us = 1e30;
         for (int ct = kFuseMaxChunkRows / T; ct >= 1 && static_cast<long long>(ct) * T >= 8192; ct >>= 1) {
@@ -1220,6 +1262,12 @@ bool scan_plan(const DevTable &t, const Program &prog, int force_tile_rows, int 
                 best_us = us;
                 best_ct = ct;
             }
+        }
+        // experiments: QPE_FUSE_CHUNK_ROWS=<rows> forces the chunk size (rounded down to whole tiles)
+        static const char *force_rows = std::getenv("QPE_FUSE_CHUNK_ROWS");
+        if (force_rows) {
+            long long fr = std::atoll(force_rows) / T;
+            if (fr >= 1 && fr * T <= kFuseMaxChunkRows) best_ct = static_cast<int>(fr);
         }
         geo->chunk_tiles = best_ct;
         geo->n_chunks = (geo->n_tiles + best_ct - 1) / best_ct;

@@ -33,6 +33,10 @@ for n in sizes:
           f"{np.median(first):5.1f} (max {first.max():5.1f}) us | evaluators done: min {evald.min():7.1f} median "
           f"{np.median(evald):7.1f} max {evald.max():7.1f} us | CTA end: min {end.min():7.1f} median {np.median(end):7.1f} "
           f"max {end.max():7.1f} us | chunks/CTA {tr[:, 5].min()}..{tr[:, 5].max()}", flush=True)
+    nk = np.maximum(tr[:, 5], 1)
+    print(f"      per chunk (median over CTAs, us): evaluators wait for a free chunk buffer {np.median(tr[:, 4] / nk) / 1e3:.2f} | "
+          f"compaction: waits for a full chunk {np.median((tr[:, 7] & 0xffffffff) / nk) / 1e3:.2f}, look-back "
+          f"{np.median(tr[:, 6] / nk) / 1e3:.2f}, expansion + stores {np.median((tr[:, 7] >> 32) / nk) / 1e3:.2f}", flush=True)
     rows.append((n, best["kernel_ms"]))
     eng.close()
 if len(rows) >= 2:
