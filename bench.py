@@ -464,6 +464,19 @@ def extra_probe(pkg, rows, n_probes=1_000_000):
     f, c, _ = eng.probe_keys("command_id", np.array([5, rows - 1, rows + 7], dtype=np.uint64))
     ids = [eng.index_slice("command_id", int(a), int(b)).tolist() for a, b in zip(f, c)]
     out["parity_sample"] = {"keys": [5, rows - 1, rows + 7], "row_ids": ids, "ok": ids == [[5], [rows - 1], []]}
+    # K4, the sort behind the index build (csrc/radix_sort.cu), on the same two key columns: device time of the sort alone
+    out["index_build"] = []
+    for attr in ("command_id", "user_id"):
+        keys = eng.fetch_column(attr)
+        best, passes = None, 0
+        for _ in range(2):
+            _, _, passes, ms = pkg.sort_pairs(keys, mode=2)
+            best = ms if best is None else min(best, ms)
+        kb = keys.dtype.itemsize
+        out["index_build"].append({"index": attr, "keys": int(keys.shape[0]), "key_bytes": kb, "digit_passes": passes,
+                                   "sort_ms": round(best, 3), "gkeys_per_s": round(keys.shape[0] / best / 1e6, 2),
+                                   "algo_gbs": round(keys.shape[0] * passes * (3 * kb + 8) / best / 1e6, 1)})
+        del keys
     eng.close()
     # CPU: the reference's findRange on a bounded sample (it walks the leaf chain to its end: O(N) per probe)
     try:

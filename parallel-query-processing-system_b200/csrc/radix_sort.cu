@@ -5,10 +5,10 @@
 // row, buildEngine-serial.c:46-53 -> engine/bplus.c:723-740) and by the sorted probe batch (probe_batch.cu).
 //
 // One pass over digit d = three launches:
-//   radix_count_kernel    per tile of 512 x ITEMS keys: histogram of the digit (warp-aggregated shared-memory adds,
-//                         so a digit that takes two values costs the same as a uniform one) -> tile_hist[digit][tile]
+//   radix_count_kernel    per tile of 512 x ITEMS keys: histogram of the digit (shared-memory adds; a warp whose keys
+//                         share the digit adds once) -> tile_hist[digit][tile]
 //   radix_scan_kernel     one CTA per digit: exclusive scan of its row over the tiles, total -> digit_total[digit]
-//   radix_scatter_kernel  per tile: every warp ranks its keys in index order (match.any per digit + a warp-private
+//   radix_scatter_kernel  per tile: every warp ranks its keys in index order (same-digit lane mask by ballots + a warp-private
 //                         counter row, no atomics), the tile is put in digit order in shared memory and leaves as runs of
 //                         consecutive addresses: out = prefix(digit_total)[d] + tile_hist[d][tile] + rank within the tile
 // HBM traffic per pass and pair: 2 x key read + payload read + key and payload write = 3 x sizeof(K) + 8 bytes.
@@ -62,6 +62,20 @@ __device__ __forceinline__ uint32_t digit_of(K key, K flip, int shift) {
     return static_cast<uint32_t>((key ^ flip) >> shift) & (kBins - 1);
 }
 
+// lanes of the warp that hold the same 8-bit digit as this lane: one ballot per digit bit.  (match.any does the same in
+// one instruction, but at ~64 cycles per warp on sm_100 -- ncu of the first version: the count and scatter kernels were
+// bound by it, 1.2 / 1.6 TB/s.)
+__device__ __forceinline__ uint32_t same_digit_lanes(uint32_t d) {
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
 // exclusive scan of one value per thread over the CTA (any number of warps <= 32); every thread must call it
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s_scan, uint32_t *total_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
@@ -103,10 +117,15 @@ __global__ void __launch_bounds__(kSortThreads)
     for (int i = 0; i < ITEMS; ++i) {
         const long long idx = base + i * kSortThreads + threadIdx.x;
         const bool valid = idx < n;
-        uint32_t d = 0xffffffffu;
+        uint32_t d = 0;
         if (valid) d = digit_of<K>(keys_in[reversed ? n - 1 - idx : idx], flip, shift);
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        if (valid && lane == __ffs(peers) - 1) atomicAdd(&hist[d], __popc(peers));
+        // a warp whose 32 keys share the digit (a byte that rarely changes) adds once; otherwise plain shared-memory adds
+        const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+        if (__all_sync(0xffffffffu, valid && d == d0)) {
+            if (lane == 0) atomicAdd(&hist[d0], 32u);
+        } else if (valid) {
+            atomicAdd(&hist[d], 1u);
+        }
     }
     __syncthreads();
     if (threadIdx.x < kBins) tile_hist[threadIdx.x * tiles + tile] = hist[threadIdx.x];
@@ -176,7 +195,7 @@ __global__ void __launch_bounds__(kSortThreads, 2)
         }
         // elements past the end (last tile only) rank behind everything: digit 255, highest indices
         const uint32_t d = valid ? digit_of<K>(key[i], flip, shift) : kBins - 1;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t peers = same_digit_lanes(d);
         const int leader = __ffs(peers) - 1;
         uint32_t prev = 0;
         if (lane == leader) {
