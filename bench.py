@@ -757,8 +757,13 @@ def run_ours(args):
         ms_e2e_sync, _, _ = timed(synced(True), steps)
         # two queries in flight
         ms_step, n_matches, clocks = timed(piped(False), steps, ClockSampler(local_rank))
+        sg.wait_breakdown(reset=True)
         ms_e2e, n_e2e, _ = timed(piped(True), steps)
         assert n_e2e == n_matches
+        wb = torch.tensor(sg.wait_breakdown(), dtype=torch.float64, device=dev)
+        wb_all = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(wb_all, wb)
+        wait_by_rank = [[round(x, 4) for x in v.tolist()] for v in wb_all]
         if rank == 0:   # the delivered ids are the packed device result, bit for bit
             host_ids = sg.host_result(n_e2e).copy()
         sg.select(sql, to_host=False, stats=False)
@@ -772,14 +777,23 @@ def run_ours(args):
         for to_host in (False, True):
             upiped(to_host)(warmup)
         u_ms, u_matches, _ = timed(upiped(False), steps)
+        sg.wait_breakdown(reset=True)
         u_e2e_ms, u_e2e_n, _ = timed(upiped(True), steps)
         assert u_e2e_n == u_matches
+        uwb = torch.tensor(sg.wait_breakdown(), dtype=torch.float64, device=dev)
+        uwb_all = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(uwb_all, uwb)
         uniform = {"query": usql, "bytes_per_row": ubpr, "matches": int(u_matches),
                    "matches_per_rank": [int(c) for c in sharding.exchange_counts(ucnt0, dev)],
                    "value": total / (u_ms * 1e-3), "ms_per_step": u_ms,
                    "e2e": {"value": total / (u_e2e_ms * 1e-3), "ms_per_step": u_e2e_ms, "unit": "rows/s",
-                           "d2h_bytes_per_step": int(4 * u_matches + 8 * world)}}
+                           "d2h_bytes_per_step": int(4 * u_matches + 8 * world),
+                           "host_wait_ms_by_rank": [[round(x, 4) for x in v.tolist()] for v in uwb_all]}}
         sync_info["link"] = link
+        sync_info["e2e_host_wait_ms_by_rank"] = {
+            "what": "per query, host clock inside qpe_shard_wait: [waiting for the counts (scan + exchange + delivery kernel), "
+                    "this rank's device->host copy, (owner) the other ranks' pieces]",
+            "by_rank": wait_by_rank}
 
     # roofline of the dominant kernel: algorithmic bytes of a rank's shard / the kernel's own event time (max over ranks)
     shard_rows = shard_of(total, world, 0)[1]

@@ -172,6 +172,9 @@ unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *nam
 int qpe_shard_pin_host_result(struct engineS *engine);
 /* NUMA node of this rank's GPU (-1 unknown); *how_out: bit 0 = mbind accepted, bit 1 = first touch under that node's CPUs */
 int qpe_shard_numa(struct engineS *engine, int *how_out);
+/* diagnostics: host time qpe_shard_wait has spent on host-result queries since the last reset (ms, summed over *n_out
+ * queries): [0] waiting for the counts, [1] this rank's device->host copy, [2] (owner) the other ranks' pieces */
+int qpe_shard_wait_breakdown(struct engineS *engine, double out_ms[3], long long *n_out, int reset);
 /* creator, after every rank has opened the buffer: drop its /dev/shm name (mappings stay valid) */
 int qpe_shard_unlink_host_result(struct engineS *engine);
 /* the packed ids of the most recent device-result / host-result query that qpe_shard_wait completed.  A host result

@@ -160,6 +160,7 @@ def load_library() -> C.CDLL:
         "qpe_shard_host_result": (vp, [vp]),
         "qpe_shard_pin_host_result": (i, [vp]),
         "qpe_shard_numa": (i, [vp, C.POINTER(i)]),
+        "qpe_shard_wait_breakdown": (i, [vp, C.POINTER(C.c_double), C.POINTER(ll), i]),
         "qpe_shard_wait": (i, [vp, C.POINTER(ull), pstats]),
         "qpe_sql_shard_submit": (i, [vp, cp, i]),
         "qpe_shard_close": (None, [vp]),

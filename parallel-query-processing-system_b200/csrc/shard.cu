@@ -128,6 +128,10 @@ struct ShardState {
     // qpe_shard_set_link_weights: PCIe links of one box can differ by 2x when all of them copy at once)
     uint32_t slice_cum[kMaxRanks + 1] = {0};
     int numa_node = -1, numa_how = 0;   // where this rank's part of the host buffer was placed, and by what (1 mbind, 2 affinity)
+    // where qpe_shard_wait spends its time on host-result queries (host clock, summed): waiting for the counts, for this
+    // rank's device->host copy, (owner) for the other ranks' pieces
+    double wait_ms[3] = {0, 0, 0};
+    long long wait_n = 0;
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
@@ -884,7 +888,9 @@ int qpe_shard_wait(struct engineS *engine, unsigned long long *counts_out, qpe_s
     for (int p = 0; p < 2; ++p)
         if (s->pending[p].active && (!pq || static_cast<int32_t>(s->pending[p].epoch - pq->epoch) < 0)) pq = &s->pending[p];
     const uint32_t epoch = pq->epoch, par = epoch & 1u;
+    const double tw0 = now_ms();
     int rc = wait_host_words(g, s, epoch);
+    const double tw1 = now_ms();
     pq->active = false;
     --s->n_pending;
     if (rc != 0) return rc;
@@ -924,6 +930,7 @@ int qpe_shard_wait(struct engineS *engine, unsigned long long *counts_out, qpe_s
         }
         // (mode 2: the kernel stored the ids and fenced before it handed the counts over)
         __atomic_store_n(&hh->done[s->rank][0], static_cast<unsigned long long>(epoch), __ATOMIC_RELEASE);
+        const double tw2 = now_ms();
         if (s->rank == s->owner && rc == 0) {
             // the result is complete when every rank has delivered its piece
             for (int r = 0; r < s->world; ++r) {
@@ -938,6 +945,10 @@ int qpe_shard_wait(struct engineS *engine, unsigned long long *counts_out, qpe_s
             }
         }
         s->last_host_parity = par;
+        s->wait_ms[0] += tw1 - tw0;
+        s->wait_ms[1] += tw2 - tw1;
+        s->wait_ms[2] += now_ms() - tw2;
+        ++s->wait_n;
     } else {
         s->last_parity = par;
     }
@@ -955,6 +966,23 @@ int qpe_shard_wait(struct engineS *engine, unsigned long long *counts_out, qpe_s
         return -5;
     }
     if (stats) qpe_gpu_last_stats(engine, stats);
+    return 0;
+}
+
+/* Diagnostics: where qpe_shard_wait has spent its time on host-result queries since the last reset (host clock, ms,
+ * summed over *n_out queries): [0] waiting for the counts (scan + exchange + delivery kernel), [1] this rank's
+ * device->host copy, [2] (owner) the other ranks' pieces. */
+int qpe_shard_wait_breakdown(struct engineS *engine, double out_ms[3], long long *n_out, int reset) {
+    EngineLock lk(engine);
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    if (!s) return -1;
+    for (int i = 0; i < 3; ++i) {
+        if (out_ms) out_ms[i] = s->wait_ms[i];
+        if (reset) s->wait_ms[i] = 0;
+    }
+    if (n_out) *n_out = s->wait_n;
+    if (reset) s->wait_n = 0;
     return 0;
 }
 

@@ -329,6 +329,16 @@ class ShardGroup:
         counts = self._counts[:self.world]
         return sum(counts), counts, (self._stats if stats else None)
 
+    def wait_breakdown(self, reset: bool = True):
+        """Host time `wait` has spent on host-result queries since the last reset, per query (ms): waiting for the counts,
+        this rank's device->host copy, (owner) the other ranks' pieces."""
+        import ctypes as C
+        out = (C.c_double * 3)()
+        n = C.c_longlong(0)
+        self.lib.qpe_shard_wait_breakdown(self._h, out, C.byref(n), 1 if reset else 0)
+        k = max(1, n.value)
+        return [out[0] / k, out[1] / k, out[2] / k]
+
     def select(self, statement: str, to_host: bool = False, stats: bool = True):
         """One sharded full-scan SELECT, start to finish.  Returns (total, per-rank counts, ScanStats).
         to_host=False: ids packed in the owner's HBM (`device_result`); True: in the shared host buffer
