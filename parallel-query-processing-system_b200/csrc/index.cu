@@ -421,6 +421,12 @@ struct ProbeParams {
 // queries per iteration and walks the lower-bound and the upper-bound descent of all of them together:
 // 2 * kProbeU independent loads in flight per lane, 4 * kProbeU descents per warp (the first version had one
 // query per warp, lanes 0-15 on the lower bound and 16-31 on the upper: 2.2 G probes/s over 100 M keys).
+// (Round 2 tried ONE descent per probe: the lower-bound descent ends in the leaf node with the first key >= lo, and when a
+// key of that node, or the next node's first key -- a shuffle away in the last separator node -- is ordered after hi, the
+// upper bound is a ballot away; a second descent only for the probes that need one, 4 probes per half-warp.  Point probes on
+// unique keys 3.25 vs 3.03 G probes/s, but ranges 2.57 vs 3.04 and a heavy-duplicate index 3.4 vs 4.0: the second descent
+// then runs AFTER the first instead of beside it, and the kernel is bound by latency, not by loads.  Dropped;
+// tests/test_gpu_scale.py::test_probe_node_boundaries, written for it, stayed.)
 constexpr int kProbeU = 2;
 
 template <typename K>

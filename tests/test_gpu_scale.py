@@ -309,3 +309,33 @@ def test_two_engines_run_side_by_side(pkg):
     for e in engines:
         e.close()
     assert not errors, errors[:3]
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 255, 256, 257, 4095, 4096, 4097, 65_537, 1_048_577])
+def test_probe_node_boundaries(pkg, n):
+    """K3 answers a probe with ONE descent when the range ends in the leaf node the lower bound falls in (or right behind
+    it) and with a second descent otherwise: index sizes around the fan-out's powers, every kind of key run (unique ids,
+    5 values, ~2 000 values), point probes on every node's first and last key, ranges of all widths, keys outside the
+    index, inverted ranges -- against numpy's searchsorted on the sorted column"""
+    eng = pkg.Engine.from_synth(n, columns=["command_id", "user_id", "risk_level"],
+                                indexes=(("command_id", 0), ("user_id", 1), ("risk_level", 1)))
+    rng = np.random.default_rng(n)
+    for attr, dt in (("command_id", np.uint64), ("user_id", np.int32), ("risk_level", np.int32)):
+        keys = np.sort(eng.fetch_column(attr), kind="stable")
+        edge = np.concatenate([keys[::16], keys[15::16], keys[-1:], keys[:1]]).astype(np.int64)
+        lo = np.concatenate([edge, edge - 1, edge + 1, rng.integers(int(keys[0]) - 3, int(keys[-1]) + 4, 500)])
+        width = rng.choice([0, 0, 0, 1, 2, 15, 16, 17, 300, 70_000], size=lo.size)
+        hi = lo + width
+        hi[::37] = lo[::37] - 1                      # inverted: nothing
+        if dt == np.uint64:
+            lo, hi = np.clip(lo, 0, None), np.clip(hi, 0, None)
+        lo, hi = lo.astype(dt), hi.astype(dt)
+        first, count, _ = eng.probe_keys(attr, lo, hi)
+        wf = np.searchsorted(keys, lo, side="left")
+        wc = np.clip(np.searchsorted(keys, hi, side="right") - wf, 0, None)
+        assert np.array_equal(first, wf.astype(np.uint32)), (n, attr)
+        assert np.array_equal(count, wc.astype(np.uint32)), (n, attr)
+        f1, c1, _ = eng.probe_keys(attr, lo)         # point form (hi = lo)
+        w1 = np.searchsorted(keys, lo, side="right") - wf
+        assert np.array_equal(f1, wf.astype(np.uint32)) and np.array_equal(c1, w1.astype(np.uint32)), (n, attr)
+    eng.close()
