@@ -861,7 +861,7 @@ static GpuEngine::TimingSlot *take_timing_slot(GpuEngine *g) {
 }
 
 bool engine_fused_enqueue(GpuEngine *g, const struct whereClauseS *wc, uint32_t *out_ids, uint64_t out_cap,
-                          uint32_t id_base, FusedEnqueue *fe, bool overlap_previous) {
+                          uint32_t id_base, FusedEnqueue *fe, bool overlap_previous, bool l2_stream) {
     cudaSetDevice(g->device);
     const DevTable &t = g->table;
     fe->slot = nullptr;
@@ -923,6 +923,7 @@ bool engine_fused_enqueue(GpuEngine *g, const struct whereClauseS *wc, uint32_t 
     F.out_cap = out_cap;
     F.d_fctl = g->d_fctl;
     F.pdl = overlap_previous;
+    F.l2_stream = l2_stream;
     if (slot) cudaEventRecord(slot->ev[0], g->stream);
     if (!cuda_ok(fused_launch(F, fg, g->stream), "fused scan kernel launch")) return false;
     if (slot) {

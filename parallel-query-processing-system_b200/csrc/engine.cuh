@@ -174,7 +174,7 @@ struct FusedEnqueue {
 };
 // overlap_previous: the scan may start while the stream's previous kernel is still running (it must not depend on it)
 bool engine_fused_enqueue(GpuEngine *g, const struct whereClauseS *wc, uint32_t *out_ids, uint64_t out_cap,
-                          uint32_t id_base, FusedEnqueue *fe, bool overlap_previous);
+                          uint32_t id_base, FusedEnqueue *fe, bool overlap_previous, bool l2_stream = false);
 void engine_fused_finish(GpuEngine *g, const FusedEnqueue &fe, uint64_t matches, int extra_launches, double t_begin_ms);
 
 // K9: the match phase of up to kMaxBatch full-scan queries in ONE pass over the columns.  On success the ids of

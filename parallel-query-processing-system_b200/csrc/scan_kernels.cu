@@ -116,6 +116,21 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// the same with an L2 eviction policy: a table is read once per scan, so its lines are the first to go (evict_first)
+// and what the query WRITES -- ids, the staging slice a sharded host result is copied from -- stays in L2
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                                  unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_desc(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -547,6 +562,21 @@ __device__ __forceinline__ void produce_tile(const ScanParams &p, uint8_t *dst, 
         tma_bulk_g2s(dst + p.smem_off[c], p.col[c] + static_cast<size_t>(tile) * T * w, static_cast<uint32_t>(T) * w, bar);
     }
 }
+// (K1f) with the streaming L2 policy; policy == 0: plain copies
+__device__ __forceinline__ void produce_tile_stream(const ScanParams &p, uint8_t *dst, long long tile, int T, uint64_t *bar,
+                                                    unsigned long long policy) {
+    if (policy == 0ull) {
+        produce_tile(p, dst, tile, T, bar);
+        return;
+    }
+    mbar_arrive_expect_tx(bar, p.stage_bytes);
+    for (int r = 0; r < p.n_ref; ++r) {
+        const int c = p.ref_col[r];
+        const uint32_t w = p.width[c];
+        tma_bulk_g2s_hint(dst + p.smem_off[c], p.col[c] + static_cast<size_t>(tile) * T * w, static_cast<uint32_t>(T) * w, bar,
+                          policy);
+    }
+}
 
 // warp-wide decoupled look-back: exclusive prefix of `tile` (sum of the aggregates of all
 // earlier tiles).  Lane l inspects tile-1-l; windows of 32 predecessors until a PREFIX is found.
@@ -757,6 +787,8 @@ struct FusedParams {
     int32_t chunk_tiles;            // tiles per chunk; chunk_tiles * tile_rows <= kFuseMaxChunkRows
     uint32_t poll_ns;               // sleep between the compaction warps' polls of the chunk barrier
     long long n_chunks;
+    uint32_t l2_stream;             // table tiles are fetched with the L2 evict_first policy
+    uint32_t pad_;
     unsigned long long *desc;       // one look-back descriptor per chunk
     uint32_t epoch;
     uint32_t id_base;
@@ -889,6 +921,7 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
     __syncthreads();
     // every evaluator warp's first tile: in flight while the program is copied into shared memory
     const bool active = warp < S;   // evaluator warp that owns a stage
+    const unsigned long long l2pol = fp.l2_stream ? l2_evict_first_policy() : 0ull;
     uint8_t *stage = stages + static_cast<size_t>(warp < EW ? warp : 0) * p.stage_bytes;
     WarpTiles nxt;                  // the next tile to FETCH (one ahead of the tile being evaluated)
     nxt.chunk = blockIdx.x;
@@ -898,7 +931,7 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
     if (active) {
         if (settle(nxt, warp, CT, S, fp.n_chunks, p.n_tiles, sh->chunk_ring)) {
             if (lane == 0) {
-                produce_tile(p, stage, nxt.chunk * CT + nxt.j, T, &sh->full[warp]);
+                produce_tile_stream(p, stage, nxt.chunk * CT + nxt.j, T, &sh->full[warp], l2pol);
                 // whoever fetches a chunk's claim tile takes the CTA's next chunk
                 if (nxt.j == claim_tile_of(nxt.nt, S)) claim_chunk(sh->chunk_ring, nxt.k + 1u, fp.fctl, gridDim.x);
             }
@@ -944,7 +977,7 @@ __global__ void __launch_bounds__(32 * (kEvalWarps + CW), 1)
                     if (settle(nxt, warp, CT, S, fp.n_chunks, p.n_tiles, sh->chunk_ring)) {
                         if (lane == 0) {
                             fence_proxy_async_smem();
-                            produce_tile(p, stage, nxt.chunk * CT + nxt.j, T, &sh->full[warp]);
+                            produce_tile_stream(p, stage, nxt.chunk * CT + nxt.j, T, &sh->full[warp], l2pol);
                             if (nxt.j == claim_tile_of(nxt.nt, S)) claim_chunk(sh->chunk_ring, nxt.k + 1u, fp.fctl, gridDim.x);
                         }
                         nxt.j += S;
@@ -1428,6 +1461,9 @@ cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStre
     fp.chunk_tiles = geo.chunk_tiles;
     fp.poll_ns = 256;  // 0 .. 1000 ns measured alike: any sleep that keeps the polls rare
     fp.n_chunks = geo.n_chunks;
+    // QPE_SCAN_L2_HINT=0 / 1 forces the streaming L2 policy off / on (experiments); else the caller decides
+    static const char *l2_env = std::getenv("QPE_SCAN_L2_HINT");
+    fp.l2_stream = l2_env ? (std::atoi(l2_env) != 0 ? 1u : 0u) : (L.l2_stream ? 1u : 0u);
     fp.desc = L.desc;
     fp.epoch = L.epoch;
     fp.id_base = L.id_base;

@@ -91,6 +91,7 @@ struct FusedLaunch {
     FusedCtl *d_fctl;                // device, zeroed once at engine creation
     unsigned long long *trace;       // diagnostics: 8 words per CTA (device), or null
     bool pdl;                        // programmatic dependent launch: may overlap the previous kernel of the stream
+    bool l2_stream;                  // fetch the table with the L2 evict_first policy (what the query writes then stays in L2)
 };
 size_t fused_param_bytes();          // bytes of K1f's kernel parameter block (carries the compiled program)
 cudaError_t fused_launch(const FusedLaunch &L, const ScanGeometry &geo, cudaStream_t stream);

@@ -838,7 +838,10 @@ int qpe_shard_submit(struct engineS *engine, struct whereClauseS *whereClause, i
     static const bool no_pdl = std::getenv("QPE_SHARD_NO_PDL") != nullptr;
     const bool overlap = s->n_pending >= 2 && s->last_was_post && !no_pdl;
     if (local_ok)
-        local_ok = engine_fused_enqueue(g, whereClause, out, out_cap, static_cast<uint32_t>(g->table.row_base), &pq.fe, overlap);
+        // (host result: the table is streamed through L2 with the evict_first policy, so that the staging slice the copy
+        // engine reads right after the delivery kernel is still in L2 while the NEXT scan saturates HBM)
+        local_ok = engine_fused_enqueue(g, whereClause, out, out_cap, static_cast<uint32_t>(g->table.row_base), &pq.fe, overlap,
+                                        to_host != 0);
     if (!local_ok) pq.local_error = last_error_cstr();
     pq.local_ok = local_ok;
     const unsigned long long *count = local_ok ? &g->d_fctl->final_count : nullptr;
