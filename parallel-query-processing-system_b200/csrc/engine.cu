@@ -585,6 +585,7 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
                 }
                 // no upload: K1f takes the program as a kernel parameter and resets its own control words
                 F.d_fctl = g->d_fctl;
+                F.l2_stream = g->fuse_l2;
                 static const bool want_trace = std::getenv("QPE_FUSE_TRACE") != nullptr;
                 if (want_trace && !g->d_trace) cudaMalloc(&g->d_trace, 8 * 8 * 1024);
                 F.trace = want_trace ? g->d_trace : nullptr;
@@ -832,10 +833,8 @@ bool engine_match(GpuEngine *g, const struct whereClauseS *wc, bool force_scan, 
     g->cur_slot->two_kernels = st.launches > 1;
     g->cur_slot->has_post = static_cast<bool>(g->post_match);
     st.matches = static_cast<int64_t>(hc->out_count);
-    // next full scan: 8 compaction warps if this one matched more than 1/8 of its rows.  (Break-even is near 10 %:
-    // QN on 1 B rows at 9.5 %: 2.19 ms with 8 warps, 2.23 with 4; the first shard of an 8-GPU table at 7.6 %,
-    // all of it in the first twelfth of the shard: 0.310 ms with 8, 0.302 with 4.)
-    if (st.path == 0 && st.rows_scanned > 0) g->fuse_cw = (st.matches * 8 > st.rows_scanned) ? 8 : 4;
+    // next full scan: see engine_adapt_fused
+    if (st.path == 0 && st.rows_scanned > 0) engine_adapt_fused(g, st.matches, st.rows_scanned);
     st.algo_bytes = st.rows_scanned * bytes_per_row + (count_only ? 0 : 4 * st.matches) +
                     (st.path == 1 ? 4 * st.candidates : 0);
     st.total_ms = now_ms() - t_begin;
@@ -858,6 +857,19 @@ static GpuEngine::TimingSlot *take_timing_slot(GpuEngine *g) {
     slot->pending = false;
     if (g->cur_slot && g->cur_slot->pending && !g->accumulate_timing) g->cur_slot->pending = false;  // never asked for
     return slot;
+}
+
+// How the NEXT full scan of this engine runs, from what this one matched (the same statement usually comes again: a
+// driver's loop, the ranks of a sharded table).  8 compaction warps from 1/16 of the rows on, and between 1/16 and 1/4 the
+// table is streamed through L2 with the evict_first policy, so that the ids the scan writes stay in the 126 MB L2 instead
+// of competing with the reads for HBM.  Measured with the final K1f (tickets, aggregates from the evaluators) on a
+// 125 M-row shard whose first 10 M rows match at 94 % -- rank 0 of an 8-GPU QN: 273 us with 4 warps, 268 with 8, 267.6
+// with 4 + the policy, 260.4 with 8 + the policy (a shard without matches: 246-250).  At 1 % the policy costs 1-3 %
+// (1.803 vs 1.788 ms on 1 B rows), at 50 % 1-2 % (the ids no longer fit L2).  (Round 1 measured the 7.6 % shard faster with 4
+// warps, 0.302 vs 0.310 ms: that was the look-back convoy, not the warps.)
+void engine_adapt_fused(GpuEngine *g, int64_t matches, int64_t rows) {
+    g->fuse_cw = (matches * 16 > rows) ? 8 : 4;
+    g->fuse_l2 = matches * 16 > rows && matches * 4 < rows;
 }
 
 bool engine_fused_enqueue(GpuEngine *g, const struct whereClauseS *wc, uint32_t *out_ids, uint64_t out_cap,
@@ -923,7 +935,7 @@ bool engine_fused_enqueue(GpuEngine *g, const struct whereClauseS *wc, uint32_t 
     F.out_cap = out_cap;
     F.d_fctl = g->d_fctl;
     F.pdl = overlap_previous;
-    F.l2_stream = l2_stream;
+    F.l2_stream = l2_stream || g->fuse_l2;
     if (slot) cudaEventRecord(slot->ev[0], g->stream);
     if (!cuda_ok(fused_launch(F, fg, g->stream), "fused scan kernel launch")) return false;
     if (slot) {
@@ -947,7 +959,7 @@ void engine_fused_finish(GpuEngine *g, const FusedEnqueue &fe, uint64_t matches,
     st.grid = fe.geo.grid;
     st.algo_bytes = st.rows_scanned * fe.bytes_per_row + 4 * st.matches;
     st.total_ms = now_ms() - t_begin_ms;
-    if (st.rows_scanned > 0) g->fuse_cw = (st.matches * 8 > st.rows_scanned) ? 8 : 4;
+    if (st.rows_scanned > 0) engine_adapt_fused(g, st.matches, st.rows_scanned);
     g->last = st;
     if (!fe.slot) g->cur_slot = nullptr;  // an overlapped (untimed) scan: no event times to resolve for it
     if (fe.slot) {

@@ -117,6 +117,7 @@ struct GpuEngine {
     // K1f compaction warps for the next full scan: 4, or 8 once a scan matched more than 1/8 of its rows
     // (the evaluators then wait for the compaction warps); QPE_FUSE_CW=4|8 pins it
     int fuse_cw = 4;
+    bool fuse_l2 = false;             // next full scan streams the table through L2 with the evict_first policy (see below)
     int force_tile_rows = 0, force_stages = 0;
     ScanStats last;
 };
@@ -173,6 +174,7 @@ struct FusedEnqueue {
     bool launched = false;                   // false: empty shard (count 0), nothing launched
 };
 // overlap_previous: the scan may start while the stream's previous kernel is still running (it must not depend on it)
+void engine_adapt_fused(GpuEngine *g, int64_t matches, int64_t rows);
 bool engine_fused_enqueue(GpuEngine *g, const struct whereClauseS *wc, uint32_t *out_ids, uint64_t out_cap,
                           uint32_t id_base, FusedEnqueue *fe, bool overlap_previous, bool l2_stream = false);
 void engine_fused_finish(GpuEngine *g, const FusedEnqueue &fe, uint64_t matches, int extra_launches, double t_begin_ms);
