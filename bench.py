@@ -718,12 +718,19 @@ def run_ours(args):
         def make_loops(statement):
             def piped(to_host):
                 def loop(n):
+                    # host results: `wait` returns once this rank's piece is in host memory; the pieces of the other
+                    # ranks are waited for when a result is taken (here: the last one, inside the timed region --
+                    # every earlier result was complete before its id array was reused, three queries later)
+                    sg.set_deferred(bool(to_host))
                     sg.submit(statement, to_host)
                     m = 0
                     for i in range(n):
                         if i + 1 < n:
                             sg.submit(statement, to_host)   # query i + 1 is in flight while query i is waited for
                         m = sg.wait(stats=False)[0]
+                    if to_host:
+                        sg.host_result()
+                        sg.set_deferred(False)
                     return m
                 return loop
 

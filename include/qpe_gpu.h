@@ -153,7 +153,7 @@ int qpe_gpu_copy_device(void *dst_device, const void *src_device, size_t bytes);
  *                                                        in the OWNER's memory (own pointer / qpe_gpu_ipc_open
  *                                                        mapping); the first shard stores straight into the
  *                                                        dense result (its offset is always 0)
- *   qpe_shard_open_host_result(engine, name, cap, create) POSIX shared-memory id buffer (2 x cap ids) all ranks
+ *   qpe_shard_open_host_result(engine, name, cap, create) POSIX shared-memory id buffer (3 x cap ids) all ranks
  *                                                        write their 1/world of a result into over their own
  *                                                        PCIe link; this rank's parts go to its GPU's NUMA node
  *   qpe_shard_pin_host_result(engine)                    after every rank has opened it: register it with CUDA
@@ -178,9 +178,17 @@ int qpe_shard_wait_breakdown(struct engineS *engine, double out_ms[3], long long
 /* creator, after every rank has opened the buffer: drop its /dev/shm name (mappings stay valid) */
 int qpe_shard_unlink_host_result(struct engineS *engine);
 /* the packed ids of the most recent device-result / host-result query that qpe_shard_wait completed.  A host result
- * stays valid until the second qpe_shard_submit after the qpe_shard_wait that returned it. */
+ * stays valid until the third qpe_shard_submit after its own. */
 const unsigned int *qpe_shard_device_result(struct engineS *engine);
 const unsigned int *qpe_shard_host_result(struct engineS *engine);
+/* the same for the most recent (back = 0) or the previous (back = 1) host-result query, with its number of ids; and
+ * deferred completion: with `on`, qpe_shard_wait returns once the counts are known and THIS rank's device->host copy
+ * is queued -- it waits neither for that copy nor (owner) for the other ranks' pieces, so the next query is submitted
+ * at once; qpe_shard_host_result / _at wait for every piece.  The shared buffer holds three id arrays (epoch % 3), so a
+ * host result stays valid until the third qpe_shard_submit after its own: a consumer takes result q after submitting
+ * q + 2.  Every rank of a group should choose the same. */
+const unsigned int *qpe_shard_host_result_at(struct engineS *engine, int back, unsigned long long *total_out);
+int qpe_shard_set_deferred(struct engineS *engine, int on);
 /* Host result path: 1 (default) = every rank reads its 1/world of the result out of the ranks' segments over NVLink
  * into its own HBM and the copy engine takes it to the host over this GPU's PCIe link; 2 = the delivery kernel
  * stores into the mapped host buffer itself.  Every rank must choose the same. */

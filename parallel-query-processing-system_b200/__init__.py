@@ -158,6 +158,8 @@ def load_library() -> C.CDLL:
         "qpe_shard_open_host_result": (vp, [vp, cp, ull, i]),
         "qpe_shard_device_result": (vp, [vp]),
         "qpe_shard_host_result": (vp, [vp]),
+        "qpe_shard_host_result_at": (vp, [vp, i, C.POINTER(ull)]),
+        "qpe_shard_set_deferred": (i, [vp, i]),
         "qpe_shard_pin_host_result": (i, [vp]),
         "qpe_shard_numa": (i, [vp, C.POINTER(i)]),
         "qpe_shard_wait_breakdown": (i, [vp, C.POINTER(C.c_double), C.POINTER(ll), i]),

@@ -67,6 +67,7 @@ namespace qpe {
 
 constexpr int kMaxRanks = 16;
 constexpr unsigned long long kCountFailed = 0xffffffffull;   // published instead of a count: this rank could not scan
+constexpr int kHostSlots = 3;                                 // id arrays of the shared host buffer: a host result of epoch e lives in slot e % 3
 constexpr int kHostWords = kMaxRanks + 2;                     // per parity: counts, [kMaxRanks] = epoch flag, [+1] = status
 
 struct ShardComm {                      // device memory of one rank, mapped by all the others; followed by its segments
@@ -113,7 +114,12 @@ struct ShardState {
     bool host_pinned = false;
     char host_name[96] = {0};
     bool host_creator = false;
-    uint32_t last_host_parity = 0;
+    // Deferred completion (qpe_shard_set_deferred): the owner's qpe_shard_wait returns once ITS piece of a host result is
+    // delivered; the other ranks' pieces are waited for when the result is asked for (qpe_shard_host_result*).
+    bool deferred = false;
+    uint32_t copy_pending[2] = {0, 0};  // [parity] epoch of a device->host copy that is queued but not yet known complete
+    uint32_t host_epoch[2] = {0, 0};    // epochs of the last two host-result queries waited: [0] the most recent
+    uint64_t host_total[2] = {0, 0};
     uint32_t *staging[2] = {nullptr, nullptr};   // this rank's slice of the result before it goes to the host
     uint64_t staging_cap = 0;
     cudaEvent_t ev_post[2] = {nullptr, nullptr};  // post-scan kernel of parity p has finished (stream2 waits for it)
@@ -380,6 +386,7 @@ static void release_host_result(ShardState *s) {
     }
     s->staging_cap = 0;
     s->host_map = nullptr;
+    s->host_epoch[0] = s->host_epoch[1] = 0;
     s->host_ids = nullptr;
     s->host_ids_dev = nullptr;
     s->host_pinned = false;
@@ -511,6 +518,37 @@ static int wait_host_words(GpuEngine *g, ShardState *s, uint32_t epoch) {
     return 0;
 }
 
+// Deferred mode: this rank's queued device->host copies are waited for (oldest first) and announced to the other ranks.
+static bool complete_own_copies(ShardState *s) {
+    bool ok = true;
+    for (int k = 0; k < 2; ++k) {
+        int p = -1;  // the parity with the older pending epoch
+        for (int q = 0; q < 2; ++q)
+            if (s->copy_pending[q] && (p < 0 || static_cast<int32_t>(s->copy_pending[q] - s->copy_pending[p]) < 0)) p = q;
+        if (p < 0) break;
+        ok = cuda_ok(cudaEventSynchronize(s->ev_copy[p]), "download ids") && ok;
+        ShardHostHeader *hh = static_cast<ShardHostHeader *>(s->host_map);
+        if (hh) __atomic_store_n(&hh->done[s->rank][0], static_cast<unsigned long long>(s->copy_pending[p]), __ATOMIC_RELEASE);
+        s->copy_pending[p] = 0;
+    }
+    return ok;
+}
+
+// every rank has delivered its piece of the host result of `epoch` (done[] only grows: later results imply earlier ones)
+static bool wait_all_delivered(ShardState *s, uint32_t epoch) {
+    ShardHostHeader *hh = static_cast<ShardHostHeader *>(s->host_map);
+    for (int r = 0; r < s->world; ++r) {
+        unsigned long long spins = 0;
+        while (static_cast<int32_t>(static_cast<uint32_t>(__atomic_load_n(&hh->done[r][0], __ATOMIC_ACQUIRE)) - epoch) < 0) {
+            if (++spins > 4000000000ull) {
+                set_error("sharded SELECT: a rank never delivered its ids");
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
 }  // namespace qpe
 
 using namespace qpe;
@@ -613,7 +651,7 @@ int qpe_shard_set_device_result(struct engineS *engine, int owner_rank, unsigned
  * create != 0 on exactly one rank (it creates /dev/shm/<name>), the others open it afterwards.  This maps the buffer
  * and places THIS rank's parts of it on the NUMA node of its GPU; qpe_shard_pin_host_result, called once every
  * rank has opened it, registers it with CUDA.  Returns the host pointer of the first id array (NULL on failure);
- * the second follows `capacity` ids behind. */
+ * three of them follow each other, `capacity` (rounded up to 1 Ki) ids apart: a host result of epoch e uses array e % 3. */
 unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *name, unsigned long long capacity,
                                          int create) {
     EngineLock lk(engine);
@@ -631,10 +669,11 @@ unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *nam
     if (s->host_map) {  // opened before: release the old buffer first
         cudaStreamSynchronize(g->stream);
         cudaStreamSynchronize(g->stream2);
+        complete_own_copies(s);
         release_host_result(s);
     }
     const uint64_t cap = (capacity + 1023) & ~uint64_t(1023);  // parity 1 starts page aligned
-    const size_t bytes = kHostHeaderBytes + sizeof(uint32_t) * (2 * cap + 16);
+    const size_t bytes = kHostHeaderBytes + sizeof(uint32_t) * (kHostSlots * cap + 16);
     const int fd = shm_open(name, create ? (O_CREAT | O_RDWR | O_TRUNC) : O_RDWR, 0600);
     if (fd < 0) {
         set_error(std::string("shm_open failed for ") + name);
@@ -661,9 +700,9 @@ unsigned int *qpe_shard_open_host_result(struct engineS *engine, const char *nam
     // rank j delivers the j-th 1/world of every result: put that part of both id arrays next to its GPU
     const int node = gpu_numa_node(g->device);
     s->numa_node = node;
-    for (int par = 0; par < 2; ++par) {
+    for (int slot = 0; slot < kHostSlots; ++slot) {
         const uint64_t lo = cap * s->rank / s->world, hi = cap * (s->rank + 1) / s->world;
-        s->numa_how = place_on_node(s->host_ids + par * cap + lo, (hi - lo) * sizeof(uint32_t), node);
+        s->numa_how = place_on_node(s->host_ids + slot * cap + lo, (hi - lo) * sizeof(uint32_t), node);
     }
     // staging for this rank's slice (mode 1)
     s->staging_cap = cap;  // any share of a result fits (qpe_shard_set_link_weights may give a fast link most of it)
@@ -758,11 +797,45 @@ const unsigned int *qpe_shard_device_result(struct engineS *engine) {
     return (s && s->dev_base) ? s->dev_base + s->last_parity * set_ids(s->world, s->dev_cap) : nullptr;
 }
 
-/* the id array the most recent host-result query (qpe_shard_wait) was delivered into */
-const unsigned int *qpe_shard_host_result(struct engineS *engine) {
+/* the id array of the most recent host-result query qpe_shard_wait completed (back = 0) or of the one before it
+ * (back = 1); *total_out = its number of ids.  Blocks until every rank has delivered its piece (a no-op unless
+ * qpe_shard_set_deferred is on).  NULL if there is no such result or a rank never delivered. */
+const unsigned int *qpe_shard_host_result_at(struct engineS *engine, int back, unsigned long long *total_out) {
+    EngineLock lk(engine);
     GpuEngine *g = as_engine(engine);
     ShardState *s = g ? shard_of(g) : nullptr;
-    return (s && s->host_ids) ? s->host_ids + s->last_host_parity * s->host_cap : nullptr;
+    if (!s || !s->host_ids || back < 0 || back > 1 || s->host_epoch[back] == 0) return nullptr;
+    const uint32_t epoch = s->host_epoch[back];
+    cudaSetDevice(g->device);
+    if (!complete_own_copies(s) || !wait_all_delivered(s, epoch)) return nullptr;
+    if (total_out) *total_out = s->host_total[back];
+    return s->host_ids + static_cast<size_t>(epoch % kHostSlots) * s->host_cap;
+}
+const unsigned int *qpe_shard_host_result(struct engineS *engine) {
+    {
+        EngineLock lk(engine);
+        GpuEngine *g = as_engine(engine);
+        ShardState *s = g ? shard_of(g) : nullptr;
+        if (s && s->host_ids && s->host_epoch[0] == 0) return s->host_ids;  // no host result yet: the first id array
+    }
+    return qpe_shard_host_result_at(engine, 0, nullptr);
+}
+
+/* Deferred completion of host results.  on != 0: qpe_shard_wait returns as soon as THIS rank's piece of a host result
+ * is in host memory -- on the owner too, which otherwise also waits for every other rank's piece before it may submit its
+ * next query (the owner's scan then starts late, and with it every rank's count exchange).  The complete result is
+ * asked for with qpe_shard_host_result / qpe_shard_host_result_at, which wait for the missing pieces; with three id
+ * arrays a result stays valid until the third qpe_shard_submit after its own, so a consumer can take result q after
+ * submitting q + 2.  Every rank may choose for itself (only the owner waits for other ranks at all). */
+int qpe_shard_set_deferred(struct engineS *engine, int on) {
+    EngineLock lk(engine);
+    GpuEngine *g = as_engine(engine);
+    ShardState *s = g ? shard_of(g) : nullptr;
+    if (!s) return -1;
+    cudaSetDevice(g->device);
+    const bool ok = complete_own_copies(s);
+    s->deferred = on != 0;
+    return ok ? 0 : -4;
 }
 
 /* NUMA node of this rank's GPU (-1: unknown) and how its part of the host buffer was placed there: bit 0 = mbind
@@ -850,9 +923,11 @@ int qpe_shard_submit(struct engineS *engine, struct whereClauseS *whereClause, i
         PeerSegs segs{};
         for (int r = 0; r < s->world; ++r) segs.seg[r] = s->seg[r] + static_cast<size_t>(par) * s->seg_cap;
         const bool direct = s->host_mode == 2;
-        uint32_t *dst = direct ? s->host_ids_dev + static_cast<size_t>(par) * s->host_cap : s->staging[par];
+        uint32_t *dst = direct ? s->host_ids_dev + static_cast<size_t>(epoch % kHostSlots) * s->host_cap : s->staging[par];
         SliceCum sc{};
         for (int r = 0; r <= s->world; ++r) sc.cum[r] = s->slice_cum[r];
+        // (deferred mode) the copy that last read this staging buffer may still be queued: the kernel waits for it
+        if (!direct && s->copy_pending[par]) cudaStreamWaitEvent(g->stream, s->ev_copy[par], 0);
         deliver_kernel<<<148 * 4, 256, 0, g->stream>>>(count, peers, segs, s->rank, s->world, epoch, words, dst, s->seg_cap,
                                                        s->host_cap, s->staging_cap, direct ? 1 : 0, sc);
     } else {
@@ -892,7 +967,10 @@ int qpe_shard_wait(struct engineS *engine, unsigned long long *counts_out, qpe_s
         if (s->pending[p].active && (!pq || static_cast<int32_t>(s->pending[p].epoch - pq->epoch) < 0)) pq = &s->pending[p];
     const uint32_t epoch = pq->epoch, par = epoch & 1u;
     const double tw0 = now_ms();
+    // (deferred mode) the copy of the query before this one: it is ahead of this query's copy on the copy stream anyway
+    const bool older_ok = complete_own_copies(s);
     int rc = wait_host_words(g, s, epoch);
+    if (!older_ok && rc == 0) rc = -4;
     const double tw1 = now_ms();
     pq->active = false;
     --s->n_pending;
@@ -917,7 +995,7 @@ int qpe_shard_wait(struct engineS *engine, unsigned long long *counts_out, qpe_s
     int extra = 1;
     if (pq->to_host) {
         ShardHostHeader *hh = static_cast<ShardHostHeader *>(s->host_map);
-        uint32_t *host_ids = s->host_ids + static_cast<size_t>(par) * s->host_cap;
+        uint32_t *host_ids = s->host_ids + static_cast<size_t>(epoch % kHostSlots) * s->host_cap;
         if (!failed && !overflow && s->host_mode == 1) {
             // this rank's 1/world of the result: local staging -> (its own PCIe link) -> host, on the copy stream, so
             // that the next query's scan (already enqueued on the main stream) runs beside it
@@ -926,28 +1004,24 @@ int qpe_shard_wait(struct engineS *engine, unsigned long long *counts_out, qpe_s
                 if (!cuda_ok(cudaMemcpyAsync(host_ids + lo, s->staging[par], (hi - lo) * sizeof(uint32_t),
                                              cudaMemcpyDeviceToHost, g->stream2),
                              "download ids") ||
-                    !cuda_ok(cudaEventRecord(s->ev_copy[par], g->stream2), "download ids") ||
-                    !cuda_ok(cudaEventSynchronize(s->ev_copy[par]), "download ids"))
+                    !cuda_ok(cudaEventRecord(s->ev_copy[par], g->stream2), "download ids"))
+                    rc = -4;
+                else if (s->deferred)
+                    s->copy_pending[par] = epoch;  // completed and announced by the next wait / when the result is taken
+                else if (!cuda_ok(cudaEventSynchronize(s->ev_copy[par]), "download ids"))
                     rc = -4;
             }
         }
         // (mode 2: the kernel stored the ids and fenced before it handed the counts over)
-        __atomic_store_n(&hh->done[s->rank][0], static_cast<unsigned long long>(epoch), __ATOMIC_RELEASE);
+        if (!s->copy_pending[par])
+            __atomic_store_n(&hh->done[s->rank][0], static_cast<unsigned long long>(epoch), __ATOMIC_RELEASE);
         const double tw2 = now_ms();
-        if (s->rank == s->owner && rc == 0) {
-            // the result is complete when every rank has delivered its piece
-            for (int r = 0; r < s->world; ++r) {
-                unsigned long long spins = 0;
-                // (>= : with two queries in flight rank r may already have delivered the next one)
-                while (static_cast<int32_t>(static_cast<uint32_t>(__atomic_load_n(&hh->done[r][0], __ATOMIC_ACQUIRE)) - epoch) < 0) {
-                    if (++spins > 4000000000ull) {
-                        set_error("qpe_shard_wait: a rank never delivered its ids");
-                        return -4;
-                    }
-                }
-            }
-        }
-        s->last_host_parity = par;
+        // the result is complete when every rank has delivered its piece (deferred: asked for with the result)
+        if (s->rank == s->owner && rc == 0 && !s->deferred && !wait_all_delivered(s, epoch)) return -4;
+        s->host_epoch[1] = s->host_epoch[0];
+        s->host_total[1] = s->host_total[0];
+        s->host_epoch[0] = epoch;
+        s->host_total[0] = (failed || overflow) ? 0 : total;
         s->wait_ms[0] += tw1 - tw0;
         s->wait_ms[1] += tw2 - tw1;
         s->wait_ms[2] += now_ms() - tw2;
@@ -1012,6 +1086,8 @@ int qpe_shard_delete(struct engineS *engine, struct whereClauseS *whereClause, u
         set_error("qpe_shard_delete: call qpe_shard_init / qpe_shard_connect first");
         return -1;
     }
+    cudaSetDevice(g->device);
+    complete_own_copies(s);
     if (s->n_pending) {
         set_error("qpe_shard_delete: queries are still in flight");
         return -1;

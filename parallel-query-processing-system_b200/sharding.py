@@ -377,15 +377,26 @@ class ShardGroup:
         """host result: 1 = staging in HBM + copy engine (default), 2 = the kernel stores into host memory"""
         self.engine._check(self.lib.qpe_shard_set_multipath(self.engine._h, mode), "qpe_shard_set_multipath")
 
-    def host_result(self, total: int):
-        """the ids of the most recent host-result query `wait` completed (a view of the shared buffer: valid until
-        the second `submit` after that `wait`)"""
+    def host_result(self, total: int = None, back: int = 0):
+        """the ids of the most recent host-result query `wait` completed (back=1: of the one before it) -- a view of the
+        shared buffer, valid until the third `submit` after the query's own.  With `set_deferred(True)` this is where
+        the other ranks' pieces are waited for."""
         import numpy as np
         C = self._C
-        p = self.lib.qpe_shard_host_result(self._h)
-        if not p or total <= 0:
+        n = C.c_ulonglong(0)
+        p = self.lib.qpe_shard_host_result_at(self._h, back, C.byref(n))
+        if total is None:
+            total = n.value
+        if not p and total > 0:
+            raise self.pkg.QpeError("host result: " + (self.lib.qpe_gpu_last_error() or b"no such result").decode())
+        if total <= 0:
             return np.zeros(0, dtype=np.uint32)
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(int(total),))
+
+    def set_deferred(self, on: bool = True):
+        """`wait` returns once THIS rank's piece of a host result is delivered (the owner does not wait for the other
+        ranks' pieces before it submits its next query); `host_result` waits for the rest."""
+        self.engine._check(self.lib.qpe_shard_set_deferred(self._h, 1 if on else 0), "qpe_shard_set_deferred")
 
     def delete(self, statement: str):
         """DELETE on the sharded table (every rank calls it): (rows deleted, rows left) over all shards.  The

@@ -73,6 +73,23 @@ def _worker(rank, world, port, ret):
         if rank == 0:
             ids = grp.host_result(total).copy() if to_host else grp.device_result(total).copy()
             piped.append((q, total, counts, ids))
+    # deferred completion: `wait` returns once this rank's piece is delivered, the owner takes result k - 1 (back=1)
+    # after query k + 1 has been submitted and k waited for -- three id arrays keep it valid that long
+    grp.set_deferred(True)
+    deferred = []
+    dplan = QUERIES + QUERIES[::-1] + QUERIES[:3]
+    grp.submit(dplan[0], True)
+    for k, q in enumerate(dplan):
+        if k + 1 < len(dplan):
+            grp.submit(dplan[k + 1], True)
+        total, counts, _ = grp.wait()
+        if rank == 0:
+            deferred.append([q, total, None])
+            if k >= 1:
+                deferred[k - 1][2] = grp.host_result(back=1).copy()
+    if rank == 0:
+        deferred[-1][2] = grp.host_result(back=0).copy()
+    grp.set_deferred(False)
     # sharded DELETE (local compaction + renumbering through the comm blocks), then the same queries again:
     # global row ids must be positions in the table AFTER the delete
     deleted, left = grp.delete(DELETE_SQL)
@@ -98,7 +115,7 @@ def _worker(rank, world, port, ret):
     small.close()
     eng.close()
     if rank == 0:
-        ret.put((out, deleted, left, after, piped, all_errors))
+        ret.put((out, deleted, left, after, piped, all_errors, deferred))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -112,7 +129,7 @@ def test_native_shard_select_equals_single_engine(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
     for p in procs:
         p.start()
-    results, deleted, left, after, piped, all_errors = ret.get(timeout=600)
+    results, deleted, left, after, piped, all_errors, deferred = ret.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -127,6 +144,9 @@ def test_native_shard_select_equals_single_engine(world):
     for q, total, counts, ids in piped:
         want, _ = whole.select_ids(q, force_scan=True)
         assert total == len(want) and sum(counts) == total and np.array_equal(ids, want), "two in flight: " + q
+    for q, total, ids in deferred:
+        want, _ = whole.select_ids(q, force_scan=True)
+        assert total == len(want) and ids is not None and np.array_equal(ids, want), "deferred: " + q
     # the same DELETE on the whole table, then the same queries
     out = whole.run(DELETE_SQL, 5)
     assert f"Rows affected: {deleted}" in out and whole.num_rows == left == TOTAL - deleted
