@@ -117,6 +117,8 @@ struct ShardState {
     // Deferred completion (qpe_shard_set_deferred): the owner's qpe_shard_wait returns once ITS piece of a host result is
     // delivered; the other ranks' pieces are waited for when the result is asked for (qpe_shard_host_result*).
     bool deferred = false;
+    double link_gbs = 0;                // this rank's device->host rate as given to qpe_shard_set_link_weights (GB/s), 0 = unknown
+    uint64_t last_bpr = 0;              // bytes per row the previous query's scan read
     uint32_t copy_pending[2] = {0, 0};  // [parity] epoch of a device->host copy that is queued but not yet known complete
     uint32_t host_epoch[2] = {0, 0};    // epochs of the last two host-result queries waited: [0] the most recent
     uint64_t host_total[2] = {0, 0};
@@ -774,6 +776,7 @@ int qpe_shard_set_link_weights(struct engineS *engine, const double *weights, in
         s->slice_cum[r + 1] = static_cast<uint32_t>(run / sum * 1048576.0 + 0.5);
     }
     s->slice_cum[n] = 1u << 20;
+    s->link_gbs = weights[s->rank];
     return 0;
 }
 
@@ -911,10 +914,24 @@ int qpe_shard_submit(struct engineS *engine, struct whereClauseS *whereClause, i
     static const bool no_pdl = std::getenv("QPE_SHARD_NO_PDL") != nullptr;
     const bool overlap = s->n_pending >= 2 && s->last_was_post && !no_pdl;
     if (local_ok)
-        // (host result: the table is streamed through L2 with the evict_first policy, so that the staging slice the copy
-        // engine reads right after the delivery kernel is still in L2 while the NEXT scan saturates HBM)
+    {
+        // Host result: the table is streamed through L2 with the evict_first policy, so that the staging slice the copy
+        // engine reads right after the delivery kernel is still in L2 while the NEXT scan saturates HBM -- when the copy
+        // is what the pipeline waits for.  The policy costs the scan 1-3 %, so it is used only if this rank's copy (its
+        // share of a result like the last one, at the link rate given to qpe_shard_set_link_weights) takes more than
+        // 0.6 of its scan (rows x bytes per row at ~6.5 TB/s): 8 GPUs of this pool (3 MB over a 13 GB/s link against a
+        // 0.25 ms scan) yes, 2 or 4 GPUs (19 / 9 MB over 46 GB/s against 0.92 / 0.49 ms) no.  Unknown rate: from 8 ranks on.
+        bool stream_l2 = false;
+        if (to_host) {
+            const double share = static_cast<double>(s->slice_cum[s->rank + 1] - s->slice_cum[s->rank]) / 1048576.0;
+            const double copy_s = s->link_gbs > 0 ? static_cast<double>(s->host_total[0]) * 4.0 * share / (s->link_gbs * 1e9) : 0.0;
+            const double scan_s = static_cast<double>(g->table.n) * static_cast<double>(s->last_bpr ? s->last_bpr : 13) / 6.5e12;
+            stream_l2 = s->link_gbs > 0 && s->host_epoch[0] ? copy_s > 0.6 * scan_s : s->world >= 8;
+        }
         local_ok = engine_fused_enqueue(g, whereClause, out, out_cap, static_cast<uint32_t>(g->table.row_base), &pq.fe, overlap,
-                                        to_host != 0);
+                                        stream_l2);
+        if (local_ok) s->last_bpr = pq.fe.bytes_per_row;
+    }
     if (!local_ok) pq.local_error = last_error_cstr();
     pq.local_ok = local_ok;
     const unsigned long long *count = local_ok ? &g->d_fctl->final_count : nullptr;
