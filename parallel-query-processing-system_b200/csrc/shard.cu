@@ -397,12 +397,15 @@ static void release_host_result(ShardState *s) {
     s->host_creator = false;
 }
 
+static bool complete_own_copies(ShardState *s);
+
 void shard_destroy(GpuEngine *g) {
     ShardState *s = shard_of(g);
     if (!s) return;
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
     cudaStreamSynchronize(g->stream2);
+    complete_own_copies(s);  // (deferred mode) announce what this rank still owes the others
     for (int r = 0; r < s->world; ++r) {
         if (!s->comm[r]) continue;
         if (r == s->rank)
