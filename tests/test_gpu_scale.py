@@ -339,3 +339,28 @@ def test_probe_node_boundaries(pkg, n):
         w1 = np.searchsorted(keys, lo, side="right") - wf
         assert np.array_equal(f1, wf.astype(np.uint32)) and np.array_equal(c1, w1.astype(np.uint32)), (n, attr)
     eng.close()
+
+
+def test_index_at_1b_rows(pkg):
+    """BASELINE's largest table with indexes (size-independent properties): K4 sorts 1 B u64 row ids (4 digit passes,
+    163 k tiles) and 1 B int user ids (2 passes); probes answer with the closed form / the scan's count, and an indexed
+    SELECT returns the key's rows in DESCENDING position order -- the reference's leaf order"""
+    n = 1_000_000_000
+    eng = pkg.Engine.from_synth(n, columns=["command_id", "user_id"], indexes=(("command_id", 0), ("user_id", 1)))
+    lo = np.array([0, 5, 123_456_789, n - 1, n, n + 5], dtype=np.uint64)
+    first, count, _ = eng.probe_keys("command_id", lo)
+    assert first.tolist() == [0, 5, 123_456_789, n - 1, n, n] and count.tolist() == [1, 1, 1, 1, 0, 0]
+    first, count, _ = eng.probe_keys("command_id", np.array([10, n - 3], dtype=np.uint64), np.array([1_000_009, n + 9], dtype=np.uint64))
+    assert first.tolist() == [10, n - 3] and count.tolist() == [1_000_000, 3]
+    assert eng.index_slice("command_id", 999_999_990, 5).tolist() == list(range(999_999_990, 999_999_995))
+    ids, st = eng.select_ids("SELECT command_id FROM Commands WHERE user_id = 1001")
+    assert st["path"] == 1
+    cnt, _, _ = eng.select_ids_device("SELECT command_id FROM Commands WHERE user_id = 1001", force_scan=True, count_only=True)
+    assert len(ids) == cnt > 0
+    assert np.all(np.diff(ids.astype(np.int64)) < 0)          # newest row first among equal keys
+    assert np.all(eng.fetch_column("user_id", int(ids[-1]), 1) == 1001)
+    # the index's key array is sorted: sample slices across it
+    for start in (0, 333_333_333, 999_000_000):
+        k = eng.index_slice_keys("user_id", start, 100_000)
+        assert np.all(k[1:] >= k[:-1])
+    eng.close()
