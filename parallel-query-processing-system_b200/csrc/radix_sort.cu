@@ -18,6 +18,8 @@
 
 #include "radix_sort.cuh"
 
+#include <type_traits>
+
 namespace qpe {
 namespace {
 
@@ -147,12 +149,15 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t *__restrict__
     if (threadIdx.x == 0) digit_total[blockIdx.x] = running;
 }
 
-template <typename K, int ITEMS>
+// MODE: how the input is read (SortInput); FULL: every element of the tile exists (all tiles but possibly the last one:
+// no bounds checks in the ranking loop); tile0: first tile of this launch.
+template <typename K, int ITEMS, int MODE, bool FULL>
 __global__ void __launch_bounds__(kSortThreads, 2)
-    radix_scatter_kernel(const K *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, long long n, int mode,
+    radix_scatter_kernel(const K *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, long long n, long long tile0,
                          int shift, K flip, const uint32_t *__restrict__ tile_hist, long long tiles,
                          const uint32_t *__restrict__ digit_total, K *__restrict__ keys_out,
                          uint32_t *__restrict__ vals_out) {
+    constexpr int mode = MODE;
     constexpr int kTile = kSortThreads * ITEMS;
     extern __shared__ __align__(16) unsigned char sort_smem[];
     K *s_keys = reinterpret_cast<K *>(sort_smem);
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     uint32_t *s_scan = s_dstart + kBins;               // 32 words
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long tile = blockIdx.x;
+    const long long tile = tile0 + blockIdx.x;
     for (int i = threadIdx.x; i < kSortWarps * kBins; i += kSortThreads) s_whist[i] = 0;
     {
         const uint32_t tot = threadIdx.x < kBins ? digit_total[threadIdx.x] : 0;
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(kSortThreads, 2)
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const long long idx = wbase + i * 32 + lane;
-        const bool valid = idx < n;
+        const bool valid = FULL || idx < n;
         key[i] = 0;
         val[i] = 0;
         if (valid) {
@@ -223,7 +228,7 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-        const bool valid = wbase + i * 32 + lane < n;
+        const bool valid = FULL || wbase + i * 32 + lane < n;
         const uint32_t d = valid ? digit_of<K>(key[i], flip, shift) : kBins - 1;
         const uint32_t pos = s_dstart[d] + wh[d] + ((rank2[i >> 1] >> (16 * (i & 1))) & 0xffffu);
         s_keys[pos] = key[i];
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     }
     __syncthreads();
     const long long left = n - tile * static_cast<long long>(kTile);
-    const int n_valid = left < kTile ? static_cast<int>(left) : kTile;
+    const int n_valid = (FULL || left >= kTile) ? kTile : static_cast<int>(left);
     for (int j = threadIdx.x; j < n_valid; j += kSortThreads) {
         const K k = s_keys[j];
         const uint32_t d = digit_of<K>(k, flip, shift);
@@ -321,9 +326,6 @@ cudaError_t radix_sort_pairs(const K *keys_in, const uint32_t *vals_in, SortInpu
     const K flip = signed_keys ? static_cast<K>(1) << (8 * kKeyBytes - 1) : 0;
     const size_t smem = static_cast<size_t>(kTile) * (sizeof(K) + sizeof(uint32_t)) +
                         (static_cast<size_t>(kSortWarps) * kBins + 2 * kBins + 32) * sizeof(uint32_t);
-    if ((e = cudaFuncSetAttribute(radix_scatter_kernel<K, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem))) != cudaSuccess)
-        return e;
     const unsigned int grid = static_cast<unsigned int>(s.tiles);
     const K *src_k = keys_in;
     const uint32_t *src_v = vals_in;
@@ -335,10 +337,37 @@ cudaError_t radix_sort_pairs(const K *keys_in, const uint32_t *vals_in, SortInpu
         radix_count_kernel<K, ITEMS><<<grid, kSortThreads, 0, stream>>>(src_k, n, src_mode == kSortReverseIota ? 1 : 0,
                                                                         shifts[k], flip, s.tile_hist, s.tiles);
         radix_scan_kernel<<<kBins, 1024, 0, stream>>>(s.tile_hist, s.tiles, s.digit_total);
-        radix_scatter_kernel<K, ITEMS><<<grid, kSortThreads, smem, stream>>>(src_k, src_v, n, src_mode, shifts[k], flip,
-                                                                             s.tile_hist, s.tiles, s.digit_total, dst_k,
-                                                                             dst_v);
-        *launches += 3;
+        // all full tiles in one launch (no bounds checks), the last, partial tile in one of its own
+        const long long full_tiles = n / kTile;
+        auto scatter = [&](auto mode_tag) -> cudaError_t {
+            constexpr int M = decltype(mode_tag)::value;
+            cudaError_t se;
+            if (full_tiles > 0) {
+                if ((se = cudaFuncSetAttribute(radix_scatter_kernel<K, ITEMS, M, true>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
+                    return se;
+                radix_scatter_kernel<K, ITEMS, M, true><<<static_cast<unsigned int>(full_tiles), kSortThreads, smem, stream>>>(
+                    src_k, src_v, n, 0, shifts[k], flip, s.tile_hist, s.tiles, s.digit_total, dst_k, dst_v);
+                ++*launches;
+            }
+            if (full_tiles < s.tiles) {
+                if ((se = cudaFuncSetAttribute(radix_scatter_kernel<K, ITEMS, M, false>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
+                    return se;
+                radix_scatter_kernel<K, ITEMS, M, false><<<static_cast<unsigned int>(s.tiles - full_tiles), kSortThreads, smem, stream>>>(
+                    src_k, src_v, n, full_tiles, shifts[k], flip, s.tile_hist, s.tiles, s.digit_total, dst_k, dst_v);
+                ++*launches;
+            }
+            return cudaSuccess;
+        };
+        if (src_mode == kSortReverseIota)
+            e = scatter(std::integral_constant<int, kSortReverseIota>());
+        else if (src_mode == kSortIota)
+            e = scatter(std::integral_constant<int, kSortIota>());
+        else
+            e = scatter(std::integral_constant<int, kSortPairs>());
+        if (e != cudaSuccess) return e;
+        *launches += 2;
         src_k = dst_k;
         src_v = dst_v;
         src_mode = kSortPairs;
