@@ -8,7 +8,7 @@
 //   radix_count_kernel    per tile of 512 x ITEMS keys: histogram of the digit (shared-memory adds; a warp whose keys
 //                         share the digit adds once) -> tile_hist[digit][tile]
 //   radix_scan_kernel     one CTA per digit: exclusive scan of its row over the tiles, total -> digit_total[digit]
-//   radix_scatter_kernel  per tile: every warp ranks its keys in index order (same-digit lane mask by ballots + a warp-private
+//   radix_scatter_kernel  per tile: every warp ranks its keys in index order (same-digit lane mask through a shared-memory word + a warp-private
 //                         counter row, no atomics), the tile is put in digit order in shared memory and leaves as runs of
 //                         consecutive addresses: out = prefix(digit_total)[d] + tile_hist[d][tile] + rank within the tile
 // HBM traffic per pass and pair: 2 x key read + payload read + key and payload write = 3 x sizeof(K) + 8 bytes.
@@ -31,11 +31,11 @@ template <typename K>
 struct SortCfg;
 template <>
 struct SortCfg<unsigned long long> {
-    static constexpr int kItems = 12;  // 6144 pairs per tile: 72 KB of stage + 17 KB of counters, two CTAs per SM
+    static constexpr int kItems = 12;  // 6144 pairs per tile: 72 KB of stage + 34 KB of counters and masks, two CTAs per SM
 };
 template <>
 struct SortCfg<uint32_t> {
-    static constexpr int kItems = 16;  // 8192 pairs per tile: 64 KB + 17 KB
+    static constexpr int kItems = 16;  // 8192 pairs per tile: 64 KB + 34 KB
 };
 
 template <typename K>
@@ -166,10 +166,14 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     uint32_t *s_gbase = s_whist + kSortWarps * kBins;  // where this tile's run of the digit starts in the output
     uint32_t *s_dstart = s_gbase + kBins;              // where the digit starts in the tile's staged order
     uint32_t *s_scan = s_dstart + kBins;               // 32 words
+    uint32_t *s_wmask = s_scan + 32;                   // [warp][digit]: lanes of the warp whose current key has the digit
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long tile = tile0 + blockIdx.x;
-    for (int i = threadIdx.x; i < kSortWarps * kBins; i += kSortThreads) s_whist[i] = 0;
+    for (int i = threadIdx.x; i < kSortWarps * kBins; i += kSortThreads) {
+        s_whist[i] = 0;
+        s_wmask[i] = 0;
+    }
     {
         const uint32_t tot = threadIdx.x < kBins ? digit_total[threadIdx.x] : 0;
         const uint32_t before = block_exclusive_scan(tot, s_scan, nullptr);
@@ -180,6 +184,7 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     // a warp owns ITEMS x 32 consecutive elements, taken 32 at a time: (i, lane) order == index order
     const long long wbase = tile * static_cast<long long>(kTile) + warp * (ITEMS * 32);
     uint32_t *wh = s_whist + warp * kBins;
+    uint32_t *wm = s_wmask + warp * kBins;
     K key[ITEMS];
     uint32_t val[ITEMS];
     uint32_t rank2[(ITEMS + 1) / 2] = {0};  // ranks within the warp's part (< 512), two per register
@@ -200,10 +205,17 @@ __global__ void __launch_bounds__(kSortThreads, 2)
         }
         // elements past the end (last tile only) rank behind everything: digit 255, highest indices
         const uint32_t d = valid ? digit_of<K>(key[i], flip, shift) : kBins - 1;
-        const uint32_t peers = same_digit_lanes(d);
+        // lanes with the same digit: every lane sets its bit in the warp's mask word of its digit (one shared-memory
+        // atomic), reads the word back, and the first of them clears it for the next element.  (Eight ballots, one per
+        // digit bit, gave the same mask for ~48 instructions per element instead of ~8: the kernel is instruction-bound.)
+        atomicOr(&wm[d], 1u << lane);
+        __syncwarp();
+        const uint32_t peers = wm[d];
+        __syncwarp();
         const int leader = __ffs(peers) - 1;
         uint32_t prev = 0;
         if (lane == leader) {
+            wm[d] = 0;
             prev = wh[d];
             wh[d] = prev + __popc(peers);
         }
@@ -325,7 +337,7 @@ cudaError_t radix_sort_pairs(const K *keys_in, const uint32_t *vals_in, SortInpu
 
     const K flip = signed_keys ? static_cast<K>(1) << (8 * kKeyBytes - 1) : 0;
     const size_t smem = static_cast<size_t>(kTile) * (sizeof(K) + sizeof(uint32_t)) +
-                        (static_cast<size_t>(kSortWarps) * kBins + 2 * kBins + 32) * sizeof(uint32_t);
+                        (2 * static_cast<size_t>(kSortWarps) * kBins + 2 * kBins + 32) * sizeof(uint32_t);
     const unsigned int grid = static_cast<unsigned int>(s.tiles);
     const K *src_k = keys_in;
     const uint32_t *src_v = vals_in;
