@@ -64,20 +64,6 @@ __device__ __forceinline__ uint32_t digit_of(K key, K flip, int shift) {
     return static_cast<uint32_t>((key ^ flip) >> shift) & (kBins - 1);
 }
 
-// lanes of the warp that hold the same 8-bit digit as this lane: one ballot per digit bit.  (match.any does the same in
-// one instruction, but at ~64 cycles per warp on sm_100 -- ncu of the first version: the count and scatter kernels were
-// bound by it, 1.2 / 1.6 TB/s.)
-__device__ __forceinline__ uint32_t same_digit_lanes(uint32_t d) {
-    uint32_t peers = 0xffffffffu;
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        const bool bit = (d >> b) & 1u;
-        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? bal : ~bal;
-    }
-    return peers;
-}
-
 // exclusive scan of one value per thread over the CTA (any number of warps <= 32); every thread must call it
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s_scan, uint32_t *total_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
@@ -206,8 +192,9 @@ __global__ void __launch_bounds__(kSortThreads, 2)
         // elements past the end (last tile only) rank behind everything: digit 255, highest indices
         const uint32_t d = valid ? digit_of<K>(key[i], flip, shift) : kBins - 1;
         // lanes with the same digit: every lane sets its bit in the warp's mask word of its digit (one shared-memory
-        // atomic), reads the word back, and the first of them clears it for the next element.  (Eight ballots, one per
-        // digit bit, gave the same mask for ~48 instructions per element instead of ~8: the kernel is instruction-bound.)
+        // atomic), reads the word back, and the first of them clears it for the next element.  (match.any gives the same
+        // mask in one instruction, but at ~64 cycles per warp on sm_100: 7.2 ms per 100 M u64 row ids; eight ballots, one
+        // per digit bit: ~48 instructions per element, 5.3 ms; this: ~8 instructions.)
         atomicOr(&wm[d], 1u << lane);
         __syncwarp();
         const uint32_t peers = wm[d];
